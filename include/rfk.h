@@ -1,0 +1,215 @@
+/*
+ * rfk.h — C ABI of librfk.so: the B200 (sm_100a) kernels behind the three-track trunk of
+ * rosettafold-pytorch (MSA row/column attention, MSA->pair outer product, pair axial attention,
+ * pair->MSA update and their LayerNorm / softmax / residual epilogues).
+ *
+ * Conventions:
+ *  - every entry point is `extern "C"`, takes plain pointers + sizes, enqueues work on `stream`
+ *    (a cudaStream_t passed as void*), never synchronises, never allocates persistent memory and
+ *    keeps no pointer after it returns; the caller owns all buffers including workspaces;
+ *  - returns 0 (RFK_OK) or an error code; never throws, never exits; rfk_strerror() names a code;
+ *  - dtypes are RFK_F32 / RFK_BF16; "mode 0" callers hand bf16 operands to the tcgen05 kernels,
+ *    "mode 1" (fp32 validation) callers hand fp32 operands to the SIMT fp32 kernels;
+ *  - all index arithmetic is in ELEMENTS (not bytes).
+ *
+ * Each function cites the reference lines (rosettafold_pytorch/rosettafold_pytorch.py unless
+ * stated otherwise) whose arithmetic it replaces.
+ */
+#ifndef RFK_H
+#define RFK_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* rfk_stream_t; /* cudaStream_t */
+
+enum { RFK_F32 = 0, RFK_BF16 = 1 };
+
+enum {
+  RFK_OK = 0,
+  RFK_ERR_BAD_DIMS = 1,
+  RFK_ERR_MISALIGNED = 2,
+  RFK_ERR_UNSUPPORTED_ARCH = 3,
+  RFK_ERR_BAD_DTYPE = 4,
+  RFK_ERR_NULL_POINTER = 5,
+  RFK_ERR_TMA_ENCODE = 6,
+  RFK_ERR_WORKSPACE = 7,
+  RFK_ERR_UNSUPPORTED = 8,
+  RFK_ERR_CUDA_BASE = 1000 /* RFK_ERR_CUDA_BASE + cudaError_t */
+};
+
+const char* rfk_strerror(int code);
+int rfk_version(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t rfk_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Generalised element addressing used by the GEMM epilogue.
+ * offset(z0,z1,z2,m,n) = z0*zs[0]+z1*zs[1]+z2*zs[2] + (m%MR)*ms[0]+(m/MR)*ms[1]
+ *                        + (n%NR)*ns[0]+(n/NR)*ns[1]
+ * It lets one GEMM write the permuted layouts the reference produces with einops
+ * rearrange copies (:38,:51,:248,:258,:403,:425,:593) without a separate transpose pass.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t zs[3];
+  int64_t ms[2];
+  int64_t ns[2];
+} rfk_addr;
+
+enum { RFK_ACT_NONE = 0, RFK_ACT_RELU = 1, RFK_ACT_ELU = 2 };
+enum { RFK_EPI_STD = 0, RFK_EPI_BLOCKLN32 = 1 };
+
+/*
+ * Batched "TN" GEMM:  C[z][m][n] = epi( alpha * sum_k A[z][m][k] * B[z][n][k] ).
+ * A is [Z][M][K] and B is [Z][N][K], both with K contiguous (nn.Linear weight layout).
+ * z = (z2*Z[1] + z1)*Z[0] + z0; a_zs/b_zs/bias_zs give the per-level strides (0 = broadcast).
+ * Epilogue:  x = alpha*acc + bias[n];  x = act(x);  x += r0[...] + r1[...];  c[...] = x.
+ * RFK_EPI_BLOCKLN32 (needs MR == NR == 32): every aligned 32x32 block (m/32, n/32) of the
+ * product is LayerNorm-ed over its 1024 entries, index (m%32)*32 + n%32, with ln_gamma/ln_beta,
+ * before bias/act/residuals are skipped and the value is stored: this is the outer product
+ * "b n i u, b n j v -> b i j (u v)" followed by LayerNorm(1024) (:424-425, :416).
+ *
+ * Replaces: nn.Linear (:195-202, :235-238, :274-277, :436, :448, :566, :574, performer
+ * to_q/to_k/to_v/to_out), the einsums at :212, :254, :257, :424, :592 and the Residual adds
+ * at :26-28, :346, :595.
+ * ab_dtype RFK_BF16 -> tcgen05/TMEM/TMA kernel (fp32 accumulate); RFK_F32 -> SIMT fp32 kernel.
+ * bf16 operands need: 16-byte aligned base pointers, lda/ldb/z-strides multiples of 8 elements.
+ */
+typedef struct {
+  const void* a;
+  const void* b;
+  int32_t ab_dtype;
+  int32_t act;
+  int64_t M, N, K;
+  int64_t Z[3];
+  int64_t lda, ldb;
+  int64_t a_zs[3];
+  int64_t b_zs[3];
+  const float* bias;
+  int64_t bias_zs[3];
+  float alpha;
+  int32_t epi;
+  int64_t MR, NR;
+  void* c;
+  const void* r0;
+  const void* r1;
+  int32_t c_dtype, r0_dtype, r1_dtype;
+  float ln_eps;
+  rfk_addr c_addr, r0_addr, r1_addr;
+  const float* ln_gamma;
+  const float* ln_beta;
+} rfk_gemm_desc;
+
+int rfk_gemm(const rfk_gemm_desc* d, rfk_stream_t stream);
+
+/*
+ * Row LayerNorm (nn.LayerNorm, eps inside the sqrt; :323,:328,:416,:435,:437,:442-443,
+ * :522-524,:565,:573,:580):  y[r, :] = (x[r, :] - mean) * rsqrt(var + eps) * gamma + beta.
+ * gamma/beta may be NULL (pure normalisation). Row strides let the output land in a column
+ * slice of a wider buffer (the 716-channel concat of :487-496 is never materialised in fp32).
+ */
+int rfk_layernorm(const void* x, int x_dtype, int64_t x_row_stride, const float* gamma,
+                  const float* beta, float eps, void* y, int y_dtype, int64_t y_row_stride,
+                  int64_t rows, int D, rfk_stream_t stream);
+
+/* Row softmax over the last dimension (:255, :569): y[r,:] = softmax(x[r,:]); x fp32. */
+int rfk_softmax_rows(const float* x, int64_t x_row_stride, void* y, int y_dtype,
+                     int64_t y_row_stride, int64_t rows, int cols, rfk_stream_t stream);
+
+/*
+ * Symmetrised tied-attention map (:263-264): att[b,i,j,h] = 0.5*(A[b,h,i,j] + A[b,h,j,i]).
+ * A: [B,H,L,lda] (bf16 or f32), att: f32 [B,L,L,H] (+ optional bf16 copy written with row
+ * stride att16_stride into a column slice of the PairUpdateWithMsa feature buffer, :493).
+ */
+int rfk_tied_att_symmetrize(const void* A, int a_dtype, int64_t lda, float* att, void* att16,
+                            int64_t att16_stride, int B, int H, int L, rfk_stream_t stream);
+
+/*
+ * PositionWiseWeightFactor (:205-217) fused with the query scaling of :252 and the
+ * "b n l (h d) -> b h l (n d)" relayout feeding the tied-logit contraction (:254).
+ *   logit[b,l,h,n] = scale * sum_d pq[b,l,h*dh+d] * pk[b,n,l,h*dh+d];  w = softmax_n(logit)
+ *   w_out[b,n,l,h] = w                                  (optional, f32)
+ *   qt[b,h,l,n*dh+d] = q[b,n,l,h*dh+d] * w * q_scale    (optional)
+ * pq: [B,L,H*dh] row stride pq_stride; pk, q: [B,N,L,H*dh] row strides pk_stride, q_stride.
+ */
+int rfk_poswise_weight(const void* pq, int64_t pq_stride, const void* pk, int64_t pk_stride,
+                       int in_dtype, float scale, float* w_out, const void* q, int64_t q_stride,
+                       float q_scale, void* qt, int qt_dtype, int B, int N, int L, int H, int dh,
+                       rfk_stream_t stream);
+
+/*
+ * Operand preparation for the outer-product sum (:469-482): from m = proj_msa(msa) [B,N,L,P]
+ * (f32) and w [B,N,L] (f32) write
+ *   xt[b, l*P+u, n] = m[b,n,l,u]            yt[b, l*P+v, n] = m[b,n,l,v] * w[b,n,l]
+ * (K-major operands of the OPM GEMM, leading dimension ldt >= N) and
+ *   msa1d[b,l,0:P] = sum_n m[b,n,l,:]        msa1d[b,l,P:2P] = m[b,0,l,:]     (f32)
+ */
+int rfk_opm_prep(const float* m, const float* w, void* xt, void* yt, int t_dtype, int64_t ldt,
+                 float* msa1d, int B, int N, int L, int P, rfk_stream_t stream);
+
+/*
+ * pair2att logits for all encoder layers at once (:563-566; the pair input is the same for
+ * every layer, :607-610):  s = 0.5*(pair[b,i,j,:] + pair[b,j,i,:]);  xhat = (s-mean)*rstd;
+ *   logits[b, c, i, j] = sum_d Wf[c,d]*xhat[d] + bf[c],  c in [0, C)   (C = layers*heads)
+ * with Wf = W*gamma and bf = W@beta + b folded on the host. pair f32 [B,L,L,D].
+ */
+int rfk_pair2att_logits(const float* pair, const float* Wf, const float* bf, float eps,
+                        float* logits, int64_t ld_logits, int B, int L, int D, int C,
+                        rfk_stream_t stream);
+
+/*
+ * Per-(batch, channel) statistics over the L*L positions of a channels-last map
+ * (nn.InstanceNorm2d, :453,:457): stats[b,0,c] = sum x, stats[b,1,c] = sum x^2 (f32, caller
+ * zeroes `stats` first; accumulated with atomics).
+ */
+int rfk_channel_stats(const void* x, int x_dtype, float* stats, int B, int64_t positions, int C,
+                      rfk_stream_t stream);
+
+/*
+ * Apply InstanceNorm2d(affine, eps) + optional residual + ELU on a channels-last map (:453-462):
+ *   y = (x - mean_c) * rsqrt(var_c + eps) * gamma_c + beta_c;  if (res) y += res;  if (elu) y = ELU(y)
+ */
+int rfk_instnorm_apply(const void* x, int x_dtype, const float* stats, const float* gamma,
+                       const float* beta, float eps, const void* res, int res_dtype, int elu,
+                       void* y, int y_dtype, int B, int64_t positions, int C, rfk_stream_t stream);
+
+/*
+ * Performer FAVOR+ attention (performer_pytorch.FastAttention as called at :313-318 and
+ * :505-518; spec in SURVEY.md section 8c), fused: feature map (softmax kernel or ReLU kernel),
+ * key-sum, context, normaliser and output in one kernel, nothing of size tokens x m leaves the SM.
+ *   q,k,v: element (g1, g0, t, h, d) at  base + g1*gs[1] + g0*gs[0] + t*ts + h*64 + d
+ *   out  : same indexing with out_gs/out_ts.
+ * `proj` is the (m x 64) f32 projection matrix buffer. kind: 0 = softmax kernel (eps 1e-4),
+ * 1 = generalised ReLU kernel (eps 1e-3). io_dtype RFK_BF16 -> tcgen05 kernel, RFK_F32 -> SIMT.
+ */
+typedef struct {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  const float* proj;
+  int32_t io_dtype;
+  int32_t kind;
+  int32_t m_features;
+  int32_t heads;
+  int64_t tokens;
+  int64_t G[2];
+  int64_t gs[2];
+  int64_t ts;
+  int64_t out_gs[2];
+  int64_t out_ts;
+} rfk_favor_desc;
+
+int rfk_favor_attention(const rfk_favor_desc* d, rfk_stream_t stream);
+
+/* Cast / copy rows between dtypes with row strides (host-side plumbing for column slices). */
+int rfk_convert_rows(const void* x, int x_dtype, int64_t x_row_stride, void* y, int y_dtype,
+                     int64_t y_row_stride, int64_t rows, int cols, rfk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RFK_H */

@@ -1,0 +1,8 @@
+"""rosettafold-pytorch_b200 — B200-native (sm_100a) three-track trunk of rosettafold-pytorch.
+
+`ops` wraps the C ABI of librfk.so (include/rfk.h); `modules` mirrors the reference's nn.Module
+classes for the trunk (same constructors, forward signatures and state_dict keys).
+"""
+from . import _lib, ops  # noqa: F401
+
+__version__ = "0.1.0"

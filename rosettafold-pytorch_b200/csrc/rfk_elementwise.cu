@@ -1,0 +1,525 @@
+// rfk_elementwise.cu — the HBM-bound kernels of the trunk: LayerNorm, row softmax, tied-attention
+// symmetrisation, position-wise weight factor, OPM operand preparation, pair2att logits,
+// InstanceNorm statistics/apply and dtype conversion. All are coalesced, 128-bit vectorised where
+// the layout allows and reduce with warp shuffles. See include/rfk.h for the contracts.
+#include "rfk_common.cuh"
+
+namespace rfk {
+
+// ----------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, the row lives in registers (VPL 4-element vectors per lane).
+// ----------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, float (&o)[4]);
+template <>
+__device__ __forceinline__ void load4<float>(const float* p, float (&o)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&o)[4]) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+  o[0] = __low2float(a); o[1] = __high2float(a); o[2] = __low2float(b); o[3] = __high2float(b);
+}
+template <typename T>
+__device__ __forceinline__ void store4(T* p, const float (&v)[4]);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <>
+__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[4]) {
+  uint2 t;
+  t.x = pack_bf16x2(v[0], v[1]);
+  t.y = pack_bf16x2(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+
+template <typename TI, typename TO, int VPL>
+__global__ void __launch_bounds__(256)
+layernorm_vec_kernel(const TI* __restrict__ x, int64_t xs, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, TO* __restrict__ y, int64_t ys,
+                     int64_t rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const TI* xr = x + row * xs;
+  float v[VPL][4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < D) {
+      load4<TI>(xr + c, v[i]);
+      s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+    } else {
+      v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f;
+    }
+  }
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < D) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float d = v[i][j] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+  TO* yr = y + row * ys;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < D) {
+      float o[4];
+      if (gamma) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+        o[0] = (v[i][0] - mean) * rstd * g.x + b.x;
+        o[1] = (v[i][1] - mean) * rstd * g.y + b.y;
+        o[2] = (v[i][2] - mean) * rstd * g.z + b.z;
+        o[3] = (v[i][3] - mean) * rstd * g.w + b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = (v[i][j] - mean) * rstd;
+      }
+      store4<TO>(yr + c, o);
+    }
+  }
+}
+
+// generic fallback (any D / alignment): one warp per row, three passes over the row
+__global__ void __launch_bounds__(256)
+layernorm_generic_kernel(const void* __restrict__ x, int xdt, int64_t xs,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                         void* __restrict__ y, int ydt, int64_t ys, int64_t rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < D; c += 32) s += load_as_float(x, xdt, row * xs + c);
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float d = load_as_float(x, xdt, row * xs + c) - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+  for (int c = lane; c < D; c += 32) {
+    float o = (load_as_float(x, xdt, row * xs + c) - mean) * rstd;
+    if (gamma) o = o * gamma[c] + beta[c];
+    store_from_float(y, ydt, row * ys + c, o);
+  }
+}
+
+template <typename TI, typename TO>
+static int launch_ln_vec(const void* x, int64_t xs, const float* g, const float* b, float eps,
+                         void* y, int64_t ys, int64_t rows, int D, cudaStream_t st) {
+  const int vecs = (D / 4 + 31) / 32;
+  const unsigned blocks = (unsigned)((rows + 7) / 8);
+  const TI* xi = reinterpret_cast<const TI*>(x);
+  TO* yo = reinterpret_cast<TO*>(y);
+  switch (vecs) {
+    case 1: layernorm_vec_kernel<TI, TO, 1><<<blocks, 256, 0, st>>>(xi, xs, g, b, eps, yo, ys, rows, D); break;
+    case 2: layernorm_vec_kernel<TI, TO, 2><<<blocks, 256, 0, st>>>(xi, xs, g, b, eps, yo, ys, rows, D); break;
+    case 3: layernorm_vec_kernel<TI, TO, 3><<<blocks, 256, 0, st>>>(xi, xs, g, b, eps, yo, ys, rows, D); break;
+    case 4: layernorm_vec_kernel<TI, TO, 4><<<blocks, 256, 0, st>>>(xi, xs, g, b, eps, yo, ys, rows, D); break;
+    case 5: case 6: case 7: case 8:
+      layernorm_vec_kernel<TI, TO, 8><<<blocks, 256, 0, st>>>(xi, xs, g, b, eps, yo, ys, rows, D); break;
+    default: return RFK_ERR_UNSUPPORTED;
+  }
+  return post_launch();
+}
+
+// ----------------------------------------------------------------------------------------------
+// row softmax (fp32 in): one warp per row
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ x, int64_t xs, void* __restrict__ y, int ydt,
+                    int64_t ys, int64_t rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * xs;
+  float mx = -INFINITY;
+  for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, xr[c]);
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s += __expf(xr[c] - mx);
+  const float inv = 1.f / warp_sum(s);
+  for (int c = lane; c < cols; c += 32)
+    store_from_float(y, ydt, row * ys + c, __expf(xr[c] - mx) * inv);
+}
+
+// ----------------------------------------------------------------------------------------------
+// att[b,i,j,h] = 0.5 * (A[b,h,i,j] + A[b,h,j,i])
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tied_att_sym_kernel(const void* __restrict__ A, int adt, int64_t lda, float* __restrict__ att,
+                    void* __restrict__ att16, int64_t att16_stride, int B, int H, int L) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * L * L;
+  if (idx >= total) return;
+  const int j = (int)(idx % L);
+  const int i = (int)((idx / L) % L);
+  const int b = (int)(idx / ((int64_t)L * L));
+  for (int h = 0; h < H; ++h) {
+    const int64_t base = ((int64_t)b * H + h) * L;
+    const float a = load_as_float(A, adt, (base + i) * lda + j);
+    const float t = load_as_float(A, adt, (base + j) * lda + i);
+    const float v = 0.5f * (a + t);
+    att[idx * H + h] = v;
+    if (att16) reinterpret_cast<__nv_bfloat16*>(att16)[idx * att16_stride + h] = __float2bfloat16_rn(v);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// PositionWiseWeightFactor: one warp per (b, l, h); logits over n staged in shared memory.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+poswise_kernel(const void* __restrict__ pq, int64_t pqs, const void* __restrict__ pk, int64_t pks,
+               int dt, float scale, float* __restrict__ w_out, const void* __restrict__ q,
+               int64_t qs, float q_scale, void* __restrict__ qt, int qtdt, int B, int N, int L,
+               int H, int dh) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t item = (int64_t)blockIdx.x * 4 + warp;
+  if (item >= (int64_t)B * L * H) return;
+  const int h = (int)(item % H);
+  const int l = (int)((item / H) % L);
+  const int b = (int)(item / ((int64_t)H * L));
+  float* lg = sm + (size_t)warp * N;
+  const int64_t pq_off = ((int64_t)b * L + l) * pqs + (int64_t)h * dh;
+  float mx = -INFINITY;
+  for (int n = lane; n < N; n += 32) {
+    const int64_t pk_off = (((int64_t)b * N + n) * L + l) * pks + (int64_t)h * dh;
+    float acc = 0.f;
+    for (int d = 0; d < dh; ++d)
+      acc = fmaf(load_as_float(pq, dt, pq_off + d), load_as_float(pk, dt, pk_off + d), acc);
+    acc *= scale;
+    lg[n] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int n = lane; n < N; n += 32) {
+    const float e = __expf(lg[n] - mx);
+    lg[n] = e;
+    s += e;
+  }
+  const float inv = 1.f / warp_sum(s);
+  __syncwarp();
+  if (w_out)
+    for (int n = lane; n < N; n += 32)
+      w_out[(((int64_t)b * N + n) * L + l) * H + h] = lg[n] * inv;
+  if (qt) {
+    const int64_t out_base = (((int64_t)b * H + h) * L + l) * ((int64_t)N * dh);
+    for (int n = 0; n < N; ++n) {
+      const float wn = lg[n] * inv * q_scale;
+      const int64_t q_off = (((int64_t)b * N + n) * L + l) * qs + (int64_t)h * dh;
+      for (int d = lane; d < dh; d += 32)
+        store_from_float(qt, qtdt, out_base + (int64_t)n * dh + d,
+                         load_as_float(q, dt, q_off + d) * wn);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// OPM operand preparation: block (32 x 8) per (b, l); transposes [n][u] -> [u][n] through smem.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+opm_prep_kernel(const float* __restrict__ m, const float* __restrict__ w, void* __restrict__ xt,
+                void* __restrict__ yt, int tdt, int64_t ldt, float* __restrict__ msa1d, int B,
+                int N, int L, int P) {
+  __shared__ float tile[32][33];
+  __shared__ float wts[32];
+  __shared__ float part[8][33];
+  const int l = blockIdx.x % L, b = blockIdx.x / L;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int u0 = 0; u0 < P; u0 += 32) {
+    float colsum = 0.f;
+    for (int n0 = 0; n0 < N; n0 += 32) {
+      __syncthreads();
+      for (int r = ty; r < 32; r += 8) {
+        const int n = n0 + r, u = u0 + tx;
+        float val = 0.f;
+        if (n < N && u < P) val = m[(((int64_t)b * N + n) * L + l) * P + u];
+        tile[r][tx] = val;
+        colsum += val;
+      }
+      if (ty == 0) wts[tx] = (n0 + tx < N) ? w[((int64_t)b * N + n0 + tx) * L + l] : 0.f;
+      __syncthreads();
+      for (int r = ty; r < 32; r += 8) {
+        const int u = u0 + r, n = n0 + tx;
+        if (u < P && n < N) {
+          const int64_t o = ((int64_t)b * L * P + (int64_t)l * P + u) * ldt + n;
+          const float val = tile[tx][r];
+          store_from_float(xt, tdt, o, val);
+          store_from_float(yt, tdt, o, val * wts[tx]);
+        }
+      }
+    }
+    __syncthreads();
+    part[ty][tx] = colsum;
+    __syncthreads();
+    if (ty == 0 && u0 + tx < P) {
+      float s = 0.f;
+      for (int r = 0; r < 8; ++r) s += part[r][tx];
+      const int64_t o = ((int64_t)b * L + l) * (2 * P);
+      msa1d[o + u0 + tx] = s;
+      msa1d[o + P + u0 + tx] = m[(((int64_t)b * N + 0) * L + l) * P + u0 + tx];
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// pair2att logits: one warp per (b, i<=j) pair of positions; weights in shared memory.
+// ----------------------------------------------------------------------------------------------
+constexpr int kP2AMaxC = 32;
+__global__ void __launch_bounds__(256)
+pair2att_kernel(const float* __restrict__ pair, const float* __restrict__ Wf,
+                const float* __restrict__ bf, float eps, float* __restrict__ logits, int64_t ldl,
+                int B, int L, int D, int C) {
+  extern __shared__ float sw[];  // [C][D]
+  for (int i = threadIdx.x; i < C * D; i += blockDim.x) sw[i] = Wf[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= (int64_t)B * L * L) return;
+  const int j = (int)(item % L);
+  const int i = (int)((item / L) % L);
+  const int b = (int)(item / ((int64_t)L * L));
+  if (i > j) return;
+  const float* pij = pair + (((int64_t)b * L + i) * L + j) * D;
+  const float* pji = pair + (((int64_t)b * L + j) * L + i) * D;
+  // D <= 32 * 16 supported
+  float v[16];
+  float s = 0.f;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    const int d = t * 32 + lane;
+    v[t] = d < D ? 0.5f * (pij[d] + pji[d]) : 0.f;
+    s += v[t];
+  }
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    const int d = t * 32 + lane;
+    const float dd = d < D ? v[t] - mean : 0.f;
+    v[t] = dd;
+    q += dd * dd;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+  for (int c = 0; c < C; ++c) {
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const int d = t * 32 + lane;
+      if (d < D) acc = fmaf(v[t], sw[c * D + d], acc);
+    }
+    acc = warp_sum(acc) * rstd + bf[c];
+    if (lane == 0) {
+      const int64_t base = ((int64_t)b * C + c) * L;
+      logits[(base + i) * ldl + j] = acc;
+      logits[(base + j) * ldl + i] = acc;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// InstanceNorm statistics and apply (channels-last)
+// ----------------------------------------------------------------------------------------------
+__global__ void channel_stats_kernel(const void* __restrict__ x, int xdt, float* __restrict__ stats,
+                                     int64_t positions, int C, int chunk) {
+  const int b = blockIdx.y;
+  const int64_t p0 = (int64_t)blockIdx.x * chunk;
+  const int64_t p1 = p0 + chunk < positions ? p0 + chunk : positions;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (int64_t p = p0; p < p1; ++p) {
+      const float v = load_as_float(x, xdt, ((int64_t)b * positions + p) * C + c);
+      s += v;
+      q = fmaf(v, v, q);
+    }
+    atomicAdd(&stats[((int64_t)b * 2 + 0) * C + c], s);
+    atomicAdd(&stats[((int64_t)b * 2 + 1) * C + c], q);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+instnorm_apply_kernel(const void* __restrict__ x, int xdt, const float* __restrict__ stats,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                      const void* __restrict__ res, int rdt, int elu, void* __restrict__ y, int ydt,
+                      int64_t positions, int C, int64_t total) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  const int64_t b = idx / ((int64_t)C * positions);
+  const float inv_n = 1.f / (float)positions;
+  const float mean = stats[(b * 2 + 0) * C + c] * inv_n;
+  const float var = fmaxf(stats[(b * 2 + 1) * C + c] * inv_n - mean * mean, 0.f);
+  float v = (load_as_float(x, xdt, idx) - mean) * rsqrtf(var + eps) * gamma[c] + beta[c];
+  if (res) v += load_as_float(res, rdt, idx);
+  if (elu) v = v > 0.f ? v : expm1f(v);
+  store_from_float(y, ydt, idx, v);
+}
+
+__global__ void __launch_bounds__(256)
+convert_rows_kernel(const void* __restrict__ x, int xdt, int64_t xs, void* __restrict__ y, int ydt,
+                    int64_t ys, int64_t rows, int cols) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const int64_t r = idx / cols;
+  const int c = (int)(idx % cols);
+  store_from_float(y, ydt, r * ys + c, load_as_float(x, xdt, r * xs + c));
+}
+
+}  // namespace rfk
+
+using namespace rfk;
+
+static inline bool dtype_ok(int d) { return d == RFK_F32 || d == RFK_BF16; }
+
+extern "C" int rfk_layernorm(const void* x, int xdt, int64_t xs, const float* gamma,
+                             const float* beta, float eps, void* y, int ydt, int64_t ys,
+                             int64_t rows, int D, rfk_stream_t stream) {
+  if (!x || !y) return RFK_ERR_NULL_POINTER;
+  if ((gamma == nullptr) != (beta == nullptr)) return RFK_ERR_NULL_POINTER;
+  if (rows < 0 || D <= 0) return RFK_ERR_BAD_DIMS;
+  if (!dtype_ok(xdt) || !dtype_ok(ydt)) return RFK_ERR_BAD_DTYPE;
+  if (rows == 0) return RFK_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int xa = xdt == RFK_F32 ? 16 : 8, ya = ydt == RFK_F32 ? 16 : 8;
+  const int xe = xdt == RFK_F32 ? 4 : 2, ye = ydt == RFK_F32 ? 4 : 2;
+  const bool vec_ok = D % 4 == 0 && D <= 1024 && (reinterpret_cast<uintptr_t>(x) % xa) == 0 &&
+                      (reinterpret_cast<uintptr_t>(y) % ya) == 0 && (xs * xe) % xa == 0 &&
+                      (ys * ye) % ya == 0 &&
+                      (!gamma || (aligned16(gamma) && aligned16(beta)));
+  if (vec_ok) {
+    if (xdt == RFK_F32 && ydt == RFK_F32)
+      return launch_ln_vec<float, float>(x, xs, gamma, beta, eps, y, ys, rows, D, st);
+    if (xdt == RFK_F32 && ydt == RFK_BF16)
+      return launch_ln_vec<float, __nv_bfloat16>(x, xs, gamma, beta, eps, y, ys, rows, D, st);
+    if (xdt == RFK_BF16 && ydt == RFK_BF16)
+      return launch_ln_vec<__nv_bfloat16, __nv_bfloat16>(x, xs, gamma, beta, eps, y, ys, rows, D, st);
+    return launch_ln_vec<__nv_bfloat16, float>(x, xs, gamma, beta, eps, y, ys, rows, D, st);
+  }
+  layernorm_generic_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, xdt, xs, gamma, beta, eps,
+                                                                      y, ydt, ys, rows, D);
+  return post_launch();
+}
+
+extern "C" int rfk_softmax_rows(const float* x, int64_t xs, void* y, int ydt, int64_t ys,
+                                int64_t rows, int cols, rfk_stream_t stream) {
+  if (!x || !y) return RFK_ERR_NULL_POINTER;
+  if (rows < 0 || cols <= 0) return RFK_ERR_BAD_DIMS;
+  if (!dtype_ok(ydt)) return RFK_ERR_BAD_DTYPE;
+  if (rows == 0) return RFK_OK;
+  softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, xs, y, ydt, ys, rows, cols);
+  return post_launch();
+}
+
+extern "C" int rfk_tied_att_symmetrize(const void* A, int adt, int64_t lda, float* att, void* att16,
+                                       int64_t att16_stride, int B, int H, int L,
+                                       rfk_stream_t stream) {
+  if (!A || !att) return RFK_ERR_NULL_POINTER;
+  if (B <= 0 || H <= 0 || L <= 0) return RFK_ERR_BAD_DIMS;
+  if (!dtype_ok(adt)) return RFK_ERR_BAD_DTYPE;
+  const int64_t total = (int64_t)B * L * L;
+  tied_att_sym_kernel<<<(unsigned)((total + 255) / 256), 256, 0,
+                        reinterpret_cast<cudaStream_t>(stream)>>>(A, adt, lda, att, att16,
+                                                                  att16_stride, B, H, L);
+  return post_launch();
+}
+
+extern "C" int rfk_poswise_weight(const void* pq, int64_t pqs, const void* pk, int64_t pks, int dt,
+                                  float scale, float* w_out, const void* q, int64_t qs,
+                                  float q_scale, void* qt, int qtdt, int B, int N, int L, int H,
+                                  int dh, rfk_stream_t stream) {
+  if (!pq || !pk) return RFK_ERR_NULL_POINTER;
+  if (qt && !q) return RFK_ERR_NULL_POINTER;
+  if (B <= 0 || N <= 0 || L <= 0 || H <= 0 || dh <= 0) return RFK_ERR_BAD_DIMS;
+  if (!dtype_ok(dt) || (qt && !dtype_ok(qtdt))) return RFK_ERR_BAD_DTYPE;
+  const size_t smem = (size_t)4 * N * sizeof(float);
+  if (smem > 48 * 1024) return RFK_ERR_BAD_DIMS;
+  const int64_t items = (int64_t)B * L * H;
+  poswise_kernel<<<(unsigned)((items + 3) / 4), 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      pq, pqs, pk, pks, dt, scale, w_out, q, qs, q_scale, qt, qtdt, B, N, L, H, dh);
+  return post_launch();
+}
+
+extern "C" int rfk_opm_prep(const float* m, const float* w, void* xt, void* yt, int tdt,
+                            int64_t ldt, float* msa1d, int B, int N, int L, int P,
+                            rfk_stream_t stream) {
+  if (!m || !w || !xt || !yt || !msa1d) return RFK_ERR_NULL_POINTER;
+  if (B <= 0 || N <= 0 || L <= 0 || P <= 0 || ldt < N) return RFK_ERR_BAD_DIMS;
+  if (!dtype_ok(tdt)) return RFK_ERR_BAD_DTYPE;
+  opm_prep_kernel<<<(unsigned)(B * L), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      m, w, xt, yt, tdt, ldt, msa1d, B, N, L, P);
+  return post_launch();
+}
+
+extern "C" int rfk_pair2att_logits(const float* pair, const float* Wf, const float* bf, float eps,
+                                   float* logits, int64_t ldl, int B, int L, int D, int C,
+                                   rfk_stream_t stream) {
+  if (!pair || !Wf || !bf || !logits) return RFK_ERR_NULL_POINTER;
+  if (B <= 0 || L <= 0 || D <= 0 || D > 512 || C <= 0 || C > kP2AMaxC || ldl < L)
+    return RFK_ERR_BAD_DIMS;
+  const size_t smem = (size_t)C * D * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(pair2att_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    configured = true;
+  }
+  const int64_t items = (int64_t)B * L * L;
+  pair2att_kernel<<<(unsigned)((items + 7) / 8), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      pair, Wf, bf, eps, logits, ldl, B, L, D, C);
+  return post_launch();
+}
+
+extern "C" int rfk_channel_stats(const void* x, int xdt, float* stats, int B, int64_t positions,
+                                 int C, rfk_stream_t stream) {
+  if (!x || !stats) return RFK_ERR_NULL_POINTER;
+  if (B <= 0 || positions <= 0 || C <= 0) return RFK_ERR_BAD_DIMS;
+  if (!dtype_ok(xdt)) return RFK_ERR_BAD_DTYPE;
+  const int chunk = 128;
+  dim3 grid((unsigned)((positions + chunk - 1) / chunk), (unsigned)B);
+  const int threads = C >= 256 ? 256 : ((C + 31) / 32) * 32;
+  channel_stats_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, xdt, stats, positions, C, chunk);
+  return post_launch();
+}
+
+extern "C" int rfk_instnorm_apply(const void* x, int xdt, const float* stats, const float* gamma,
+                                  const float* beta, float eps, const void* res, int rdt, int elu,
+                                  void* y, int ydt, int B, int64_t positions, int C,
+                                  rfk_stream_t stream) {
+  if (!x || !stats || !gamma || !beta || !y) return RFK_ERR_NULL_POINTER;
+  if (B <= 0 || positions <= 0 || C <= 0) return RFK_ERR_BAD_DIMS;
+  if (!dtype_ok(xdt) || !dtype_ok(ydt) || (res && !dtype_ok(rdt))) return RFK_ERR_BAD_DTYPE;
+  const int64_t total = (int64_t)B * positions * C;
+  instnorm_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0,
+                          reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, xdt, stats, gamma, beta, eps, res, rdt, elu, y, ydt, positions, C, total);
+  return post_launch();
+}
+
+extern "C" int rfk_convert_rows(const void* x, int xdt, int64_t xs, void* y, int ydt, int64_t ys,
+                                int64_t rows, int cols, rfk_stream_t stream) {
+  if (!x || !y) return RFK_ERR_NULL_POINTER;
+  if (rows < 0 || cols <= 0) return RFK_ERR_BAD_DIMS;
+  if (!dtype_ok(xdt) || !dtype_ok(ydt)) return RFK_ERR_BAD_DTYPE;
+  if (rows == 0) return RFK_OK;
+  const int64_t total = rows * cols;
+  convert_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0,
+                        reinterpret_cast<cudaStream_t>(stream)>>>(x, xdt, xs, y, ydt, ys, rows, cols);
+  return post_launch();
+}

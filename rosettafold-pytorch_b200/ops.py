@@ -1,0 +1,360 @@
+"""Tensor-level wrappers over the C ABI (include/rfk.h).
+
+Every function takes CUDA tensors (or strided views of them), validates shapes/strides, and
+enqueues exactly one librfk kernel on the current CUDA stream. Nothing here computes with
+PyTorch: torch is used for device memory and streams only. Calling any op without librfk.so or
+on a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_ELU, ACT_NONE, ACT_RELU, EPI_BLOCKLN32, EPI_STD, RFK_BF16, RFK_F32,
+                   RfkAddr, RfkFavorDesc, RfkGemmDesc)
+
+__all__ = [
+    "ACT_NONE", "ACT_RELU", "ACT_ELU", "EPI_STD", "EPI_BLOCKLN32",
+    "gemm", "layernorm", "softmax_rows", "tied_att_symmetrize", "poswise_weight", "opm_prep",
+    "pair2att_logits", "channel_stats", "instnorm_apply", "favor_attention", "convert_rows",
+]
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return RFK_F32
+    if t.dtype == torch.bfloat16:
+        return RFK_BF16
+    raise TypeError(f"rfk ops take float32 or bfloat16 tensors, got {t.dtype}")
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32ptr(t, name):
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise TypeError(f"{name} must be a contiguous float32 tensor")
+    return C.c_void_p(t.data_ptr())
+
+
+class _CudaBackend:
+    """Calls librfk.so. The only backend the package ships."""
+
+    name = "librfk"
+
+    def __init__(self):
+        self.lib = _lib.load()
+
+    @staticmethod
+    def _stream(t: torch.Tensor):
+        if not t.is_cuda:
+            raise RuntimeError("rfk ops run on CUDA tensors only (no CPU path exists)")
+        return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+    # -- gemm ---------------------------------------------------------------------------------
+    def gemm(self, a, b, c_view, bias, act, alpha, r0, r1, epi, ln_gamma, ln_beta, ln_eps):
+        d = RfkGemmDesc()
+        Z = list(a.shape[:3])
+        M, K = a.shape[3], a.shape[4]
+        N = b.shape[3]
+        d.a, d.b = a.data_ptr(), b.data_ptr()
+        d.ab_dtype = _dt(a)
+        d.act = act
+        d.M, d.N, d.K = M, N, K
+        for i in range(3):  # Z[0] is the fastest level = tensor dim 2
+            d.Z[i] = Z[2 - i]
+            d.a_zs[i] = a.stride(2 - i) if Z[2 - i] > 1 else 0
+            d.b_zs[i] = b.stride(2 - i) if b.shape[2 - i] > 1 else 0
+            d.bias_zs[i] = 0
+        d.lda, d.ldb = a.stride(3), b.stride(3)
+        d.bias = None if bias is None else bias.data_ptr()
+        d.alpha = alpha
+        d.epi = epi
+        d.MR, d.NR = c_view.shape[4], c_view.shape[6]
+        d.c = c_view.data_ptr()
+        d.c_dtype = _dt(c_view)
+
+        def fill(addr: RfkAddr, t):
+            for i in range(3):
+                addr.zs[i] = t.stride(2 - i) if t.shape[2 - i] > 1 else 0
+            addr.ms[0] = t.stride(4) if t.shape[4] > 1 else 0
+            addr.ms[1] = t.stride(3) if t.shape[3] > 1 else 0
+            addr.ns[0] = t.stride(6) if t.shape[6] > 1 else 0
+            addr.ns[1] = t.stride(5) if t.shape[5] > 1 else 0
+
+        fill(d.c_addr, c_view)
+        if r0 is not None:
+            d.r0, d.r0_dtype = r0.data_ptr(), _dt(r0)
+            fill(d.r0_addr, r0)
+        if r1 is not None:
+            d.r1, d.r1_dtype = r1.data_ptr(), _dt(r1)
+            fill(d.r1_addr, r1)
+        d.ln_eps = ln_eps
+        d.ln_gamma = None if ln_gamma is None else ln_gamma.data_ptr()
+        d.ln_beta = None if ln_beta is None else ln_beta.data_ptr()
+        _lib.check(self.lib.rfk_gemm(C.byref(d), self._stream(a)), "rfk_gemm")
+
+    def layernorm(self, x, gamma, beta, eps, out):
+        _lib.check(self.lib.rfk_layernorm(_ptr(x), _dt(x), x.stride(0), _f32ptr(gamma, "gamma"),
+                                          _f32ptr(beta, "beta"), eps, _ptr(out), _dt(out),
+                                          out.stride(0), x.shape[0], x.shape[1], self._stream(x)),
+                   "rfk_layernorm")
+
+    def softmax_rows(self, x, out):
+        _lib.check(self.lib.rfk_softmax_rows(_ptr(x), x.stride(0), _ptr(out), _dt(out), out.stride(0),
+                                             x.shape[0], x.shape[1], self._stream(x)),
+                   "rfk_softmax_rows")
+
+    def tied_att_symmetrize(self, A, att, att16):
+        B, H, L, _ = A.shape
+        _lib.check(self.lib.rfk_tied_att_symmetrize(
+            _ptr(A), _dt(A), A.stride(2), _ptr(att), _ptr(att16),
+            0 if att16 is None else att16.stride(2), B, H, L, self._stream(A)),
+            "rfk_tied_att_symmetrize")
+
+    def poswise_weight(self, pq, pk, scale, w_out, q, q_scale, qt, H, dh):
+        B, N, L, _ = pk.shape
+        _lib.check(self.lib.rfk_poswise_weight(
+            _ptr(pq), pq.stride(1), _ptr(pk), pk.stride(2), _dt(pk), scale, _ptr(w_out), _ptr(q),
+            0 if q is None else q.stride(2), q_scale, _ptr(qt), 0 if qt is None else _dt(qt),
+            B, N, L, H, dh, self._stream(pk)), "rfk_poswise_weight")
+
+    def opm_prep(self, m, w, xt, yt, msa1d):
+        B, N, L, P = m.shape
+        _lib.check(self.lib.rfk_opm_prep(_ptr(m), _ptr(w), _ptr(xt), _ptr(yt), _dt(xt), xt.stride(1),
+                                         _ptr(msa1d), B, N, L, P, self._stream(m)), "rfk_opm_prep")
+
+    def pair2att_logits(self, pair, Wf, bf, eps, logits):
+        B, L, _, D = pair.shape
+        Cn = Wf.shape[0]
+        _lib.check(self.lib.rfk_pair2att_logits(_ptr(pair), _ptr(Wf), _ptr(bf), eps, _ptr(logits),
+                                                logits.stride(2), B, L, D, Cn, self._stream(pair)),
+                   "rfk_pair2att_logits")
+
+    def channel_stats(self, x, stats):
+        B, P, Cn = x.shape
+        _lib.check(self.lib.rfk_channel_stats(_ptr(x), _dt(x), _ptr(stats), B, P, Cn, self._stream(x)),
+                   "rfk_channel_stats")
+
+    def instnorm_apply(self, x, stats, gamma, beta, eps, res, elu, out):
+        B, P, Cn = x.shape
+        _lib.check(self.lib.rfk_instnorm_apply(
+            _ptr(x), _dt(x), _ptr(stats), _f32ptr(gamma, "gamma"), _f32ptr(beta, "beta"), eps,
+            _ptr(res), 0 if res is None else _dt(res), 1 if elu else 0, _ptr(out), _dt(out), B, P, Cn,
+            self._stream(x)), "rfk_instnorm_apply")
+
+    def favor_attention(self, q, k, v, out, proj, kind, heads):
+        d = RfkFavorDesc()
+        d.q, d.k, d.v, d.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+        d.proj = proj.data_ptr()
+        d.io_dtype = _dt(q)
+        d.kind = kind
+        d.m_features = proj.shape[0]
+        d.heads = heads
+        G1, G0, T, _ = q.shape
+        d.tokens = T
+        d.G[0], d.G[1] = G0, G1
+        d.gs[0], d.gs[1] = q.stride(1), q.stride(0)
+        d.ts = q.stride(2)
+        d.out_gs[0], d.out_gs[1] = out.stride(1), out.stride(0)
+        d.out_ts = out.stride(2)
+        _lib.check(self.lib.rfk_favor_attention(C.byref(d), self._stream(q)), "rfk_favor_attention")
+
+    def convert_rows(self, x, out):
+        _lib.check(self.lib.rfk_convert_rows(_ptr(x), _dt(x), x.stride(0), _ptr(out), _dt(out),
+                                             out.stride(0), x.shape[0], x.shape[1], self._stream(x)),
+                   "rfk_convert_rows")
+
+
+_backend = None
+
+
+def backend():
+    global _backend
+    if _backend is None:
+        _backend = _CudaBackend()
+    return _backend
+
+
+def _set_backend_for_tests(b):
+    """tests/ only: swap in the oracle-backed emulation to check host logic without a GPU."""
+    global _backend
+    prev = _backend
+    _backend = b
+    return prev
+
+
+# ---------------------------------------------------------------------------------------------
+# public wrappers (shape / stride validation common to every backend)
+# ---------------------------------------------------------------------------------------------
+def _lead(t: torch.Tensor, nd: int) -> torch.Tensor:
+    while t.dim() < nd:
+        t = t.unsqueeze(0)
+    return t
+
+
+def gemm(a, b, c_view, *, bias=None, act=ACT_NONE, alpha=1.0, r0=None, r1=None, epi=EPI_STD,
+         ln_gamma=None, ln_beta=None, ln_eps=1e-5):
+    """C[z][m][n] = epi(alpha * sum_k a[z][m][k] b[z][n][k]).
+
+    a: (..Z, M, K) and b: (..Z, N, K) with up to three leading batch dims (b may have size-1 dims
+    that broadcast); the last dim must be contiguous. c_view / r0 / r1 are 7-D strided views
+    indexed [Z2, Z1, Z0, M1, MR, N1, NR] with m = M1*MR + mr, n = N1*NR + nr (use .expand for
+    broadcast addends): the kernel writes/reads exactly those strides.
+    """
+    a, b = _lead(a, 5), _lead(b, 5)
+    if a.dim() != 5 or b.dim() != 5 or c_view.dim() != 7:
+        raise ValueError("gemm: a, b must be <=5-D and c_view 7-D")
+    if a.dtype != b.dtype:
+        raise TypeError("gemm: a and b dtypes differ")
+    if a.stride(4) != 1 or b.stride(4) != 1:
+        raise ValueError("gemm: K must be the contiguous dimension of a and b")
+    if a.shape[4] != b.shape[4]:
+        raise ValueError(f"gemm: K mismatch {a.shape} vs {b.shape}")
+    for i in range(3):
+        if b.shape[i] not in (1, a.shape[i]):
+            raise ValueError("gemm: b batch dims must match a or be 1")
+    Zs, M, N = tuple(a.shape[:3]), a.shape[3], b.shape[3]
+    for name, t in (("c_view", c_view), ("r0", r0), ("r1", r1)):
+        if t is None:
+            continue
+        if tuple(t.shape[:3]) != Zs or t.shape[3] * t.shape[4] != M or t.shape[5] * t.shape[6] != N:
+            raise ValueError(f"gemm: {name} shape {tuple(t.shape)} does not match Z={Zs} M={M} N={N}")
+        if tuple(t.shape[3:]) != tuple(c_view.shape[3:]):
+            raise ValueError("gemm: residual views must share c_view's (M1,MR,N1,NR) split")
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
+        raise ValueError("gemm: bias must be contiguous float32 of length N")
+    backend().gemm(a, b, c_view, bias, act, float(alpha), r0, r1, epi, ln_gamma, ln_beta, float(ln_eps))
+    return c_view
+
+
+def cview(t: torch.Tensor, shape7) -> torch.Tensor:
+    """Reshape a 2-D [M, N] tensor (row stride arbitrary) to the trivial 7-D gemm view."""
+    M, N = t.shape
+    return t.as_strided((1, 1, 1, 1, M, 1, N), (0, 0, 0, 0, t.stride(0), 0, t.stride(1)))
+
+
+def layernorm(x, gamma, beta, eps, out):
+    if x.dim() != 2 or out.dim() != 2 or x.shape != out.shape:
+        raise ValueError("layernorm: x and out must be 2-D with equal shapes")
+    if x.stride(1) != 1 or out.stride(1) != 1:
+        raise ValueError("layernorm: last dim must be contiguous")
+    backend().layernorm(x, gamma, beta, float(eps), out)
+    return out
+
+
+def softmax_rows(x, out):
+    if x.dim() != 2 or out.shape != x.shape or x.dtype != torch.float32:
+        raise ValueError("softmax_rows: x must be 2-D float32 and out the same shape")
+    if x.stride(1) != 1 or out.stride(1) != 1:
+        raise ValueError("softmax_rows: last dim must be contiguous")
+    backend().softmax_rows(x, out)
+    return out
+
+
+def tied_att_symmetrize(A, att, att16=None):
+    """A: [B,H,L,L] view (row stride free); att: contiguous f32 [B,L,L,H]; att16: [B,L,L,H] view
+    of a wider bf16 buffer (stride(2) = row stride)."""
+    B, H, L, L2 = A.shape
+    if L != L2 or tuple(att.shape) != (B, L, L, H) or not att.is_contiguous() or att.dtype != torch.float32:
+        raise ValueError("tied_att_symmetrize: bad shapes")
+    if A.stride(3) != 1 or A.stride(1) != L * A.stride(2) or A.stride(0) != H * A.stride(1):
+        raise ValueError("tied_att_symmetrize: A must be [B,H,L,ld] packed")
+    backend().tied_att_symmetrize(A, att, att16)
+    return att
+
+
+def poswise_weight(pq, pk, scale, *, w_out=None, q=None, q_scale=1.0, qt=None, heads, d_head):
+    """pq: [B,L,H*dh] view, pk/q: [B,N,L,H*dh] views (last dim contiguous, rows packed over
+    (b,n,l)); w_out: contiguous f32 [B,N,L,H]; qt: contiguous [B,H,L,N*dh]."""
+    B, N, L, D = pk.shape
+    if D != heads * d_head or tuple(pq.shape) != (B, L, D):
+        raise ValueError("poswise_weight: bad shapes")
+    if pq.dtype != pk.dtype or (q is not None and q.dtype != pk.dtype):
+        raise TypeError("poswise_weight: pq, pk, q dtypes differ")
+    for t in (pk, q):
+        if t is not None and (t.stride(3) != 1 or t.stride(1) != L * t.stride(2) or t.stride(0) != N * t.stride(1)):
+            raise ValueError("poswise_weight: pk/q rows must be packed over (b,n,l)")
+    if pq.stride(2) != 1 or pq.stride(0) != L * pq.stride(1):
+        raise ValueError("poswise_weight: pq rows must be packed over (b,l)")
+    if w_out is not None and (tuple(w_out.shape) != (B, N, L, heads) or not w_out.is_contiguous()):
+        raise ValueError("poswise_weight: w_out must be contiguous [B,N,L,H]")
+    if qt is not None and (tuple(qt.shape) != (B, heads, L, N * d_head) or not qt.is_contiguous()):
+        raise ValueError("poswise_weight: qt must be contiguous [B,H,L,N*dh]")
+    backend().poswise_weight(pq, pk, float(scale), w_out, q, float(q_scale), qt, heads, d_head)
+
+
+def opm_prep(m, w, xt, yt, msa1d):
+    B, N, L, P = m.shape
+    if not (m.is_contiguous() and w.is_contiguous() and msa1d.is_contiguous()):
+        raise ValueError("opm_prep: m, w, msa1d must be contiguous")
+    if m.dtype != torch.float32 or w.dtype != torch.float32 or msa1d.dtype != torch.float32:
+        raise TypeError("opm_prep: m, w, msa1d are float32")
+    if w.numel() != B * N * L or tuple(msa1d.shape) != (B, L, 2 * P):
+        raise ValueError("opm_prep: bad shapes")
+    for t in (xt, yt):
+        if tuple(t.shape) != (B, L * P, N) or t.stride(2) != 1 or t.stride(0) != L * P * t.stride(1):
+            raise ValueError("opm_prep: xt/yt must be [B, L*P, N] views with packed rows")
+    if xt.stride(1) != yt.stride(1) or xt.dtype != yt.dtype:
+        raise ValueError("opm_prep: xt and yt must share leading dimension and dtype")
+    backend().opm_prep(m, w, xt, yt, msa1d)
+
+
+def pair2att_logits(pair, Wf, bf, eps, logits):
+    B, L, L2, D = pair.shape
+    Cn = Wf.shape[0]
+    if L != L2 or not pair.is_contiguous() or pair.dtype != torch.float32:
+        raise ValueError("pair2att_logits: pair must be contiguous f32 [B,L,L,D]")
+    if tuple(Wf.shape) != (Cn, D) or tuple(bf.shape) != (Cn,) or not Wf.is_contiguous():
+        raise ValueError("pair2att_logits: bad weight shapes")
+    if tuple(logits.shape) != (B, Cn, L, L) or logits.dtype != torch.float32 or logits.stride(3) != 1 \
+            or logits.stride(1) != L * logits.stride(2) or logits.stride(0) != Cn * logits.stride(1):
+        raise ValueError("pair2att_logits: logits must be a packed [B,C,L,ld] f32 view")
+    backend().pair2att_logits(pair, Wf, bf, float(eps), logits)
+    return logits
+
+
+def channel_stats(x, stats):
+    B, P, Cn = x.shape
+    if not x.is_contiguous() or tuple(stats.shape) != (B, 2, Cn) or stats.dtype != torch.float32:
+        raise ValueError("channel_stats: x contiguous [B,P,C], stats f32 [B,2,C] (pre-zeroed)")
+    backend().channel_stats(x, stats)
+    return stats
+
+
+def instnorm_apply(x, stats, gamma, beta, eps, out, *, res=None, elu=False):
+    if not x.is_contiguous() or not out.is_contiguous() or x.shape != out.shape:
+        raise ValueError("instnorm_apply: x/out must be contiguous and equal-shaped")
+    if res is not None and (res.shape != x.shape or not res.is_contiguous()):
+        raise ValueError("instnorm_apply: res must match x")
+    backend().instnorm_apply(x, stats, gamma, beta, float(eps), res, elu, out)
+    return out
+
+
+def favor_attention(q, k, v, out, proj, *, kind, heads):
+    """q,k,v,out: [G1, G0, T, heads*64] strided views (same strides for q,k,v; last dim
+    contiguous); proj: contiguous f32 [m, 64]; kind 0 = softmax kernel, 1 = ReLU kernel."""
+    if q.dim() != 4 or q.shape != k.shape or q.shape != v.shape or q.shape != out.shape:
+        raise ValueError("favor_attention: q,k,v,out must be equal-shaped 4-D views")
+    if q.shape[3] != heads * 64:
+        raise ValueError("favor_attention: dim_head is fixed at 64")
+    if not (q.stride() == k.stride() == v.stride()) or q.stride(3) != 1 or out.stride(3) != 1:
+        raise ValueError("favor_attention: q,k,v must share strides, last dim contiguous")
+    if not (q.dtype == k.dtype == v.dtype == out.dtype):
+        raise TypeError("favor_attention: dtype mismatch")
+    if proj.dtype != torch.float32 or not proj.is_contiguous() or proj.shape[1] != 64:
+        raise ValueError("favor_attention: proj must be contiguous f32 [m,64]")
+    backend().favor_attention(q, k, v, out, proj, int(kind), int(heads))
+    return out
+
+
+def convert_rows(x, out):
+    if x.dim() != 2 or x.shape != out.shape or x.stride(1) != 1 or out.stride(1) != 1:
+        raise ValueError("convert_rows: 2-D views with contiguous last dim")
+    backend().convert_rows(x, out)
+    return out
