@@ -6,3 +6,10 @@ classes for the trunk (same constructors, forward signatures and state_dict keys
 from . import _lib, ops  # noqa: F401
 
 __version__ = "0.1.0"
+from . import modules  # noqa: E402,F401
+from .modules import (ColWise, EncoderLayer, FeedForward, MsaUpdateUsingSelfAttention,  # noqa: E402,F401
+                      MsaUpdateWithPair, MsaUpdateWithPairLayer, OuterProductMean,
+                      PairUpdateWithAxialAttention, PairUpdateWithAxialAttentionLayer,
+                      PairUpdateWithMsa, PerformerSelfAttention, PositionWiseWeightFactor, Residual,
+                      RowWise, SoftTiedAttentionOverResidues, Symmetrization, TrunkBlocks,
+                      TwoTrackBlock, get_mode, load_reference_weights, set_mode)

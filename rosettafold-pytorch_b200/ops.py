@@ -233,8 +233,8 @@ def gemm(a, b, c_view, *, bias=None, act=ACT_NONE, alpha=1.0, r0=None, r1=None, 
     return c_view
 
 
-def cview(t: torch.Tensor, shape7) -> torch.Tensor:
-    """Reshape a 2-D [M, N] tensor (row stride arbitrary) to the trivial 7-D gemm view."""
+def cview(t: torch.Tensor) -> torch.Tensor:
+    """A 2-D [M, N] tensor (row stride arbitrary) as the trivial 7-D gemm view."""
     M, N = t.shape
     return t.as_strided((1, 1, 1, 1, M, 1, N), (0, 0, 0, 0, t.stride(0), 0, t.stride(1)))
 

@@ -1,0 +1,110 @@
+"""CPU tests of the host logic: the b200 nn.Modules (layout views, weight packing, residual
+wiring, API surface) run with the oracle's per-op emulation swapped in for librfk and are
+compared with the golden vectors of the unmodified reference. No CUDA kernel runs here; the
+`-m gpu` tests repeat the comparison through the real library."""
+import ctypes
+
+import pytest
+import torch
+
+import rosettafold_pytorch_b200 as rf
+from oracle.ops_ref import RefBackend
+from rosettafold_pytorch_b200 import _lib, ops
+from tests.helpers import STAGES, build_block, load_golden, rel_l2, run_stages
+
+
+@pytest.fixture()
+def emulated_ops():
+    prev = ops._set_backend_for_tests(RefBackend())
+    yield
+    ops._set_backend_for_tests(prev)
+    rf.set_mode("bf16")
+
+
+@pytest.mark.parametrize("name", ["two_track_small", "two_track_default"])
+def test_block_fp32_mode_matches_golden(emulated_ops, name):
+    gold = load_golden(name)
+    blk, _, msa, pair = build_block(gold["config"])
+    rf.set_mode("fp32")
+    out = run_stages(blk, msa, pair)
+    for k in STAGES:
+        assert rel_l2(out[k], gold[k]) < 1e-4, k  # north-star fp32-validation tolerance
+
+
+def test_block_bf16_storage_within_budget(emulated_ops):
+    """bf16 operand storage with exact accumulation: the rounding budget of the bf16 mode."""
+    gold = load_golden("two_track_small")
+    blk, _, msa, pair = build_block(gold["config"])
+    rf.set_mode("bf16")
+    out = run_stages(blk, msa, pair, teacher=gold)
+    for k in STAGES:
+        assert rel_l2(out[k], gold[k]) < 1e-2, k  # north-star bf16 tolerance
+
+
+def test_state_dict_keys_cover_reference_layout():
+    blk = rf.TwoTrackBlock(96, 72, n_encoder_layers=1)
+    keys = set(blk.state_dict())
+    for k in ["msa_update_using_self_att.residue_wise_encoder_layers.0.attn.poswise_weight.to_q.0.weight",
+              "msa_update_using_self_att.sequence_wise_encoder_layers.0.attn.fast_attention.projection_matrix",
+              "pair_update_with_msa.resnet.1.fn.5.weight",
+              "pair_update_with_axial_attention.layers.0.layer.1.fn.1.fn.to_out.bias",
+              "pair_update_with_axial_attention.layers.0.row_attn.to_q.weight",
+              "msa_update_with_pair.encoder_layers.0.pair2att.2.weight"]:
+        assert k in keys, k
+    assert blk.msa_update_using_self_att.sequence_wise_encoder_layers[0].attn.fast_attention.projection_matrix.shape == (266, 64)
+
+
+def test_error_conventions():
+    with pytest.raises(AssertionError):
+        rf.PositionWiseWeightFactor(d_msa=100, n_heads=12)  # reference :188-190
+    with pytest.raises(AssertionError):
+        rf.SoftTiedAttentionOverResidues(d_msa=100, n_heads=12)  # :223-225
+    with pytest.raises(NotImplementedError):
+        rf.EncoderLayer(tied=False, performer=False)  # :319-320
+    with pytest.raises(NotImplementedError):
+        rf.EncoderLayer(performer=True, return_att=True)  # :309-312
+
+
+def test_public_module_shapes(emulated_ops):
+    """Shape contract of reference tests/test_module.py (:180-200, :216-231, :293-309, :322-339,
+    :390-402, :425-438, :645-661)."""
+    rf.set_mode("fp32")
+    B, N, L = 2, 4, 10
+    x = torch.randn(B, N, L, 96)
+    w = rf.PositionWiseWeightFactor(96, 12)(x)
+    assert w.shape == (B, N, 12, L, 1) and torch.allclose(w.sum(1), torch.ones(B, 12, L, 1), atol=1e-5)
+    out, att = rf.SoftTiedAttentionOverResidues(96, 12, return_att=True)(x)
+    assert out.shape == x.shape and att.shape == (B, L, L, 12)
+    assert torch.allclose(att, att.transpose(1, 2), atol=1e-6)
+    assert rf.EncoderLayer(96, 384, 12, performer=True)(x).shape == x.shape
+    y, att = rf.MsaUpdateUsingSelfAttention(96, 384, 12, n_encoder_layers=1)(x)
+    assert y.shape == x.shape and att.shape == (B, L, L, 12)
+    p = rf.OuterProductMean(32, 72)(torch.randn(B, N, L, 32))
+    assert p.shape == (B, L, L, 72)
+    pair = torch.randn(B, L, L, 72)
+    assert rf.PairUpdateWithMsa(96, 32, 72, 12)(x, pair, att).shape == pair.shape
+    assert rf.PairUpdateWithAxialAttention(72, 288, 8, 0.1, 1)(pair).shape == pair.shape
+    assert rf.MsaUpdateWithPair(96, 72, 4, n_encoder_layers=2)(x, pair).shape == x.shape
+    s = rf.Symmetrization()(pair)
+    assert torch.equal(s, s.transpose(1, 2))
+    m, pr = rf.TwoTrackBlock(96, 72, 1)(x, pair)
+    assert m.shape == x.shape and pr.shape == pair.shape
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """librfk.so loads and exports every function include/rfk.h declares (no compute calls)."""
+    import os
+    import re
+
+    hdr = open(os.path.join(os.path.dirname(_lib.LIB_PATH), "..", "include", "rfk.h")).read()
+    declared = set(re.findall(r"\b(rfk_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().rfk_strerror(0) == b"ok" and _lib.load().rfk_version() >= 1
+
+
+def test_ops_refuse_cpu_tensors():
+    with pytest.raises(RuntimeError):
+        ops.layernorm(torch.randn(4, 32), None, None, 1e-5, torch.empty(4, 32))

@@ -1,0 +1,62 @@
+"""CPU tests of the oracle itself: the functional restatement (oracle/trunk_ref.py) against the
+golden vectors produced by the unmodified reference, and — in the build container, where
+/root/reference exists — against the live reference at a second shape."""
+import pytest
+import torch
+
+from oracle import reference_loader as rl
+from oracle import trunk_ref
+from oracle.weights import checksum, push_to_reference, synth_inputs, synth_state_dict
+from tests.helpers import STAGES, build_block, load_golden, rel_l2
+
+
+@pytest.mark.parametrize("name", ["two_track_small", "two_track_default"])
+def test_restatement_matches_golden(name):
+    gold = load_golden(name)
+    cfg = gold["config"]
+    _, sd, msa, pair = build_block(cfg)
+    assert abs(checksum(sd) - gold["weight_checksum"]) < 1e-6 * gold["weight_checksum"], \
+        "synthetic weights differ from the ones the fixture was generated with"
+    stages = {}
+    with torch.no_grad():
+        trunk_ref.two_track_block(msa, pair, sd, cfg["n_layers"], stages=stages)
+    for k in STAGES:
+        assert rel_l2(stages[k], gold[k]) < 2e-5, k
+
+
+@pytest.mark.skipif(not rl.available(), reason="reference source only exists in the build container")
+def test_restatement_matches_live_reference():
+    ref = rl.load()
+    import rosettafold_pytorch_b200 as rf
+
+    d_msa, d_pair, nl = 48, 40, 1
+    mine = rf.TwoTrackBlock(d_msa, d_pair, n_encoder_layers=nl)
+    sd = synth_state_dict(mine.state_dict(), seed=11)
+    rblk = rl.fix_eval(push_to_reference(ref.TwoTrackBlock(d_msa, d_pair, n_encoder_layers=nl), sd))
+    msa, pair = synth_inputs(1, 9, 13, d_msa, d_pair, seed=12)
+    with torch.no_grad():
+        m_ref, p_ref = rblk(msa, pair)
+        m, p = trunk_ref.two_track_block(msa, pair, sd, nl)
+    assert rel_l2(m, m_ref) < 2e-5 and rel_l2(p, p_ref) < 2e-5
+
+
+def test_performer_restatement_properties():
+    """FAVOR+ sanity: positive features, rows of the implied attention sum to one, and the
+    softmax-kernel estimate approaches exact softmax attention as features grow."""
+    from oracle.performer_ref import (gaussian_orthogonal_random_matrix, linear_attention,
+                                      softmax_features)
+
+    g = torch.Generator().manual_seed(0)
+    q = torch.randn(1, 1, 16, 64, generator=g, dtype=torch.float64) * 0.5
+    k = torch.randn(1, 1, 16, 64, generator=g, dtype=torch.float64) * 0.5
+    v = torch.randn(1, 1, 16, 64, generator=g, dtype=torch.float64)
+    proj = gaussian_orthogonal_random_matrix(4096, 64, generator=g).double()
+    qf, kf = softmax_features(q, proj, True, eps=0.0), softmax_features(k, proj, False, eps=0.0)
+    assert (qf > 0).all() and (kf > 0).all()
+    ones = torch.ones_like(v[..., :1])
+    assert torch.allclose(linear_attention(qf, kf, ones), ones)
+    exact = torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1) @ v
+    assert rel_l2(linear_attention(qf, kf, v), exact) < 0.15
+    blocks = gaussian_orthogonal_random_matrix(128, 64, generator=g)
+    unit = blocks / blocks.norm(dim=1, keepdim=True)
+    assert torch.allclose(unit[:64] @ unit[:64].T, torch.eye(64), atol=1e-5)
