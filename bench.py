@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — trunk forward throughput (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py --gpus 1 --steps 3 --warmup 3            # b200 arm (librfk kernels)
+  python bench.py --impl reference --steps 1 --warmup 0     # CPU reference arm (oracle port)
+  torchrun ... bench.py --gpus N ...                        # one rank per GPU, weak scaling
+
+Workload: the three-track trunk (13 block executions = README depth 8 two-track + 5 three-track,
+4 encoder layers, d_msa 384, d_pair 288) on one protein of L=512 residues, Nseq=128 per GPU,
+synthetic MSA/pair embeddings, random-init weights, eval mode. A step = one trunk forward of one
+sample per GPU; value = samples/s over all GPUs. Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+D_MSA, D_PAIR, N_LAYERS = 384, 288, 4
+METRIC = "trunk fwd samples/s (L=512, Nseq=128)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--L", type=int, default=512)
+    ap.add_argument("--N", type=int, default=128)
+    ap.add_argument("--blocks", type=int, default=13)
+    ap.add_argument("--batch", type=int, default=1, help="samples per GPU per step")
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-slice", type=int, default=8,
+                    help="CPU legs evaluate batch-separable stages on 1/slice of their batch axis")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference leg (oracle port of the reference's trunk, timed on the host cores)
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(args, torch, threads):
+    """One bounded sample of the trunk workload on the CPU: one encoder layer of each stage of one
+    block at the full (1, N, L) shape; batch-separable stages (Performer column attention, pair
+    axial layer) run on 1/slice of their batch axis and are scaled back (they are exactly linear in
+    that axis). Returns seconds per full trunk forward (blocks x (4 layers x stages + MSA->pair))."""
+    from oracle import trunk_ref
+    from oracle.weights import synth_inputs, synth_state_dict
+    import rosettafold_pytorch_b200 as rf
+
+    torch.set_num_threads(threads)
+    L, N, s = args.L, args.N, max(1, args.cpu_slice)
+    blk = rf.TwoTrackBlock(D_MSA, D_PAIR, n_encoder_layers=1)
+    sd = synth_state_dict(blk.state_dict(), seed=1)
+    del blk
+    W = trunk_ref.W
+    msa, pair = synth_inputs(1, N, L, D_MSA, D_PAIR, seed=2)
+    att = torch.softmax(torch.randn(1, L, L, 12), dim=2)
+    t = {}
+
+    def timed(name, fn):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            out = fn()
+        t[name] = time.perf_counter() - t0
+        return out
+
+    wA = W(sd, "msa_update_using_self_att.")
+    timed("tied_row_layer", lambda: trunk_ref.encoder_layer_tied(msa, wA.sub("residue_wise_encoder_layers.0"), 12))
+    ls = max(1, L // s)
+    x_cols = msa.transpose(1, 2)[:, :ls].contiguous()  # (b, l/s, n, d): attention over n
+    timed("performer_col_layer", lambda: trunk_ref.encoder_layer_performer(x_cols, wA.sub("sequence_wise_encoder_layers.0"), 12))
+    timed("pair_update_with_msa", lambda: trunk_ref.pair_update_with_msa(msa, pair, att, W(sd, "pair_update_with_msa.")))
+    wC = W(sd, "pair_update_with_axial_attention.layers.0.")
+    # row attention batches over columns j, column attention over rows i: slice each batch axis
+    pr = pair[:, :, :ls].contiguous()
+    pc = pair[:, :ls].contiguous()
+    xn = trunk_ref.layer_norm(pr, wC, "layer.0.fn.0").transpose(1, 2).reshape(ls, L, D_PAIR)
+    timed("pair_row_attn", lambda: trunk_ref.performer_attention(xn, wC.sub("row_attn"), 8, True))
+    xn2 = trunk_ref.layer_norm(pc, wC, "layer.1.fn.0").reshape(ls, L, D_PAIR)
+    timed("pair_col_attn", lambda: trunk_ref.performer_attention(xn2, wC.sub("col_attn"), 8, True))
+    timed("pair_ff", lambda: pc + trunk_ref.feed_forward(trunk_ref.layer_norm(pc, wC, "layer.2.fn.0"), wC.sub("ff")))
+    timed("msa_update_with_pair_layer", lambda: trunk_ref.msa_update_with_pair_layer(
+        msa, pair, W(sd, "msa_update_with_pair.encoder_layers.0.")))
+    scale = L / ls
+    per_layer = (t["tied_row_layer"] + scale * t["performer_col_layer"] +
+                 scale * (t["pair_row_attn"] + t["pair_col_attn"] + t["pair_ff"]) + t["msa_update_with_pair_layer"])
+    block_s = N_LAYERS * per_layer + t["pair_update_with_msa"]
+    return args.blocks * block_s, t
+
+
+def sample_desc(args):
+    return (f"oracle port (oracle/trunk_ref.py), fp32: 1 of {N_LAYERS} encoder layers of each stage of 1 of "
+            f"{args.blocks} blocks at (1,{args.N},{args.L}); Performer column / pair axial stages on 1/{args.cpu_slice} "
+            f"of their batch axis; scaled linearly to the full trunk")
+
+
+def run_reference(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    warm = argparse.Namespace(**{**vars(args), "L": 64, "N": 16})
+    cpu_sample(warm, torch, threads)  # first-call overheads (thread pools, oneDNN primitives)
+    for _ in range(args.warmup):
+        cpu_sample(args, torch, threads)
+    times = []
+    for _ in range(max(1, args.steps)):
+        sec, _ = cpu_sample(args, torch, threads)
+        times.append(sec)
+    sec = sum(times) / len(times)
+    value = 1.0 / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"trunk forward, {args.blocks} blocks, B=1, Nseq={args.N}, L={args.L}, d_msa 384, d_pair 288"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": sample_desc(args)},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([c.strip() for c in ln.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# b200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import rosettafold_pytorch_b200 as rf
+    from rosettafold_pytorch_b200 import ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    rf.set_mode(args.mode)
+
+    torch.manual_seed(1234 + rank)
+    trunk = rf.TrunkBlocks(D_MSA, D_PAIR, n_blocks=args.blocks, n_encoder_layers=N_LAYERS).eval().to(dev)
+    B, N, L = args.batch, args.N, args.L
+    g = torch.Generator().manual_seed(99 + rank)
+    msa_h = torch.randn((B, N, L, D_MSA), generator=g).pin_memory()
+    pair_h = torch.randn((B, L, L, D_PAIR), generator=g).pin_memory()
+    msa_out_h = torch.empty_like(msa_h).pin_memory()
+    pair_out_h = torch.empty_like(pair_h).pin_memory()
+    msa_d, pair_d = msa_h.to(dev), pair_h.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return trunk(msa_d, pair_d)
+
+    def step_e2e():
+        m = msa_h.to(dev, non_blocking=True)
+        p = pair_h.to(dev, non_blocking=True)
+        mo, po = trunk(m, p)
+        msa_out_h.copy_(mo, non_blocking=True)
+        pair_out_h.copy_(po, non_blocking=True)
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    clocks = Clocks(local)
+    clocks.start()
+    n0 = rf._lib.launch_count()
+    # per-kernel-family device timing on the launching stream, live in the timed region
+    ops.start_timing(["gemm_bf16", "gemm_f32", "favor_attention", "layernorm"])
+    total_ms = timed(step_resident, args.steps)
+    fam = ops.stop_timing()
+    launches = rf._lib.launch_count() - n0
+    step_e2e()  # warm the pinned-copy path
+    e2e_ms = timed(step_e2e, args.steps)
+    clk = clocks.stop()
+
+    ms_per_step = total_ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+    e2e_value = world * B / (e2e_ms / args.steps * 1e-3)
+
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "MEASURED_PEAKS.json (sustained bf16)" if peaks else "fallback"
+
+    def tflops(f):
+        return f["work"] / (f["ms"] * 1e-3) / 1e12 if f["ms"] > 0 else 0.0
+
+    tensor_fams = {k: v for k, v in fam.items() if k in ("gemm_bf16", "favor_attention", "gemm_f32") and v["calls"]}
+    dom = max(tensor_fams, key=lambda k: tensor_fams[k]["ms"]) if tensor_fams else None
+    roofline = None
+    if dom:
+        f = fam[dom]
+        ach = tflops(f)
+        roofline = {"kernel": {"gemm_bf16": "rfk::gemm_tc_kernel (tcgen05)", "favor_attention": "rfk::favor kernel",
+                               "gemm_f32": "rfk::gemm_f32_kernel"}[dom],
+                    "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                    "traffic": None, "peak_source": peak_src,
+                    "launches_per_step": f["calls"] / args.steps, "avg_launch_ms": f["ms"] / max(1, f["calls"]),
+                    "share_of_step": f["ms"] / total_ms}
+    families = {k: {"ms_per_step": v["ms"] / args.steps, "calls_per_step": v["calls"] / args.steps,
+                    ("GB/s" if k == "layernorm" else "TFLOP/s"): (v["work"] / (v["ms"] * 1e-3) / (1e9 if k == "layernorm" else 1e12)) if v["ms"] > 0 else 0.0}
+                for k, v in fam.items() if v["calls"]}
+    if "layernorm" in families:
+        families["layernorm"]["frac_of_hbm_peak"] = families["layernorm"]["GB/s"] / hbm_peak
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": f"trunk forward, {args.blocks} blocks x 4 encoder layers, B={B}/GPU, Nseq={N}, L={L}, d_msa 384, d_pair 288",
+                   "parallelism": f"replicas x{world} (one sample per GPU, no data-path collective)",
+                   "l2": "working set (msa 101 MB + pair 302 MB fp32 + intermediates) exceeds the 126 MB L2; no explicit flush",
+                   "ms_per_block": ms_per_step / args.blocks},
+        "e2e": {"value": e2e_value, "unit": "samples/s",
+                "h2d_bytes_per_step": int(msa_h.numel() * 4 + pair_h.numel() * 4),
+                "d2h_bytes_per_step": int(msa_out_h.numel() * 4 + pair_out_h.numel() * 4)},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": roofline,
+        "kernel_families": families,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        warm = argparse.Namespace(**{**vars(args), "L": 64, "N": 16})
+        cpu_sample(warm, torch, threads)  # first-call overheads (thread pools, oneDNN primitives)
+        sec, parts = cpu_sample(args, torch, threads)
+        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "samples/s", "cores": threads, "kind": "port",
+                                "sample": sample_desc(args), "parts_s": {k: round(v, 3) for k, v in parts.items()}}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

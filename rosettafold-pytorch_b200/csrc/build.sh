@@ -16,5 +16,5 @@ for f in rfk_api rfk_gemm rfk_elementwise rfk_favor rfk_favor_tc; do
   fi
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o $OUT build/rfk_api.o build/rfk_gemm.o build/rfk_elementwise.o build/rfk_favor.o build/rfk_favor_tc.o -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT build/rfk_api.o build/rfk_gemm.o build/rfk_elementwise.o build/rfk_favor.o build/rfk_favor_tc.o -lcudart
 echo "built $(realpath $OUT)"

@@ -173,6 +173,47 @@ class _CudaBackend:
 
 _backend = None
 
+# Optional per-op device timing (bench.py's roofline leg): CUDA events recorded on the launching
+# stream around every call of the selected ops; durations are read after a synchronize.
+_timing = None
+
+
+def start_timing(names):
+    """names: iterable of op names ("gemm", "favor_attention", "layernorm", ...)."""
+    global _timing
+    _timing = {n: [] for n in names}
+
+
+def stop_timing():
+    """Returns {name: dict(ms=total, calls=n, work=total algorithmic work)}; synchronises."""
+    global _timing
+    rec, _timing = _timing, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, items in (rec or {}).items():
+        out[name] = dict(ms=sum(a.elapsed_time(b) for a, b, _ in items), calls=len(items),
+                         work=float(sum(w for _, _, w in items)))
+    return out
+
+
+class _Timed:
+    def __init__(self, name, work):
+        self.on = _timing is not None and name in _timing
+        if self.on:
+            self.name, self.work = name, work
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+
+    def __enter__(self):
+        if self.on:
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.b.record()
+            _timing[self.name].append((self.a, self.b, self.work))
+        return False
+
 
 def backend():
     global _backend
@@ -229,7 +270,9 @@ def gemm(a, b, c_view, *, bias=None, act=ACT_NONE, alpha=1.0, r0=None, r1=None, 
             raise ValueError("gemm: residual views must share c_view's (M1,MR,N1,NR) split")
     if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
         raise ValueError("gemm: bias must be contiguous float32 of length N")
-    backend().gemm(a, b, c_view, bias, act, float(alpha), r0, r1, epi, ln_gamma, ln_beta, float(ln_eps))
+    name = "gemm_bf16" if a.dtype == torch.bfloat16 else "gemm_f32"
+    with _Timed(name, 2.0 * Zs[0] * Zs[1] * Zs[2] * M * N * a.shape[4]):  # algorithmic FLOPs
+        backend().gemm(a, b, c_view, bias, act, float(alpha), r0, r1, epi, ln_gamma, ln_beta, float(ln_eps))
     return c_view
 
 
@@ -244,7 +287,8 @@ def layernorm(x, gamma, beta, eps, out):
         raise ValueError("layernorm: x and out must be 2-D with equal shapes")
     if x.stride(1) != 1 or out.stride(1) != 1:
         raise ValueError("layernorm: last dim must be contiguous")
-    backend().layernorm(x, gamma, beta, float(eps), out)
+    with _Timed("layernorm", float(x.numel() * x.element_size() + out.numel() * out.element_size())):  # bytes
+        backend().layernorm(x, gamma, beta, float(eps), out)
     return out
 
 
@@ -349,7 +393,10 @@ def favor_attention(q, k, v, out, proj, *, kind, heads):
         raise TypeError("favor_attention: dtype mismatch")
     if proj.dtype != torch.float32 or not proj.is_contiguous() or proj.shape[1] != 64:
         raise ValueError("favor_attention: proj must be contiguous f32 [m,64]")
-    backend().favor_attention(q, k, v, out, proj, int(kind), int(heads))
+    # algorithmic FLOPs: feature maps 2*(2*T*h*64*m) + context/output 2*(2*T*h*64*m)
+    tokens_total = q.shape[0] * q.shape[1] * q.shape[2]
+    with _Timed("favor_attention", 8.0 * tokens_total * heads * 64 * proj.shape[0]):
+        backend().favor_attention(q, k, v, out, proj, int(kind), int(heads))
     return out
 
 
