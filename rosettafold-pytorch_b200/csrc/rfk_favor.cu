@@ -8,6 +8,8 @@
 //       q' = ratio*(exp(u - diag - max_m u) + 1e-4)     k' = ratio*(exp(u - diag - max_{n,m} u) + 1e-4)
 //   relu kernel:    q' = relu(u) + 1e-3, k' likewise
 //   ksum = sum_n k';  ctx = k'^T v;  out = (q' ctx) / (q' . ksum)
+#include <cstdlib>
+
 #include "rfk_common.cuh"
 
 namespace rfk {
@@ -203,7 +205,8 @@ extern "C" int rfk_favor_attention(const rfk_favor_desc* d, rfk_stream_t stream_
   if (d->kind != 0 && d->kind != 1) return RFK_ERR_UNSUPPORTED;
   if (d->io_dtype != RFK_F32 && d->io_dtype != RFK_BF16) return RFK_ERR_BAD_DTYPE;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (d->io_dtype == RFK_BF16) {
+  static const bool force_simt = getenv("RFK_FAVOR_FORCE_SIMT") != nullptr;  // A/B debugging aid
+  if (d->io_dtype == RFK_BF16 && !force_simt) {
     int rc = favor_tc_launch(d, stream);
     if (rc != RFK_ERR_UNSUPPORTED) return rc;
     // shapes the tensor-core kernel does not cover run on the SIMT kernel (same arithmetic)
