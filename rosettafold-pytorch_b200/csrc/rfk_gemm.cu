@@ -5,318 +5,9 @@
 //     with tcgen05.ld and run the epilogue while the next tile's MMAs are already in flight.
 //   mode 1 (fp32 operands): plain SIMT fp32 kernel (validation mode, same epilogue code).
 // See include/rfk.h for the contract and the reference lines this replaces.
-#include "rfk_common.cuh"
+#include "rfk_gemm_device.cuh"
 
 namespace rfk {
-
-struct GemmDev {
-  int64_t M, N, K;
-  int64_t Z0, Z1, Z2;
-  int64_t MR, NR;
-  float alpha;
-  int act;
-  int epi;
-  float ln_eps;
-  const float* bias;
-  int64_t bias_zs[3];
-  void* c;
-  const void* r0;
-  const void* r1;
-  int c_dtype, r0_dtype, r1_dtype;
-  rfk_addr c_addr, r0_addr, r1_addr;
-  const float* ln_gamma;
-  const float* ln_beta;
-  // tcgen05 path only
-  int bmask[3];  // 0 -> broadcast B over that z level
-  // SIMT path only
-  const float* a32;
-  const float* b32;
-  int64_t lda, ldb;
-  int64_t a_zs[3], b_zs[3];
-};
-
-__device__ __forceinline__ int64_t addr_zm(const rfk_addr& a, int64_t z0, int64_t z1, int64_t z2,
-                                           int64_t m, int64_t MR) {
-  return z0 * a.zs[0] + z1 * a.zs[1] + z2 * a.zs[2] + (m % MR) * a.ms[0] + (m / MR) * a.ms[1];
-}
-__device__ __forceinline__ int64_t addr_n(const rfk_addr& a, int64_t n, int64_t NR) {
-  return (n % NR) * a.ns[0] + (n / NR) * a.ns[1];
-}
-
-// Epilogue for CH consecutive columns [n0, n0+CH) of one row m (one thread).
-template <int CH>
-__device__ __forceinline__ void epilogue_row_chunk(const GemmDev& p, int64_t z0, int64_t z1,
-                                                   int64_t z2, int64_t m, int64_t n0,
-                                                   float (&v)[CH]) {
-  if (m >= p.M || n0 >= p.N) return;
-  const bool full = (n0 + CH <= p.N);
-  const bool same_block = ((n0 % p.NR) + CH <= p.NR);
-  const float* bias = p.bias ? p.bias + z0 * p.bias_zs[0] + z1 * p.bias_zs[1] + z2 * p.bias_zs[2]
-                             : nullptr;
-#pragma unroll
-  for (int i = 0; i < CH; ++i) {
-    float x = v[i] * p.alpha;
-    if (bias && (full || n0 + i < p.N)) x += __ldg(bias + n0 + i);
-    v[i] = apply_act(x, p.act);
-  }
-  // residual addends
-#pragma unroll
-  for (int which = 0; which < 2; ++which) {
-    const void* r = which == 0 ? p.r0 : p.r1;
-    if (!r) continue;
-    const rfk_addr& ra = which == 0 ? p.r0_addr : p.r1_addr;
-    const int rdt = which == 0 ? p.r0_dtype : p.r1_dtype;
-    const int64_t base = addr_zm(ra, z0, z1, z2, m, p.MR);
-    if (full && same_block && ra.ns[0] == 1) {
-      const int64_t off = base + addr_n(ra, n0, p.NR);
-      if (rdt == RFK_F32) {
-        const float* rp = reinterpret_cast<const float*>(r) + off;
-        if ((reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
-#pragma unroll
-          for (int i = 0; i < CH; i += 4) {
-            float4 t = __ldg(reinterpret_cast<const float4*>(rp + i));
-            v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < CH; ++i) v[i] += __ldg(rp + i);
-        }
-      } else {
-        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(r) + off;
-#pragma unroll
-        for (int i = 0; i < CH; ++i) v[i] += __bfloat162float(rp[i]);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < CH; ++i)
-        if (full || n0 + i < p.N) v[i] += load_as_float(r, rdt, base + addr_n(ra, n0 + i, p.NR));
-    }
-  }
-  // store
-  const int64_t cbase = addr_zm(p.c_addr, z0, z1, z2, m, p.MR);
-  if (full && same_block && p.c_addr.ns[0] == 1) {
-    const int64_t off = cbase + addr_n(p.c_addr, n0, p.NR);
-    if (p.c_dtype == RFK_F32) {
-      float* cp = reinterpret_cast<float*>(p.c) + off;
-      if ((reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
-#pragma unroll
-        for (int i = 0; i < CH; i += 4)
-          *reinterpret_cast<float4*>(cp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < CH; ++i) cp[i] = v[i];
-      }
-    } else {
-      __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.c) + off;
-      if (CH % 8 == 0 && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
-#pragma unroll
-        for (int i = 0; i + 7 < CH; i += 8) {
-          uint4 t;
-          t.x = pack_bf16x2(v[i], v[i + 1]);
-          t.y = pack_bf16x2(v[i + 2], v[i + 3]);
-          t.z = pack_bf16x2(v[i + 4], v[i + 5]);
-          t.w = pack_bf16x2(v[i + 6], v[i + 7]);
-          *reinterpret_cast<uint4*>(cp + i) = t;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < CH; ++i) cp[i] = __float2bfloat16_rn(v[i]);
-      }
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < CH; ++i)
-      if (full || n0 + i < p.N)
-        store_from_float(p.c, p.c_dtype, cbase + addr_n(p.c_addr, n0 + i, p.NR), v[i]);
-  }
-}
-
-// LayerNorm over an aligned 32x32 block held by one warp: lane = m%32, v[i] = column n0+i.
-// Every lane of the warp must call this (rows/columns outside the problem hold zeros).
-__device__ __forceinline__ void blockln32(const GemmDev& p, int lane, float (&v)[32]) {
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) s += v[i];
-  const float mean = warp_sum(s) * (1.f / 1024.f);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const float d = v[i] - mean;
-    q += d * d;
-  }
-  const float rstd = rsqrtf(warp_sum(q) * (1.f / 1024.f) + p.ln_eps);
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    float x = (v[i] - mean) * rstd;
-    if (p.ln_gamma) x = x * __ldg(p.ln_gamma + lane * 32 + i) + __ldg(p.ln_beta + lane * 32 + i);
-    v[i] = x;
-  }
-}
-
-// ----------------------------------------------------------------------------------------------
-// tcgen05 kernel
-// ----------------------------------------------------------------------------------------------
-constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;
-constexpr int kGemmThreads = 192;
-
-template <int BN>
-struct GemmCfg {
-  static constexpr int kStageBytes = kBlockM * 128 + BN * 128;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
-  static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128
-                                   : 2 * BN <= 256 ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-};
-
-template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const GemmDev p) {
-  using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * Cfg::kStageBytes;
-  // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem slot
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
-  auto smem_a = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
-  auto smem_b = [&](int s) { return smem_base + s * Cfg::kStageBytes + kBlockM * 128; };
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
-    }
-    fence_barrier_init();
-    tma_prefetch_desc(&tma_a);
-    tma_prefetch_desc(&tma_b);
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-  const int64_t m_blocks = (p.M + kBlockM - 1) / kBlockM;
-  const int64_t n_blocks = (p.N + BN - 1) / BN;
-  const int64_t k_blocks = (p.K + kBlockK - 1) / kBlockK;
-  const int64_t Z = p.Z0 * p.Z1 * p.Z2;
-  const int64_t tiles = Z * m_blocks * n_blocks;
-
-  if (warp == 0 && lane == 0) {
-    // ===== TMA producer =====
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-      const int64_t nb = t % n_blocks;
-      const int64_t mb = (t / n_blocks) % m_blocks;
-      const int64_t z = t / (n_blocks * m_blocks);
-      const int z0 = (int)(z % p.Z0), z1 = (int)((z / p.Z0) % p.Z1), z2 = (int)(z / (p.Z0 * p.Z1));
-      for (int64_t kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-        tma_load_5d(&tma_a, full_bar(stage), smem_a(stage), (int)(kb * kBlockK),
-                    (int)(mb * kBlockM), z0, z1, z2);
-        tma_load_5d(&tma_b, full_bar(stage), smem_b(stage), (int)(kb * kBlockK), (int)(nb * BN),
-                    z0 & p.bmask[0], z1 & p.bmask[1], z2 & p.bmask[2]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-      }
-    }
-  } else if (warp == 1 && lane == 0) {
-    // ===== MMA issuer =====
-    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-      for (int64_t kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(full_bar(stage), phase);
-        tc_fence_after();
-        const uint64_t adesc = umma_desc_sw128(smem_a(stage));
-        const uint64_t bdesc = umma_desc_sw128(smem_b(stage));
-#pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k)
-          umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                    (kb > 0 || k > 0) ? 1u : 0u);
-        umma_commit(empty_bar(stage));
-        if (kb == k_blocks - 1) umma_commit(tfull_bar(acc));
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-    }
-  } else if (warp >= 2) {
-    // ===== epilogue warps (TMEM lane group = warp % 4) =====
-    const int lg = warp & 3;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-      const int64_t nb = t % n_blocks;
-      const int64_t mb = (t / n_blocks) % m_blocks;
-      const int64_t z = t / (n_blocks * m_blocks);
-      const int64_t z0 = z % p.Z0, z1 = (z / p.Z0) % p.Z1, z2 = z / (p.Z0 * p.Z1);
-      const int64_t m = mb * kBlockM + lg * 32 + lane;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BN);
-      if constexpr (BN % 32 == 0) {
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c * 32, r);
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          // BLOCKLN32: host guarantees alpha == 1 and no bias/act/residual, so the standard
-          // epilogue below degenerates to the (scattered) store of the normalised block.
-          if (p.epi == RFK_EPI_BLOCKLN32) blockln32(p, lane, v);
-          epilogue_row_chunk<32>(p, z0, z1, z2, m, nb * BN + c * 32, v);
-        }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < BN / 16; ++c) {
-          uint32_t r[16];
-          tmem_ld_32x16(taddr + c * 16, r);
-          tmem_ld_wait();
-          float v[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-          epilogue_row_chunk<16>(p, z0, z1, z2, m, nb * BN + c * 16, v);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
-  }
-}
 
 // ----------------------------------------------------------------------------------------------
 // SIMT fp32 kernel (validation mode): 64x64 tile, 16x16 threads, 4x4 micro-tile, BK = 16.
@@ -423,26 +114,9 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, int64_t K, int64_t rows, i
   return r == CUDA_SUCCESS ? RFK_OK : RFK_ERR_TMA_ENCODE;
 }
 
-template <int BN>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles,
-                     cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  static bool configured = false;  // benign race: the attribute call is idempotent
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return cuda_status(e);
-    configured = true;
-  }
-  int grid = num_sms();
-  if (tiles < grid) grid = (int)tiles;
-  gemm_tc_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
-  return post_launch();
-}
-
 static int pick_bn(int64_t N) {
   // smallest tile-count first, then the least padding; N up to a few thousand
-  const int cands[] = {256, 192, 144, 128, 96, 64, 32};
+  const int cands[] = {256, 192, 128, 96, 64, 32};
   int best = 32;
   double best_cost = 1e30;
   for (int bn : cands) {
@@ -462,6 +136,7 @@ extern "C" int rfk_gemm(const rfk_gemm_desc* d, rfk_stream_t stream_) {
   if (!d) return RFK_ERR_NULL_POINTER;
   if (!d->a || !d->b || !d->c) return RFK_ERR_NULL_POINTER;
   if (d->M <= 0 || d->N <= 0 || d->K <= 0) return RFK_ERR_BAD_DIMS;
+  if (d->M > 0x7fffffffLL || d->N > 0x7fffffffLL || d->K > 0x7fffffffLL) return RFK_ERR_BAD_DIMS;
   for (int i = 0; i < 3; ++i)
     if (d->Z[i] <= 0) return RFK_ERR_BAD_DIMS;
   if (d->MR <= 0 || d->NR <= 0) return RFK_ERR_BAD_DIMS;
@@ -515,13 +190,27 @@ extern "C" int rfk_gemm(const rfk_gemm_desc* d, rfk_stream_t stream_) {
   for (int i = 0; i < 3; ++i)
     if (d->Z[i] > 1 && d->a_zs[i] == 0) return RFK_ERR_UNSUPPORTED;
   const int64_t tiles = Z * ((d->M + kBlockM - 1) / kBlockM) * ((d->N + bn - 1) / bn);
-  switch (bn) {
-    case 256: return launch_tc<256>(ta, tb, p, tiles, stream);
-    case 192: return launch_tc<192>(ta, tb, p, tiles, stream);
-    case 144: return launch_tc<144>(ta, tb, p, tiles, stream);
-    case 128: return launch_tc<128>(ta, tb, p, tiles, stream);
-    case 96: return launch_tc<96>(ta, tb, p, tiles, stream);
-    case 64: return launch_tc<64>(ta, tb, p, tiles, stream);
-    default: return launch_tc<32>(ta, tb, p, tiles, stream);
-  }
+  // ---- pick the epilogue flavour (rfk_gemm_device.cuh) ----
+  auto addr_aligned = [](const void* ptr, const rfk_addr& a, int es) {
+    const int64_t q = 16 / es;  // elements per 16 bytes
+    if (reinterpret_cast<uintptr_t>(ptr) & 15) return false;
+    for (int i = 0; i < 3; ++i)
+      if (a.zs[i] % q) return false;
+    return a.ms[0] % q == 0 && a.ms[1] % q == 0 && a.ns[1] % q == 0 && a.ns[0] == 1;
+  };
+  const bool rows_affine = (d->MR % 32 == 0) || d->MR >= d->M;
+  const bool cols_chunked = (d->NR % 32 == 0) || d->NR >= d->N;
+  bool lean = d->alpha == 1.f && d->N % 32 == 0 && rows_affine && cols_chunked &&
+              (d->act == RFK_ACT_NONE || d->act == RFK_ACT_RELU) &&
+              (!d->bias || aligned16(d->bias)) && d->ln_gamma == nullptr;
+  for (int i = 0; i < 3; ++i) lean = lean && (d->bias_zs[i] % 4 == 0);
+  int epi = 0;
+  if (lean && d->c_dtype == RFK_BF16 && !d->r0 && !d->r1 && addr_aligned(d->c, d->c_addr, 2)) epi = 1;
+  if (lean && d->c_dtype == RFK_F32 && d->epi == RFK_EPI_STD && addr_aligned(d->c, d->c_addr, 4) &&
+      (!d->r0 || (d->r0_dtype == RFK_F32 && addr_aligned(d->r0, d->r0_addr, 4))) &&
+      (!d->r1 || (d->r1_dtype == RFK_F32 && addr_aligned(d->r1, d->r1_addr, 4))))
+    epi = 2;
+  if (epi == 1) return launch_tc_epi1(bn, ta, tb, p, tiles, stream);
+  if (epi == 2) return launch_tc_epi2(bn, ta, tb, p, tiles, stream);
+  return launch_tc_epi0(bn, ta, tb, p, tiles, stream);
 }

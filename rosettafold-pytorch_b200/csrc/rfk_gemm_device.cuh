@@ -1,0 +1,679 @@
+// rfk_gemm_device.cuh — device code of the batched TN GEMM (tcgen05 kernel + epilogues).
+#pragma once
+#include "rfk_common.cuh"
+
+namespace rfk {
+
+struct GemmDev {
+  int64_t M, N, K;
+  int64_t Z0, Z1, Z2;
+  int64_t MR, NR;
+  float alpha;
+  int act;
+  int epi;
+  float ln_eps;
+  const float* bias;
+  int64_t bias_zs[3];
+  void* c;
+  const void* r0;
+  const void* r1;
+  int c_dtype, r0_dtype, r1_dtype;
+  rfk_addr c_addr, r0_addr, r1_addr;
+  const float* ln_gamma;
+  const float* ln_beta;
+  // tcgen05 path only
+  int bmask[3];  // 0 -> broadcast B over that z level
+  // SIMT path only
+  const float* a32;
+  const float* b32;
+  int64_t lda, ldb;
+  int64_t a_zs[3], b_zs[3];
+};
+
+// m, n, MR, NR all fit 32 bits (checked on the host): 32-bit div/mod is several times cheaper
+__device__ __forceinline__ int64_t addr_zm(const rfk_addr& a, int64_t z0, int64_t z1, int64_t z2,
+                                           int64_t m, int64_t MR) {
+  const uint32_t mu = (uint32_t)m, mr = (uint32_t)MR;
+  const uint32_t q = mu / mr, r = mu - q * mr;
+  return z0 * a.zs[0] + z1 * a.zs[1] + z2 * a.zs[2] + (int64_t)r * a.ms[0] + (int64_t)q * a.ms[1];
+}
+__device__ __forceinline__ int64_t addr_n(const rfk_addr& a, int64_t n, int64_t NR) {
+  const uint32_t nu = (uint32_t)n, nr = (uint32_t)NR;
+  const uint32_t q = nu / nr, r = nu - q * nr;
+  return (int64_t)r * a.ns[0] + (int64_t)q * a.ns[1];
+}
+
+// Epilogue for CH consecutive columns [n0, n0+CH) of one row m (one thread).
+template <int CH>
+__device__ __forceinline__ void epilogue_row_chunk(const GemmDev& p, int64_t z0, int64_t z1,
+                                                   int64_t z2, int64_t m, int64_t n0,
+                                                   float (&v)[CH]) {
+  if (m >= p.M || n0 >= p.N) return;
+  const bool full = (n0 + CH <= p.N);
+  const bool same_block = (((uint32_t)n0 % (uint32_t)p.NR) + CH <= (uint32_t)p.NR);
+  const float* bias = p.bias ? p.bias + z0 * p.bias_zs[0] + z1 * p.bias_zs[1] + z2 * p.bias_zs[2]
+                             : nullptr;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    float x = v[i] * p.alpha;
+    if (bias && (full || n0 + i < p.N)) x += __ldg(bias + n0 + i);
+    v[i] = apply_act(x, p.act);
+  }
+  // residual addends
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    const void* r = which == 0 ? p.r0 : p.r1;
+    if (!r) continue;
+    const rfk_addr& ra = which == 0 ? p.r0_addr : p.r1_addr;
+    const int rdt = which == 0 ? p.r0_dtype : p.r1_dtype;
+    const int64_t base = addr_zm(ra, z0, z1, z2, m, p.MR);
+    if (full && same_block && ra.ns[0] == 1) {
+      const int64_t off = base + addr_n(ra, n0, p.NR);
+      if (rdt == RFK_F32) {
+        const float* rp = reinterpret_cast<const float*>(r) + off;
+        if ((reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
+#pragma unroll
+          for (int i = 0; i < CH; i += 4) {
+            float4 t = __ldg(reinterpret_cast<const float4*>(rp + i));
+            v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) v[i] += __ldg(rp + i);
+        }
+      } else {
+        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(r) + off;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) v[i] += __bfloat162float(rp[i]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < CH; ++i)
+        if (full || n0 + i < p.N) v[i] += load_as_float(r, rdt, base + addr_n(ra, n0 + i, p.NR));
+    }
+  }
+  // store
+  const int64_t cbase = addr_zm(p.c_addr, z0, z1, z2, m, p.MR);
+  if (full && same_block && p.c_addr.ns[0] == 1) {
+    const int64_t off = cbase + addr_n(p.c_addr, n0, p.NR);
+    if (p.c_dtype == RFK_F32) {
+      float* cp = reinterpret_cast<float*>(p.c) + off;
+      if ((reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+#pragma unroll
+        for (int i = 0; i < CH; i += 4)
+          *reinterpret_cast<float4*>(cp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) cp[i] = v[i];
+      }
+    } else {
+      __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.c) + off;
+      if (CH % 8 == 0 && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+#pragma unroll
+        for (int i = 0; i + 7 < CH; i += 8) {
+          uint4 t;
+          t.x = pack_bf16x2(v[i], v[i + 1]);
+          t.y = pack_bf16x2(v[i + 2], v[i + 3]);
+          t.z = pack_bf16x2(v[i + 4], v[i + 5]);
+          t.w = pack_bf16x2(v[i + 6], v[i + 7]);
+          *reinterpret_cast<uint4*>(cp + i) = t;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) cp[i] = __float2bfloat16_rn(v[i]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < CH; ++i)
+      if (full || n0 + i < p.N)
+        store_from_float(p.c, p.c_dtype, cbase + addr_n(p.c_addr, n0 + i, p.NR), v[i]);
+  }
+}
+
+// LayerNorm over an aligned 32x32 block held by one warp: lane = m%32, v[i] = column n0+i.
+// Every lane of the warp must call this (rows/columns outside the problem hold zeros).
+__device__ __forceinline__ void blockln32(const GemmDev& p, int lane, float (&v)[32]) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.f / 1024.f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float d = v[i] - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / 1024.f) + p.ln_eps);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float x = (v[i] - mean) * rstd;
+    if (p.ln_gamma) x = x * __ldg(p.ln_gamma + lane * 32 + i) + __ldg(p.ln_beta + lane * 32 + i);
+    v[i] = x;
+  }
+}
+
+
+// ----------------------------------------------------------------------------------------------
+// Warp-cooperative epilogue for a 32-row x CW-column chunk (tcgen05 kernel). After tcgen05.ld a
+// thread owns one ROW of the chunk; writing it out directly makes every store instruction touch 32
+// different rows. The chunk is therefore staged through shared memory ([32][CW+1] floats per
+// warp, conflict-free both ways) and re-read so that a store instruction covers whole 64/128-byte
+// row segments ("mode R": columns contiguous in memory) or whole 64/128-byte column segments
+// ("mode C": rows contiguous in memory — the K^T/V^T relayouts). Residual loads are coalesced the
+// same way. Anything else falls back to the per-thread path.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load4_any(const void* r, int rdt, int64_t off, float (&o)[4]) {
+  if (rdt == RFK_F32) {
+    const float* rp = reinterpret_cast<const float*>(r) + off;
+    if ((reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(rp));
+      o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = __ldg(rp + j);
+    }
+  } else {
+    const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(r) + off;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = __bfloat162float(rp[j]);
+  }
+}
+
+template <int CW>
+__device__ __forceinline__ void epilogue_warp_chunk(const GemmDev& p, float* st, int lane, int64_t z0,
+                                                    int64_t z1, int64_t z2, int64_t m_warp0, int64_t n0,
+                                                    float (&v)[CW], int64_t c_row, int64_t r0_row,
+                                                    int64_t r1_row, const float* bias) {
+  if (n0 >= p.N || m_warp0 >= p.M) return;  // warp-uniform
+  const bool full = (n0 + CW <= p.N);
+  const bool same_block = (((uint32_t)n0 % (uint32_t)p.NR) + CW <= (uint32_t)p.NR);
+  const bool res_rowmajor = (!p.r0 || p.r0_addr.ns[0] == 1) && (!p.r1 || p.r1_addr.ns[0] == 1);
+  const bool modeR = full && same_block && p.c_addr.ns[0] == 1 && res_rowmajor;
+  const bool rows_ok = (m_warp0 + 32 <= p.M) && (((uint32_t)m_warp0 % (uint32_t)p.MR) + 32 <= (uint32_t)p.MR);
+  const bool modeC = !modeR && full && rows_ok && p.c_addr.ms[0] == 1 && !p.r0 && !p.r1;
+  if (!modeR && !modeC) {
+    epilogue_row_chunk<CW>(p, z0, z1, z2, m_warp0 + lane, n0, v);
+    return;
+  }
+  constexpr int LD = CW + 1;
+  if (modeR) {
+    // row-major staging with the 16-byte chunk index XOR-swizzled by (row & 7): 128-bit stores by
+    // row owners and 128-bit loads by (row, chunk) owners are both bank-conflict free
+    constexpr int CPRW = CW / 4;  // 16-byte chunks per row
+    float4* st4 = reinterpret_cast<float4*>(st);
+#pragma unroll
+    for (int c = 0; c < CPRW; ++c)
+      st4[lane * CPRW + (c ^ (lane & (CPRW - 1) & 7))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    __syncwarp();
+    auto ld4 = [&](int row, int col, float (&o)[4]) {
+      const float4 t = st4[row * CPRW + ((col >> 2) ^ (row & (CPRW - 1) & 7))];
+      o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+    };
+    const int64_t ccol = addr_n(p.c_addr, n0, p.NR);
+    const int64_t r0col = p.r0 ? addr_n(p.r0_addr, n0, p.NR) : 0;
+    const int64_t r1col = p.r1 ? addr_n(p.r1_addr, n0, p.NR) : 0;
+    if (p.c_dtype == RFK_F32) {
+      constexpr int LPR = CW / 4, RPI = 32 / LPR, ITERS = 32 / RPI;
+      const int rsub = lane / LPR, col = (lane % LPR) * 4;
+      float ra[ITERS][4], rb[ITERS][4];
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int row = it * RPI + rsub;
+        const int64_t o0 = __shfl_sync(0xffffffffu, r0_row, row);
+        const int64_t o1 = __shfl_sync(0xffffffffu, r1_row, row);
+        const bool ok = m_warp0 + row < p.M;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ra[it][j] = rb[it][j] = 0.f;
+        if (ok && p.r0) load4_any(p.r0, p.r0_dtype, o0 + r0col + col, ra[it]);
+        if (ok && p.r1) load4_any(p.r1, p.r1_dtype, o1 + r1col + col, rb[it]);
+      }
+      float bv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (bias) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bv[j] = __ldg(bias + n0 + col + j);
+      }
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int row = it * RPI + rsub;
+        const int64_t oc = __shfl_sync(0xffffffffu, c_row, row);
+        if (m_warp0 + row < p.M) {
+          float x[4];
+          ld4(row, col, x);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) x[j] = apply_act(x[j] * p.alpha + bv[j], p.act) + ra[it][j] + rb[it][j];
+          float* cp = reinterpret_cast<float*>(p.c) + oc + ccol + col;
+          if ((reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+            *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cp[j] = x[j];
+          }
+        }
+      }
+    } else {
+      constexpr int LPR = CW / 8, RPI = 32 / LPR, ITERS = 32 / RPI;
+      const int rsub = lane / LPR, col = (lane % LPR) * 8;
+      float bv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bv[j] = bias ? __ldg(bias + n0 + col + j) : 0.f;
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int row = it * RPI + rsub;
+        const int64_t oc = __shfl_sync(0xffffffffu, c_row, row);
+        const int64_t o0 = __shfl_sync(0xffffffffu, r0_row, row);
+        const int64_t o1 = __shfl_sync(0xffffffffu, r1_row, row);
+        if (m_warp0 + row < p.M) {
+          float x[8];
+          {
+            float a4[4], b4[4];
+            ld4(row, col, a4);
+            ld4(row, col + 4, b4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { x[j] = a4[j]; x[4 + j] = b4[j]; }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j] * p.alpha + bv[j], p.act);
+          if (p.r0) {
+            float t[4];
+            load4_any(p.r0, p.r0_dtype, o0 + r0col + col, t);
+            x[0] += t[0]; x[1] += t[1]; x[2] += t[2]; x[3] += t[3];
+            load4_any(p.r0, p.r0_dtype, o0 + r0col + col + 4, t);
+            x[4] += t[0]; x[5] += t[1]; x[6] += t[2]; x[7] += t[3];
+          }
+          if (p.r1) {
+            float t[4];
+            load4_any(p.r1, p.r1_dtype, o1 + r1col + col, t);
+            x[0] += t[0]; x[1] += t[1]; x[2] += t[2]; x[3] += t[3];
+            load4_any(p.r1, p.r1_dtype, o1 + r1col + col + 4, t);
+            x[4] += t[0]; x[5] += t[1]; x[6] += t[2]; x[7] += t[3];
+          }
+          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.c) + oc + ccol + col;
+          if ((reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+            uint4 t;
+            t.x = pack_bf16x2(x[0], x[1]); t.y = pack_bf16x2(x[2], x[3]);
+            t.z = pack_bf16x2(x[4], x[5]); t.w = pack_bf16x2(x[6], x[7]);
+            *reinterpret_cast<uint4*>(cp) = t;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cp[j] = __float2bfloat16_rn(x[j]);
+          }
+        }
+      }
+    }
+  } else {
+    // mode C: rows are contiguous in memory; lane i (< CW) owns the offset/bias of column n0 + i
+#pragma unroll
+    for (int i = 0; i < CW; ++i) st[lane * LD + i] = v[i];
+    __syncwarp();
+    const int64_t coff_mine = lane < CW ? addr_n(p.c_addr, n0 + lane, p.NR) : 0;
+    const float bias_mine = (bias && lane < CW) ? __ldg(bias + n0 + lane) : 0.f;
+    const int64_t rowbase = __shfl_sync(0xffffffffu, c_row, 0);
+    if (p.c_dtype == RFK_BF16) {
+      const int csub = lane >> 2, r8 = (lane & 3) * 8;
+#pragma unroll
+      for (int it = 0; it < CW / 8; ++it) {
+        const int col = it * 8 + csub;
+        const int64_t coff = __shfl_sync(0xffffffffu, coff_mine, col);
+        const float b = __shfl_sync(0xffffffffu, bias_mine, col);
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = apply_act(st[(r8 + j) * LD + col] * p.alpha + b, p.act);
+        __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.c) + rowbase + r8 + coff;
+        if ((reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+          uint4 t;
+          t.x = pack_bf16x2(x[0], x[1]); t.y = pack_bf16x2(x[2], x[3]);
+          t.z = pack_bf16x2(x[4], x[5]); t.w = pack_bf16x2(x[6], x[7]);
+          *reinterpret_cast<uint4*>(cp) = t;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cp[j] = __float2bfloat16_rn(x[j]);
+        }
+      }
+    } else {
+      const int csub = lane >> 3, r4 = (lane & 7) * 4;
+#pragma unroll
+      for (int it = 0; it < CW / 4; ++it) {
+        const int col = it * 4 + csub;
+        const int64_t coff = __shfl_sync(0xffffffffu, coff_mine, col);
+        const float b = __shfl_sync(0xffffffffu, bias_mine, col);
+        float x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = apply_act(st[(r4 + j) * LD + col] * p.alpha + b, p.act);
+        float* cp = reinterpret_cast<float*>(p.c) + rowbase + r4 + coff;
+        if ((reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+          *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cp[j] = x[j];
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+
+// ----------------------------------------------------------------------------------------------
+// Lean epilogues (EPI 1 / 2). The host only selects them when: alpha == 1, N % 32 == 0, output (and
+// residual) columns contiguous (ns[0] == 1) with every 32-column chunk inside one NR block, the 32
+// rows of a warp inside one MR block (MR % 32 == 0 or MR >= M) so row offsets are affine, and all
+// base pointers / strides 16-byte aligned. That removes every per-element predicate, alignment
+// test and shuffle from the hot loop.
+//   EPI 1: bf16 output, no residual.     EPI 2: f32 output, up to two f32 residual addends.
+// ----------------------------------------------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ void epilogue_fast_chunk(const GemmDev& p, float4* st4, int lane,
+                                                    int rows_valid, int64_t n0, float (&v)[32],
+                                                    int64_t c_base, int64_t r0_base, int64_t r1_base,
+                                                    const float* bias) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    st4[lane * 8 + (c ^ (lane & 7))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+  __syncwarp();
+  const int64_t ccol = addr_n(p.c_addr, n0, p.NR);
+  if constexpr (EPI == 1) {
+    const int rsub = lane >> 2, col = (lane & 3) * 8;
+    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+    if (bias) {
+      b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + col));
+      b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + col + 4));
+    }
+    const bool relu = p.act == RFK_ACT_RELU;
+    __nv_bfloat16* cbase = reinterpret_cast<__nv_bfloat16*>(p.c) + c_base + ccol + col;
+    const int64_t ms0 = p.c_addr.ms[0];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int row = it * 8 + rsub;
+      const int sw = row & 7;
+      float4 a = st4[row * 8 + ((col >> 2) ^ sw)];
+      float4 b = st4[row * 8 + (((col >> 2) + 1) ^ sw)];
+      a.x += b0.x; a.y += b0.y; a.z += b0.z; a.w += b0.w;
+      b.x += b1.x; b.y += b1.y; b.z += b1.z; b.w += b1.w;
+      if (relu) {
+        a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+        b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
+      }
+      uint4 t;
+      t.x = pack_bf16x2(a.x, a.y); t.y = pack_bf16x2(a.z, a.w);
+      t.z = pack_bf16x2(b.x, b.y); t.w = pack_bf16x2(b.z, b.w);
+      if (row < rows_valid) *reinterpret_cast<uint4*>(cbase + row * ms0) = t;
+    }
+  } else {
+    const int rsub = lane >> 3, col = (lane & 7) * 4;
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + col));
+    const bool relu = p.act == RFK_ACT_RELU;
+    float4 ra[8], rb[8];
+    if (p.r0) {
+      const float* rp = reinterpret_cast<const float*>(p.r0) + r0_base + addr_n(p.r0_addr, n0, p.NR) + col;
+      const int64_t rs = p.r0_addr.ms[0];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + rsub;
+        ra[it] = row < rows_valid ? __ldg(reinterpret_cast<const float4*>(rp + row * rs)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    if (p.r1) {
+      const float* rp = reinterpret_cast<const float*>(p.r1) + r1_base + addr_n(p.r1_addr, n0, p.NR) + col;
+      const int64_t rs = p.r1_addr.ms[0];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + rsub;
+        rb[it] = row < rows_valid ? __ldg(reinterpret_cast<const float4*>(rp + row * rs)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    float* cbase = reinterpret_cast<float*>(p.c) + c_base + ccol + col;
+    const int64_t ms0 = p.c_addr.ms[0];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = it * 4 + rsub;
+      float4 a = st4[row * 8 + ((col >> 2) ^ (row & 7))];
+      a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
+      if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+      if (p.r0) { a.x += ra[it].x; a.y += ra[it].y; a.z += ra[it].z; a.w += ra[it].w; }
+      if (p.r1) { a.x += rb[it].x; a.y += rb[it].y; a.z += rb[it].z; a.w += rb[it].w; }
+      if (row < rows_valid) *reinterpret_cast<float4*>(cbase + row * ms0) = a;
+    }
+  }
+  __syncwarp();
+}
+
+// ----------------------------------------------------------------------------------------------
+// tcgen05 kernel
+// ----------------------------------------------------------------------------------------------
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kGemmThreads = 320;  // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kEpiWarps = 8;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStageBytes = kBlockM * 128 + BN * 128;
+  static constexpr int kStagingBytes = kEpiWarps * 32 * 33 * 4;  // epilogue transpose buffers
+  static constexpr int kBudget = 232448 - 1024 - 256 - kStagingBytes;
+  static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
+  static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128
+                                   : 2 * BN <= 256 ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStagingBytes;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const GemmDev p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::kStageBytes;
+  // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto smem_a = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
+  auto smem_b = [&](int s) { return smem_base + s * Cfg::kStageBytes + kBlockM * 128; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), kEpiWarps);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int64_t m_blocks = (p.M + kBlockM - 1) / kBlockM;
+  const int64_t n_blocks = (p.N + BN - 1) / BN;
+  const int64_t k_blocks = (p.K + kBlockK - 1) / kBlockK;
+  const int64_t Z = p.Z0 * p.Z1 * p.Z2;
+  const int64_t tiles = Z * m_blocks * n_blocks;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int64_t nb = t % n_blocks;
+      const int64_t mb = (t / n_blocks) % m_blocks;
+      const int64_t z = t / (n_blocks * m_blocks);
+      const int z0 = (int)(z % p.Z0), z1 = (int)((z / p.Z0) % p.Z1), z2 = (int)(z / (p.Z0 * p.Z1));
+      for (int64_t kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+        tma_load_5d(&tma_a, full_bar(stage), smem_a(stage), (int)(kb * kBlockK),
+                    (int)(mb * kBlockM), z0, z1, z2);
+        tma_load_5d(&tma_b, full_bar(stage), smem_b(stage), (int)(kb * kBlockK), (int)(nb * BN),
+                    z0 & p.bmask[0], z1 & p.bmask[1], z2 & p.bmask[2]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int64_t kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_sw128(smem_a(stage));
+        const uint64_t bdesc = umma_desc_sw128(smem_b(stage));
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k)
+          umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                    (kb > 0 || k > 0) ? 1u : 0u);
+        umma_commit(empty_bar(stage));
+        if (kb == k_blocks - 1) umma_commit(tfull_bar(acc));
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else if (warp >= 2) {
+    // ===== epilogue warps (TMEM lane group = warp % 4) =====
+    const int lg = warp & 3;
+    float* stage = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw))) + (warp - 2) * 32 * 33;
+    const int chalf = (warp - 2) >> 2;  // two warps share a TMEM lane group and alternate chunks
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int64_t nb = t % n_blocks;
+      const int64_t mb = (t / n_blocks) % m_blocks;
+      const int64_t z = t / (n_blocks * m_blocks);
+      const int64_t z0 = z % p.Z0, z1 = (z / p.Z0) % p.Z1, z2 = z / (p.Z0 * p.Z1);
+      const int64_t m_warp0 = mb * kBlockM + lg * 32;
+      const float* bias = p.bias ? p.bias + z0 * p.bias_zs[0] + z1 * p.bias_zs[1] + z2 * p.bias_zs[2] : nullptr;
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BN);
+      if constexpr (EPI == 0) {
+        const int64_t m = m_warp0 + lane;
+        // this lane's row offsets (shared across the warp by shuffle in the staged epilogue)
+        const int64_t mm = m < p.M ? m : 0;
+        const int64_t c_row = addr_zm(p.c_addr, z0, z1, z2, mm, p.MR);
+        const int64_t r0_row = p.r0 ? addr_zm(p.r0_addr, z0, z1, z2, mm, p.MR) : 0;
+        const int64_t r1_row = p.r1 ? addr_zm(p.r1_addr, z0, z1, z2, mm, p.MR) : 0;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = chalf; c < BN / 32; c += 2) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (p.epi == RFK_EPI_BLOCKLN32) blockln32(p, lane, v);
+          epilogue_warp_chunk<32>(p, stage, lane, z0, z1, z2, m_warp0, nb * BN + c * 32, v, c_row, r0_row,
+                                  r1_row, bias);
+        }
+        if (BN % 32 != 0 && chalf == ((BN / 32) & 1)) {
+          uint32_t r[16];
+          tmem_ld_32x16(taddr + (BN / 32) * 32, r);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+          epilogue_warp_chunk<16>(p, stage, lane, z0, z1, z2, m_warp0, nb * BN + (BN / 32) * 32, v, c_row,
+                                  r0_row, r1_row, bias);
+        }
+      } else {
+        static_assert(EPI == 0 || BN % 32 == 0, "lean epilogues need 32-column chunks");
+        // rows of this warp are affine in memory: offset(row) = base + row * ms[0]
+        const int64_t mw = m_warp0 < p.M ? m_warp0 : 0;
+        const int64_t c_base = addr_zm(p.c_addr, z0, z1, z2, mw, p.MR);
+        const int64_t r0_base = (EPI == 2 && p.r0) ? addr_zm(p.r0_addr, z0, z1, z2, mw, p.MR) : 0;
+        const int64_t r1_base = (EPI == 2 && p.r1) ? addr_zm(p.r1_addr, z0, z1, z2, mw, p.MR) : 0;
+        const int64_t left = p.M - m_warp0;
+        const int rows_valid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = chalf; c < BN / 32; c += 2) {
+          const int64_t n0 = nb * BN + c * 32;
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (n0 >= p.N) continue;
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (EPI == 1 && p.epi == RFK_EPI_BLOCKLN32) blockln32(p, lane, v);
+          epilogue_fast_chunk<EPI>(p, reinterpret_cast<float4*>(stage), lane, rows_valid, n0, v, c_base,
+                                   r0_base, r1_base, bias);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+
+template <int BN, int EPI>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles,
+                     cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;  // benign race: the attribute call is idempotent
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return cuda_status(e);
+    configured = true;
+  }
+  int grid = num_sms();
+  if (tiles < grid) grid = (int)tiles;
+  gemm_tc_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  return post_launch();
+}
+
+template <int EPI>
+static int launch_tc_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p,
+                        int64_t tiles, cudaStream_t stream) {
+  switch (bn) {
+    case 256: return launch_tc<256, EPI>(ta, tb, p, tiles, stream);
+    case 192: return launch_tc<192, EPI>(ta, tb, p, tiles, stream);
+    case 128: return launch_tc<128, EPI>(ta, tb, p, tiles, stream);
+    case 96: return launch_tc<96, EPI>(ta, tb, p, tiles, stream);
+    case 64: return launch_tc<64, EPI>(ta, tb, p, tiles, stream);
+    case 32: return launch_tc<32, EPI>(ta, tb, p, tiles, stream);
+    default: return RFK_ERR_UNSUPPORTED;
+  }
+}
+
+// one translation unit per epilogue flavour (parallel compilation, smaller kernels)
+int launch_tc_epi0(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s);
+int launch_tc_epi1(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s);
+int launch_tc_epi2(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s);
+
+}  // namespace rfk

@@ -469,8 +469,15 @@ class OuterProductMean(nn.Module):
                                     nn.Linear(in_features ** 2, out_features))
 
     def _pack(self):
-        return _packed(self, lambda: dict(g=_f(self.to_out[0].weight), b=_f(self.to_out[0].bias),
-                                          W=_w(self.to_out[1].weight), bias=_f(self.to_out[1].bias)))
+        def build():
+            ln, lin = self.to_out[0], self.to_out[1]
+            g, b = ln.weight.detach().float(), ln.bias.detach().float()
+            Wl, bl = lin.weight.detach().float(), lin.bias.detach().float()
+            # bf16 mode: the LayerNorm(1024) affine is folded into the Linear (exact algebra), so the
+            # GEMM epilogue only normalises: Linear(g*xhat + b) = (W*g) xhat + (W b + bias)
+            return dict(g=g.contiguous(), b=b.contiguous(), W=_w(lin.weight), bias=_f(lin.bias),
+                        Wfold=_w(Wl * g[None, :]), bfold=(bl + Wl @ b).contiguous())
+        return _packed(self, build)
 
     def _run(self, xt, yt, B, L):
         """xt, yt: [B, L*P, N] K-major operands. Returns Linear(LN(outer-product sum)) f32 [B*L*L, out]."""
@@ -480,14 +487,16 @@ class OuterProductMean(nn.Module):
         ln = self.to_out[0]
         o = _empty((B, L, L, P * P), adt, xt)
         ov = o.view(B, L, L, P, P).permute(0, 1, 3, 2, 4)[None, None]  # [1,1,b,i,u,j,v]
-        if _MODE == 0 and P == 32:
-            ops.gemm(xt, yt, ov, epi=EPI_BLOCKLN32, ln_gamma=pk["g"], ln_beta=pk["b"], ln_eps=ln.eps)
+        fused = _MODE == 0 and P == 32
+        if fused:
+            ops.gemm(xt, yt, ov, epi=EPI_BLOCKLN32, ln_eps=ln.eps)
         else:
             ops.gemm(xt, yt, ov)
             o2 = o.view(-1, P * P)
             ops.layernorm(o2, pk["g"], pk["b"], ln.eps, o2)
         out = _empty((B * L * L, pk["W"].shape[0]), torch.float32, xt)
-        ops.gemm(o.view(-1, P * P), pk["W"], cview(out), bias=pk["bias"])
+        ops.gemm(o.view(-1, P * P), pk["Wfold" if fused else "W"], cview(out),
+                 bias=pk["bfold" if fused else "bias"])
         return out
 
     @torch.no_grad()

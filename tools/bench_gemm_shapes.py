@@ -70,4 +70,4 @@ lin("Linear716 (588)->288 f32", TP, 288, 592, f32)
 xt, yt = rnd(B, L * 32, N), rnd(B, L * 32, N)
 g, bt = torch.ones(1024, device=dev), torch.zeros(1024, device=dev)
 oo = torch.empty(B, L, L, 1024, dtype=bf, device=dev)
-timeit("OPM outer product + LN1024 (blockln32)", lambda: ops.gemm(xt, yt, oo.view(B, L, L, 32, 32).permute(0, 1, 3, 2, 4)[None, None], epi=ops.EPI_BLOCKLN32, ln_gamma=g, ln_beta=bt), 2.0 * (L * 32) ** 2 * N)
+timeit("OPM outer product + LN1024 (blockln32)", lambda: ops.gemm(xt, yt, oo.view(B, L, L, 32, 32).permute(0, 1, 3, 2, 4)[None, None], epi=ops.EPI_BLOCKLN32), 2.0 * (L * 32) ** 2 * N)
