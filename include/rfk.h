@@ -205,6 +205,16 @@ typedef struct {
 
 int rfk_favor_attention(const rfk_favor_desc* d, rfk_stream_t stream);
 
+/*
+ * 3x3 "same" convolution, no bias, on a channels-last map (nn.Conv2d(d_pair, d_pair, 3,
+ * padding="same", bias=False), :452 and :456) as an implicit GEMM on the tcgen05 kernel.
+ *   x: bf16 [B][L][L][C] (C % 8 == 0);  y: bf16 or f32 [B][L][L][Cout] (Cout % 32 == 0)
+ *   w_packed: bf16 [Cout][9][Cpad], Cpad = ceil(C/64)*64, w_packed[o][3*di+dj][c] = W[o][c][di][dj],
+ *   zero for c >= C.
+ */
+int rfk_conv3x3_nhwc(const void* x, const void* w_packed, void* y, int y_dtype, int B, int L, int C,
+                     int Cout, rfk_stream_t stream);
+
 /* Cast / copy rows between dtypes with row strides (host-side plumbing for column slices). */
 int rfk_convert_rows(const void* x, int x_dtype, int64_t x_row_stride, void* y, int y_dtype,
                      int64_t y_row_stride, int64_t rows, int cols, rfk_stream_t stream);

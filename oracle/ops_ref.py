@@ -158,5 +158,13 @@ class RefBackend:
         o = torch.einsum("...me,...tm,...t->...te", ctx, qf, dinv)  # g1 g0 h t d
         out.copy_(o.permute(0, 1, 3, 2, 4).reshape(G1, G0, T, heads * 64).to(out.dtype))
 
+    # nn.Conv2d(C, C, 3, padding="same", bias=False) on b l1 l2 d (:451-457)
+    def conv3x3(self, x, w_packed, out):
+        Cout, _, cpad = w_packed.shape
+        Cin = x.shape[3]
+        w = w_packed.to(self.acc)[:, :, :Cin].reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
+        y = torch.nn.functional.conv2d(x.to(self.acc).permute(0, 3, 1, 2), w, padding=1)
+        out.copy_(y.permute(0, 2, 3, 1).to(out.dtype))
+
     def convert_rows(self, x, out):
         out.copy_(x.to(out.dtype))

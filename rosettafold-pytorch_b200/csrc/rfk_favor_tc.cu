@@ -23,7 +23,8 @@ namespace rfk {
 
 namespace {
 
-constexpr int kThreads = 288;  // warp 0: control (TMA + MMA issue), warps 1..8: feature/epilogue
+constexpr int kFeatWarps = 16;
+constexpr int kThreads = 32 * (1 + kFeatWarps);  // warp 0: control (TMA + MMA issue), the rest: feature/epilogue
 constexpr int kMP = 272;       // padded feature count (17 * 16)
 constexpr int kTile = 128;     // tokens per tile
 constexpr uint32_t kOmegaBytes = kMP * 128;        // 34816
@@ -37,7 +38,7 @@ constexpr uint32_t kOffFeat = kOffCslab + kSlabBytes;
 constexpr uint32_t kOffCtx = kOffFeat + 5 * kSlabBytes;
 constexpr uint32_t kOffBar = kOffCtx + 5 * kCtxSlabBytes;  // barriers + scratch
 constexpr uint32_t kOffScratch = kOffBar + 64;
-constexpr uint32_t kSmemBytes = kOffScratch + (2 * 128 + 16) * 4 + 1024;
+constexpr uint32_t kSmemBytes = kOffScratch + (4 * 128 + 16) * 4 + 1024;
 static_assert(kOffCslab % 1024 == 0 && kOffK % 1024 == 0 && kOffFeat % 1024 == 0 && kOffCtx % 1024 == 0, "align");
 
 constexpr uint32_t kColD2 = 0, kColU = 272, kColD3 = 416;
@@ -110,30 +111,38 @@ __device__ __forceinline__ float row_half_sqnorm(uint32_t tile, int row) {
   return s * (0.5f * 0.125f);  // dn^2 = 64^-1/2 = 1/8
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const FavorTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t s_omega = base + kOffOmega, s_cslab = base + kOffCslab, s_k = base + kOffK,
-                 s_v = base + kOffV, s_feat = base + kOffFeat, s_ctx = base + kOffCtx;
-  const uint32_t bar_k = base + kOffBar, bar_v = bar_k + 8, bar_mma = bar_k + 16, bar_feat = bar_k + 24;
-  const uint32_t tmem_slot = bar_k + 32;
+  const uint32_t s_omega = base + kOffOmega, s_cslab = base + kOffCslab, s_feat = base + kOffFeat,
+                 s_ctx = base + kOffCtx;
+  const uint32_t s_buf[2] = {base + kOffK, base + kOffV};       // [0] = "k" buffer, [1] = "v" buffer
+  const uint32_t bar_ld[2] = {base + kOffBar, base + kOffBar + 8};
+  const uint32_t bar_mma = base + kOffBar + 16, bar_feat = base + kOffBar + 24;
+  const uint32_t tmem_slot = base + kOffBar + 32;
   float* scratch = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + kOffScratch);
-  float* rowmax = scratch;         // [2][128]
-  float* red = scratch + 256;      // [8]
+  float* rowmax = scratch;            // [4][128]
+  float* red = scratch + 4 * 128;     // [16]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool softmax_kind = p.kind == 0;
-  const int ntiles = (p.tokens + kTile - 1) / kTile;
+  const int nt = (p.tokens + kTile - 1) / kTile;
 
   // ---- one-time setup ----
   if (warp == 0) {
     if (lane == 0) {
-      mbar_init(bar_k, 1);
-      mbar_init(bar_v, 1);
+      mbar_init(bar_ld[0], 1);
+      mbar_init(bar_ld[1], 1);
       mbar_init(bar_mma, 1);
-      mbar_init(bar_feat, 8);
+      mbar_init(bar_feat, kFeatWarps);
       fence_barrier_init();
       tma_prefetch_desc(&tm_q);
       tma_prefetch_desc(&tm_k);
@@ -173,16 +182,25 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
 
-  uint32_t ph_k = 0, ph_v = 0, ph_mma = 0, ph_feat = 0;  // every thread tracks every phase
+  // Loads completed so far on each TMA barrier; every thread advances the same deterministic
+  // schedule (whether or not it actually waits), parity of the next wait = count & 1.
+  uint32_t nld[2] = {0, 0};
+  uint32_t ph_mma = 0, ph_feat = 0;
   const float ratio = rsqrtf((float)p.m);
+  constexpr float kLog2e = 1.4426950408889634f;
 
-  // feature-warp geometry
-  const int fw = warp - 1;                  // 0..7 (valid for warp >= 1)
+  // feature-warp geometry: 4 warps share a TMEM lane group and split the column chunks
+  const int fw = warp - 1;                  // 0..15 (valid for warp >= 1)
   const int lg = warp & 3;                  // TMEM lane group this warp may touch
-  const int half = fw >> 2;                 // which part of the columns this warp handles
+  const int quarter = fw >> 2;
   const int row = lg * 32 + lane;           // token row in the tile / TMEM lane
   const uint32_t t_lane = ((uint32_t)(lg * 32) << 16);
+  auto split = [&](int n, int& c0, int& c1) {
+    c0 = (n * quarter) >> 2;
+    c1 = (n * (quarter + 1)) >> 2;
+  };
 
+  bool pre_issued = false;  // control thread: first loads of this item already in flight
   for (int64_t item = blockIdx.x; item < p.items; item += gridDim.x) {
     const int h = (int)(item % p.heads);
     const int64_t g = item / p.heads;
@@ -191,9 +209,14 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (warp == 0) {
       if (lane == 0) {
         // =================== control thread ===================
-        auto load_tile = [&](const CUtensorMap* tm, uint32_t bar, uint32_t dst, int t) {
-          mbar_arrive_expect_tx(bar, kSlabBytes);
-          tma_load_4d(tm, bar, dst, h * 64, t * kTile, g0, g1);
+        auto issue = [&](const CUtensorMap* tm, int b, int t, int hh, int gg0, int gg1) {
+          mbar_arrive_expect_tx(bar_ld[b], kSlabBytes);
+          tma_load_4d(tm, bar_ld[b], s_buf[b], hh * 64, t * kTile, gg0, gg1);
+        };
+        auto wait_ld = [&](int b) {
+          mbar_wait(bar_ld[b], nld[b] & 1u);
+          ++nld[b];
+          tc_fence_after();
         };
         auto mma_u_full = [&](uint32_t tile) {  // U[128 x 272] = tile . omega'^T into cols [0,272)
 #pragma unroll
@@ -211,59 +234,78 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           ph_feat ^= 1u;
           tc_fence_after();
         };
-        // ---- S0: global key max (softmax kernel) ----
+        // ---- S0: global key max (softmax kernel); tiles alternate between the two buffers ----
         if (softmax_kind) {
-          for (int t = 0; t < ntiles; ++t) {
-            load_tile(&tm_k, bar_k, s_k, t);
-            mbar_wait(bar_k, ph_k); ph_k ^= 1u;
-            tc_fence_after();
-            mma_u_full(s_k);
+          if (!pre_issued) issue(&tm_k, 0, 0, h, g0, g1);
+          for (int t = 0; t < nt; ++t) {
+            if (t + 1 < nt) issue(&tm_k, (t + 1) & 1, t + 1, h, g0, g1);
+            wait_ld(t & 1);
+            mma_u_full(s_buf[t & 1]);
             step();
           }
+          issue(&tm_k, 0, 0, h, g0, g1);
+          issue(&tm_v, 1, 0, h, g0, g1);
+        } else if (!pre_issued) {
+          issue(&tm_k, 0, 0, h, g0, g1);
+          issue(&tm_v, 1, 0, h, g0, g1);
         }
         // ---- S1: context ----
-        for (int t = 0; t < ntiles; ++t) {
-          load_tile(&tm_k, bar_k, s_k, t);
-          load_tile(&tm_v, bar_v, s_v, t);
-          mbar_wait(bar_k, ph_k); ph_k ^= 1u;
-          tc_fence_after();
+        for (int t = 0; t < nt; ++t) {
+          wait_ld(0);
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // half A: m 0..143
-            umma_bf16(tmem + kColU, umma_desc_sw128(s_k) + 2 * k, umma_desc_sw128(s_omega) + 2 * k,
+            umma_bf16(tmem + kColU, umma_desc_sw128(s_buf[0]) + 2 * k, umma_desc_sw128(s_omega) + 2 * k,
                       umma_idesc_bf16(128, 144), k > 0);
           step();
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // half B: m 144..271
-            umma_bf16(tmem + kColU, umma_desc_sw128(s_k) + 2 * k,
+            umma_bf16(tmem + kColU, umma_desc_sw128(s_buf[0]) + 2 * k,
                       umma_desc_sw128(s_omega + 144 * 128) + 2 * k, umma_idesc_bf16(128, 128), k > 0);
           step();
-          mbar_wait(bar_v, ph_v); ph_v ^= 1u;
-          tc_fence_after();
+          // K buffer is free: prefetch the next K tile, or the first Q tile
+          if (t + 1 < nt) issue(&tm_k, 0, t + 1, h, g0, g1);
+          else issue(&tm_q, 0, 0, h, g0, g1);
+          wait_ld(1);
           // [ctx^T ; ksum][128 x 272] += [V | 1]^T (K = tokens) . k'   — both operands MN-major
-          const uint32_t lbo_a = s_cslab - s_v;
+          const uint32_t lbo_a = s_cslab - s_buf[1];
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            const uint64_t ad = desc_mn_sw128(s_v + k * 2048, lbo_a);
+            const uint64_t ad = desc_mn_sw128(s_buf[1] + k * 2048, lbo_a);
             umma_bf16(tmem + kColD2, ad, desc_mn_sw128(s_feat + k * 2048, kSlabBytes),
                       idesc_bf16_major(128, 128, 1, 1), (t > 0 || k > 0));
             umma_bf16(tmem + kColD2 + 128, ad, desc_mn_sw128(s_feat + 2 * kSlabBytes + k * 2048, kSlabBytes),
                       idesc_bf16_major(128, 144, 1, 1), (t > 0 || k > 0));
           }
           step();  // feature warps: no-op, or the ctx^T read-out after the last tile
+          if (t + 1 < nt) issue(&tm_v, 1, t + 1, h, g0, g1);
+          else if (nt > 1) issue(&tm_q, 1, 1, h, g0, g1);
         }
-        // ---- S3: queries ----
-        for (int t = 0; t < ntiles; ++t) {
-          load_tile(&tm_q, bar_k, s_k, t);
-          mbar_wait(bar_k, ph_k); ph_k ^= 1u;
-          tc_fence_after();
-          mma_u_full(s_k);
+        // ---- S3: queries (tile t lives in buffer t & 1) ----
+        pre_issued = false;
+        for (int t = 0; t < nt; ++t) {
+          const int b = t & 1;
+          wait_ld(b);
+          mma_u_full(s_buf[b]);
           step();
+          if (t + 2 < nt) issue(&tm_q, b, t + 2, h, g0, g1);
           // out|den [128 tok x 80] = q'[128 x 272] . [ctx^T;ksum]^T
 #pragma unroll
           for (int ks = 0; ks < 17; ++ks) {
             const int kb = ks >> 2, kk = ks & 3;
             umma_bf16(tmem + kColD3, umma_desc_sw128(s_feat + kb * kSlabBytes) + 2 * kk,
                       umma_desc_sw128(s_ctx + kb * kCtxSlabBytes) + 2 * kk, umma_idesc_bf16(128, 80), ks > 0);
+          }
+          if (t == nt - 1) {
+            // both tile buffers are free: start the next item's first loads behind this epilogue
+            const int64_t nitem = item + gridDim.x;
+            if (nitem < p.items) {
+              const int nh = (int)(nitem % p.heads);
+              const int64_t ng = nitem / p.heads;
+              const int ng0 = (int)(ng % p.G0), ng1 = (int)(ng / p.G0);
+              issue(&tm_k, 0, 0, nh, ng0, ng1);
+              if (!softmax_kind) issue(&tm_v, 1, 0, nh, ng0, ng1);
+              pre_issued = true;
+            }
           }
           step();
         }
@@ -282,19 +324,39 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_feat);
       };
-      // column-chunk split between the two warps of a lane group: [c0, c1) of `n` 16-col chunks
-      auto split = [&](int n, int& c0, int& c1) {
-        const int lo = (n + 1) >> 1;
-        c0 = half == 0 ? 0 : lo;
-        c1 = half == 0 ? lo : n;
+      // consume one completed load on buffer b; only the softmax kernel reads the tile (|x|^2)
+      auto consume_ld = [&](int b, bool need) {
+        if (need) mbar_wait(bar_ld[b], nld[b] & 1u);
+        ++nld[b];
+      };
+      // feature map of 16 accumulator columns -> bf16 features in shared memory
+      auto feat_chunk = [&](uint32_t tcol, int m0, bool valid, bool full, float sub) {
+        uint32_t r[16];
+        tmem_ld_32x16(tmem + t_lane + tcol, r);
+        tmem_ld_wait();
+        float f[16];
+        if (softmax_kind) {
+          const float bias = ratio * 1e-4f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            f[i] = fmaf(ratio, ex2_approx(fmaf(__uint_as_float(r[i]), kLog2e, -sub)), bias);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = fmaxf(__uint_as_float(r[i]), 0.f) + 1e-3f;
+        }
+        if (!full) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = (valid && m0 + i < p.m) ? f[i] : 0.f;
+        }
+        write_feat16(s_feat, row, m0, f);
       };
 
       float gmax = 0.f;
       if (softmax_kind) {
         // ---- S0 ----
         float mx = -INFINITY;
-        for (int t = 0; t < ntiles; ++t) {
-          mbar_wait(bar_k, ph_k); ph_k ^= 1u;
+        for (int t = 0; t < nt; ++t) {
+          consume_ld(t & 1, false);
           wait_mma();
           const bool valid = t * kTile + row < p.tokens;
           int c0, c1;
@@ -313,42 +375,34 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         mx = warp_max(mx);
         if (lane == 0) red[fw] = mx;
-        named_bar_sync(1, 256);
+        named_bar_sync(1, kFeatWarps * 32);
         gmax = red[0];
 #pragma unroll
-        for (int i = 1; i < 8; ++i) gmax = fmaxf(gmax, red[i]);
+        for (int i = 1; i < kFeatWarps; ++i) gmax = fmaxf(gmax, red[i]);
       }
 
       // ---- S1 ----
-      for (int t = 0; t < ntiles; ++t) {
-        mbar_wait(bar_k, ph_k); ph_k ^= 1u;
+      for (int t = 0; t < nt; ++t) {
+        consume_ld(0, softmax_kind);
         const bool valid = t * kTile + row < p.tokens;
-        float diag = 0.f;
+        const bool tile_full = (t + 1) * kTile <= p.tokens;
+        float sub = 0.f;
         for (int hf = 0; hf < 2; ++hf) {
           wait_mma();
-          if (hf == 0 && softmax_kind) diag = row_half_sqnorm(s_k, row);
+          if (hf == 0 && softmax_kind) sub = (row_half_sqnorm(s_buf[0], row) + gmax) * kLog2e;
           const int nch = hf == 0 ? 9 : 8, moff = hf == 0 ? 0 : 144;
           int c0, c1;
           split(nch, c0, c1);
           for (int c = c0; c < c1; ++c) {
-            uint32_t r[16];
-            tmem_ld_32x16(tmem + t_lane + kColU + c * 16, r);
-            tmem_ld_wait();
-            float f[16];
             const int m0 = moff + c * 16;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float u = __uint_as_float(r[i]);
-              float v = softmax_kind ? ratio * (__expf(u - diag - gmax) + 1e-4f) : fmaxf(u, 0.f) + 1e-3f;
-              f[i] = (valid && m0 + i < p.m) ? v : 0.f;
-            }
-            write_feat16(s_feat, row, m0, f);
+            feat_chunk(kColU + c * 16, m0, valid, tile_full && m0 + 16 <= p.m, sub);
           }
           arrive(true);
         }
-        wait_mma();  // context MMAs of this tile done (K, V, feat buffers free again)
+        wait_mma();  // context MMAs of this tile done (V, feat buffers free again)
+        consume_ld(1, false);
         bool wrote = false;
-        if (t == ntiles - 1 && lg != 3) {
+        if (t == nt - 1 && lg != 3) {
           // read out [ctx^T ; ksum] rows 0..79 -> ctxt (bf16, K-major over m). Lane groups 0,1:
           // ctx^T rows; group 2: rows 64..79 (row 64 = ksum, the rest are exact zeros).
           const bool owner = lg < 2 || lane < 16;  // every lane executes the aligned TMEM loads
@@ -380,16 +434,18 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
 
       // ---- S3 ----
-      for (int t = 0; t < ntiles; ++t) {
-        mbar_wait(bar_k, ph_k); ph_k ^= 1u;
+      for (int t = 0; t < nt; ++t) {
+        const int b = t & 1;
+        consume_ld(b, softmax_kind);
         wait_mma();
         const bool valid = t * kTile + row < p.tokens;
+        const bool tile_full = (t + 1) * kTile <= p.tokens;
         int c0, c1;
         split(17, c0, c1);
-        float diag = 0.f, mx = 0.f;
+        float sub = 0.f;
         if (softmax_kind) {
-          diag = row_half_sqnorm(s_k, row);
-          mx = -INFINITY;
+          const float diag = row_half_sqnorm(s_buf[b], row);
+          float mx = -INFINITY;
           for (int c = c0; c < c1; ++c) {
             uint32_t r[16];
             tmem_ld_32x16(tmem + t_lane + kColD2 + c * 16, r);
@@ -398,60 +454,42 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             for (int i = 0; i < 16; ++i)
               if (c * 16 + i < p.m) mx = fmaxf(mx, __uint_as_float(r[i]));
           }
-          rowmax[half * 128 + row] = mx;
-          named_bar_sync(1, 256);
-          mx = fmaxf(rowmax[row], rowmax[128 + row]);
+          rowmax[quarter * 128 + row] = mx;
+          named_bar_sync(1, kFeatWarps * 32);
+          mx = fmaxf(fmaxf(rowmax[row], rowmax[128 + row]), fmaxf(rowmax[256 + row], rowmax[384 + row]));
+          sub = (diag + mx) * kLog2e;
         }
         for (int c = c0; c < c1; ++c) {
-          uint32_t r[16];
-          tmem_ld_32x16(tmem + t_lane + kColD2 + c * 16, r);
-          tmem_ld_wait();
-          float f[16];
           const int m0 = c * 16;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float u = __uint_as_float(r[i]);
-            float v = softmax_kind ? ratio * (__expf(u - diag - mx) + 1e-4f) : fmaxf(u, 0.f) + 1e-3f;
-            f[i] = (valid && m0 + i < p.m) ? v : 0.f;
-          }
-          write_feat16(s_feat, row, m0, f);
+          feat_chunk(kColD2 + c * 16, m0, valid, tile_full && m0 + 16 <= p.m, sub);
         }
         arrive(true);
-        // ---- output tile ----
+        // ---- output tile: each quarter stores 16 of the 64 head channels ----
         wait_mma();
         {
-          uint32_t rd[16];
+          uint32_t rd[16], r0[16];
           tmem_ld_32x16(tmem + t_lane + kColD3 + 64, rd);  // column 64 = normaliser
-          tmem_ld_wait();
-          const float inv = 1.f / __uint_as_float(rd[0]);
-          // low warp: d 0..31, high warp: d 32..63
-          uint32_t r0[16], r1[16];
-          tmem_ld_32x16(tmem + t_lane + kColD3 + half * 32, r0);
-          tmem_ld_32x16(tmem + t_lane + kColD3 + half * 32 + 16, r1);
+          tmem_ld_32x16(tmem + t_lane + kColD3 + quarter * 16, r0);
           tmem_ld_wait();
           if (valid) {
+            const float inv = 1.f / __uint_as_float(rd[0]);
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)g1 * p.ogs1 +
-                                (int64_t)g0 * p.ogs0 + (int64_t)(t * kTile + row) * p.ots + h * 64 + half * 32;
-            uint4 w[4];
-            uint32_t* wp = reinterpret_cast<uint32_t*>(w);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              wp[i] = pack_bf16x2(__uint_as_float(r0[2 * i]) * inv, __uint_as_float(r0[2 * i + 1]) * inv);
-              wp[8 + i] = pack_bf16x2(__uint_as_float(r1[2 * i]) * inv, __uint_as_float(r1[2 * i + 1]) * inv);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(op)[i] = w[i];
+                                (int64_t)g0 * p.ogs0 + (int64_t)(t * kTile + row) * p.ots + h * 64 + quarter * 16;
+            uint4 w0, w1;
+            w0.x = pack_bf16x2(__uint_as_float(r0[0]) * inv, __uint_as_float(r0[1]) * inv);
+            w0.y = pack_bf16x2(__uint_as_float(r0[2]) * inv, __uint_as_float(r0[3]) * inv);
+            w0.z = pack_bf16x2(__uint_as_float(r0[4]) * inv, __uint_as_float(r0[5]) * inv);
+            w0.w = pack_bf16x2(__uint_as_float(r0[6]) * inv, __uint_as_float(r0[7]) * inv);
+            w1.x = pack_bf16x2(__uint_as_float(r0[8]) * inv, __uint_as_float(r0[9]) * inv);
+            w1.y = pack_bf16x2(__uint_as_float(r0[10]) * inv, __uint_as_float(r0[11]) * inv);
+            w1.z = pack_bf16x2(__uint_as_float(r0[12]) * inv, __uint_as_float(r0[13]) * inv);
+            w1.w = pack_bf16x2(__uint_as_float(r0[14]) * inv, __uint_as_float(r0[15]) * inv);
+            reinterpret_cast<uint4*>(op)[0] = w0;
+            reinterpret_cast<uint4*>(op)[1] = w1;
           }
         }
         arrive(false);
       }
-    }
-    // keep the control warp's idle lanes and everyone's phase counters in step across items
-    if (warp == 0) {
-      // the control thread advanced ph_k/ph_v/ph_feat; broadcast so lanes stay consistent
-      ph_k = __shfl_sync(0xffffffffu, ph_k, 0);
-      ph_v = __shfl_sync(0xffffffffu, ph_v, 0);
-      ph_feat = __shfl_sync(0xffffffffu, ph_feat, 0);
     }
   }
   tc_fence_before();

@@ -114,6 +114,23 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, int64_t K, int64_t rows, i
   return r == CUDA_SUCCESS ? RFK_OK : RFK_ERR_TMA_ENCODE;
 }
 
+int make_tmap_bf16_raw(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return RFK_ERR_TMA_ENCODE;
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) {
+    if (strides_bytes[i] % 16) return RFK_ERR_MISALIGNED;
+    st[i] = strides_bytes[i];
+  }
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), d, st, bx,
+                   es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? RFK_OK : RFK_ERR_TMA_ENCODE;
+}
+
 static int pick_bn(int64_t N) {
   // smallest tile-count first, then the least padding; N up to a few thousand
   const int cands[] = {256, 192, 128, 96, 64, 32};

@@ -1,0 +1,80 @@
+// rfk_gemm_conv.cu — 3x3 'same' convolution on a channels-last map as an implicit GEMM on the
+// tcgen05 GEMM kernel (CONV instances): nn.Conv2d(d_pair, d_pair, 3, padding="same", bias=False) of
+// PairUpdateWithMsa (rosettafold_pytorch.py:451-457). The im2col matrix is never built: each of the
+// 9 taps is a TMA box shifted by (di, dj) over the NHWC tensor, with the border zero-filled by TMA.
+#include "rfk_gemm_device.cuh"
+
+namespace rfk {
+int launch_tc_conv(int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p,
+                   int64_t tiles, cudaStream_t s) {
+  if (epi == 0) return launch_tc<32, 0, true>(ta, tb, p, tiles, s);
+  if (epi == 1) {
+    switch (bn) {
+      case 256: return launch_tc<256, 1, true>(ta, tb, p, tiles, s);
+      case 128: return launch_tc<128, 1, true>(ta, tb, p, tiles, s);
+      case 96: return launch_tc<96, 1, true>(ta, tb, p, tiles, s);
+      case 64: return launch_tc<64, 1, true>(ta, tb, p, tiles, s);
+      default: return launch_tc<32, 1, true>(ta, tb, p, tiles, s);
+    }
+  }
+  switch (bn) {
+    case 256: return launch_tc<256, 2, true>(ta, tb, p, tiles, s);
+    case 128: return launch_tc<128, 2, true>(ta, tb, p, tiles, s);
+    case 96: return launch_tc<96, 2, true>(ta, tb, p, tiles, s);
+    case 64: return launch_tc<64, 2, true>(ta, tb, p, tiles, s);
+    default: return launch_tc<32, 2, true>(ta, tb, p, tiles, s);
+  }
+}
+}  // namespace rfk
+
+using namespace rfk;
+
+extern "C" int rfk_conv3x3_nhwc(const void* x, const void* w_packed, void* y, int y_dtype, int B, int L,
+                                int C, int Cout, rfk_stream_t stream_) {
+  if (!x || !w_packed || !y) return RFK_ERR_NULL_POINTER;
+  if (B <= 0 || L <= 0 || C <= 0 || Cout <= 0) return RFK_ERR_BAD_DIMS;
+  if (C % 8) return RFK_ERR_BAD_DIMS;  // TMA stride rule (16-byte rows)
+  if (y_dtype != RFK_BF16 && y_dtype != RFK_F32) return RFK_ERR_BAD_DTYPE;
+  if (!aligned16(x) || !aligned16(w_packed) || !aligned16(y)) return RFK_ERR_MISALIGNED;
+  int rc = check_arch();
+  if (rc != RFK_OK) return rc;
+  const int cblocks = (C + 63) / 64, cpad = cblocks * 64;
+  const int Lp = (L + kBlockM - 1) / kBlockM * kBlockM;
+  int bn = 32;
+  for (int cand : {256, 128, 96, 64, 32})
+    if (Cout % cand == 0) { bn = cand; break; }
+  const bool lean = Cout % 32 == 0 && (y_dtype == RFK_BF16 ? Cout % 8 == 0 : Cout % 4 == 0);
+
+  GemmDev p{};
+  p.M = (int64_t)B * L * Lp;  // padded so that every tile lies inside one image row
+  p.N = Cout;
+  p.K = (int64_t)9 * cpad;
+  p.Z0 = p.Z1 = p.Z2 = 1;
+  p.MR = Lp; p.NR = Cout;
+  p.alpha = 1.f; p.act = RFK_ACT_NONE; p.epi = RFK_EPI_STD;
+  p.c = y; p.c_dtype = y_dtype;
+  p.c_addr.ms[0] = Cout;                 // j
+  p.c_addr.ms[1] = (int64_t)L * Cout;    // (b, i)
+  p.c_addr.ns[0] = 1; p.c_addr.ns[1] = 0;
+  p.conv_L = L; p.conv_Lp = Lp; p.conv_cblocks = cblocks; p.conv_cpad = cpad;
+  p.conv_last_k16 = (C - (cblocks - 1) * 64 + 15) / 16;
+
+  CUtensorMap ta, tb;
+  {
+    const uint64_t dims[5] = {(uint64_t)C, (uint64_t)L, (uint64_t)L, (uint64_t)B, 1};
+    const uint64_t strides[4] = {(uint64_t)C * 2, (uint64_t)L * C * 2, (uint64_t)L * L * C * 2,
+                                 (uint64_t)B * L * L * C * 2};
+    const uint32_t box[5] = {64, (uint32_t)kBlockM, 1, 1, 1};
+    if ((rc = make_tmap_bf16_raw(&ta, x, 5, dims, strides, box)) != RFK_OK) return rc;
+  }
+  {
+    const uint64_t dims[5] = {(uint64_t)9 * cpad, (uint64_t)Cout, 1, 1, 1};
+    const uint64_t strides[4] = {(uint64_t)9 * cpad * 2, (uint64_t)9 * cpad * 2 * Cout,
+                                 (uint64_t)9 * cpad * 2 * Cout, (uint64_t)9 * cpad * 2 * Cout};
+    const uint32_t box[5] = {64, (uint32_t)bn, 1, 1, 1};
+    if ((rc = make_tmap_bf16_raw(&tb, w_packed, 5, dims, strides, box)) != RFK_OK) return rc;
+  }
+  const int64_t tiles = (p.M / kBlockM) * ((Cout + bn - 1) / bn);
+  return launch_tc_conv(bn, !lean ? 0 : (y_dtype == RFK_BF16 ? 1 : 2), ta, tb, p, tiles,
+                        reinterpret_cast<cudaStream_t>(stream_));
+}

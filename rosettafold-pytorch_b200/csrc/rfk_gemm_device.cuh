@@ -23,6 +23,9 @@ struct GemmDev {
   const float* ln_beta;
   // tcgen05 path only
   int bmask[3];  // 0 -> broadcast B over that z level
+  // implicit-GEMM 3x3 convolution mode (CONV kernels): A is the NHWC image [B][L][L][C]; a tile is
+  // 128 consecutive columns j of one image row; K runs over 9 taps x conv_cblocks 64-channel blocks
+  int conv_L, conv_Lp, conv_cblocks, conv_last_k16, conv_cpad;
   // SIMT path only
   const float* a32;
   const float* b32;
@@ -458,7 +461,7 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStagingBytes;
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool CONV = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const GemmDev p) {
@@ -504,7 +507,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   const int64_t m_blocks = (p.M + kBlockM - 1) / kBlockM;
   const int64_t n_blocks = (p.N + BN - 1) / BN;
-  const int64_t k_blocks = (p.K + kBlockK - 1) / kBlockK;
+  const int64_t k_blocks = CONV ? (int64_t)9 * p.conv_cblocks : (p.K + kBlockK - 1) / kBlockK;
   const int64_t Z = p.Z0 * p.Z1 * p.Z2;
   const int64_t tiles = Z * m_blocks * n_blocks;
 
@@ -517,14 +520,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const int64_t mb = (t / n_blocks) % m_blocks;
       const int64_t z = t / (n_blocks * m_blocks);
       const int z0 = (int)(z % p.Z0), z1 = (int)((z / p.Z0) % p.Z1), z2 = (int)(z / (p.Z0 * p.Z1));
-      for (int64_t kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-        tma_load_5d(&tma_a, full_bar(stage), smem_a(stage), (int)(kb * kBlockK),
-                    (int)(mb * kBlockM), z0, z1, z2);
-        tma_load_5d(&tma_b, full_bar(stage), smem_b(stage), (int)(kb * kBlockK), (int)(nb * BN),
-                    z0 & p.bmask[0], z1 & p.bmask[1], z2 & p.bmask[2]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      if constexpr (CONV) {
+        // tile -> (image b, row i, first column j0); taps shift the TMA box, out-of-image rows and
+        // columns are zero-filled by the TMA unit ('same' padding for free)
+        const int64_t m0 = mb * kBlockM;
+        const int img_row = (int)(m0 / p.conv_Lp), j0 = (int)(m0 % p.conv_Lp);
+        const int bi = img_row / p.conv_L, ii = img_row % p.conv_L;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int di = tap / 3 - 1, dj = tap % 3 - 1;
+          for (int cb = 0; cb < p.conv_cblocks; ++cb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            tma_load_5d(&tma_a, full_bar(stage), smem_a(stage), cb * kBlockK, j0 + dj, ii + di, bi, 0);
+            tma_load_5d(&tma_b, full_bar(stage), smem_b(stage), tap * p.conv_cpad + cb * kBlockK,
+                        (int)(nb * BN), 0, 0, 0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      } else {
+        for (int64_t kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          tma_load_5d(&tma_a, full_bar(stage), smem_a(stage), (int)(kb * kBlockK),
+                      (int)(mb * kBlockM), z0, z1, z2);
+          tma_load_5d(&tma_b, full_bar(stage), smem_b(stage), (int)(kb * kBlockK), (int)(nb * BN),
+                      z0 & p.bmask[0], z1 & p.bmask[1], z2 & p.bmask[2]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -543,10 +565,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         tc_fence_after();
         const uint64_t adesc = umma_desc_sw128(smem_a(stage));
         const uint64_t bdesc = umma_desc_sw128(smem_b(stage));
+        // conv: the last channel block of a tap may hold fewer than 64 real channels
+        const int nk16 = (CONV && (int)(kb % p.conv_cblocks) == p.conv_cblocks - 1) ? p.conv_last_k16
+                                                                                  : kBlockK / 16;
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k)
-          umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                    (kb > 0 || k > 0) ? 1u : 0u);
+          if (k < nk16)
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
         umma_commit(empty_bar(stage));
         if (kb == k_blocks - 1) umma_commit(tfull_bar(acc));
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -568,7 +594,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const int64_t m_warp0 = mb * kBlockM + lg * 32;
       const float* bias = p.bias ? p.bias + z0 * p.bias_zs[0] + z1 * p.bias_zs[1] + z2 * p.bias_zs[2] : nullptr;
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BN);
-      if constexpr (EPI == 0) {
+      if constexpr (EPI == 0 && CONV) {
+        // generic conv epilogue (channel counts that are not multiples of 32): per-thread rows,
+        // rows in the padding of an image row are skipped
+        const int64_t m = m_warp0 + lane;
+        const bool row_ok = m < p.M && (int)((uint32_t)m % (uint32_t)p.conv_Lp) < p.conv_L;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = chalf; c < BN / 32; c += 2) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          epilogue_row_chunk<32>(p, z0, z1, z2, row_ok ? m : p.M, nb * BN + c * 32, v);
+        }
+      } else if constexpr (EPI == 0) {
         const int64_t m = m_warp0 + lane;
         // this lane's row offsets (shared across the warp by shuffle in the staged epilogue)
         const int64_t mm = m < p.M ? m : 0;
@@ -606,7 +649,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int64_t c_base = addr_zm(p.c_addr, z0, z1, z2, mw, p.MR);
         const int64_t r0_base = (EPI == 2 && p.r0) ? addr_zm(p.r0_addr, z0, z1, z2, mw, p.MR) : 0;
         const int64_t r1_base = (EPI == 2 && p.r1) ? addr_zm(p.r1_addr, z0, z1, z2, mw, p.MR) : 0;
-        const int64_t left = p.M - m_warp0;
+        const int64_t left = CONV ? (int64_t)p.conv_L - (int64_t)((uint32_t)m_warp0 % (uint32_t)p.conv_Lp)
+                                  : p.M - m_warp0;
         const int rows_valid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
@@ -640,20 +684,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 }
 
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool CONV = false>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles,
                      cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;  // benign race: the attribute call is idempotent
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, CONV>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return cuda_status(e);
     configured = true;
   }
   int grid = num_sms();
   if (tiles < grid) grid = (int)tiles;
-  gemm_tc_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  gemm_tc_kernel<BN, EPI, CONV><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   return post_launch();
 }
 
@@ -675,5 +719,7 @@ static int launch_tc_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, co
 int launch_tc_epi0(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s);
 int launch_tc_epi1(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s);
 int launch_tc_epi2(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s);
+int launch_tc_conv(int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s);
+int make_tmap_bf16_raw(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
 
 }  // namespace rfk

@@ -4,8 +4,8 @@ Same class names, constructor signatures, forward signatures/returns and paramet
 (state_dict keys) as the reference lines cited on each class, so reference weights load
 one-to-one. The forwards are inference (eval-mode) computations built ONLY from librfk kernels
 (`ops`): dropout is the identity and autograd is not recorded. torch is used for allocation and
-views; the single exception is the 3x3 Conv2d pair of PairUpdateWithMsa (:451-457), which stays
-on cuDNN this round ("next" row 2).
+views. The 3x3 Conv2d pair of PairUpdateWithMsa (:451-457) runs on the tcgen05 implicit-GEMM kernel
+in bf16 mode; only the fp32 validation mode still calls the library convolution for it.
 
 Residual streams (msa, pair) are float32. `set_mode("bf16")` (default) feeds bf16 operands to the
 tcgen05 kernels with fp32 accumulation; `set_mode("fp32")` is the fp32 validation mode.
@@ -551,13 +551,19 @@ class PairUpdateWithMsa(nn.Module):
                 Wf=_w(torch.cat([W[:, :c0], W[:, c2:c3], W[:, c3:]], 1)), bf=_f(self.resnet[0].bias),
                 # rank-1 parts: row-tiled and column-tiled msa_1d (fp32 SIMT GEMMs, K = 2Q)
                 Wr=W[:, c0:c1].detach().float().contiguous(), Wc=W[:, c1:c2].detach().float().contiguous(),
-                conv1=fn[1].weight.detach().to(adt).contiguous(memory_format=torch.channels_last),
-                conv2=fn[5].weight.detach().to(adt).contiguous(memory_format=torch.channels_last),
+                # bf16 mode: tap-major packed weights of the implicit-GEMM conv kernel; fp32
+                # validation mode: plain fp32 weights for the library convolution
+                conv1=ops.pack_conv3x3_weight(fn[1].weight) if _MODE == 0 else fn[1].weight.detach().float().contiguous(memory_format=torch.channels_last),
+                conv2=ops.pack_conv3x3_weight(fn[5].weight) if _MODE == 0 else fn[5].weight.detach().float().contiguous(memory_format=torch.channels_last),
                 g1=_f(fn[2].weight), b1=_f(fn[2].bias), g2=_f(fn[6].weight), b2=_f(fn[6].bias))
         return _packed(self, build)
 
     def _conv(self, x_bllc, w):
-        """3x3 'same' convolution on a channels-last [B,L,L,C] map (cuDNN; see module docstring)."""
+        """3x3 'same' convolution on a channels-last [B,L,L,C] map: rfk_conv3x3_nhwc (tcgen05
+        implicit GEMM) in bf16 mode; the fp32 validation mode uses the library convolution."""
+        if _MODE == 0:
+            B, L, _, _ = x_bllc.shape
+            return ops.conv3x3(x_bllc, w, _empty((B, L, L, w.shape[0]), torch.bfloat16, x_bllc))
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
             y = F.conv2d(x_bllc.permute(0, 3, 1, 2), w, padding=1)
         return y.permute(0, 2, 3, 1).contiguous()

@@ -19,6 +19,7 @@ __all__ = [
     "ACT_NONE", "ACT_RELU", "ACT_ELU", "EPI_STD", "EPI_BLOCKLN32",
     "gemm", "layernorm", "softmax_rows", "tied_att_symmetrize", "poswise_weight", "opm_prep",
     "pair2att_logits", "channel_stats", "instnorm_apply", "favor_attention", "convert_rows",
+    "conv3x3", "pack_conv3x3_weight",
 ]
 
 
@@ -164,6 +165,11 @@ class _CudaBackend:
         d.out_gs[0], d.out_gs[1] = out.stride(1), out.stride(0)
         d.out_ts = out.stride(2)
         _lib.check(self.lib.rfk_favor_attention(C.byref(d), self._stream(q)), "rfk_favor_attention")
+
+    def conv3x3(self, x, w_packed, out):
+        B, L, _, Cin = x.shape
+        _lib.check(self.lib.rfk_conv3x3_nhwc(_ptr(x), _ptr(w_packed), _ptr(out), _dt(out), B, L, Cin,
+                                             out.shape[3], self._stream(x)), "rfk_conv3x3_nhwc")
 
     def convert_rows(self, x, out):
         _lib.check(self.lib.rfk_convert_rows(_ptr(x), _dt(x), x.stride(0), _ptr(out), _dt(out),
@@ -397,6 +403,31 @@ def favor_attention(q, k, v, out, proj, *, kind, heads):
     tokens_total = q.shape[0] * q.shape[1] * q.shape[2]
     with _Timed("favor_attention", 8.0 * tokens_total * heads * 64 * proj.shape[0]):
         backend().favor_attention(q, k, v, out, proj, int(kind), int(heads))
+    return out
+
+
+def pack_conv3x3_weight(w: torch.Tensor) -> torch.Tensor:
+    """nn.Conv2d weight [Cout, Cin, 3, 3] -> bf16 [Cout, 9, Cpad] (tap-major, channels padded to a
+    multiple of 64 with zeros): the K-major B operand of the implicit GEMM."""
+    Cout, Cin = w.shape[:2]
+    cpad = (Cin + 63) // 64 * 64
+    out = torch.zeros((Cout, 9, cpad), dtype=torch.bfloat16, device=w.device)
+    out[:, :, :Cin] = w.detach().permute(0, 2, 3, 1).reshape(Cout, 9, Cin).to(torch.bfloat16)
+    return out
+
+
+def conv3x3(x, w_packed, out):
+    """3x3 'same' convolution without bias on a channels-last map: x bf16 [B,L,L,Cin] contiguous,
+    w_packed from pack_conv3x3_weight, out bf16/f32 [B,L,L,Cout] contiguous."""
+    if x.dim() != 4 or x.shape[1] != x.shape[2] or not x.is_contiguous() or x.dtype != torch.bfloat16:
+        raise ValueError("conv3x3: x must be contiguous bf16 [B,L,L,C]")
+    Cout, taps, cpad = w_packed.shape
+    if taps != 9 or cpad != (x.shape[3] + 63) // 64 * 64 or w_packed.dtype != torch.bfloat16 or not w_packed.is_contiguous():
+        raise ValueError("conv3x3: w_packed must come from pack_conv3x3_weight for this channel count")
+    if tuple(out.shape) != (x.shape[0], x.shape[1], x.shape[2], Cout) or not out.is_contiguous():
+        raise ValueError("conv3x3: bad output shape")
+    with _Timed("conv3x3", 2.0 * x.shape[0] * x.shape[1] * x.shape[2] * 9 * x.shape[3] * Cout):
+        backend().conv3x3(x, w_packed, out)
     return out
 
 

@@ -272,3 +272,21 @@ def test_launch_counter_and_errors(cuda_device):
     with pytest.raises(RuntimeError):
         ops.layernorm(torch.randn(8, 32), None, None, 1e-5, torch.empty(8, 32))  # CPU tensor: no fallback
     assert math.isfinite(float(x.sum()))
+
+
+@pytest.mark.parametrize("cfg", [(1, 24, 288, 288), (2, 130, 72, 96), (1, 256, 288, 288), (2, 20, 72, 72)])
+def test_conv3x3_implicit_gemm(cuda_device, cfg):
+    """3x3 'same' conv as implicit GEMM vs F.conv2d on the same bf16-rounded inputs
+    (reference :452, :456); L=130 exercises the padded-row tiles, C=72 the short last K block."""
+    dev = cuda_device
+    B, L, Cin, Cout = cfg
+    x = _rand((B, L, L, Cin), torch.bfloat16, dev, 90)
+    w = _rand((Cout, Cin, 3, 3), torch.float32, dev, 91, (9 * Cin) ** -0.5)
+    wp = ops.pack_conv3x3_weight(w)
+    for odt in (torch.bfloat16, torch.float32):
+        out = torch.empty((B, L, L, Cout), dtype=odt, device=dev)
+        ops.conv3x3(x, wp, out)
+        ref = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w.to(torch.bfloat16).double(), padding=1)
+        torch.cuda.synchronize()
+        e = rel_l2(out, ref.permute(0, 2, 3, 1))
+        assert e < tol(odt), f"{odt}: rel-l2 {e}"
