@@ -5,6 +5,8 @@
 //     with tcgen05.ld and run the epilogue while the next tile's MMAs are already in flight.
 //   mode 1 (fp32 operands): plain SIMT fp32 kernel (validation mode, same epilogue code).
 // See include/rfk.h for the contract and the reference lines this replaces.
+#include <cstdlib>
+
 #include "rfk_gemm_device.cuh"
 
 namespace rfk {
@@ -112,6 +114,55 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, int64_t K, int64_t rows, i
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? RFK_OK : RFK_ERR_TMA_ENCODE;
+}
+
+static int make_tmap_raw(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapDataType dt,
+                        CUtensorMapSwizzle sw) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return RFK_ERR_TMA_ENCODE;
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) {
+    if (strides_bytes[i] % 16) return RFK_ERR_MISALIGNED;
+    st[i] = strides_bytes[i];
+  }
+  CUresult r = enc(map, dt, (cuuint32_t)rank, const_cast<void*>(ptr), d, st, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? RFK_OK : RFK_ERR_TMA_ENCODE;
+}
+
+// Tensor map of an epilogue operand described by an rfk_addr (output or residual): logical dims
+// {n%NR, n/NR, m%MR, m/MR, z0, z1, z2} with size-1 dims dropped; box = 32 x 32 over (n%NR, m%MR).
+// Returns RFK_ERR_UNSUPPORTED when the view needs more than 5 dims or breaks a TMA rule.
+int make_epi_tmap(CUtensorMap* map, int cmap[5], const void* ptr, int dtype, const rfk_addr& a,
+                  const int64_t ext[7]) {
+  const int es = dtype == RFK_BF16 ? 2 : 4;
+  if (!aligned16(ptr) || a.ns[0] != 1) return RFK_ERR_UNSUPPORTED;
+  const int64_t strides[7] = {a.ns[0], a.ns[1], a.ms[0], a.ms[1], a.zs[0], a.zs[1], a.zs[2]};
+  uint64_t dims[5] = {1, 1, 1, 1, 1}, sb[4] = {16, 16, 16, 16};
+  uint32_t box[5] = {1, 1, 1, 1, 1};
+  int nd = 0;
+  for (int l = 0; l < 7; ++l) {
+    const bool keep = l == 0 || l == 2 || ext[l] > 1;
+    if (!keep) continue;
+    if (nd == 5) return RFK_ERR_UNSUPPORTED;
+    if (l != 0) {
+      const int64_t st = ext[l] > 1 ? strides[l] : (int64_t)(16 / es);
+      if (st <= 0 || (st * es) % 16) return RFK_ERR_UNSUPPORTED;  // no broadcast / misaligned dims
+      sb[nd - 1] = (uint64_t)st * es;
+    }
+    dims[nd] = (uint64_t)ext[l];
+    box[nd] = (l == 0 || l == 2) ? 32 : 1;
+    cmap[nd] = l;
+    ++nd;
+  }
+  for (int d = nd; d < 5; ++d) cmap[d] = -1;
+  return make_tmap_raw(map, ptr, 5, dims, sb, box,
+                       dtype == RFK_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                       dtype == RFK_BF16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 int make_tmap_bf16_raw(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims,
@@ -227,6 +278,33 @@ extern "C" int rfk_gemm(const rfk_gemm_desc* d, rfk_stream_t stream_) {
       (!d->r0 || (d->r0_dtype == RFK_F32 && addr_aligned(d->r0, d->r0_addr, 4))) &&
       (!d->r1 || (d->r1_dtype == RFK_F32 && addr_aligned(d->r1, d->r1_addr, 4))))
     epi = 2;
+  // TMA-store flavours (3: bf16, 4: f32 + optional TMA-fetched residual) when the views fit a tensor map
+  static const bool no_tma_epi = getenv("RFK_GEMM_NO_TMA_EPILOGUE") != nullptr;  // A/B debugging aid
+  // flavour 4 pays for its 96 KB residual/result ring with pipeline stages: only worth it for the
+  // short-K GEMMs that are bound by the fp32 residual stream, not by the tensor pipe
+  if ((epi == 1 || (epi == 2 && d->r0 && !d->r1 && d->K <= 768)) && !no_tma_epi) {
+    const bool n_split = d->NR < d->N, m_split = d->MR < d->M;
+    if ((!n_split || d->N % d->NR == 0) && (!m_split || d->M % d->MR == 0)) {
+      const int64_t ext[7] = {n_split ? d->NR : d->N, n_split ? d->N / d->NR : 1,
+                              m_split ? d->MR : d->M, m_split ? d->M / d->MR : 1,
+                              d->Z[0], d->Z[1], d->Z[2]};
+      EpiMaps em{};
+      int cmap_c[5], cmap_r[5];
+      bool ok = make_epi_tmap(&em.c, cmap_c, d->c, d->c_dtype, d->c_addr, ext) == RFK_OK;
+      bool res_tma = false;
+      if (ok && epi == 2 && d->r0) {
+        res_tma = make_epi_tmap(&em.r, cmap_r, d->r0, RFK_F32, d->r0_addr, ext) == RFK_OK;
+        for (int i = 0; i < 5 && res_tma; ++i) res_tma = cmap_r[i] == cmap_c[i];
+        ok = res_tma;  // a residual that cannot be fetched by TMA (broadcast addends) keeps flavour 2
+      }
+      if (ok) {
+        for (int i = 0; i < 5; ++i) p.cmap[i] = cmap_c[i];
+        p.has_rmap = res_tma ? 1 : 0;
+        return epi == 1 ? launch_tc_epi3(bn, ta, tb, p, tiles, stream, &em)
+                        : launch_tc_epi4(bn, ta, tb, p, tiles, stream, &em);
+      }
+    }
+  }
   if (epi == 1) return launch_tc_epi1(bn, ta, tb, p, tiles, stream);
   if (epi == 2) return launch_tc_epi2(bn, ta, tb, p, tiles, stream);
   return launch_tc_epi0(bn, ta, tb, p, tiles, stream);

@@ -26,6 +26,10 @@ struct GemmDev {
   // implicit-GEMM 3x3 convolution mode (CONV kernels): A is the NHWC image [B][L][L][C]; a tile is
   // 128 consecutive columns j of one image row; K runs over 9 taps x conv_cblocks 64-channel blocks
   int conv_L, conv_Lp, conv_cblocks, conv_last_k16, conv_cpad;
+  // TMA-store epilogues (EPI 3/4): tensor-map dimension d takes logical coordinate cmap[d] of
+  // {0: n % NR, 1: n / NR, 2: m % MR, 3: m / MR, 4: z0, 5: z1, 6: z2}; -1 -> 0
+  int cmap[5];
+  int has_rmap;  // residual r0 is fetched with TMA (map tma_r)
   // SIMT path only
   const float* a32;
   const float* b32;
@@ -365,6 +369,29 @@ __device__ __forceinline__ void epilogue_warp_chunk(const GemmDev& p, float* st,
 // test and shuffle from the hot loop.
 //   EPI 1: bf16 output, no residual.     EPI 2: f32 output, up to two f32 residual addends.
 // ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2,
+                                             int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_fast_chunk(const GemmDev& p, float4* st4, int lane,
                                                     int rows_valid, int64_t n0, float (&v)[32],
@@ -450,22 +477,27 @@ constexpr int kBlockK = 64;
 constexpr int kGemmThreads = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kEpiWarps = 8;
 
-template <int BN>
+template <int BN, int EPI = 0>
 struct GemmCfg {
   static constexpr int kStageBytes = kBlockM * 128 + BN * 128;
-  static constexpr int kStagingBytes = kEpiWarps * 32 * 33 * 4;  // epilogue transpose buffers
-  static constexpr int kBudget = 232448 - 1024 - 256 - kStagingBytes;
+  // epilogue staging: EPI 0-2 one [32][33] f32 transpose buffer per warp; EPI 3: two 2 KB bf16
+  // tiles per warp; EPI 4: three 4 KB f32 tiles per warp (residual-in / result-out ring)
+  static constexpr int kStagingBytes = EPI == 3 ? kEpiWarps * 2 * 2048
+                                       : EPI == 4 ? kEpiWarps * 3 * 4096 : kEpiWarps * 32 * 33 * 4;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kBudget = 232448 - 2048 - kBarBytes - kStagingBytes;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128
                                    : 2 * BN <= 256 ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStagingBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2048 /*align*/ + kBarBytes + kStagingBytes;
 };
 
 template <int BN, int EPI, bool CONV = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r,
                const GemmDev p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPI>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -476,6 +508,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  // EPI 4: one residual-arrival barrier per (epilogue warp, ring slot)
+  auto res_bar = [&](int w, int slot) { return bar_base + 256u + 8u * (w * 3 + slot); };
+  // staging area, 1024-byte aligned (TMA-store swizzle patterns are address based)
+  const uint32_t stg_base = (bar_base + Cfg::kBarBytes + 1023u) & ~1023u;
   auto smem_a = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
   auto smem_b = [&](int s) { return smem_base + s * Cfg::kStageBytes + kBlockM * 128; };
 
@@ -491,6 +527,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kEpiWarps);
     }
+    if constexpr (EPI == 4)
+      for (int w = 0; w < kEpiWarps; ++w)
+        for (int sl = 0; sl < 3; ++sl) mbar_init(res_bar(w, sl), 1);
     fence_barrier_init();
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -566,8 +605,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const uint64_t adesc = umma_desc_sw128(smem_a(stage));
         const uint64_t bdesc = umma_desc_sw128(smem_b(stage));
         // conv: the last channel block of a tap may hold fewer than 64 real channels
-        const int nk16 = (CONV && (int)(kb % p.conv_cblocks) == p.conv_cblocks - 1) ? p.conv_last_k16
-                                                                                  : kBlockK / 16;
+        // (the K tail of a plain GEMM is zero-filled by TMA: skip the all-zero k16 steps too)
+        const int nk16 = CONV ? (((int)(kb % p.conv_cblocks) == p.conv_cblocks - 1) ? p.conv_last_k16 : kBlockK / 16)
+                              : ((kb == k_blocks - 1) ? (int)((p.K - kb * kBlockK + 15) / 16) : kBlockK / 16);
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k)
           if (k < nk16)
@@ -582,8 +622,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   } else if (warp >= 2) {
     // ===== epilogue warps (TMEM lane group = warp % 4) =====
     const int lg = warp & 3;
-    float* stage = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw))) + (warp - 2) * 32 * 33;
+    float* stage = reinterpret_cast<float*>(smem_raw + (stg_base - smem_u32(smem_raw))) + (warp - 2) * 32 * 33;
     const int chalf = (warp - 2) >> 2;  // two warps share a TMEM lane group and alternate chunks
+    uint32_t epi_count = 0;  // chunks stored so far by this warp (ring slot / residual barrier parity)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
@@ -642,6 +683,125 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           epilogue_warp_chunk<16>(p, stage, lane, z0, z1, z2, m_warp0, nb * BN + (BN / 32) * 32, v, c_row,
                                   r0_row, r1_row, bias);
         }
+      } else if constexpr (EPI >= 3) {
+        // ---- TMA-store epilogues: registers -> swizzled smem tile -> cp.async.bulk.tensor store.
+        // No per-row address arithmetic, no transposing reads; partial tiles are clipped by TMA.
+        static_assert(BN % 32 == 0, "TMA epilogues need 32-column chunks");
+        constexpr uint32_t kBuf = EPI == 3 ? 2048u : 4096u;
+        constexpr int kRing = EPI == 3 ? 2 : 3;
+        const int ew = warp - 2;
+        const uint32_t ring = stg_base + (uint32_t)ew * kRing * kBuf;
+        int lc[7];
+        {
+          const uint32_t mu = (uint32_t)m_warp0, mr = (uint32_t)p.MR;
+          lc[3] = (int)(mu / mr); lc[2] = (int)(mu - (uint32_t)lc[3] * mr);
+          lc[4] = (int)z0; lc[5] = (int)z1; lc[6] = (int)z2;
+        }
+        auto coord = [&](int d) { return p.cmap[d] < 0 ? 0 : lc[p.cmap[d]]; };
+        auto set_n = [&](int64_t n0) {
+          const uint32_t nu = (uint32_t)n0, nr = (uint32_t)p.NR;
+          lc[1] = (int)(nu / nr); lc[0] = (int)(nu - (uint32_t)lc[1] * nr);
+        };
+        const bool row_tile_ok = m_warp0 < p.M;
+        int nch = 0;  // chunks of this tile owned by this warp: c = chalf + 2 i
+        for (int c = chalf; c < BN / 32 && nb * BN + c * 32 < p.N; c += 2) ++nch;
+        const bool use_res = EPI == 4 && p.has_rmap != 0;
+        if (use_res && row_tile_ok) {
+          // every earlier store of this warp has been read out of the ring: prefetch two residual tiles
+          if (lane == 0) {
+            bulk_wait_read<0>();
+            for (int i = 0; i < 2 && i < nch; ++i) {
+              set_n(nb * BN + (chalf + 2 * i) * 32);
+              mbar_arrive_expect_tx(res_bar(ew, (int)((epi_count + i) % 3)), kBuf);
+              tma_load_5d(&tma_r, res_bar(ew, (int)((epi_count + i) % 3)), ring + (uint32_t)((epi_count + i) % 3) * kBuf,
+                          coord(0), coord(1), coord(2), coord(3), coord(4));
+            }
+          }
+          __syncwarp();
+        }
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t myrow = (uint32_t)lane;
+#pragma unroll 1
+        for (int i = 0; i < nch; ++i) {
+          const int c = chalf + 2 * i;
+          const int64_t n0 = nb * BN + c * 32;
+          const int slot = (int)(epi_count % kRing);
+          const uint32_t buf = ring + (uint32_t)slot * kBuf;
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          // bias of the 32 columns (same addresses in every lane: broadcast loads)
+          float4 bq[8];
+          if (bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(bias + n0) + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[4 * j] = __uint_as_float(r[4 * j]) + bq[j].x;
+            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bq[j].y;
+            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bq[j].z;
+            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bq[j].w;
+          }
+          if (EPI == 3 && p.epi == RFK_EPI_BLOCKLN32) blockln32(p, lane, v);
+          if (p.act == RFK_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (!row_tile_ok) continue;  // ring slots / barrier parities only advance with real stores
+          if constexpr (EPI == 3) {
+            // the store issued two chunks ago (same slot) must have finished reading the tile
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+            const uint32_t rowb = buf + myrow * 64u, sw = (myrow >> 1) & 3u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              st_shared_v4u(rowb + ((((uint32_t)q) ^ sw) << 4), pack_bf16x2(v[8 * q], v[8 * q + 1]),
+                            pack_bf16x2(v[8 * q + 2], v[8 * q + 3]), pack_bf16x2(v[8 * q + 4], v[8 * q + 5]),
+                            pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+          } else {
+            const uint32_t rowb = buf + myrow * 128u, sw = myrow & 7u;
+            if (use_res) {
+              mbar_wait(res_bar(ew, slot), (uint32_t)((epi_count / 3) & 1));
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 t = ld_shared_f4(rowb + ((((uint32_t)q) ^ sw) << 4));
+                v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+              }
+            } else {
+              if (lane == 0) bulk_wait_read<2>();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              st_shared_v4u(rowb + ((((uint32_t)q) ^ sw) << 4), __float_as_uint(v[4 * q]),
+                            __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
+                            __float_as_uint(v[4 * q + 3]));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            set_n(n0);
+            tma_store_5d(&tma_c, buf, coord(0), coord(1), coord(2), coord(3), coord(4));
+            bulk_commit();
+            if (use_res && i + 2 < nch) {
+              // slot of chunk i+2 was last used by chunk i-1: its store may still be in flight
+              bulk_wait_read<1>();
+              set_n(nb * BN + (chalf + 2 * (i + 2)) * 32);
+              const int s2 = (int)((epi_count + 2) % 3);
+              mbar_arrive_expect_tx(res_bar(ew, s2), kBuf);
+              tma_load_5d(&tma_r, res_bar(ew, s2), ring + (uint32_t)s2 * kBuf, coord(0), coord(1), coord(2),
+                          coord(3), coord(4));
+            }
+          }
+          __syncwarp();
+          ++epi_count;
+        }
       } else {
         static_assert(EPI == 0 || BN % 32 == 0, "lean epilogues need 32-column chunks");
         // rows of this warp are affine in memory: offset(row) = base + row * ms[0]
@@ -675,6 +835,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
+  if (EPI >= 3 && warp >= 2 && lane == 0) bulk_wait_all();  // smem tiles must outlive their bulk stores
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -684,10 +845,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 }
 
 
+struct EpiMaps {
+  CUtensorMap c, r;
+};
+
 template <int BN, int EPI, bool CONV = false>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles,
-                     cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+                     cudaStream_t stream, const EpiMaps* em = nullptr) {
+  using Cfg = GemmCfg<BN, EPI>;
+  static const EpiMaps kNoMaps{};
+  if (!em) em = &kNoMaps;
   static bool configured = false;  // benign race: the attribute call is idempotent
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, CONV>,
@@ -697,20 +864,20 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev
   }
   int grid = num_sms();
   if (tiles < grid) grid = (int)tiles;
-  gemm_tc_kernel<BN, EPI, CONV><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  gemm_tc_kernel<BN, EPI, CONV><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, em->c, em->r, p);
   return post_launch();
 }
 
 template <int EPI>
 static int launch_tc_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p,
-                        int64_t tiles, cudaStream_t stream) {
+                        int64_t tiles, cudaStream_t stream, const EpiMaps* em = nullptr) {
   switch (bn) {
-    case 256: return launch_tc<256, EPI>(ta, tb, p, tiles, stream);
-    case 192: return launch_tc<192, EPI>(ta, tb, p, tiles, stream);
-    case 128: return launch_tc<128, EPI>(ta, tb, p, tiles, stream);
-    case 96: return launch_tc<96, EPI>(ta, tb, p, tiles, stream);
-    case 64: return launch_tc<64, EPI>(ta, tb, p, tiles, stream);
-    case 32: return launch_tc<32, EPI>(ta, tb, p, tiles, stream);
+    case 256: return launch_tc<256, EPI>(ta, tb, p, tiles, stream, em);
+    case 192: return launch_tc<192, EPI>(ta, tb, p, tiles, stream, em);
+    case 128: return launch_tc<128, EPI>(ta, tb, p, tiles, stream, em);
+    case 96: return launch_tc<96, EPI>(ta, tb, p, tiles, stream, em);
+    case 64: return launch_tc<64, EPI>(ta, tb, p, tiles, stream, em);
+    case 32: return launch_tc<32, EPI>(ta, tb, p, tiles, stream, em);
     default: return RFK_ERR_UNSUPPORTED;
   }
 }
@@ -719,6 +886,8 @@ static int launch_tc_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, co
 int launch_tc_epi0(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s);
 int launch_tc_epi1(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s);
 int launch_tc_epi2(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s);
+int launch_tc_epi3(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s, const EpiMaps* em);
+int launch_tc_epi4(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s, const EpiMaps* em);
 int launch_tc_conv(int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s);
 int make_tmap_bf16_raw(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
 
