@@ -231,7 +231,7 @@ def run_b200(args):
     clocks.start()
     n0 = rf._lib.launch_count()
     # per-kernel-family device timing on the launching stream, live in the timed region
-    ops.start_timing(["gemm_bf16", "gemm_f32", "favor_attention", "layernorm"])
+    ops.start_timing(["gemm_bf16", "gemm_f32", "favor_attention", "conv3x3", "layernorm"])
     total_ms = timed(step_resident, args.steps)
     fam = ops.stop_timing()
     launches = rf._lib.launch_count() - n0
@@ -254,14 +254,14 @@ def run_b200(args):
     def tflops(f):
         return f["work"] / (f["ms"] * 1e-3) / 1e12 if f["ms"] > 0 else 0.0
 
-    tensor_fams = {k: v for k, v in fam.items() if k in ("gemm_bf16", "favor_attention", "gemm_f32") and v["calls"]}
+    tensor_fams = {k: v for k, v in fam.items() if k in ("gemm_bf16", "favor_attention", "gemm_f32", "conv3x3") and v["calls"]}
     dom = max(tensor_fams, key=lambda k: tensor_fams[k]["ms"]) if tensor_fams else None
     roofline = None
     if dom:
         f = fam[dom]
         ach = tflops(f)
         roofline = {"kernel": {"gemm_bf16": "rfk::gemm_tc_kernel (tcgen05)", "favor_attention": "rfk::favor kernel",
-                               "gemm_f32": "rfk::gemm_f32_kernel"}[dom],
+                               "gemm_f32": "rfk::gemm_f32_kernel", "conv3x3": "rfk::gemm_tc_kernel<CONV> (implicit GEMM)"}[dom],
                     "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
                     "traffic": None, "peak_source": peak_src,
                     "launches_per_step": f["calls"] / args.steps, "avg_launch_ms": f["ms"] / max(1, f["calls"]),

@@ -13,3 +13,5 @@ from .modules import (ColWise, EncoderLayer, FeedForward, MsaUpdateUsingSelfAtte
                       PairUpdateWithMsa, PerformerSelfAttention, PositionWiseWeightFactor, Residual,
                       RowWise, SoftTiedAttentionOverResidues, Symmetrization, TrunkBlocks,
                       TwoTrackBlock, get_mode, load_reference_weights, set_mode)
+from . import replicas  # noqa: E402,F401
+from .integration import accelerate, accelerate_block  # noqa: E402,F401

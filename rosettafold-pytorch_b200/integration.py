@@ -1,0 +1,60 @@
+"""Swap the trunk of a *reference* model for the B200 modules, in place.
+
+Works on any reference block that owns the four trunk children (`TwoTrackBlock`,
+`ThreeTrackBlock`, `FinalBlock`, rosettafold_pytorch.py:923-1127) and on a whole `RoseTTAFold`.
+Hyper-parameters are read off the reference instance, weights are copied (including the layers the
+reference keeps in plain lists), everything else of the model is left untouched.
+"""
+from __future__ import annotations
+
+import torch.nn as nn
+
+from . import modules as M
+
+TRUNK_CHILDREN = ("msa_update_using_self_att", "pair_update_with_msa",
+                  "pair_update_with_axial_attention", "msa_update_with_pair")
+
+
+def _make(name: str, ref: nn.Module) -> nn.Module:
+    if name == "msa_update_using_self_att":
+        l0 = ref.residue_wise_encoder_layers[0]
+        return M.MsaUpdateUsingSelfAttention(
+            d_msa=l0.ln.normalized_shape[0], d_ff=l0.ff.fn[1].net[0].out_features,
+            n_heads=l0.attn.n_heads, n_encoder_layers=len(ref.residue_wise_encoder_layers))
+    if name == "pair_update_with_msa":
+        return M.PairUpdateWithMsa(
+            d_msa=ref.proj_msa[0].normalized_shape[0], d_proj=ref.proj_msa[1].out_features,
+            d_pair=ref.ln_pair.normalized_shape[0],
+            n_heads=ref.resnet[0].in_features - 2 * ref.ln_pair.normalized_shape[0] - 4 * ref.proj_msa[1].out_features)
+    if name == "pair_update_with_axial_attention":
+        l0 = ref.layers[0]
+        return M.PairUpdateWithAxialAttention(
+            d_pair=l0.ff.net[0].in_features, d_ff=l0.ff.net[0].out_features, n_heads=l0.row_attn.heads,
+            p_dropout=0.0, n_encoder_layers=len(ref.layers))
+    if name == "msa_update_with_pair":
+        l0 = ref.encoder_layers[0]
+        return M.MsaUpdateWithPair(
+            d_msa=l0.msa2value[1].in_features, d_pair=l0.pair2att[1].normalized_shape[0],
+            n_heads=l0.pair2att[2].out_features, n_encoder_layers=len(ref.encoder_layers))
+    raise KeyError(name)
+
+
+def accelerate_block(block: nn.Module, device=None) -> nn.Module:
+    """Replace the four trunk children of one reference block."""
+    for name in TRUNK_CHILDREN:
+        old = getattr(block, name)
+        new = M.load_reference_weights(_make(name, old), old).eval()
+        setattr(block, name, new.to(device) if device is not None else new)
+    return block
+
+
+def accelerate(model: nn.Module, device=None) -> nn.Module:
+    """Replace the trunk of every block of a reference RoseTTAFold (rosettafold_pytorch.py:1220-1267)."""
+    blocks = list(getattr(model, "two_track_blocks", [])) + list(getattr(model, "three_track_blocks", []))
+    if hasattr(model, "final_block"):
+        blocks.append(model.final_block)
+    if not blocks and all(hasattr(model, n) for n in TRUNK_CHILDREN):
+        blocks = [model]
+    for blk in blocks:
+        accelerate_block(blk, device)
+    return model

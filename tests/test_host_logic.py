@@ -108,3 +108,25 @@ def test_c_abi_exports_every_declared_symbol():
 def test_ops_refuse_cpu_tensors():
     with pytest.raises(RuntimeError):
         ops.layernorm(torch.randn(4, 32), None, None, 1e-5, torch.empty(4, 32))
+
+
+@pytest.mark.skipif(not __import__("oracle.reference_loader", fromlist=["x"]).available(),
+                    reason="reference source only exists in the build container")
+def test_accelerate_swaps_trunk_of_reference_block(emulated_ops):
+    """the reference TwoTrackBlock.forward runs unchanged on the swapped-in trunk."""
+    from oracle import reference_loader as rl
+    from oracle.weights import push_to_reference, synth_inputs, synth_state_dict
+
+    ref = rl.load()
+    mine = rf.TwoTrackBlock(48, 40, n_encoder_layers=1)
+    sd = synth_state_dict(mine.state_dict(), seed=31)
+    rblk = rl.fix_eval(push_to_reference(ref.TwoTrackBlock(48, 40, n_encoder_layers=1), sd))
+    msa, pair = synth_inputs(1, 5, 12, 48, 40, seed=32)
+    with torch.no_grad():
+        m_ref, p_ref = rblk(msa, pair)
+    rf.set_mode("fp32")
+    rf.accelerate(rblk)
+    assert type(rblk.msa_update_with_pair).__module__.startswith("rosettafold_pytorch_b200")
+    with torch.no_grad():
+        m, p = rblk(msa, pair)  # the reference's own forward (:962-968) on the b200 modules
+    assert rel_l2(m, m_ref) < 1e-4 and rel_l2(p, p_ref) < 1e-4
