@@ -16,9 +16,12 @@ def load():
     """Returns the reference module `rosettafold_pytorch.rosettafold_pytorch`."""
     if not available():
         raise RuntimeError(f"reference not found at {REFERENCE_ROOT}")
-    for p in (_SHIMS, REFERENCE_ROOT):
+    # appended (not prepended): the reference tree has its own top-level `tests/` directory that
+    # must not shadow this repository's `tests` package; real installs of the shimmed
+    # dependencies, if any, also win over the shims this way
+    for p in (REFERENCE_ROOT, _SHIMS):
         if p not in sys.path:
-            sys.path.insert(0, p)
+            sys.path.append(p)
     import warnings
 
     with warnings.catch_warnings():
