@@ -1,20 +1,22 @@
 // rfk_favor_tc.cu — fused Performer FAVOR+ attention on tcgen05 / TMEM / TMA (bf16 operands,
 // fp32 accumulation). One persistent CTA per SM loops over (group, head) items; for every item
-// nothing of size tokens x m ever leaves the SM. Per item the work is a sequence of tile STEPS
-//   S0 (softmax kernel only): key tiles  -> U = K.Omega'^T -> global max
-//   S1: key tiles   -> U -> k' features (smem) -> ctx[m, d | 1] += k'^T [V | 1]      (TMEM)
-//   S3: query tiles -> U -> q' features (smem) -> out = q'.ctx ; den = q'.ksum       -> out/den
-// software-pipelined across steps: one control thread issues TMA loads and tcgen05.mma half a
-// step ahead, 16 feature warps turn accumulator halves into features while the tensor pipe
-// already runs the next U and the previous contraction (ctx / out).
+// nothing of size tokens x m ever leaves the SM:
 //
-// Feature halves: A = m in [0,128) (feature slabs 0,1), B = m in [128,272) (slabs 2,3,4).
-// Shared memory (1024-byte aligned tiles, 128-byte swizzle):
-//   omega [272 m][64 d] K-major | X0, X1 [128 tok][64] K/Q tiles | V [128 tok][64] | cslab (col 0 = 1)
-//   feat 5 x [128 tok][64 m]: MN-major A of the ctx MMAs *and* K-major A of the out MMAs
-//   ct [272 m][64 d]: MN-major B of the out MMAs | ksum[272] f32 | den partials | row max
-// TMEM (512 cols): S1: ctx blocks 3 x 80 cols [0,240) | U_A [240,368) | U_B [368,512)
-//                  S3: out tiles 2 x 64 cols [0,128)  | U_A, U_B as above
+//   keys   : TMA K,V tile -> U = K.Omega'^T (tcgen05, TMEM) -> feature map k' (CUDA cores, from
+//            TMEM) -> bf16 k' tile in shared memory -> [ctx^T ; ksum] += [V | 1]^T k' (tcgen05,
+//            both operands MN-major so neither V nor k' is ever transposed)
+//   queries: TMA Q tile -> U = Q.Omega'^T -> q' -> out|den = q'.[ctx^T ; ksum]^T (tcgen05) ->
+//            out/den -> global
+//
+// Shared memory (all tiles 1024-byte aligned, 128-byte swizzle):
+//   omega  [272 m][64 d]      bf16, K-major   (dn * projection matrix, rows >= m zero)
+//   cslab  [128 tok][64]      bf16, column 0 = 1: second MN-chunk of the "A = [V | 1]" operand
+//   kbuf   [128 tok][64 d]    K or Q tile (TMA);   vbuf [128 tok][64 d] V tile (TMA)
+//   feat   5 x [128 tok][64 m] k'/q' features: MN-major B of the context MMA *and* K-major A of
+//                              the output MMA (same bytes)
+//   ctxt   5 x [80][64 m]     rows 0..63 ctx^T, row 64 ksum, K-major B of the output MMA
+// TMEM (512 columns): D2 = [ctx^T;ksum] cols [0,272) | U halves cols [272,416) | D3 cols [416,496);
+// the full-width U of the key-max pre-pass and of the query phase reuses cols [0,272).
 #include "rfk_common.cuh"
 
 namespace rfk {
@@ -22,28 +24,24 @@ namespace rfk {
 namespace {
 
 constexpr int kFeatWarps = 16;
-constexpr int kThreads = 32 * (1 + kFeatWarps);  // warp 0: control (TMA + MMA issue), the rest: features
+constexpr int kThreads = 32 * (1 + kFeatWarps);  // warp 0: control (TMA + MMA issue), the rest: feature/epilogue
 constexpr int kMP = 272;       // padded feature count (17 * 16)
 constexpr int kTile = 128;     // tokens per tile
 constexpr uint32_t kOmegaBytes = kMP * 128;        // 34816
 constexpr uint32_t kSlabBytes = kTile * 128;       // 16384
-constexpr uint32_t kCtBytes = kMP * 128;           // 34816
+constexpr uint32_t kCtxSlabBytes = 80 * 128;       // 10240
 constexpr uint32_t kOffOmega = 0;
-constexpr uint32_t kOffX0 = kOffOmega + kOmegaBytes;
-constexpr uint32_t kOffX1 = kOffX0 + kSlabBytes;
-constexpr uint32_t kOffV = kOffX1 + kSlabBytes;
+constexpr uint32_t kOffK = kOffOmega + kOmegaBytes;
+constexpr uint32_t kOffV = kOffK + kSlabBytes;
 constexpr uint32_t kOffCslab = kOffV + kSlabBytes;  // directly after V: LBO of the [V | 1] operand
 constexpr uint32_t kOffFeat = kOffCslab + kSlabBytes;
-constexpr uint32_t kOffCt = kOffFeat + 5 * kSlabBytes;
-constexpr uint32_t kOffBar = kOffCt + kCtBytes;     // 13 mbarriers + tmem slot
-constexpr uint32_t kOffScratch = kOffBar + 192;
-// scratch floats: ksum[272] | den[3][4][128] | rowmax[2][4][128] | red[16]
-constexpr uint32_t kScratchFloats = 272 + 3 * 4 * 128 + 2 * 4 * 128 + 16;
-constexpr uint32_t kSmemBytes = kOffScratch + kScratchFloats * 4 + 1024;
-static_assert(kOffX0 % 1024 == 0 && kOffV % 1024 == 0 && kOffFeat % 1024 == 0 && kOffCt % 1024 == 0, "align");
-static_assert(kSmemBytes <= 232448, "shared memory budget");
+constexpr uint32_t kOffCtx = kOffFeat + 5 * kSlabBytes;
+constexpr uint32_t kOffBar = kOffCtx + 5 * kCtxSlabBytes;  // barriers + scratch
+constexpr uint32_t kOffScratch = kOffBar + 64;
+constexpr uint32_t kSmemBytes = kOffScratch + (4 * 128 + 16) * 4 + 1024;
+static_assert(kOffCslab % 1024 == 0 && kOffK % 1024 == 0 && kOffFeat % 1024 == 0 && kOffCtx % 1024 == 0, "align");
 
-constexpr uint32_t kColCtx = 0, kColOut = 0, kColUA = 240, kColUB = 368;
+constexpr uint32_t kColD2 = 0, kColU = 272, kColD3 = 416;
 
 struct FavorTcParams {
   const float* proj;
@@ -82,16 +80,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) {
 }
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
-// write 16 consecutive bf16 values (c0 % 16 == 0) of row `row` into a [rows][64] swizzled slab set
-__device__ __forceinline__ void write_row16(uint32_t base, uint32_t slab_bytes, int row, int c0, const float (&f)[16]) {
-  const uint32_t slab = base + (uint32_t)(c0 >> 6) * slab_bytes;
-  const int c = c0 & 63;
+// write 16 consecutive features (m0 % 16 == 0) of token row `row` into the feature slabs
+__device__ __forceinline__ void write_feat16(uint32_t feat_base, int row, int m0, const float (&f)[16]) {
+  const uint32_t slab = feat_base + (uint32_t)(m0 >> 6) * kSlabBytes;
+  const int c = m0 & 63;
   uint4 a, b;
   a.x = pack_bf16x2(f[0], f[1]);   a.y = pack_bf16x2(f[2], f[3]);
   a.z = pack_bf16x2(f[4], f[5]);   a.w = pack_bf16x2(f[6], f[7]);
@@ -118,44 +111,38 @@ __device__ __forceinline__ float row_half_sqnorm(uint32_t tile, int row) {
   return s * (0.5f * 0.125f);  // dn^2 = 64^-1/2 = 1/8
 }
 
-enum { kS0 = 0, kS1 = 1, kS3 = 2 };
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const FavorTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t s_omega = base + kOffOmega, s_v = base + kOffV, s_cslab = base + kOffCslab,
-                 s_feat = base + kOffFeat, s_ct = base + kOffCt;
-  const uint32_t s_x[2] = {base + kOffX0, base + kOffX1};
-  const uint32_t bb = base + kOffBar;
-  const uint32_t bar_x[2] = {bb, bb + 8};
-  const uint32_t bar_v = bb + 16, bar_uA = bb + 24, bar_uB = bb + 32, bar_fA = bb + 40, bar_fB = bb + 48,
-                 bar_ctx = bb + 56, bar_ro = bb + 64;
-  const uint32_t bar_out[2] = {bb + 72, bb + 80}, bar_epi[2] = {bb + 88, bb + 96};
-  const uint32_t tmem_slot = bb + 128;
+  const uint32_t s_omega = base + kOffOmega, s_cslab = base + kOffCslab, s_feat = base + kOffFeat,
+                 s_ctx = base + kOffCtx;
+  const uint32_t s_buf[2] = {base + kOffK, base + kOffV};       // [0] = "k" buffer, [1] = "v" buffer
+  const uint32_t bar_ld[2] = {base + kOffBar, base + kOffBar + 8};
+  const uint32_t bar_mma = base + kOffBar + 16, bar_feat = base + kOffBar + 24;
+  const uint32_t tmem_slot = base + kOffBar + 32;
   float* scratch = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + kOffScratch);
-  float* ksum = scratch;                 // [272]
-  float* den_sm = scratch + 272;         // [3][4][128]
-  float* rowmax = den_sm + 3 * 4 * 128;  // [2][4][128]
-  float* red = rowmax + 2 * 4 * 128;     // [16]
-  (void)s_cslab;
+  float* rowmax = scratch;            // [4][128]
+  float* red = scratch + 4 * 128;     // [16]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool softmax_kind = p.kind == 0;
   const int nt = (p.tokens + kTile - 1) / kTile;
-  const int S = (softmax_kind ? nt : 0) + 2 * nt;  // tile steps per item
-  const int s1_begin = softmax_kind ? nt : 0, s3_begin = s1_begin + nt;
 
   // ---- one-time setup ----
   if (warp == 0) {
     if (lane == 0) {
-      mbar_init(bar_x[0], 1); mbar_init(bar_x[1], 1); mbar_init(bar_v, 1);
-      mbar_init(bar_uA, 1); mbar_init(bar_uB, 1);
-      mbar_init(bar_fA, kFeatWarps); mbar_init(bar_fB, kFeatWarps);
-      mbar_init(bar_ctx, 1); mbar_init(bar_ro, kFeatWarps);
-      mbar_init(bar_out[0], 1); mbar_init(bar_out[1], 1);
-      mbar_init(bar_epi[0], kFeatWarps); mbar_init(bar_epi[1], kFeatWarps);
+      mbar_init(bar_ld[0], 1);
+      mbar_init(bar_ld[1], 1);
+      mbar_init(bar_mma, 1);
+      mbar_init(bar_feat, kFeatWarps);
       fence_barrier_init();
       tma_prefetch_desc(&tm_q);
       tma_prefetch_desc(&tm_k);
@@ -166,8 +153,7 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tmem_relinquish();
   }
   {
-    // omega' = dn * proj (rows >= m zero), K-major swizzled; constant slab: column 0 = 1;
-    // feature slab 4 (only 16 of its 64 columns are ever written) zeroed once
+    // omega' = dn * proj (rows >= m zero), K-major swizzled; constant slab: column 0 = 1
     const float dn = 0.35355339059327373f;  // 64^-1/4
     for (int i = threadIdx.x; i < kMP * 8; i += kThreads) {
       const int r = i >> 3, c = (i & 7) * 8;
@@ -183,9 +169,11 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const int r = i >> 3, c = (i & 7) * 8;
       uint4 v = make_uint4(0, 0, 0, 0);
       if (c == 0) v.x = 0x00003F80u;  // bf16(1.0) in element 0
-      st_shared_v4(base + kOffCslab + sw128_offset(r, c), v);
-      st_shared_v4(s_feat + 4 * kSlabBytes + sw128_offset(r, c), make_uint4(0, 0, 0, 0));
+      st_shared_v4(s_cslab + sw128_offset(r, c), v);
     }
+    // rows 65..79 of ctxt are never written by the context read-out: zero the whole buffer once
+    for (int i = threadIdx.x; i < (int)(5 * kCtxSlabBytes / 16); i += kThreads)
+      st_shared_v4(s_ctx + i * 16, make_uint4(0, 0, 0, 0));
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -194,374 +182,313 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
 
-  // number of items this CTA processes; global step g = k * S + s over its item sequence
-  const int64_t my_items = p.items > blockIdx.x ? (p.items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const int64_t total_steps = my_items * S;
-  auto item_coords = [&](int64_t k, int& h, int& g0, int& g1) {
-    const int64_t item = blockIdx.x + k * gridDim.x;
-    h = (int)(item % p.heads);
-    const int64_t g = item / p.heads;
-    g0 = (int)(g % p.G0);
-    g1 = (int)(g / p.G0);
+  // Loads completed so far on each TMA barrier; every thread advances the same deterministic
+  // schedule (whether or not it actually waits), parity of the next wait = count & 1.
+  uint32_t nld[2] = {0, 0};
+  uint32_t ph_mma = 0, ph_feat = 0;
+  const float ratio = rsqrtf((float)p.m);
+  constexpr float kLog2e = 1.4426950408889634f;
+
+  // feature-warp geometry: 4 warps share a TMEM lane group and split the column chunks
+  const int fw = warp - 1;                  // 0..15 (valid for warp >= 1)
+  const int lg = warp & 3;                  // TMEM lane group this warp may touch
+  const int quarter = fw >> 2;
+  const int row = lg * 32 + lane;           // token row in the tile / TMEM lane
+  const uint32_t t_lane = ((uint32_t)(lg * 32) << 16);
+  auto split = [&](int n, int& c0, int& c1) {
+    c0 = (n * quarter) >> 2;
+    c1 = (n * (quarter + 1)) >> 2;
   };
-  auto step_kind = [&](int s) { return s < s1_begin ? kS0 : (s < s3_begin ? kS1 : kS3); };
-  auto step_tile = [&](int s) { return s < s1_begin ? s : (s < s3_begin ? s - s1_begin : s - s3_begin); };
 
-  if (warp == 0) {
-    if (lane == 0 && total_steps > 0) {
-      // =================== control thread ===================
-      auto issue_x = [&](int64_t g) {  // X tile (K or Q) of global step g -> X[g & 1]
-        const int64_t k = g / S;
-        const int s = (int)(g % S);
-        int h, g0, g1;
-        item_coords(k, h, g0, g1);
-        const int b = (int)(g & 1);
-        mbar_arrive_expect_tx(bar_x[b], kSlabBytes);
-        tma_load_4d(step_kind(s) == kS3 ? &tm_q : &tm_k, bar_x[b], s_x[b], h * 64, step_tile(s) * kTile, g0, g1);
-      };
-      auto issue_v = [&](int64_t vtile) {  // V tile of global key-tile index vtile = k * nt + t
-        const int64_t k = vtile / nt;
-        int h, g0, g1;
-        item_coords(k, h, g0, g1);
-        mbar_arrive_expect_tx(bar_v, kSlabBytes);
-        tma_load_4d(&tm_v, bar_v, s_v, h * 64, (int)(vtile % nt) * kTile, g0, g1);
-      };
-      auto issue_ua = [&](int64_t g) {
-        const uint32_t x = s_x[g & 1];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem + kColUA, umma_desc_sw128(x) + 2 * k, umma_desc_sw128(s_omega) + 2 * k,
-                    umma_idesc_bf16(128, 128), k > 0);
-      };
-      auto issue_ub = [&](int64_t g) {
-        const uint32_t x = s_x[g & 1];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem + kColUB, umma_desc_sw128(x) + 2 * k, umma_desc_sw128(s_omega + 128 * 128) + 2 * k,
-                    umma_idesc_bf16(128, 144), k > 0);
-      };
-      auto wait_x = [&](int64_t g) {
-        mbar_wait(bar_x[g & 1], (uint32_t)((g >> 1) & 1));
-        tc_fence_after();
-      };
-      // prologue
-      issue_x(0);
-      if (total_steps > 1) issue_x(1);
-      issue_v(0);
-      wait_x(0);
-      issue_ua(0);
-      umma_commit(bar_uA);
-      issue_ub(0);
-      umma_commit(bar_uB);
+  bool pre_issued = false;  // control thread: first loads of this item already in flight
+  for (int64_t item = blockIdx.x; item < p.items; item += gridDim.x) {
+    const int h = (int)(item % p.heads);
+    const int64_t g = item / p.heads;
+    const int g0 = (int)(g % p.G0), g1 = (int)(g / p.G0);
 
-      for (int64_t g = 0; g < total_steps; ++g) {
-        const int64_t k = g / S;
-        const int s = (int)(g % S);
-        const int kind = step_kind(s), t = step_tile(s);
-        const bool has_next = g + 1 < total_steps;
-        const int64_t vt = k * nt + t;  // global key-tile / query-tile index
-        const int pbuf = (int)(vt & 1);
-        // ---------------- half A ----------------
-        mbar_wait(bar_fA, (uint32_t)(g & 1));
-        tc_fence_after();
-        if (kind == kS1) {
-          mbar_wait(bar_v, (uint32_t)(vt & 1));
+    if (warp == 0) {
+      if (lane == 0) {
+        // =================== control thread ===================
+        auto issue = [&](const CUtensorMap* tm, int b, int t, int hh, int gg0, int gg1) {
+          mbar_arrive_expect_tx(bar_ld[b], kSlabBytes);
+          tma_load_4d(tm, bar_ld[b], s_buf[b], hh * 64, t * kTile, gg0, gg1);
+        };
+        auto wait_ld = [&](int b) {
+          mbar_wait(bar_ld[b], nld[b] & 1u);
+          ++nld[b];
           tc_fence_after();
-          if (t == 0 && k > 0) {
-            // the ctx accumulators overlap the previous item's out tiles: their epilogues must be done
-            const int64_t w1 = k * nt - 1;
-            if (nt >= 2) mbar_wait(bar_epi[(w1 - 1) & 1], (uint32_t)(((w1 - 1) >> 1) & 1));
-            mbar_wait(bar_epi[w1 & 1], (uint32_t)((w1 >> 1) & 1));
-            tc_fence_after();
-          }
-          // ctx block 0 (m 0..127): A = feat slabs 0,1 (MN-major), B = [V | 1] (MN-major), K = tokens
+        };
+        auto mma_u_full = [&](uint32_t tile) {  // U[128 x 272] = tile . omega'^T into cols [0,272)
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_bf16(tmem + kColCtx, desc_mn_sw128(s_feat + kk * 2048, kSlabBytes),
-                      desc_mn_sw128(s_v + kk * 2048, kSlabBytes), idesc_bf16_major(128, 80, 1, 1),
-                      (t > 0 || kk > 0) ? 1u : 0u);
-        } else if (kind == kS3) {
-          if (t == 0) {  // ctx read-out (ct / ksum) of this item finished
-            mbar_wait(bar_ro, (uint32_t)(k & 1));
-            tc_fence_after();
-          }
-          if (t >= 2) {  // out tile buffer drained by the epilogue two tiles ago
-            mbar_wait(bar_epi[pbuf], (uint32_t)(((vt - 2) >> 1) & 1));
-            tc_fence_after();
-          }
-          // out part A: k16 steps over feat slabs 0,1 (K-major A) x ct rows 0..127 (MN-major B)
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + kColD2, umma_desc_sw128(tile) + 2 * k, umma_desc_sw128(s_omega) + 2 * k,
+                      umma_idesc_bf16(128, 144), k > 0);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            umma_bf16(tmem + kColOut + pbuf * 64, umma_desc_sw128(s_feat + (ks >> 2) * kSlabBytes) + 2 * (ks & 3),
-                      desc_mn_sw128(s_ct + ks * 2048, 0), idesc_bf16_major(128, 64, 0, 1), ks > 0 ? 1u : 0u);
-        }
-        if (has_next) {
-          wait_x(g + 1);
-          issue_ua(g + 1);
-          umma_commit(bar_uA);
-        }
-        // ---------------- half B ----------------
-        mbar_wait(bar_fB, (uint32_t)(g & 1));
-        tc_fence_after();
-        if (kind == kS1) {
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint64_t bd = desc_mn_sw128(s_v + kk * 2048, kSlabBytes);
-            umma_bf16(tmem + kColCtx + 80, desc_mn_sw128(s_feat + 2 * kSlabBytes + kk * 2048, kSlabBytes), bd,
-                      idesc_bf16_major(128, 80, 1, 1), (t > 0 || kk > 0) ? 1u : 0u);
-            // block 2 = m 256..383: only slab 4 exists, LBO 0 mirrors it into the unused upper half
-            umma_bf16(tmem + kColCtx + 160, desc_mn_sw128(s_feat + 4 * kSlabBytes + kk * 2048, 0), bd,
-                      idesc_bf16_major(128, 80, 1, 1), (t > 0 || kk > 0) ? 1u : 0u);
-          }
-          umma_commit(bar_ctx);
-        } else if (kind == kS3) {
-#pragma unroll
-          for (int ks = 8; ks < 17; ++ks)
-            umma_bf16(tmem + kColOut + pbuf * 64, umma_desc_sw128(s_feat + (ks >> 2) * kSlabBytes) + 2 * (ks & 3),
-                      desc_mn_sw128(s_ct + ks * 2048, 0), idesc_bf16_major(128, 64, 0, 1), 1u);
-          umma_commit(bar_out[pbuf]);
-        }
-        if (has_next) {
-          issue_ub(g + 1);
-          umma_commit(bar_uB);
-        }
-        // X[g & 1] is free again (its U MMAs completed before the features could be produced)
-        if (g + 2 < total_steps) issue_x(g + 2);
-        if (kind == kS1) {
-          // V is free once the ctx MMAs of this tile are done: prefetch the next key tile's V
-          mbar_wait(bar_ctx, (uint32_t)(vt & 1));
-          if (vt + 1 < my_items * nt) issue_v(vt + 1);
-        }
-      }
-      // the last out tiles of the last item are drained by the feature warps; consume their barriers
-      {
-        const int64_t w1 = my_items * nt - 1;
-        if (nt >= 2) mbar_wait(bar_epi[(w1 - 1) & 1], (uint32_t)(((w1 - 1) >> 1) & 1));
-        mbar_wait(bar_epi[w1 & 1], (uint32_t)((w1 >> 1) & 1));
-      }
-    }
-  } else {
-    // =================== feature / epilogue warps ===================
-    const int fw = warp - 1;        // 0..15
-    const int lg = warp & 3;        // TMEM lane group this warp may touch
-    const int quarter = fw >> 2;    // 4 warps share a lane group and split the column chunks
-    const int row = lg * 32 + lane; // token row in the tile / TMEM lane
-    const uint32_t t_lane = ((uint32_t)(lg * 32) << 16);
-    const float ratio = rsqrtf((float)p.m);
-    constexpr float kLog2e = 1.4426950408889634f;
-    auto split = [&](int n, int& c0, int& c1) {
-      c0 = (n * quarter) >> 2;
-      c1 = (n * (quarter + 1)) >> 2;
-    };
-    auto arrive = [&](uint32_t bar, bool wrote_smem) {
-      if (wrote_smem) fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar);
-    };
-    // feature map of 16 accumulator columns (feature index m0..m0+15); returns sum f * ksum if `query`
-    auto feat_chunk = [&](uint32_t tcol, int m0, bool valid, bool full, float sub, bool query) -> float {
-      uint32_t r[16];
-      tmem_ld_32x16(tmem + t_lane + tcol, r);
-      tmem_ld_wait();
-      float f[16];
-      if (softmax_kind) {
-        const float bias = ratio * 1e-4f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          f[i] = fmaf(ratio, ex2_approx(fmaf(__uint_as_float(r[i]), kLog2e, -sub)), bias);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = fmaxf(__uint_as_float(r[i]), 0.f) + 1e-3f;
-      }
-      if (!full) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = (valid && m0 + i < p.m) ? f[i] : 0.f;
-      }
-      write_row16(s_feat, kSlabBytes, row, m0, f);
-      float d = 0.f;
-      if (query) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 ks = *reinterpret_cast<const float4*>(ksum + m0 + 4 * j);
-          d = fmaf(f[4 * j], ks.x, d); d = fmaf(f[4 * j + 1], ks.y, d);
-          d = fmaf(f[4 * j + 2], ks.z, d); d = fmaf(f[4 * j + 3], ks.w, d);
-        }
-      }
-      return d;
-    };
-    auto scan_max = [&](uint32_t tcol, int m_base, int nch, float mx) -> float {
-      int c0, c1;
-      split(nch, c0, c1);
-      for (int c = c0; c < c1; ++c) {
-        uint32_t r[16];
-        tmem_ld_32x16(tmem + t_lane + tcol + c * 16, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (m_base + c * 16 + i < p.m) mx = fmaxf(mx, __uint_as_float(r[i]));
-      }
-      return mx;
-    };
-    // epilogue of out tile w (global query-tile index), tile t of item (h, g0, g1)
-    auto epilogue = [&](int64_t w, int t, int h, int g0, int g1) {
-      const int pb = (int)(w & 1);
-      mbar_wait(bar_out[pb], (uint32_t)((w >> 1) & 1));
-      tc_fence_after();
-      uint32_t r0[16];
-      tmem_ld_32x16(tmem + t_lane + kColOut + pb * 64 + quarter * 16, r0);
-      tmem_ld_wait();
-      const float* dp = den_sm + (int)(w % 3) * 512 + row;
-      const float den = (dp[0] + dp[128]) + (dp[256] + dp[384]);
-      if (t * kTile + row < p.tokens) {
-        const float inv = 1.f / den;
-        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)g1 * p.ogs1 + (int64_t)g0 * p.ogs0 +
-                            (int64_t)(t * kTile + row) * p.ots + h * 64 + quarter * 16;
-        uint4 w0, w1;
-        w0.x = pack_bf16x2(__uint_as_float(r0[0]) * inv, __uint_as_float(r0[1]) * inv);
-        w0.y = pack_bf16x2(__uint_as_float(r0[2]) * inv, __uint_as_float(r0[3]) * inv);
-        w0.z = pack_bf16x2(__uint_as_float(r0[4]) * inv, __uint_as_float(r0[5]) * inv);
-        w0.w = pack_bf16x2(__uint_as_float(r0[6]) * inv, __uint_as_float(r0[7]) * inv);
-        w1.x = pack_bf16x2(__uint_as_float(r0[8]) * inv, __uint_as_float(r0[9]) * inv);
-        w1.y = pack_bf16x2(__uint_as_float(r0[10]) * inv, __uint_as_float(r0[11]) * inv);
-        w1.z = pack_bf16x2(__uint_as_float(r0[12]) * inv, __uint_as_float(r0[13]) * inv);
-        w1.w = pack_bf16x2(__uint_as_float(r0[14]) * inv, __uint_as_float(r0[15]) * inv);
-        reinterpret_cast<uint4*>(op)[0] = w0;
-        reinterpret_cast<uint4*>(op)[1] = w1;
-      }
-      arrive(bar_epi[pb], false);
-    };
-
-    float gmax = 0.f, mx_run = -INFINITY;
-    // deferred epilogue state (out tile of the previous S3 step)
-    bool pend = false;
-    int64_t pend_w = 0;
-    int pend_t = 0, pend_h = 0, pend_g0 = 0, pend_g1 = 0;
-
-    for (int64_t g = 0; g < total_steps; ++g) {
-      const int64_t k = g / S;
-      const int s = (int)(g % S);
-      const int kind = step_kind(s), t = step_tile(s);
-      const int64_t vt = k * nt + t;
-      const uint32_t xbuf = s_x[g & 1];
-      const bool valid = t * kTile + row < p.tokens;
-      const bool tile_full = (t + 1) * kTile <= p.tokens;
-      const uint32_t par = (uint32_t)(g & 1);
-      if (s == 0) mx_run = -INFINITY;
-
-      if (kind == kS0) {
-        mbar_wait(bar_uA, par);
-        tc_fence_after();
-        float mx = scan_max(kColUA, 0, 8, -INFINITY);
-        arrive(bar_fA, false);
-        mbar_wait(bar_uB, par);
-        tc_fence_after();
-        mx = scan_max(kColUB, 128, 9, mx);
-        if (valid) mx_run = fmaxf(mx_run, mx);
-        arrive(bar_fB, false);
-        if (s == s1_begin - 1) {  // last S0 step: block-wide max
-          const float wm = warp_max(mx_run);
-          if (lane == 0) red[fw] = wm;
-          named_bar_sync(1, kFeatWarps * 32);
-          gmax = red[0];
-#pragma unroll
-          for (int i = 1; i < kFeatWarps; ++i) gmax = fmaxf(gmax, red[i]);
-          named_bar_sync(1, kFeatWarps * 32);  // red[] may be rewritten by the next item's S0
-        }
-        continue;
-      }
-
-      if (kind == kS1) {
-        float sub = 0.f;
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + kColD2 + 144, umma_desc_sw128(tile) + 2 * k,
+                      umma_desc_sw128(s_omega + 144 * 128) + 2 * k, umma_idesc_bf16(128, 128), k > 0);
+        };
+        auto step = [&]() {  // hand the MMA results to the feature warps and wait for them
+          umma_commit(bar_mma);
+          mbar_wait(bar_feat, ph_feat);
+          ph_feat ^= 1u;
+          tc_fence_after();
+        };
+        // ---- S0: global key max (softmax kernel); tiles alternate between the two buffers ----
         if (softmax_kind) {
-          mbar_wait(bar_x[g & 1], (uint32_t)((g >> 1) & 1));
-          sub = (row_half_sqnorm(xbuf, row) + gmax) * kLog2e;
+          if (!pre_issued) issue(&tm_k, 0, 0, h, g0, g1);
+          for (int t = 0; t < nt; ++t) {
+            if (t + 1 < nt) issue(&tm_k, (t + 1) & 1, t + 1, h, g0, g1);
+            wait_ld(t & 1);
+            mma_u_full(s_buf[t & 1]);
+            step();
+          }
+          issue(&tm_k, 0, 0, h, g0, g1);
+          issue(&tm_v, 1, 0, h, g0, g1);
+        } else if (!pre_issued) {
+          issue(&tm_k, 0, 0, h, g0, g1);
+          issue(&tm_v, 1, 0, h, g0, g1);
         }
-        mbar_wait(bar_uA, par);
-        tc_fence_after();
-        int c0, c1;
-        split(8, c0, c1);
-        for (int c = c0; c < c1; ++c) feat_chunk(kColUA + c * 16, c * 16, valid, tile_full, sub, false);
-        arrive(bar_fA, true);
-        mbar_wait(bar_uB, par);
-        tc_fence_after();
-        split(9, c0, c1);
-        for (int c = c0; c < c1; ++c) {
-          const int m0 = 128 + c * 16;
-          feat_chunk(kColUB + c * 16, m0, valid, tile_full && m0 + 16 <= p.m, sub, false);
-        }
-        arrive(bar_fB, true);
-        if (t == nt - 1) {
-          // ---- ctx read-out: TMEM lanes are feature rows m; ct[m][0..63] (bf16) and ksum[m] ----
-          mbar_wait(bar_ctx, (uint32_t)(vt & 1));
-          tc_fence_after();
-          // quarter j of each lane group reads ctx block j (rows m = 128 j + row); quarter 3 idles
-          for (int j = quarter; j < 3; j += 4) {
-            const int mrow = j * 128 + row;
-#pragma unroll 1
-            for (int c = 0; c < 5; ++c) {
-              uint32_t r[16];
-              tmem_ld_32x16(tmem + t_lane + kColCtx + j * 80 + c * 16, r);
-              tmem_ld_wait();
-              if (mrow < kMP) {
-                if (c < 4) {
-                  float f[16];
+        // ---- S1: context ----
+        for (int t = 0; t < nt; ++t) {
+          wait_ld(0);
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(r[i]);
-                  write_row16(s_ct, kCtBytes, mrow, c * 16, f);
-                } else {
-                  ksum[mrow] = __uint_as_float(r[0]);
-                }
-              }
+          for (int k = 0; k < 4; ++k)  // half A: m 0..143
+            umma_bf16(tmem + kColU, umma_desc_sw128(s_buf[0]) + 2 * k, umma_desc_sw128(s_omega) + 2 * k,
+                      umma_idesc_bf16(128, 144), k > 0);
+          step();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // half B: m 144..271
+            umma_bf16(tmem + kColU, umma_desc_sw128(s_buf[0]) + 2 * k,
+                      umma_desc_sw128(s_omega + 144 * 128) + 2 * k, umma_idesc_bf16(128, 128), k > 0);
+          step();
+          // K buffer is free: prefetch the next K tile, or the first Q tile
+          if (t + 1 < nt) issue(&tm_k, 0, t + 1, h, g0, g1);
+          else issue(&tm_q, 0, 0, h, g0, g1);
+          wait_ld(1);
+          // [ctx^T ; ksum][128 x 272] += [V | 1]^T (K = tokens) . k'   — both operands MN-major
+          const uint32_t lbo_a = s_cslab - s_buf[1];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t ad = desc_mn_sw128(s_buf[1] + k * 2048, lbo_a);
+            umma_bf16(tmem + kColD2, ad, desc_mn_sw128(s_feat + k * 2048, kSlabBytes),
+                      idesc_bf16_major(128, 128, 1, 1), (t > 0 || k > 0));
+            umma_bf16(tmem + kColD2 + 128, ad, desc_mn_sw128(s_feat + 2 * kSlabBytes + k * 2048, kSlabBytes),
+                      idesc_bf16_major(128, 144, 1, 1), (t > 0 || k > 0));
+          }
+          step();  // feature warps: no-op, or the ctx^T read-out after the last tile
+          if (t + 1 < nt) issue(&tm_v, 1, t + 1, h, g0, g1);
+          else if (nt > 1) issue(&tm_q, 1, 1, h, g0, g1);
+        }
+        // ---- S3: queries (tile t lives in buffer t & 1) ----
+        pre_issued = false;
+        for (int t = 0; t < nt; ++t) {
+          const int b = t & 1;
+          wait_ld(b);
+          mma_u_full(s_buf[b]);
+          step();
+          if (t + 2 < nt) issue(&tm_q, b, t + 2, h, g0, g1);
+          // out|den [128 tok x 80] = q'[128 x 272] . [ctx^T;ksum]^T
+#pragma unroll
+          for (int ks = 0; ks < 17; ++ks) {
+            const int kb = ks >> 2, kk = ks & 3;
+            umma_bf16(tmem + kColD3, umma_desc_sw128(s_feat + kb * kSlabBytes) + 2 * kk,
+                      umma_desc_sw128(s_ctx + kb * kCtxSlabBytes) + 2 * kk, umma_idesc_bf16(128, 80), ks > 0);
+          }
+          if (t == nt - 1) {
+            // both tile buffers are free: start the next item's first loads behind this epilogue
+            const int64_t nitem = item + gridDim.x;
+            if (nitem < p.items) {
+              const int nh = (int)(nitem % p.heads);
+              const int64_t ng = nitem / p.heads;
+              const int ng0 = (int)(ng % p.G0), ng1 = (int)(ng / p.G0);
+              issue(&tm_k, 0, 0, nh, ng0, ng1);
+              if (!softmax_kind) issue(&tm_v, 1, 0, nh, ng0, ng1);
+              pre_issued = true;
             }
           }
-          arrive(bar_ro, true);
-          named_bar_sync(1, kFeatWarps * 32);  // ksum visible to every feature warp before S3
+          step();
         }
-        continue;
+      }
+      // lanes 1..31 of the control warp idle until the next item / teardown
+    } else {
+      // =================== feature / epilogue warps ===================
+      auto wait_mma = [&]() {
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1u;
+        tc_fence_after();
+      };
+      auto arrive = [&](bool wrote_smem) {
+        if (wrote_smem) fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_feat);
+      };
+      // consume one completed load on buffer b; only the softmax kernel reads the tile (|x|^2)
+      auto consume_ld = [&](int b, bool need) {
+        if (need) mbar_wait(bar_ld[b], nld[b] & 1u);
+        ++nld[b];
+      };
+      // feature map of 16 accumulator columns -> bf16 features in shared memory
+      auto feat_chunk = [&](uint32_t tcol, int m0, bool valid, bool full, float sub) {
+        uint32_t r[16];
+        tmem_ld_32x16(tmem + t_lane + tcol, r);
+        tmem_ld_wait();
+        float f[16];
+        if (softmax_kind) {
+          const float bias = ratio * 1e-4f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            f[i] = fmaf(ratio, ex2_approx(fmaf(__uint_as_float(r[i]), kLog2e, -sub)), bias);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = fmaxf(__uint_as_float(r[i]), 0.f) + 1e-3f;
+        }
+        if (!full) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = (valid && m0 + i < p.m) ? f[i] : 0.f;
+        }
+        write_feat16(s_feat, row, m0, f);
+      };
+
+      float gmax = 0.f;
+      if (softmax_kind) {
+        // ---- S0 ----
+        float mx = -INFINITY;
+        for (int t = 0; t < nt; ++t) {
+          consume_ld(t & 1, false);
+          wait_mma();
+          const bool valid = t * kTile + row < p.tokens;
+          int c0, c1;
+          split(17, c0, c1);
+          for (int c = c0; c < c1; ++c) {
+            uint32_t r[16];
+            tmem_ld_32x16(tmem + t_lane + kColD2 + c * 16, r);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c * 16 + i < p.m) mx = fmaxf(mx, __uint_as_float(r[i]));
+            }
+          }
+          arrive(false);
+        }
+        mx = warp_max(mx);
+        if (lane == 0) red[fw] = mx;
+        named_bar_sync(1, kFeatWarps * 32);
+        gmax = red[0];
+#pragma unroll
+        for (int i = 1; i < kFeatWarps; ++i) gmax = fmaxf(gmax, red[i]);
       }
 
-      // ---------------- kS3: query tile ----------------
-      int h, g0, g1;
-      item_coords(k, h, g0, g1);
-      float sub = 0.f;
-      mbar_wait(bar_uA, par);
-      tc_fence_after();
-      if (softmax_kind) {
-        mbar_wait(bar_x[g & 1], (uint32_t)((g >> 1) & 1));
-        const float diag = row_half_sqnorm(xbuf, row);
-        mbar_wait(bar_uB, par);
-        tc_fence_after();
-        float mx = scan_max(kColUA, 0, 8, -INFINITY);
-        mx = scan_max(kColUB, 128, 9, mx);
-        float* rm = rowmax + (int)(g & 1) * 512;
-        rm[quarter * 128 + row] = mx;
-        named_bar_sync(1, kFeatWarps * 32);
-        mx = fmaxf(fmaxf(rm[row], rm[128 + row]), fmaxf(rm[256 + row], rm[384 + row]));
-        sub = (diag + mx) * kLog2e;
+      // ---- S1 ----
+      for (int t = 0; t < nt; ++t) {
+        consume_ld(0, softmax_kind);
+        const bool valid = t * kTile + row < p.tokens;
+        const bool tile_full = (t + 1) * kTile <= p.tokens;
+        float sub = 0.f;
+        for (int hf = 0; hf < 2; ++hf) {
+          wait_mma();
+          if (hf == 0 && softmax_kind) sub = (row_half_sqnorm(s_buf[0], row) + gmax) * kLog2e;
+          const int nch = hf == 0 ? 9 : 8, moff = hf == 0 ? 0 : 144;
+          int c0, c1;
+          split(nch, c0, c1);
+          for (int c = c0; c < c1; ++c) {
+            const int m0 = moff + c * 16;
+            feat_chunk(kColU + c * 16, m0, valid, tile_full && m0 + 16 <= p.m, sub);
+          }
+          arrive(true);
+        }
+        wait_mma();  // context MMAs of this tile done (V, feat buffers free again)
+        consume_ld(1, false);
+        bool wrote = false;
+        if (t == nt - 1 && lg != 3) {
+          // read out [ctx^T ; ksum] rows 0..79 -> ctxt (bf16, K-major over m). Lane groups 0,1:
+          // ctx^T rows; group 2: rows 64..79 (row 64 = ksum, the rest are exact zeros).
+          const bool owner = lg < 2 || lane < 16;  // every lane executes the aligned TMEM loads
+          int c0, c1;
+          split(17, c0, c1);
+          for (int c = c0; c < c1; ++c) {
+            uint32_t r[16];
+            tmem_ld_32x16(tmem + t_lane + kColD2 + c * 16, r);
+            tmem_ld_wait();
+            if (owner) {
+              const int m0 = c * 16;
+              const uint32_t slab = s_ctx + (uint32_t)(m0 >> 6) * kCtxSlabBytes;
+              uint4 a, b;
+              a.x = pack_bf16x2(__uint_as_float(r[0]), __uint_as_float(r[1]));
+              a.y = pack_bf16x2(__uint_as_float(r[2]), __uint_as_float(r[3]));
+              a.z = pack_bf16x2(__uint_as_float(r[4]), __uint_as_float(r[5]));
+              a.w = pack_bf16x2(__uint_as_float(r[6]), __uint_as_float(r[7]));
+              b.x = pack_bf16x2(__uint_as_float(r[8]), __uint_as_float(r[9]));
+              b.y = pack_bf16x2(__uint_as_float(r[10]), __uint_as_float(r[11]));
+              b.z = pack_bf16x2(__uint_as_float(r[12]), __uint_as_float(r[13]));
+              b.w = pack_bf16x2(__uint_as_float(r[14]), __uint_as_float(r[15]));
+              st_shared_v4(slab + sw128_offset(row, m0 & 63), a);
+              st_shared_v4(slab + sw128_offset(row, (m0 & 63) + 8), b);
+            }
+          }
+          wrote = true;
+        }
+        arrive(wrote);
       }
-      float den = 0.f;
-      int c0, c1;
-      split(8, c0, c1);
-      for (int c = c0; c < c1; ++c) den += feat_chunk(kColUA + c * 16, c * 16, valid, tile_full, sub, true);
-      arrive(bar_fA, true);
-      if (!softmax_kind) {
-        mbar_wait(bar_uB, par);
-        tc_fence_after();
-      }
-      split(9, c0, c1);
-      for (int c = c0; c < c1; ++c) {
-        const int m0 = 128 + c * 16;
-        den += feat_chunk(kColUB + c * 16, m0, valid, tile_full && m0 + 16 <= p.m, sub, true);
-      }
-      den_sm[(int)(vt % 3) * 512 + quarter * 128 + row] = den;
-      arrive(bar_fB, true);
-      // deferred epilogue of the previous query tile (its out MMAs ran behind this tile's features)
-      if (pend) epilogue(pend_w, pend_t, pend_h, pend_g0, pend_g1);
-      pend = true; pend_w = vt; pend_t = t; pend_h = h; pend_g0 = g0; pend_g1 = g1;
-      if (t == nt - 1) {  // last tile of the item: drain now (the ctx accumulators get reused next)
-        epilogue(pend_w, pend_t, pend_h, pend_g0, pend_g1);
-        pend = false;
+
+      // ---- S3 ----
+      for (int t = 0; t < nt; ++t) {
+        const int b = t & 1;
+        consume_ld(b, softmax_kind);
+        wait_mma();
+        const bool valid = t * kTile + row < p.tokens;
+        const bool tile_full = (t + 1) * kTile <= p.tokens;
+        int c0, c1;
+        split(17, c0, c1);
+        float sub = 0.f;
+        if (softmax_kind) {
+          const float diag = row_half_sqnorm(s_buf[b], row);
+          float mx = -INFINITY;
+          for (int c = c0; c < c1; ++c) {
+            uint32_t r[16];
+            tmem_ld_32x16(tmem + t_lane + kColD2 + c * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c * 16 + i < p.m) mx = fmaxf(mx, __uint_as_float(r[i]));
+          }
+          rowmax[quarter * 128 + row] = mx;
+          named_bar_sync(1, kFeatWarps * 32);
+          mx = fmaxf(fmaxf(rowmax[row], rowmax[128 + row]), fmaxf(rowmax[256 + row], rowmax[384 + row]));
+          sub = (diag + mx) * kLog2e;
+        }
+        for (int c = c0; c < c1; ++c) {
+          const int m0 = c * 16;
+          feat_chunk(kColD2 + c * 16, m0, valid, tile_full && m0 + 16 <= p.m, sub);
+        }
+        arrive(true);
+        // ---- output tile: each quarter stores 16 of the 64 head channels ----
+        wait_mma();
+        {
+          uint32_t rd[16], r0[16];
+          tmem_ld_32x16(tmem + t_lane + kColD3 + 64, rd);  // column 64 = normaliser
+          tmem_ld_32x16(tmem + t_lane + kColD3 + quarter * 16, r0);
+          tmem_ld_wait();
+          if (valid) {
+            const float inv = 1.f / __uint_as_float(rd[0]);
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)g1 * p.ogs1 +
+                                (int64_t)g0 * p.ogs0 + (int64_t)(t * kTile + row) * p.ots + h * 64 + quarter * 16;
+            uint4 w0, w1;
+            w0.x = pack_bf16x2(__uint_as_float(r0[0]) * inv, __uint_as_float(r0[1]) * inv);
+            w0.y = pack_bf16x2(__uint_as_float(r0[2]) * inv, __uint_as_float(r0[3]) * inv);
+            w0.z = pack_bf16x2(__uint_as_float(r0[4]) * inv, __uint_as_float(r0[5]) * inv);
+            w0.w = pack_bf16x2(__uint_as_float(r0[6]) * inv, __uint_as_float(r0[7]) * inv);
+            w1.x = pack_bf16x2(__uint_as_float(r0[8]) * inv, __uint_as_float(r0[9]) * inv);
+            w1.y = pack_bf16x2(__uint_as_float(r0[10]) * inv, __uint_as_float(r0[11]) * inv);
+            w1.z = pack_bf16x2(__uint_as_float(r0[12]) * inv, __uint_as_float(r0[13]) * inv);
+            w1.w = pack_bf16x2(__uint_as_float(r0[14]) * inv, __uint_as_float(r0[15]) * inv);
+            reinterpret_cast<uint4*>(op)[0] = w0;
+            reinterpret_cast<uint4*>(op)[1] = w1;
+          }
+        }
+        arrive(false);
       }
     }
   }
