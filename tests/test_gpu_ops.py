@@ -64,6 +64,17 @@ def test_gemm_plain(cuda_device, dtype, shape):
     assert e < 2e-5, f"rel-l2 {e}"
 
 
+@pytest.mark.parametrize("shape", [(40000, 768, 384), (33000, 1536, 288), (2 * 17000, 384, 384)])
+def test_gemm_large_m_bf16_out(cuda_device, shape):
+    """Large-M, short-K projections with bf16 output take the TMA-store epilogue path
+    (many waves of tiles per CTA, ragged last m-block)."""
+    M, N, K = shape
+    for act, bias in ((ops.ACT_NONE, False), (ops.ACT_RELU, True)):
+        e = _gemm_case(cuda_device, torch.bfloat16, (), M, N, K, out_dtype=torch.bfloat16, bias=bias,
+                       act=act, res=False)
+        assert e < tol(torch.bfloat16), f"rel-l2 {e}"
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_gemm_epilogues(cuda_device, dtype):
     for out_dtype in (torch.float32, torch.bfloat16):
