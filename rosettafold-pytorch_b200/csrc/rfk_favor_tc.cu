@@ -1,56 +1,75 @@
 // rfk_favor_tc.cu — fused Performer FAVOR+ attention on tcgen05 / TMEM / TMA (bf16 operands,
-// fp32 accumulation). One persistent CTA per SM loops over (group, head) items; for every item
-// nothing of size tokens x m ever leaves the SM:
+// fp32 accumulation), software-pipelined ("v4"). One persistent CTA per SM walks a stream of
+// chunk JOBS; nothing of size tokens x m ever leaves the SM.
 //
-//   keys   : TMA K,V tile -> U = K.Omega'^T (tcgen05, TMEM) -> feature map k' (CUDA cores, from
-//            TMEM) -> bf16 k' tile in shared memory -> [ctx^T ; ksum] += [V | 1]^T k' (tcgen05,
-//            both operands MN-major so neither V nor k' is ever transposed)
-//   queries: TMA Q tile -> U = Q.Omega'^T -> q' -> out|den = q'.[ctx^T ; ksum]^T (tcgen05) ->
-//            out/den -> global
+// A job is (item = (group, head), type, 128-token tile t, feature chunk c); the 272 (padded)
+// features are split into chunks of 128 | 128 | 16 columns. Job types:
+//   KMAX  U = K.Omega_c'^T                       -> running max            (softmax kernel only)
+//   K     U = K.Omega_c'^T -> k'_c (CUDA cores)  -> ctx_c[m, d|1] += k'_c^T . [V | 1]
+//   QMAX  U = Q.Omega_c'^T                       -> per-row max            (softmax kernel only)
+//   Q     U = Q.Omega_c'^T -> q'_c               -> out|den += q'_c . ctx_c
+// Per item: relu kernel  K(t,c)*, read-out of ctx, Q(t,c)*;
+//           softmax      KMAX(t,c)*, K(t,c)*, read-out, then per tile QMAX(t,c)*, Q(t,c)*.
 //
-// Shared memory (all tiles 1024-byte aligned, 128-byte swizzle):
-//   omega  [272 m][64 d]      bf16, K-major   (dn * projection matrix, rows >= m zero)
-//   cslab  [128 tok][64]      bf16, column 0 = 1: second MN-chunk of the "A = [V | 1]" operand
-//   kbuf   [128 tok][64 d]    K or Q tile (TMA);   vbuf [128 tok][64 d] V tile (TMA)
-//   feat   5 x [128 tok][64 m] k'/q' features: MN-major B of the context MMA *and* K-major A of
-//                              the output MMA (same bytes)
-//   ctxt   5 x [80][64 m]     rows 0..63 ctx^T, row 64 ksum, K-major B of the output MMA
-// TMEM (512 columns): D2 = [ctx^T;ksum] cols [0,272) | U halves cols [272,416) | D3 cols [416,496);
-// the full-width U of the key-max pre-pass and of the query phase reuses cols [0,272).
+// Three roles run decoupled and only meet at mbarriers:
+//   warp 0 lane 0  TMA producer: K/V/Q tiles into a 3-slot ring (runs ahead across items)
+//   warp 1 lane 0  MMA issuer:   U(j+1) is issued BEFORE the consumer MMA of job j, so the tensor
+//                  pipe always has [consumer(j), U(j+2)] queued while features(j+1) are computed
+//   warps 2..17    feature/epilogue warps in two groups of 8 that alternate jobs (group = job
+//                  parity = U slot = feature buffer; 2 warps per TMEM lane group, 64 columns each):
+//                  TMEM -> feature map -> bf16 smem; ctx read-out; out/den epilogue, deferred
+//                  behind the next tile's first job so it never waits for the tensor pipe
+//
+// TMEM (512 columns): ctx^T blocks b=0..2 (lanes = m - 128 b, 80 columns = d | 1) at [0,240);
+//   U ring 2 x 128 columns at [256,512); out|den accumulators D3[s] alias ctx blocks 0/1 (dead in
+//   the query phase; the issuer orders the reuse through the d3free barriers).
+// Shared memory (1024-byte aligned tiles, 128-byte swizzle):
+//   omega [272][64] bf16 K-major | tile ring 3 x [128 tok][64 d] | cslab [128 tok][64], col 0 = 1
+//   (second MN chunk of the "[V | 1]" operand) | feat ring 2 x 2 slabs [128 tok][64 m] (MN-major A of
+//   the context MMA and K-major A of the output MMA: same bytes) | ctx 5 x [80][64 m] K-major B.
+#include <cstdio>
+#include <cstdlib>
+#include <type_traits>
+
 #include "rfk_common.cuh"
 
 namespace rfk {
 
 namespace {
 
-constexpr int kFeatWarps = 16;
-constexpr int kThreads = 32 * (1 + kFeatWarps);  // warp 0: control (TMA + MMA issue), the rest: feature/epilogue
-constexpr int kMP = 272;       // padded feature count (17 * 16)
-constexpr int kTile = 128;     // tokens per tile
-constexpr uint32_t kOmegaBytes = kMP * 128;        // 34816
-constexpr uint32_t kSlabBytes = kTile * 128;       // 16384
-constexpr uint32_t kCtxSlabBytes = 80 * 128;       // 10240
+constexpr int kFeatWarps = 8;
+constexpr int kThreads = 32 * (3 + kFeatWarps);  // TMA producer, two MMA issuers, feature warps
+constexpr int kMP = 272;    // padded feature count
+constexpr int kTile = 128;  // tokens per tile
+constexpr int kRing = 3;
+constexpr uint32_t kSlabBytes = kTile * 128;   // 16384
+constexpr uint32_t kOmegaBytes = kMP * 128;    // 34816
+constexpr uint32_t kCtxSlabBytes = 80 * 128;   // 10240
 constexpr uint32_t kOffOmega = 0;
-constexpr uint32_t kOffK = kOffOmega + kOmegaBytes;
-constexpr uint32_t kOffV = kOffK + kSlabBytes;
-constexpr uint32_t kOffCslab = kOffV + kSlabBytes;  // directly after V: LBO of the [V | 1] operand
+constexpr uint32_t kOffRing = kOffOmega + kOmegaBytes;
+constexpr uint32_t kOffCslab = kOffRing + kRing * kSlabBytes;  // after the ring: LBO of [V | 1] > 0
 constexpr uint32_t kOffFeat = kOffCslab + kSlabBytes;
-constexpr uint32_t kOffCtx = kOffFeat + 5 * kSlabBytes;
-constexpr uint32_t kOffBar = kOffCtx + 5 * kCtxSlabBytes;  // barriers + scratch
-constexpr uint32_t kOffScratch = kOffBar + 64;
-constexpr uint32_t kSmemBytes = kOffScratch + (4 * 128 + 16) * 4 + 1024;
-static_assert(kOffCslab % 1024 == 0 && kOffK % 1024 == 0 && kOffFeat % 1024 == 0 && kOffCtx % 1024 == 0, "align");
+constexpr uint32_t kOffCtx = kOffFeat + 4 * kSlabBytes;
+constexpr uint32_t kOffBar = kOffCtx + 5 * kCtxSlabBytes;
+constexpr uint32_t kOffScratch = kOffBar + 256;
+constexpr uint32_t kScratchFloats = 4 * 128 + 4 * 128 + 16;  // diag partials, row maxima, block max
+constexpr uint32_t kSmemBytes = kOffScratch + kScratchFloats * 4 + 1024;
+static_assert(kOffRing % 1024 == 0 && kOffCslab % 1024 == 0 && kOffFeat % 1024 == 0 && kOffCtx % 1024 == 0, "align");
+static_assert(kSmemBytes <= 232448, "shared memory budget");
 
-constexpr uint32_t kColD2 = 0, kColU = 272, kColD3 = 416;
+constexpr uint32_t kColCtx = 0, kColU = 256;
 
 struct FavorTcParams {
   const float* proj;
   void* out;
-  int kind, m, heads;
+  int m, heads;
   int tokens;
   int64_t G0, G1, items;
   int64_t ogs0, ogs1, ots;
+  int dbg;  // timing experiments only (RFK_FAVOR_DBG): skip parts of the pipeline
+  long long* trace;  // developer timeline (RFK_FAVOR_TRACE): [4 roles][kTraceMax][2] (event, clock) of CTA 0
 };
+constexpr int kTraceMax = 1024;
 
 // MN-major SW128 descriptor: rows are K indices (128 B each, 8-row groups SBO=1024 apart),
 // 64-element MN chunks are `lbo_bytes` apart.
@@ -70,85 +89,138 @@ __host__ __device__ constexpr uint32_t idesc_bf16_major(int M, int N, int a_mn, 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void st_shared_b16(uint32_t addr, float f) {
+  const unsigned short h = __bfloat16_as_ushort(__float2bfloat16_rn(f));
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(h) : "memory");
+}
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// one lane of the (fully active) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// pointer flavours of the TMEM loads (sub-ranges of one register array)
+__device__ __forceinline__ void tmem_ld_32x32p(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16p(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int n) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
-
-// write 16 consecutive features (m0 % 16 == 0) of token row `row` into the feature slabs
-__device__ __forceinline__ void write_feat16(uint32_t feat_base, int row, int m0, const float (&f)[16]) {
-  const uint32_t slab = feat_base + (uint32_t)(m0 >> 6) * kSlabBytes;
-  const int c = m0 & 63;
-  uint4 a, b;
-  a.x = pack_bf16x2(f[0], f[1]);   a.y = pack_bf16x2(f[2], f[3]);
-  a.z = pack_bf16x2(f[4], f[5]);   a.w = pack_bf16x2(f[6], f[7]);
-  b.x = pack_bf16x2(f[8], f[9]);   b.y = pack_bf16x2(f[10], f[11]);
-  b.z = pack_bf16x2(f[12], f[13]); b.w = pack_bf16x2(f[14], f[15]);
-  st_shared_v4(slab + sw128_offset(row, c), a);
-  st_shared_v4(slab + sw128_offset(row, c + 8), b);
-}
-
-// 0.5 * dn^2 * |x|^2 of row `row` of a [128][64] bf16 swizzled tile
-__device__ __forceinline__ float row_half_sqnorm(uint32_t tile, int row) {
-  float s = 0.f;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const uint4 v = ld_shared_v4(tile + sw128_offset(row, j * 8));
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float a = bf16lo(w[i]), b = bf16hi(w[i]);
-      s = fmaf(a, a, s);
-      s = fmaf(b, b, s);
-    }
-  }
-  return s * (0.5f * 0.125f);  // dn^2 = 64^-1/2 = 1/8
-}
-
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// {bf16(max(lo,0)), bf16(max(hi,0))} in one instruction
+__device__ __forceinline__ uint32_t cvt_relu_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
 
+template <int KIND>  // 0: softmax kernel (exp features, stabilisers), 1: generalized ReLU kernel
 __global__ void __launch_bounds__(kThreads, 1)
 favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const FavorTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t s_omega = base + kOffOmega, s_cslab = base + kOffCslab, s_feat = base + kOffFeat,
-                 s_ctx = base + kOffCtx;
-  const uint32_t s_buf[2] = {base + kOffK, base + kOffV};       // [0] = "k" buffer, [1] = "v" buffer
-  const uint32_t bar_ld[2] = {base + kOffBar, base + kOffBar + 8};
-  const uint32_t bar_mma = base + kOffBar + 16, bar_feat = base + kOffBar + 24;
-  const uint32_t tmem_slot = base + kOffBar + 32;
+  const uint32_t s_omega = base + kOffOmega, s_ring = base + kOffRing, s_cslab = base + kOffCslab,
+                 s_feat = base + kOffFeat, s_ctx = base + kOffCtx;
+  const uint32_t bars = base + kOffBar;
+  auto bar_tfull = [&](uint32_t s) { return bars + 8u * s; };
+  auto bar_tempty = [&](uint32_t s) { return bars + 24u + 8u * s; };
+  auto bar_ufull = [&](uint32_t s) { return bars + 48u + 8u * s; };
+  auto bar_ufree = [&](uint32_t s) { return bars + 64u + 8u * s; };
+  auto bar_fready = [&](uint32_t s) { return bars + 80u + 8u * s; };
+  auto bar_ffree = [&](uint32_t s) { return bars + 96u + 8u * s; };
+  auto bar_d3full = [&](uint32_t s) { return bars + 112u + 8u * s; };
+  auto bar_d3free = [&](uint32_t s) { return bars + 128u + 8u * s; };
+  const uint32_t bar_ctxfull = bars + 144u, bar_ctxready = bars + 152u;
+  const uint32_t tmem_slot = bars + 160u;
   float* scratch = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + kOffScratch);
-  float* rowmax = scratch;            // [4][128]
-  float* red = scratch + 4 * 128;     // [16]
+  float* part = scratch;             // [4][128] partial |x|^2 of the four column quarters
+  float* rmaxs = scratch + 512;      // [4][128] partial row maxima
+  float* red = scratch + 1024;       // [16] per-warp maxima
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool softmax_kind = p.kind == 0;
   const int nt = (p.tokens + kTile - 1) / kTile;
+  const int64_t istride = gridDim.x;
+  // developer timeline: role 0 = U issuer, 1 = consumer issuer, 2 / 3 = first warp of feature group 0 / 1
+  int tr_n = 0;
+  const int tr_role = warp == 1 ? 0 : warp == 2 ? 1 : warp == 3 ? 2 : warp == 7 ? 3 : -1;  // warps 3 / 7: lane group 3 of group 0 / 1
+  auto TR = [&](int ev) {
+    if (p.trace && blockIdx.x == 0 && lane == 0 && tr_role >= 0 && tr_n < kTraceMax) {
+      p.trace[((int64_t)tr_role * kTraceMax + tr_n) * 2] = ev;
+      p.trace[((int64_t)tr_role * kTraceMax + tr_n) * 2 + 1] = clock64();
+      ++tr_n;
+    }
+  };
 
   // ---- one-time setup ----
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_init(bar_ld[0], 1);
-      mbar_init(bar_ld[1], 1);
-      mbar_init(bar_mma, 1);
-      mbar_init(bar_feat, kFeatWarps);
-      fence_barrier_init();
-      tma_prefetch_desc(&tm_q);
-      tma_prefetch_desc(&tm_k);
-      tma_prefetch_desc(&tm_v);
+  if (warp == 0 && lane == 0) {
+    for (uint32_t s = 0; s < kRing; ++s) {
+      mbar_init(bar_tfull(s), 1);
+      mbar_init(bar_tempty(s), 1);
     }
-    __syncwarp();
+    for (uint32_t s = 0; s < 2; ++s) {
+      mbar_init(bar_ufull(s), 1);
+      mbar_init(bar_ufree(s), kFeatWarps / 2);   // one 4-warp group owns each U slot / feature buffer
+      mbar_init(bar_fready(s), kFeatWarps / 2);
+      mbar_init(bar_ffree(s), 1);
+      mbar_init(bar_d3full(s), 1);
+      mbar_init(bar_d3free(s), kFeatWarps);
+    }
+    mbar_init(bar_ctxfull, 1);
+    mbar_init(bar_ctxready, kFeatWarps);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+  }
+  if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -171,9 +243,11 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (c == 0) v.x = 0x00003F80u;  // bf16(1.0) in element 0
       st_shared_v4(s_cslab + sw128_offset(r, c), v);
     }
-    // rows 65..79 of ctxt are never written by the context read-out: zero the whole buffer once
+    // ctx rows 65..79 and feature slabs (stale columns feed never-read accumulator rows): zero once
     for (int i = threadIdx.x; i < (int)(5 * kCtxSlabBytes / 16); i += kThreads)
       st_shared_v4(s_ctx + i * 16, make_uint4(0, 0, 0, 0));
+    for (int i = threadIdx.x; i < (int)(4 * kSlabBytes / 16); i += kThreads)
+      st_shared_v4(s_feat + i * 16, make_uint4(0, 0, 0, 0));
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -182,319 +256,529 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
 
-  // Loads completed so far on each TMA barrier; every thread advances the same deterministic
-  // schedule (whether or not it actually waits), parity of the next wait = count & 1.
-  uint32_t nld[2] = {0, 0};
-  uint32_t ph_mma = 0, ph_feat = 0;
-  const float ratio = rsqrtf((float)p.m);
-  constexpr float kLog2e = 1.4426950408889634f;
-
-  // feature-warp geometry: 4 warps share a TMEM lane group and split the column chunks
-  const int fw = warp - 1;                  // 0..15 (valid for warp >= 1)
-  const int lg = warp & 3;                  // TMEM lane group this warp may touch
-  const int quarter = fw >> 2;
-  const int row = lg * 32 + lane;           // token row in the tile / TMEM lane
-  const uint32_t t_lane = ((uint32_t)(lg * 32) << 16);
-  auto split = [&](int n, int& c0, int& c1) {
-    c0 = (n * quarter) >> 2;
-    c1 = (n * (quarter + 1)) >> 2;
-  };
-
-  bool pre_issued = false;  // control thread: first loads of this item already in flight
-  for (int64_t item = blockIdx.x; item < p.items; item += gridDim.x) {
-    const int h = (int)(item % p.heads);
-    const int64_t g = item / p.heads;
-    const int g0 = (int)(g % p.G0), g1 = (int)(g / p.G0);
-
-    if (warp == 0) {
-      if (lane == 0) {
-        // =================== control thread ===================
-        auto issue = [&](const CUtensorMap* tm, int b, int t, int hh, int gg0, int gg1) {
-          mbar_arrive_expect_tx(bar_ld[b], kSlabBytes);
-          tma_load_4d(tm, bar_ld[b], s_buf[b], hh * 64, t * kTile, gg0, gg1);
-        };
-        auto wait_ld = [&](int b) {
-          mbar_wait(bar_ld[b], nld[b] & 1u);
-          ++nld[b];
-          tc_fence_after();
-        };
-        auto mma_u_full = [&](uint32_t tile) {  // U[128 x 272] = tile . omega'^T into cols [0,272)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem + kColD2, umma_desc_sw128(tile) + 2 * k, umma_desc_sw128(s_omega) + 2 * k,
-                      umma_idesc_bf16(128, 144), k > 0);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem + kColD2 + 144, umma_desc_sw128(tile) + 2 * k,
-                      umma_desc_sw128(s_omega + 144 * 128) + 2 * k, umma_idesc_bf16(128, 128), k > 0);
-        };
-        auto step = [&]() {  // hand the MMA results to the feature warps and wait for them
-          umma_commit(bar_mma);
-          mbar_wait(bar_feat, ph_feat);
-          ph_feat ^= 1u;
-          tc_fence_after();
-        };
-        // ---- S0: global key max (softmax kernel); tiles alternate between the two buffers ----
-        if (softmax_kind) {
-          if (!pre_issued) issue(&tm_k, 0, 0, h, g0, g1);
-          for (int t = 0; t < nt; ++t) {
-            if (t + 1 < nt) issue(&tm_k, (t + 1) & 1, t + 1, h, g0, g1);
-            wait_ld(t & 1);
-            mma_u_full(s_buf[t & 1]);
-            step();
-          }
-          issue(&tm_k, 0, 0, h, g0, g1);
-          issue(&tm_v, 1, 0, h, g0, g1);
-        } else if (!pre_issued) {
-          issue(&tm_k, 0, 0, h, g0, g1);
-          issue(&tm_v, 1, 0, h, g0, g1);
+  if (warp == 0) {
+    if (lane == 0) {
+      // =================== TMA producer ===================
+      // The 3-slot ring only covers ~1 tile of look-ahead (two slots are held by the K and V tile in
+      // use), far less than the HBM latency; a second cursor therefore runs kPrefetch tiles ahead
+      // and pulls them into L2 (cp.async.bulk.prefetch.tensor), so the ring loads hit L2.
+      struct Cursor {
+        int64_t item;
+        int ph, i;  // phase: 0 = key-max pass (softmax kernel), 1 = K/V pairs, 2 = Q
+      };
+      auto cur_init = [&](Cursor& c) { c.item = blockIdx.x; c.ph = KIND == 0 ? 0 : 1; c.i = 0; };
+      auto cur_get = [&](const Cursor& c, const CUtensorMap*& tm, int& t) {
+        if (c.ph == 1) { tm = (c.i & 1) ? &tm_v : &tm_k; t = c.i >> 1; }
+        else { tm = c.ph == 0 ? &tm_k : &tm_q; t = c.i; }
+      };
+      auto cur_next = [&](Cursor& c) {
+        const int n = c.ph == 1 ? 2 * nt : nt;
+        if (++c.i < n) return;
+        c.i = 0;
+        if (++c.ph == 3) { c.ph = KIND == 0 ? 0 : 1; c.item += istride; }
+      };
+      auto coords = [&](int64_t item, int& h, int& g0, int& g1) {
+        h = (int)(item % p.heads);
+        const int64_t g = item / p.heads;
+        g0 = (int)(g % p.G0);
+        g1 = (int)(g / p.G0);
+      };
+      constexpr int kPrefetch = 6;
+      Cursor pf, ld;
+      cur_init(pf);
+      cur_init(ld);
+      auto prefetch_one = [&]() {
+        if (pf.item >= p.items) return;
+        const CUtensorMap* tm; int t, h, g0, g1;
+        cur_get(pf, tm, t);
+        coords(pf.item, h, g0, g1);
+        tma_prefetch_4d(tm, h * 64, t * kTile, g0, g1);
+        cur_next(pf);
+      };
+      for (int i = 0; i < kPrefetch; ++i) prefetch_one();
+      uint32_t slot = 0, par = 0;
+      while (ld.item < p.items) {
+        if (!(p.dbg & 16)) prefetch_one();
+        const CUtensorMap* tm; int t, h, g0, g1;
+        cur_get(ld, tm, t);
+        coords(ld.item, h, g0, g1);
+        mbar_wait(bar_tempty(slot), par ^ 1u);
+        if (p.dbg & 16) {
+          mbar_arrive(bar_tfull(slot));
+        } else {
+          mbar_arrive_expect_tx(bar_tfull(slot), kSlabBytes);
+          tma_load_4d(tm, bar_tfull(slot), s_ring + slot * kSlabBytes, h * 64, t * kTile, g0, g1);
         }
-        // ---- S1: context ----
-        for (int t = 0; t < nt; ++t) {
-          wait_ld(0);
+        if (++slot == kRing) { slot = 0; par ^= 1u; }
+        cur_next(ld);
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    // =================== MMA issuers ===================
+    // Everything an issuer does per job is on the critical path of the whole CTA, and a single warp
+    // retires a dependent instruction only every ~6-8 cycles. Two warps therefore share the work:
+    //   warp 1: U = X.Omega_c'^T for every job, as far ahead as the two U slots allow
+    //   warp 2: the consumer MMAs (context / output accumulation) of the K and Q jobs
+    // All 32 lanes run the warp-uniform control flow and one elected lane issues the tcgen05
+    // instructions (a lane-0-only branch makes the compiler wrap every UTCHMMA in a divergence
+    // waterfall). Both walk the same nest (item, pass = (kind, tile), chunk).
+    constexpr int kPassM = 0, kPassK = 1, kPassX = 2, kPassQ = 3;  // key max, keys, query max, queries
+    const int P = KIND == 0 ? 4 * nt : 2 * nt;
+    auto decode = [&](int ps, int& t) -> int {
+      if (KIND == 1) {
+        if (ps < nt) { t = ps; return kPassK; }
+        t = ps - nt;
+        return kPassQ;
+      }
+      if (ps < nt) { t = ps; return kPassM; }
+      if (ps < 2 * nt) { t = ps - nt; return kPassK; }
+      const int r = ps - 2 * nt;
+      t = r >> 1;
+      return (r & 1) ? kPassQ : kPassX;
+    };
+    struct Tile { uint32_t slot, par; };
+    uint32_t r_slot = 0, r_par = 0;  // ring position of the next tile to allocate
+    auto alloc = [&]() {
+      Tile x{r_slot, r_par};
+      if (++r_slot == kRing) { r_slot = 0; r_par ^= 1u; }
+      return x;
+    };
+    auto commit_dbg = [&](uint32_t bar) { if (p.dbg & 128) mbar_arrive(bar); else umma_commit(bar); };
+    using C0 = std::integral_constant<int, 0>;
+    using C1 = std::integral_constant<int, 1>;
+    using C2 = std::integral_constant<int, 2>;
+    if (warp == 1) {
+      const uint64_t d_omega = umma_desc_sw128(s_omega);  // + c * 1024 + 2 k
+      const uint64_t d_ring = umma_desc_sw128(s_ring);    // + slot * 1024 + 2 k
+      uint32_t nJ = 0;  // U chunks issued (job parity = U slot = feature buffer = warp group)
+      auto issue_u = [&](const Tile& a, auto cc, bool release) {
+        constexpr int C = decltype(cc)::value;
+        const uint32_t us = nJ & 1u;
+        mbar_wait(bar_ufree(us), ((nJ >> 1) & 1u) ^ 1u);
+        TR(10 + C);
+        if (C == 0) mbar_wait(bar_tfull(a.slot), a.par);
+        TR(13);
+        tc_fence_after();
+        const uint64_t da = d_ring + (uint64_t)(a.slot * 1024u);
+        const uint64_t db = d_omega + (uint64_t)(C * 1024);
+        constexpr uint32_t idesc = C == 2 ? umma_idesc_bf16(128, 16) : umma_idesc_bf16(128, 128);
+        if (elect_one()) {
+          if (!(p.dbg & 4)) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // half A: m 0..143
-            umma_bf16(tmem + kColU, umma_desc_sw128(s_buf[0]) + 2 * k, umma_desc_sw128(s_omega) + 2 * k,
-                      umma_idesc_bf16(128, 144), k > 0);
-          step();
-#pragma unroll
-          for (int k = 0; k < 4; ++k)  // half B: m 144..271
-            umma_bf16(tmem + kColU, umma_desc_sw128(s_buf[0]) + 2 * k,
-                      umma_desc_sw128(s_omega + 144 * 128) + 2 * k, umma_idesc_bf16(128, 128), k > 0);
-          step();
-          // K buffer is free: prefetch the next K tile, or the first Q tile
-          if (t + 1 < nt) issue(&tm_k, 0, t + 1, h, g0, g1);
-          else issue(&tm_q, 0, 0, h, g0, g1);
-          wait_ld(1);
-          // [ctx^T ; ksum][128 x 272] += [V | 1]^T (K = tokens) . k'   — both operands MN-major
-          const uint32_t lbo_a = s_cslab - s_buf[1];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint64_t ad = desc_mn_sw128(s_buf[1] + k * 2048, lbo_a);
-            umma_bf16(tmem + kColD2, ad, desc_mn_sw128(s_feat + k * 2048, kSlabBytes),
-                      idesc_bf16_major(128, 128, 1, 1), (t > 0 || k > 0));
-            umma_bf16(tmem + kColD2 + 128, ad, desc_mn_sw128(s_feat + 2 * kSlabBytes + k * 2048, kSlabBytes),
-                      idesc_bf16_major(128, 144, 1, 1), (t > 0 || k > 0));
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem + kColU + us * 128u, da + 2 * k, db + 2 * k, idesc, k > 0);
           }
-          step();  // feature warps: no-op, or the ctx^T read-out after the last tile
-          if (t + 1 < nt) issue(&tm_v, 1, t + 1, h, g0, g1);
-          else if (nt > 1) issue(&tm_q, 1, 1, h, g0, g1);
+          commit_dbg(bar_ufull(us));
+          if (C == 2 && release) commit_dbg(bar_tempty(a.slot));
         }
-        // ---- S3: queries (tile t lives in buffer t & 1) ----
-        pre_issued = false;
-        for (int t = 0; t < nt; ++t) {
-          const int b = t & 1;
-          wait_ld(b);
-          mma_u_full(s_buf[b]);
-          step();
-          if (t + 2 < nt) issue(&tm_q, b, t + 2, h, g0, g1);
-          // out|den [128 tok x 80] = q'[128 x 272] . [ctx^T;ksum]^T
-#pragma unroll
-          for (int ks = 0; ks < 17; ++ks) {
-            const int kb = ks >> 2, kk = ks & 3;
-            umma_bf16(tmem + kColD3, umma_desc_sw128(s_feat + kb * kSlabBytes) + 2 * kk,
-                      umma_desc_sw128(s_ctx + kb * kCtxSlabBytes) + 2 * kk, umma_idesc_bf16(128, 80), ks > 0);
-          }
-          if (t == nt - 1) {
-            // both tile buffers are free: start the next item's first loads behind this epilogue
-            const int64_t nitem = item + gridDim.x;
-            if (nitem < p.items) {
-              const int nh = (int)(nitem % p.heads);
-              const int64_t ng = nitem / p.heads;
-              const int ng0 = (int)(ng % p.G0), ng1 = (int)(ng / p.G0);
-              issue(&tm_k, 0, 0, nh, ng0, ng1);
-              if (!softmax_kind) issue(&tm_v, 1, 0, nh, ng0, ng1);
-              pre_issued = true;
-            }
-          }
-          step();
+        __syncwarp();
+        TR(14);
+        ++nJ;
+      };
+      Tile a{0, 0};
+      for (int64_t item = blockIdx.x; item < p.items; item += istride) {
+        for (int ps = 0; ps < P; ++ps) {
+          int t;
+          const int kind = decode(ps, t);
+          if (!(KIND == 0 && kind == kPassQ)) a = alloc();  // a softmax Q pass reuses its QMAX tile
+          if (kind == kPassK) (void)alloc();                 // the V tile
+          issue_u(a, C0{}, false);
+          issue_u(a, C1{}, false);
+          issue_u(a, C2{}, kind != kPassX);
         }
       }
-      // lanes 1..31 of the control warp idle until the next item / teardown
     } else {
-      // =================== feature / epilogue warps ===================
-      auto wait_mma = [&]() {
-        mbar_wait(bar_mma, ph_mma);
-        ph_mma ^= 1u;
+      const uint64_t d_feat_k = umma_desc_sw128(s_feat);              // K-major A of the output MMA
+      const uint64_t d_ctx = umma_desc_sw128(s_ctx);                  // + slab * 640 + 2 k
+      const uint64_t d_feat_mn = desc_mn_sw128(s_feat, kSlabBytes);   // MN-major A of the context MMA
+      const uint64_t d_v0 = desc_mn_sw128(s_ring, s_cslab - s_ring);  // [V | 1] in ring slot 0 / 1 / 2
+      const uint64_t d_v1 = desc_mn_sw128(s_ring + kSlabBytes, s_cslab - s_ring - kSlabBytes);
+      const uint64_t d_v2 = desc_mn_sw128(s_ring + 2 * kSlabBytes, s_cslab - s_ring - 2 * kSlabBytes);
+      uint32_t nC = 0;               // jobs consumed
+      uint32_t nF0 = 0, nF1 = 0;     // feature jobs consumed per feature buffer
+      uint32_t nD3 = 0, d3u0 = 0, d3u1 = 0;  // output tiles started / fills per D3 slot
+      uint32_t nItems = 0;
+      auto wait_d3_region = [&](uint32_t s) {
+        const uint32_t uses = s ? d3u1 : d3u0;
+        if (uses > 0) mbar_wait(bar_d3free(s), (uses - 1u) & 1u);
+      };
+      // ctx_c[128 m x 80] (+)= k'_c^T (A, MN-major, K = tokens) . [V | 1] (B, MN-major)
+      auto consume_k = [&](const Tile& v, int t, auto cc) {
+        constexpr int C = decltype(cc)::value;
+        const uint32_t fs = nC & 1u;
+        ++nC;
+        const uint32_t nF = fs ? nF1++ : nF0++;
+        if (t == 0 && C < 2) wait_d3_region((uint32_t)C);  // ctx block c aliases D3[c]
+        if (C == 0) mbar_wait(bar_tfull(v.slot), v.par);
+        TR(20 + C);
+        mbar_wait(bar_fready(fs), nF & 1u);
+        TR(23);
         tc_fence_after();
-      };
-      auto arrive = [&](bool wrote_smem) {
-        if (wrote_smem) fence_proxy_async_smem();
-        tc_fence_before();
+        const uint64_t da = d_feat_mn + (uint64_t)(fs * 2048u);
+        const uint64_t db = v.slot == 0 ? d_v0 : (v.slot == 1 ? d_v1 : d_v2);
+        if (elect_one()) {
+          if (!(p.dbg & 1)) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_bf16(tmem + kColCtx + 80u * C, da + 128 * k, db + 128 * k, idesc_bf16_major(128, 80, 1, 1), (t > 0 || k > 0));
+          }
+          commit_dbg(bar_ffree(fs));
+          if (C == 2) {
+            commit_dbg(bar_tempty(v.slot));
+            if (t == nt - 1) commit_dbg(bar_ctxfull);
+          }
+        }
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_feat);
+        TR(24);
       };
-      // consume one completed load on buffer b; only the softmax kernel reads the tile (|x|^2)
-      auto consume_ld = [&](int b, bool need) {
-        if (need) mbar_wait(bar_ld[b], nld[b] & 1u);
-        ++nld[b];
-      };
-      // feature map of 16 accumulator columns -> bf16 features in shared memory
-      auto feat_chunk = [&](uint32_t tcol, int m0, bool valid, bool full, float sub) {
-        uint32_t r[16];
-        tmem_ld_32x16(tmem + t_lane + tcol, r);
-        tmem_ld_wait();
-        float f[16];
-        if (softmax_kind) {
-          const float bias = ratio * 1e-4f;
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            f[i] = fmaf(ratio, ex2_approx(fmaf(__uint_as_float(r[i]), kLog2e, -sub)), bias);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = fmaxf(__uint_as_float(r[i]), 0.f) + 1e-3f;
+      // out|den [128 tok x 80] (+)= q'_c (A, K-major) . ctx_c (B, K-major over m)
+      auto consume_q = [&](int t, auto cc) {
+        constexpr int C = decltype(cc)::value;
+        const uint32_t fs = nC & 1u;
+        ++nC;
+        const uint32_t nF = fs ? nF1++ : nF0++;
+        const uint32_t ds = nD3 & 1u;
+        if (C == 0) {
+          if (t == 0) {
+            mbar_wait(bar_ctxready, nItems & 1u);
+            ++nItems;
+          }
+          wait_d3_region(ds);
         }
-        if (!full) {
+        TR(30 + C);
+        mbar_wait(bar_fready(fs), nF & 1u);
+        TR(33);
+        tc_fence_after();
+        const uint64_t da = d_feat_k + (uint64_t)(fs * 2048u);
+        const uint64_t db = d_ctx + (uint64_t)(2 * C * 640);
+        if (elect_one()) {
+          if (!(p.dbg & 2)) {
+            constexpr int NK = C == 2 ? 1 : 8;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = (valid && m0 + i < p.m) ? f[i] : 0.f;
+            for (int k = 0; k < NK; ++k)
+              umma_bf16(tmem + kColCtx + 80u * ds, da + (k >> 2) * 1024 + 2 * (k & 3), db + (k >> 2) * 640 + 2 * (k & 3),
+                        umma_idesc_bf16(128, 80), (C > 0 || k > 0));
+          }
+          commit_dbg(bar_ffree(fs));
+          if (C == 2) commit_dbg(bar_d3full(ds));
         }
-        write_feat16(s_feat, row, m0, f);
+        __syncwarp();
+        TR(34);
+        if (C == 2) {
+          if (ds) ++d3u1; else ++d3u0;
+          ++nD3;
+        }
       };
+      Tile v{0, 0};
+      for (int64_t item = blockIdx.x; item < p.items; item += istride) {
+        for (int ps = 0; ps < P; ++ps) {
+          int t;
+          const int kind = decode(ps, t);
+          if (!(KIND == 0 && kind == kPassQ)) (void)alloc();
+          if (kind == kPassK) {
+            v = alloc();
+            consume_k(v, t, C0{});
+            consume_k(v, t, C1{});
+            consume_k(v, t, C2{});
+          } else if (kind == kPassQ) {
+            consume_q(t, C0{});
+            consume_q(t, C1{});
+            consume_q(t, C2{});
+          } else {
+            nC += 3;
+          }
+        }
+      }
+    }
+  } else {
+    // =================== feature / epilogue warps ===================
+    // Two groups of 4 warps alternate jobs (group = job parity = U slot = feature buffer). Inside a
+    // group a thread owns one token row (TMEM lane) and all 128 columns of the chunk: few, fat
+    // warps keep the per-job bookkeeping small and leave 168 registers per thread, so a whole
+    // accumulator row is loaded at once and the U slot is handed back before the arithmetic.
+    const int fw = warp - 3;           // 0..7
+    const int lg = warp & 3;           // TMEM lane group this warp may touch
+    const uint32_t grp = (uint32_t)(fw >> 2);
+    const int row = lg * 32 + lane;    // token row of the tile / TMEM lane
+    const uint32_t t_lane = ((uint32_t)(lg * 32) << 16);
+    constexpr float kLog2e = 1.4426950408889634f;
+    constexpr float kEps = KIND == 0 ? 1e-4f : 1e-3f;
+    const uint32_t eps2 = pack_bf16x2(kEps, kEps);
+    const uint32_t ucol = tmem + t_lane + kColU + grp * 128u;
+    // this thread's 128-byte rows of its group's two feature slabs; 16-byte chunk i at (i ^ r7) << 4
+    const uint32_t frow = s_feat + grp * 2u * kSlabBytes + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+    const uint32_t r7 = (uint32_t)(row & 7);
+    const uint32_t b_ufull = bar_ufull(grp), b_ufree = bar_ufree(grp), b_fready = bar_fready(grp), b_ffree = bar_ffree(grp);
 
-      float gmax = 0.f;
-      if (softmax_kind) {
-        // ---- S0 ----
-        float mx = -INFINITY;
-        for (int t = 0; t < nt; ++t) {
-          consume_ld(t & 1, false);
-          wait_mma();
-          const bool valid = t * kTile + row < p.tokens;
-          int c0, c1;
-          split(17, c0, c1);
-          for (int c = c0; c < c1; ++c) {
-            uint32_t r[16];
-            tmem_ld_32x16(tmem + t_lane + kColD2 + c * 16, r);
-            tmem_ld_wait();
-            if (valid) {
+    uint32_t mine = grp;           // toggled before every job: 1 when the job parity equals grp
+    uint32_t nJg = 0, nFg = 0;     // jobs / feature jobs this group has processed
+    uint32_t nItems = 0, nD3 = 0, tile_seq = 0;
+    float gmax = 0.f, sub = 0.f, diag = 0.f;
+
+    // out/den epilogue: group g stores channels [32 g, 32 g + 32) of its token row
+    auto epilogue = [&](int64_t item, int t) {
+      const uint32_t ds = nD3 & 1u;
+      TR(50);
+      mbar_wait(bar_d3full(ds), (nD3 >> 1) & 1u);
+      TR(51);
+      tc_fence_after();
+      uint32_t rd[16], r0[32];
+      tmem_ld_32x16(tmem + t_lane + kColCtx + 80u * ds + 64, rd);  // column 64 = normaliser
+      tmem_ld_32x32(tmem + t_lane + kColCtx + 80u * ds + grp * 32u, r0);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_d3free(ds));
+      ++nD3;
+      if (t * kTile + row < p.tokens && !(p.dbg & 32)) {
+        const int h = (int)(item % p.heads);
+        const int64_t g = item / p.heads;
+        const int64_t g0 = g % p.G0, g1 = g / p.G0;
+        const float inv = 1.f / __uint_as_float(rd[0]);
+        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + g1 * p.ogs1 + g0 * p.ogs0 +
+                                             (int64_t)(t * kTile + row) * p.ots + h * 64 + grp * 32);
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (c * 16 + i < p.m) mx = fmaxf(mx, __uint_as_float(r[i]));
+        for (int q = 0; q < 4; ++q) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(r0[8 * q]) * inv, __uint_as_float(r0[8 * q + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(r0[8 * q + 2]) * inv, __uint_as_float(r0[8 * q + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(r0[8 * q + 4]) * inv, __uint_as_float(r0[8 * q + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(r0[8 * q + 6]) * inv, __uint_as_float(r0[8 * q + 7]) * inv);
+          op[q] = w;
+        }
+      }
+    };
+
+    // 0.5 * dn^2 * |x|^2 of this thread's row of the K/Q tile (softmax kernel): each group sums 32
+    // of the 64 channels, the two partials meet in shared memory (all 8 warps take part)
+    auto row_diag = [&](uint32_t a_seq) {
+      mbar_wait(bar_tfull(a_seq % kRing), (a_seq / kRing) & 1u);  // TMA bytes visible to this thread
+      const uint32_t tile = s_ring + (a_seq % kRing) * kSlabBytes;
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 v = ld_shared_v4(tile + sw128_offset(row, grp * 32 + j * 8));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float a = bf16lo(w[i]), b = bf16hi(w[i]);
+          s = fmaf(a, a, s);
+          s = fmaf(b, b, s);
+        }
+      }
+      part[grp * 128 + row] = s;
+      named_bar_sync(1, kFeatWarps * 32);
+      return (part[row] + part[128 + row]) * (0.5f * 0.125f);
+    };
+
+    // load this thread's accumulator row of chunk C: 128 columns (C < 2) or 16 (C == 2)
+    auto load_u = [&](auto cc, uint32_t (&r)[128]) {
+      constexpr int C = decltype(cc)::value;
+      if constexpr (C < 2) {
+        tmem_ld_32x32p(ucol, r);
+        tmem_ld_32x32p(ucol + 32u, r + 32);
+        tmem_ld_32x32p(ucol + 64u, r + 64);
+        tmem_ld_32x32p(ucol + 96u, r + 96);
+      } else {
+        tmem_ld_32x16p(ucol, r);
+      }
+      tmem_ld_wait();
+    };
+
+    // stabiliser pass over one chunk (softmax kernel): max of the raw projections
+    auto max_job = [&](auto cc, float& acc) {
+      constexpr int C = decltype(cc)::value;
+      constexpr int NC = C < 2 ? 128 : 16;
+      mbar_wait(b_ufull, nJg & 1u);
+      tc_fence_after();
+      uint32_t r[128];
+      load_u(cc, r);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_ufree);
+      const int lim = p.m - C * 128;
+      float mx = -INFINITY;
+      if (lim >= NC) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+          if (i < lim) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+      acc = fmaxf(acc, mx);
+      ++nJg;
+    };
+
+    // feature map of one chunk: TMEM -> bf16 features in this group's smem buffer
+    auto feat_job = [&](auto cc, bool zero_row) {
+      constexpr int C = decltype(cc)::value;
+      constexpr int NC = C < 2 ? 128 : 16;
+      TR(40 + C);
+      mbar_wait(b_ufull, nJg & 1u);
+      TR(43);
+      tc_fence_after();
+      uint32_t r[128];
+      load_u(cc, r);
+      // the accumulator row is in registers: hand the U slot back before the arithmetic
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_ufree);
+      TR(44);
+      mbar_wait(b_ffree, (nFg & 1u) ^ 1u);  // the MMAs that read this buffer two jobs ago are done
+      TR(46);
+      {
+        // padding: feature columns >= m, and key rows beyond the sequence, must contribute nothing
+        const int lim = zero_row ? 0 : p.m - C * 128;
+        // 32 columns at a time: convert, (mask,) store 4 x 16 bytes
+#pragma unroll
+        for (int q = 0; q < (NC + 31) / 32; ++q) {
+          constexpr int NQ = NC < 32 ? NC : 32;
+          uint32_t pk[NQ / 2];
+          if (KIND == 0) {
+#pragma unroll
+            for (int i = 0; i < NQ / 2; ++i) {
+              const float a = ex2_approx(fmaf(__uint_as_float(r[32 * q + 2 * i]), kLog2e, -sub));
+              const float b = ex2_approx(fmaf(__uint_as_float(r[32 * q + 2 * i + 1]), kLog2e, -sub));
+              pk[i] = add_bf16x2(pack_bf16x2(a, b), eps2);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < NQ / 2; ++i)
+              pk[i] = add_bf16x2(cvt_relu_bf16x2(__uint_as_float(r[32 * q + 2 * i]), __uint_as_float(r[32 * q + 2 * i + 1])), eps2);
+          }
+          if (lim < NC) {
+#pragma unroll
+            for (int i = 0; i < NQ / 2; ++i) {
+              if (32 * q + 2 * i >= lim) pk[i] = 0u;
+              else if (32 * q + 2 * i + 1 >= lim) pk[i] &= 0x0000ffffu;
             }
           }
-          arrive(false);
+#pragma unroll
+          for (int i = 0; i < NQ / 8; ++i) {
+            const int ch = 4 * q + i;  // 16-byte chunk index within the 2 x 128-byte feature rows
+            st_shared_v4(frow + (uint32_t)(ch >> 3) * kSlabBytes + ((((uint32_t)(ch & 7)) ^ r7) << 4),
+                         make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]));
+          }
         }
-        mx = warp_max(mx);
-        if (lane == 0) red[fw] = mx;
+        TR(47);
+        fence_proxy_async_smem();
+        TR(48);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_fready);
+      TR(49);
+      ++nJg;
+      ++nFg;
+    };
+    using C0 = std::integral_constant<int, 0>;
+    using C1 = std::integral_constant<int, 1>;
+    using C2 = std::integral_constant<int, 2>;
+
+    for (int64_t item = blockIdx.x; item < p.items; item += istride) {
+      if (KIND == 0) {
+        // ---- key stabiliser: global max of K.Omega'^T over the valid tokens ----
+        float kmx = -INFINITY;
+        for (int t = 0; t < nt; ++t) {
+          ++tile_seq;
+          float mx = -INFINITY;
+          if ((mine ^= 1u)) max_job(C0{}, mx);
+          if ((mine ^= 1u)) max_job(C1{}, mx);
+          if ((mine ^= 1u)) max_job(C2{}, mx);
+          if (t * kTile + row < p.tokens) kmx = fmaxf(kmx, mx);
+        }
+        kmx = warp_max(kmx);
+        if (lane == 0) red[fw] = kmx;
         named_bar_sync(1, kFeatWarps * 32);
         gmax = red[0];
 #pragma unroll
         for (int i = 1; i < kFeatWarps; ++i) gmax = fmaxf(gmax, red[i]);
       }
-
-      // ---- S1 ----
+      // ---- keys: k' chunks feed the context MMAs ----
       for (int t = 0; t < nt; ++t) {
-        consume_ld(0, softmax_kind);
-        const bool valid = t * kTile + row < p.tokens;
-        const bool tile_full = (t + 1) * kTile <= p.tokens;
-        float sub = 0.f;
-        for (int hf = 0; hf < 2; ++hf) {
-          wait_mma();
-          if (hf == 0 && softmax_kind) sub = (row_half_sqnorm(s_buf[0], row) + gmax) * kLog2e;
-          const int nch = hf == 0 ? 9 : 8, moff = hf == 0 ? 0 : 144;
-          int c0, c1;
-          split(nch, c0, c1);
-          for (int c = c0; c < c1; ++c) {
-            const int m0 = moff + c * 16;
-            feat_chunk(kColU + c * 16, m0, valid, tile_full && m0 + 16 <= p.m, sub);
-          }
-          arrive(true);
-        }
-        wait_mma();  // context MMAs of this tile done (V, feat buffers free again)
-        consume_ld(1, false);
-        bool wrote = false;
-        if (t == nt - 1 && lg != 3) {
-          // read out [ctx^T ; ksum] rows 0..79 -> ctxt (bf16, K-major over m). Lane groups 0,1:
-          // ctx^T rows; group 2: rows 64..79 (row 64 = ksum, the rest are exact zeros).
-          const bool owner = lg < 2 || lane < 16;  // every lane executes the aligned TMEM loads
-          int c0, c1;
-          split(17, c0, c1);
-          for (int c = c0; c < c1; ++c) {
-            uint32_t r[16];
-            tmem_ld_32x16(tmem + t_lane + kColD2 + c * 16, r);
-            tmem_ld_wait();
-            if (owner) {
-              const int m0 = c * 16;
-              const uint32_t slab = s_ctx + (uint32_t)(m0 >> 6) * kCtxSlabBytes;
-              uint4 a, b;
-              a.x = pack_bf16x2(__uint_as_float(r[0]), __uint_as_float(r[1]));
-              a.y = pack_bf16x2(__uint_as_float(r[2]), __uint_as_float(r[3]));
-              a.z = pack_bf16x2(__uint_as_float(r[4]), __uint_as_float(r[5]));
-              a.w = pack_bf16x2(__uint_as_float(r[6]), __uint_as_float(r[7]));
-              b.x = pack_bf16x2(__uint_as_float(r[8]), __uint_as_float(r[9]));
-              b.y = pack_bf16x2(__uint_as_float(r[10]), __uint_as_float(r[11]));
-              b.z = pack_bf16x2(__uint_as_float(r[12]), __uint_as_float(r[13]));
-              b.w = pack_bf16x2(__uint_as_float(r[14]), __uint_as_float(r[15]));
-              st_shared_v4(slab + sw128_offset(row, m0 & 63), a);
-              st_shared_v4(slab + sw128_offset(row, (m0 & 63) + 8), b);
-            }
-          }
-          wrote = true;
-        }
-        arrive(wrote);
+        if (KIND == 0) sub = (row_diag(tile_seq) + gmax) * kLog2e;
+        tile_seq += 2;
+        const bool zero_row = t * kTile + row >= p.tokens;
+        if ((mine ^= 1u)) feat_job(C0{}, zero_row);
+        if ((mine ^= 1u)) feat_job(C1{}, zero_row);
+        if ((mine ^= 1u)) feat_job(C2{}, zero_row);
       }
-
-      // ---- S3 ----
-      for (int t = 0; t < nt; ++t) {
-        const int b = t & 1;
-        consume_ld(b, softmax_kind);
-        wait_mma();
-        const bool valid = t * kTile + row < p.tokens;
-        const bool tile_full = (t + 1) * kTile <= p.tokens;
-        int c0, c1;
-        split(17, c0, c1);
-        float sub = 0.f;
-        if (softmax_kind) {
-          const float diag = row_half_sqnorm(s_buf[b], row);
-          float mx = -INFINITY;
-          for (int c = c0; c < c1; ++c) {
-            uint32_t r[16];
-            tmem_ld_32x16(tmem + t_lane + kColD2 + c * 16, r);
+      // ---- context read-out: TMEM ctx^T blocks -> bf16 K-major smem; group g takes block g ----
+      {
+        TR(60);
+        mbar_wait(bar_ctxfull, nItems & 1u);
+        TR(61);
+        ++nItems;
+        tc_fence_after();
+        if (!(p.dbg & 64)) {
+          const int m = 128 * (int)grp + row;
+          const uint32_t mc = (uint32_t)m & 63u;
+          const uint32_t slab = s_ctx + (uint32_t)(m >> 6) * kCtxSlabBytes + (mc & 7u) * 2u;
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem + t_lane + kColCtx + 80u * grp + 32u * hlf, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (c * 16 + i < p.m) mx = fmaxf(mx, __uint_as_float(r[i]));
+            for (int i = 0; i < 32; ++i) {
+              const uint32_t n = 32u * hlf + i;
+              st_shared_b16(slab + (n >> 3) * 1024u + (n & 7u) * 128u + ((((mc >> 3) ^ n) & 7u) << 4), __uint_as_float(r[i]));
+            }
           }
-          rowmax[quarter * 128 + row] = mx;
-          named_bar_sync(1, kFeatWarps * 32);
-          mx = fmaxf(fmaxf(rowmax[row], rowmax[128 + row]), fmaxf(rowmax[256 + row], rowmax[384 + row]));
-          sub = (diag + mx) * kLog2e;
-        }
-        for (int c = c0; c < c1; ++c) {
-          const int m0 = c * 16;
-          feat_chunk(kColD2 + c * 16, m0, valid, tile_full && m0 + 16 <= p.m, sub);
-        }
-        arrive(true);
-        // ---- output tile: each quarter stores 16 of the 64 head channels ----
-        wait_mma();
-        {
-          uint32_t rd[16], r0[16];
-          tmem_ld_32x16(tmem + t_lane + kColD3 + 64, rd);  // column 64 = normaliser
-          tmem_ld_32x16(tmem + t_lane + kColD3 + quarter * 16, r0);
+          uint32_t r2[16];
+          tmem_ld_32x16(tmem + t_lane + kColCtx + 80u * grp + 64u, r2);
           tmem_ld_wait();
-          if (valid) {
-            const float inv = 1.f / __uint_as_float(rd[0]);
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)g1 * p.ogs1 +
-                                (int64_t)g0 * p.ogs0 + (int64_t)(t * kTile + row) * p.ots + h * 64 + quarter * 16;
-            uint4 w0, w1;
-            w0.x = pack_bf16x2(__uint_as_float(r0[0]) * inv, __uint_as_float(r0[1]) * inv);
-            w0.y = pack_bf16x2(__uint_as_float(r0[2]) * inv, __uint_as_float(r0[3]) * inv);
-            w0.z = pack_bf16x2(__uint_as_float(r0[4]) * inv, __uint_as_float(r0[5]) * inv);
-            w0.w = pack_bf16x2(__uint_as_float(r0[6]) * inv, __uint_as_float(r0[7]) * inv);
-            w1.x = pack_bf16x2(__uint_as_float(r0[8]) * inv, __uint_as_float(r0[9]) * inv);
-            w1.y = pack_bf16x2(__uint_as_float(r0[10]) * inv, __uint_as_float(r0[11]) * inv);
-            w1.z = pack_bf16x2(__uint_as_float(r0[12]) * inv, __uint_as_float(r0[13]) * inv);
-            w1.w = pack_bf16x2(__uint_as_float(r0[14]) * inv, __uint_as_float(r0[15]) * inv);
-            reinterpret_cast<uint4*>(op)[0] = w0;
-            reinterpret_cast<uint4*>(op)[1] = w1;
+          st_shared_b16(slab + 8u * 1024u + (((mc >> 3) & 7u) << 4), __uint_as_float(r2[0]));  // n = 64
+        }
+        if (lg == 0 && !(p.dbg & 64)) {
+          // block 2: features 256..271 live in lanes 0..15; group g takes columns [32 g, 32 g + 32)
+          uint32_t r[32], r2[16];
+          tmem_ld_32x32(tmem + kColCtx + 160u + 32u * grp, r);
+          if (grp == 1) tmem_ld_32x16(tmem + kColCtx + 160u + 64u, r2);
+          tmem_ld_wait();
+          if (lane < 16) {
+            const uint32_t mc = (uint32_t)lane;
+            const uint32_t slab = s_ctx + 4u * kCtxSlabBytes + (mc & 7u) * 2u;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const uint32_t n = 32u * grp + i;
+              st_shared_b16(slab + (n >> 3) * 1024u + (n & 7u) * 128u + ((((mc >> 3) ^ n) & 7u) << 4), __uint_as_float(r[i]));
+            }
+            if (grp == 1) st_shared_b16(slab + 8u * 1024u + (((mc >> 3) & 7u) << 4), __uint_as_float(r2[0]));
           }
         }
-        arrive(false);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_ctxready);
+        TR(62);
       }
+      // ---- queries: q' chunks feed the output MMAs; the out/den epilogue of tile t runs behind
+      //      this group's first job of tile t+1 ----
+      bool pending = false;
+      for (int t = 0; t < nt; ++t) {
+        if (KIND == 0) {
+          diag = row_diag(tile_seq);
+          float rmx = -INFINITY;
+          if ((mine ^= 1u)) max_job(C0{}, rmx);
+          if ((mine ^= 1u)) max_job(C1{}, rmx);
+          if ((mine ^= 1u)) max_job(C2{}, rmx);
+          if (pending) { epilogue(item, t - 1); pending = false; }
+          rmaxs[grp * 128 + row] = rmx;
+          named_bar_sync(1, kFeatWarps * 32);
+          sub = (diag + fmaxf(rmaxs[row], rmaxs[128 + row])) * kLog2e;
+        }
+        ++tile_seq;
+        if ((mine ^= 1u)) { feat_job(C0{}, false); if (pending) { epilogue(item, t - 1); pending = false; } }
+        if ((mine ^= 1u)) { feat_job(C1{}, false); if (pending) { epilogue(item, t - 1); pending = false; } }
+        if ((mine ^= 1u)) feat_job(C2{}, false);
+        pending = true;
+      }
+      epilogue(item, nt - 1);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -528,6 +812,21 @@ int make_head_tmap(CUtensorMap* map, const void* ptr, const rfk_favor_desc* d) {
   return r == CUDA_SUCCESS ? RFK_OK : RFK_ERR_TMA_ENCODE;
 }
 
+template <int KIND>
+int launch_kind(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const FavorTcParams& p,
+                cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(favor_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return cuda_status(e);
+    configured = true;
+  }
+  int grid = num_sms();
+  if (p.items < grid) grid = (int)p.items;
+  favor_tc_kernel<KIND><<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, p);
+  return post_launch();
+}
+
 }  // namespace
 
 int favor_tc_launch(const rfk_favor_desc* d, cudaStream_t stream) {
@@ -544,20 +843,35 @@ int favor_tc_launch(const rfk_favor_desc* d, cudaStream_t stream) {
   if ((rc = make_head_tmap(&tk, d->k, d)) != RFK_OK) return rc;
   if ((rc = make_head_tmap(&tv, d->v, d)) != RFK_OK) return rc;
   FavorTcParams p{};
-  p.proj = d->proj; p.out = d->out; p.kind = d->kind; p.m = d->m_features; p.heads = d->heads;
+  p.proj = d->proj; p.out = d->out; p.m = d->m_features; p.heads = d->heads;
   p.tokens = (int)d->tokens; p.G0 = d->G[0]; p.G1 = d->G[1];
   p.items = d->G[0] * d->G[1] * d->heads;
   p.ogs0 = d->out_gs[0]; p.ogs1 = d->out_gs[1]; p.ots = d->out_ts;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(favor_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e != cudaSuccess) return cuda_status(e);
-    configured = true;
+  {
+    static const int dbg = []() { const char* e = getenv("RFK_FAVOR_DBG"); return e ? atoi(e) : 0; }();
+    p.dbg = dbg;
   }
-  int grid = num_sms();
-  if (p.items < grid) grid = (int)p.items;
-  favor_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, p);
-  return post_launch();
+  static const char* trace_path = getenv("RFK_FAVOR_TRACE");
+  if (trace_path) {
+    // developer tool: timeline of CTA 0 (clock64 per event), dumped after a synchronous launch
+    const size_t bytes = sizeof(long long) * 4 * kTraceMax * 2;
+    cudaMalloc(&p.trace, bytes);
+    cudaMemsetAsync(p.trace, 0, bytes, stream);
+    rc = d->kind == 0 ? launch_kind<0>(tq, tk, tv, p, stream) : launch_kind<1>(tq, tk, tv, p, stream);
+    cudaStreamSynchronize(stream);
+    long long* h = (long long*)malloc(bytes);
+    cudaMemcpy(h, p.trace, bytes, cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int r = 0; r < 4; ++r)
+        for (int i = 0; i < kTraceMax && h[((size_t)r * kTraceMax + i) * 2 + 1]; ++i)
+          fprintf(f, "%d %lld %lld\n", r, h[((size_t)r * kTraceMax + i) * 2], h[((size_t)r * kTraceMax + i) * 2 + 1]);
+      fclose(f);
+    }
+    free(h);
+    cudaFree(p.trace);
+    return rc;
+  }
+  return d->kind == 0 ? launch_kind<0>(tq, tk, tv, p, stream) : launch_kind<1>(tq, tk, tv, p, stream);
 }
 
 }  // namespace rfk
