@@ -37,7 +37,7 @@ namespace rfk {
 
 namespace {
 
-constexpr int kFeatWarps = 8;
+constexpr int kFeatWarps = 12;
 constexpr int kThreads = 32 * (3 + kFeatWarps);  // TMA producer, two MMA issuers, feature warps
 constexpr int kMP = 272;    // padded feature count
 constexpr int kTile = 128;  // tokens per tile
@@ -207,8 +207,8 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     for (uint32_t s = 0; s < 2; ++s) {
       mbar_init(bar_ufull(s), 1);
-      mbar_init(bar_ufree(s), kFeatWarps / 2);   // one 4-warp group owns each U slot / feature buffer
-      mbar_init(bar_fready(s), kFeatWarps / 2);
+      mbar_init(bar_ufree(s), kFeatWarps);
+      mbar_init(bar_fready(s), kFeatWarps);
       mbar_init(bar_ffree(s), 1);
       mbar_init(bar_d3full(s), 1);
       mbar_init(bar_d3free(s), kFeatWarps);
@@ -491,39 +491,46 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
   } else {
     // =================== feature / epilogue warps ===================
-    // Two groups of 4 warps alternate jobs (group = job parity = U slot = feature buffer). Inside a
-    // group a thread owns one token row (TMEM lane) and all 128 columns of the chunk: few, fat
-    // warps keep the per-job bookkeeping small and leave 168 registers per thread, so a whole
-    // accumulator row is loaded at once and the U slot is handed back before the arithmetic.
-    const int fw = warp - 3;           // 0..7
+    // 12 warps, all of them on every job: three warps share a TMEM lane group and split the 128
+    // columns of a chunk 48 | 40 | 40 (a thread owns one token row). 15 warps per CTA leave 128
+    // registers per thread, so every address below stays in a register instead of being
+    // recomputed per job, and the U slot is handed back as soon as the row is in registers.
+    const int fw = warp - 3;           // 0..11
     const int lg = warp & 3;           // TMEM lane group this warp may touch
-    const uint32_t grp = (uint32_t)(fw >> 2);
+    const int third = fw >> 2;         // which column range of the chunk
     const int row = lg * 32 + lane;    // token row of the tile / TMEM lane
     const uint32_t t_lane = ((uint32_t)(lg * 32) << 16);
     constexpr float kLog2e = 1.4426950408889634f;
     constexpr float kEps = KIND == 0 ? 1e-4f : 1e-3f;
     const uint32_t eps2 = pack_bf16x2(kEps, kEps);
-    const uint32_t ucol = tmem + t_lane + kColU + grp * 128u;
-    // this thread's 128-byte rows of its group's two feature slabs; 16-byte chunk i at (i ^ r7) << 4
-    const uint32_t frow = s_feat + grp * 2u * kSlabBytes + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+    // column ranges [0,48) | [40,88) | [80,128): uniform x32 + x16 loads for every warp; the 8-column
+    // overlaps are converted and stored twice with identical values
+    const int col0 = third * 40;
+    constexpr int ncol = 48;
+    const uint32_t ubase = tmem + t_lane + kColU + (uint32_t)col0;
+    // this thread's feature row: 16-byte chunk ch (0..15 over the two slabs of a buffer)
+    const uint32_t frow = s_feat + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
     const uint32_t r7 = (uint32_t)(row & 7);
-    const uint32_t b_ufull = bar_ufull(grp), b_ufree = bar_ufree(grp), b_fready = bar_fready(grp), b_ffree = bar_ffree(grp);
+    auto fchunk = [&](int ch) { return (uint32_t)(ch >> 3) * kSlabBytes + ((((uint32_t)(ch & 7)) ^ r7) << 4); };
 
-    uint32_t mine = grp;           // toggled before every job: 1 when the job parity equals grp
-    uint32_t nJg = 0, nFg = 0;     // jobs / feature jobs this group has processed
+    uint32_t nJ = 0;               // jobs processed (job parity = U slot = feature buffer)
+    uint32_t nF0 = 0, nF1 = 0;     // feature jobs processed per feature buffer
     uint32_t nItems = 0, nD3 = 0, tile_seq = 0;
     float gmax = 0.f, sub = 0.f, diag = 0.f;
+    const int64_t last_item = blockIdx.x + ((p.items - 1 - blockIdx.x) / istride) * istride;
 
-    // out/den epilogue: group g stores channels [32 g, 32 g + 32) of its token row
+    // out/den epilogue: the three warps of a lane group store channels [0,24) | [24,48) | [48,64)
     auto epilogue = [&](int64_t item, int t) {
       const uint32_t ds = nD3 & 1u;
       TR(50);
       mbar_wait(bar_d3full(ds), (nD3 >> 1) & 1u);
       TR(51);
       tc_fence_after();
-      uint32_t rd[16], r0[32];
+      const int ch0 = third * 24;
+      uint32_t rd[16], r0[16], r1[16];
       tmem_ld_32x16(tmem + t_lane + kColCtx + 80u * ds + 64, rd);  // column 64 = normaliser
-      tmem_ld_32x32(tmem + t_lane + kColCtx + 80u * ds + grp * 32u, r0);
+      tmem_ld_32x16(tmem + t_lane + kColCtx + 80u * ds + ch0, r0);
+      tmem_ld_32x16(tmem + t_lane + kColCtx + 80u * ds + ch0 + 8, r1);  // columns ch0+8 .. ch0+23
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -535,145 +542,151 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const int64_t g0 = g % p.G0, g1 = g / p.G0;
         const float inv = 1.f / __uint_as_float(rd[0]);
         uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + g1 * p.ogs1 + g0 * p.ogs0 +
-                                             (int64_t)(t * kTile + row) * p.ots + h * 64 + grp * 32);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(r0[8 * q]) * inv, __uint_as_float(r0[8 * q + 1]) * inv);
-          w.y = pack_bf16x2(__uint_as_float(r0[8 * q + 2]) * inv, __uint_as_float(r0[8 * q + 3]) * inv);
-          w.z = pack_bf16x2(__uint_as_float(r0[8 * q + 4]) * inv, __uint_as_float(r0[8 * q + 5]) * inv);
-          w.w = pack_bf16x2(__uint_as_float(r0[8 * q + 6]) * inv, __uint_as_float(r0[8 * q + 7]) * inv);
-          op[q] = w;
+                                             (int64_t)(t * kTile + row) * p.ots + h * 64 + ch0);
+        uint4 w;
+        w.x = pack_bf16x2(__uint_as_float(r0[0]) * inv, __uint_as_float(r0[1]) * inv);
+        w.y = pack_bf16x2(__uint_as_float(r0[2]) * inv, __uint_as_float(r0[3]) * inv);
+        w.z = pack_bf16x2(__uint_as_float(r0[4]) * inv, __uint_as_float(r0[5]) * inv);
+        w.w = pack_bf16x2(__uint_as_float(r0[6]) * inv, __uint_as_float(r0[7]) * inv);
+        op[0] = w;
+        w.x = pack_bf16x2(__uint_as_float(r1[0]) * inv, __uint_as_float(r1[1]) * inv);
+        w.y = pack_bf16x2(__uint_as_float(r1[2]) * inv, __uint_as_float(r1[3]) * inv);
+        w.z = pack_bf16x2(__uint_as_float(r1[4]) * inv, __uint_as_float(r1[5]) * inv);
+        w.w = pack_bf16x2(__uint_as_float(r1[6]) * inv, __uint_as_float(r1[7]) * inv);
+        op[1] = w;
+        if (third < 2) {
+          w.x = pack_bf16x2(__uint_as_float(r1[8]) * inv, __uint_as_float(r1[9]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(r1[10]) * inv, __uint_as_float(r1[11]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(r1[12]) * inv, __uint_as_float(r1[13]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(r1[14]) * inv, __uint_as_float(r1[15]) * inv);
+          op[2] = w;
         }
       }
     };
 
-    // 0.5 * dn^2 * |x|^2 of this thread's row of the K/Q tile (softmax kernel): each group sums 32
-    // of the 64 channels, the two partials meet in shared memory (all 8 warps take part)
+    // 0.5 * dn^2 * |x|^2 of this thread's row of the K/Q tile (softmax kernel): the three warps of a
+    // lane group sum channels [0,24) | [24,48) | [48,64), the partials meet in shared memory
     auto row_diag = [&](uint32_t a_seq) {
       mbar_wait(bar_tfull(a_seq % kRing), (a_seq / kRing) & 1u);  // TMA bytes visible to this thread
       const uint32_t tile = s_ring + (a_seq % kRing) * kSlabBytes;
       float s = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 v = ld_shared_v4(tile + sw128_offset(row, grp * 32 + j * 8));
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      for (int j = 0; j < 3; ++j) {
+        if (j < 2 || third < 2) {
+          const uint4 v = ld_shared_v4(tile + sw128_offset(row, third * 24 + j * 8));
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float a = bf16lo(w[i]), b = bf16hi(w[i]);
+            s = fmaf(a, a, s);
+            s = fmaf(b, b, s);
+          }
+        }
+      }
+      part[third * 128 + row] = s;
+      named_bar_sync(1, kFeatWarps * 32);
+      return (part[row] + part[128 + row] + part[256 + row]) * (0.5f * 0.125f);
+    };
+
+    // ---- software pipeline over jobs: while the packed features of job j are stored, fenced and
+    // handed to the MMA issuer, the accumulator columns of job j+1 are already on their way from
+    // TMEM into `raw`. Every job: (a) finish my load, release the U slot; (b) arithmetic into packed
+    // registers; (c) prefetch the next job; (d) store / publish.
+    uint32_t raw[48];
+    // issue the TMEM loads of job nJ (chunk shape C): 48 columns, or the 16 columns of chunk 2
+    auto prefetch = [&](auto cc) {
+      constexpr int C = decltype(cc)::value;
+      const uint32_t us = nJ & 1u;
+      mbar_wait(bar_ufull(us), (nJ >> 1) & 1u);
+      tc_fence_after();
+      if constexpr (C < 2) {
+        tmem_ld_32x32p(ubase + us * 128u, raw);
+        tmem_ld_32x16p(ubase + us * 128u + 32u, raw + 32);
+      } else {
+        tmem_ld_32x16p(tmem + t_lane + kColU + us * 128u, raw);  // every warp reads columns 0..15
+      }
+    };
+    // the loads of job nJ have landed: the U slot can be overwritten
+    auto release_u = [&]() {
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_ufree(nJ & 1u));
+    };
+    // 8 accumulator columns -> 4 packed bf16x2 features (columns >= lim are padding)
+    auto feat8 = [&](const uint32_t* r, int c0, int lim, bool masked, uint32_t* pk) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float x0 = __uint_as_float(r[2 * i]), x1 = __uint_as_float(r[2 * i + 1]);
+        if (KIND == 0)
+          pk[i] = add_bf16x2(pack_bf16x2(ex2_approx(fmaf(x0, kLog2e, -sub)), ex2_approx(fmaf(x1, kLog2e, -sub))), eps2);
+        else
+          pk[i] = add_bf16x2(cvt_relu_bf16x2(x0, x1), eps2);
+      }
+      if (masked) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float a = bf16lo(w[i]), b = bf16hi(w[i]);
-          s = fmaf(a, a, s);
-          s = fmaf(b, b, s);
+          if (c0 + 2 * i >= lim) pk[i] = 0u;
+          else if (c0 + 2 * i + 1 >= lim) pk[i] &= 0x0000ffffu;
         }
       }
-      part[grp * 128 + row] = s;
-      named_bar_sync(1, kFeatWarps * 32);
-      return (part[row] + part[128 + row]) * (0.5f * 0.125f);
     };
 
-    // load this thread's accumulator row of chunk C: 128 columns (C < 2) or 16 (C == 2)
-    auto load_u = [&](auto cc, uint32_t (&r)[128]) {
+    // stabiliser pass over one chunk (softmax kernel): max of the raw projections.
+    // `next`: chunk shape of the following job (std::integral_constant), has_next: it exists
+    auto max_job = [&](auto cc, auto next, bool has_next, float& acc) {
       constexpr int C = decltype(cc)::value;
-      if constexpr (C < 2) {
-        tmem_ld_32x32p(ucol, r);
-        tmem_ld_32x32p(ucol + 32u, r + 32);
-        tmem_ld_32x32p(ucol + 64u, r + 64);
-        tmem_ld_32x32p(ucol + 96u, r + 96);
-      } else {
-        tmem_ld_32x16p(ucol, r);
-      }
-      tmem_ld_wait();
-    };
-
-    // stabiliser pass over one chunk (softmax kernel): max of the raw projections
-    auto max_job = [&](auto cc, float& acc) {
-      constexpr int C = decltype(cc)::value;
-      constexpr int NC = C < 2 ? 128 : 16;
-      mbar_wait(b_ufull, nJg & 1u);
-      tc_fence_after();
-      uint32_t r[128];
-      load_u(cc, r);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(b_ufree);
-      const int lim = p.m - C * 128;
+      release_u();
+      const int lim = C < 2 ? p.m - (C * 128 + col0) : (third == 0 ? p.m - 256 : 0);
+      constexpr int NC = C < 2 ? 48 : 16;
       float mx = -INFINITY;
-      if (lim >= NC) {
 #pragma unroll
-        for (int i = 0; i < NC; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-      } else {
-#pragma unroll
-        for (int i = 0; i < NC; ++i)
-          if (i < lim) mx = fmaxf(mx, __uint_as_float(r[i]));
-      }
+      for (int i = 0; i < NC; ++i)
+        if (i < lim) mx = fmaxf(mx, __uint_as_float(raw[i]));
       acc = fmaxf(acc, mx);
-      ++nJg;
+      ++nJ;
+      if (has_next) prefetch(next);
     };
 
-    // feature map of one chunk: TMEM -> bf16 features in this group's smem buffer
-    auto feat_job = [&](auto cc, bool zero_row) {
+    // feature map of one chunk: packed features -> the job's smem buffer -> fready
+    auto feat_job = [&](auto cc, auto next, bool has_next, bool zero_row) {
       constexpr int C = decltype(cc)::value;
-      constexpr int NC = C < 2 ? 128 : 16;
+      constexpr int NC = C < 2 ? 48 : 16;
+      const uint32_t us = nJ & 1u;  // U slot = feature buffer = job parity
+      const uint32_t nF = us ? nF1++ : nF0++;
       TR(40 + C);
-      mbar_wait(b_ufull, nJg & 1u);
-      TR(43);
-      tc_fence_after();
-      uint32_t r[128];
-      load_u(cc, r);
-      // the accumulator row is in registers: hand the U slot back before the arithmetic
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(b_ufree);
+      release_u();
       TR(44);
-      mbar_wait(b_ffree, (nFg & 1u) ^ 1u);  // the MMAs that read this buffer two jobs ago are done
+      // padding: feature columns >= m, and key rows beyond the sequence, must contribute nothing
+      const int lim = zero_row ? 0 : p.m - (C * 128 + (C < 2 ? col0 : 0));
+      const bool masked = lim < NC;
+      uint32_t pk[NC / 2];
+#pragma unroll
+      for (int q = 0; q < NC / 8; ++q) feat8(raw + 8 * q, 8 * q, lim, masked, pk + 4 * q);
+      TR(45);
+      ++nJ;
+      if (has_next) prefetch(next);
       TR(46);
-      {
-        // padding: feature columns >= m, and key rows beyond the sequence, must contribute nothing
-        const int lim = zero_row ? 0 : p.m - C * 128;
-        // 32 columns at a time: convert, (mask,) store 4 x 16 bytes
+      mbar_wait(bar_ffree(us), (nF & 1u) ^ 1u);  // the MMAs that last read this buffer are done
+      const uint32_t fb = frow + us * 2u * kSlabBytes;
+      if (C < 2 || third == 0) {
+        const int ch0 = C < 2 ? (col0 >> 3) : 0;
 #pragma unroll
-        for (int q = 0; q < (NC + 31) / 32; ++q) {
-          constexpr int NQ = NC < 32 ? NC : 32;
-          uint32_t pk[NQ / 2];
-          if (KIND == 0) {
-#pragma unroll
-            for (int i = 0; i < NQ / 2; ++i) {
-              const float a = ex2_approx(fmaf(__uint_as_float(r[32 * q + 2 * i]), kLog2e, -sub));
-              const float b = ex2_approx(fmaf(__uint_as_float(r[32 * q + 2 * i + 1]), kLog2e, -sub));
-              pk[i] = add_bf16x2(pack_bf16x2(a, b), eps2);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < NQ / 2; ++i)
-              pk[i] = add_bf16x2(cvt_relu_bf16x2(__uint_as_float(r[32 * q + 2 * i]), __uint_as_float(r[32 * q + 2 * i + 1])), eps2);
-          }
-          if (lim < NC) {
-#pragma unroll
-            for (int i = 0; i < NQ / 2; ++i) {
-              if (32 * q + 2 * i >= lim) pk[i] = 0u;
-              else if (32 * q + 2 * i + 1 >= lim) pk[i] &= 0x0000ffffu;
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < NQ / 8; ++i) {
-            const int ch = 4 * q + i;  // 16-byte chunk index within the 2 x 128-byte feature rows
-            st_shared_v4(frow + (uint32_t)(ch >> 3) * kSlabBytes + ((((uint32_t)(ch & 7)) ^ r7) << 4),
-                         make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]));
-          }
-        }
+        for (int q = 0; q < NC / 8; ++q)
+          st_shared_v4(fb + fchunk(ch0 + q), make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]));
         TR(47);
         fence_proxy_async_smem();
-        TR(48);
       }
+      TR(48);
       __syncwarp();
-      if (lane == 0) mbar_arrive(b_fready);
+      if (lane == 0) mbar_arrive(bar_fready(us));
       TR(49);
-      ++nJg;
-      ++nFg;
     };
     using C0 = std::integral_constant<int, 0>;
     using C1 = std::integral_constant<int, 1>;
     using C2 = std::integral_constant<int, 2>;
 
+    if ((int64_t)blockIdx.x < p.items) prefetch(C0{});
     for (int64_t item = blockIdx.x; item < p.items; item += istride) {
       if (KIND == 0) {
         // ---- key stabiliser: global max of K.Omega'^T over the valid tokens ----
@@ -681,9 +694,9 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int t = 0; t < nt; ++t) {
           ++tile_seq;
           float mx = -INFINITY;
-          if ((mine ^= 1u)) max_job(C0{}, mx);
-          if ((mine ^= 1u)) max_job(C1{}, mx);
-          if ((mine ^= 1u)) max_job(C2{}, mx);
+          max_job(C0{}, C1{}, true, mx);
+          max_job(C1{}, C2{}, true, mx);
+          max_job(C2{}, C0{}, true, mx);
           if (t * kTile + row < p.tokens) kmx = fmaxf(kmx, mx);
         }
         kmx = warp_max(kmx);
@@ -698,25 +711,26 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (KIND == 0) sub = (row_diag(tile_seq) + gmax) * kLog2e;
         tile_seq += 2;
         const bool zero_row = t * kTile + row >= p.tokens;
-        if ((mine ^= 1u)) feat_job(C0{}, zero_row);
-        if ((mine ^= 1u)) feat_job(C1{}, zero_row);
-        if ((mine ^= 1u)) feat_job(C2{}, zero_row);
+        feat_job(C0{}, C1{}, true, zero_row);
+        feat_job(C1{}, C2{}, true, zero_row);
+        feat_job(C2{}, C0{}, true, zero_row);
       }
-      // ---- context read-out: TMEM ctx^T blocks -> bf16 K-major smem; group g takes block g ----
+      // ---- context read-out: TMEM ctx^T blocks -> bf16 K-major smem; warps of third b take block b ----
       {
         TR(60);
         mbar_wait(bar_ctxfull, nItems & 1u);
         TR(61);
         ++nItems;
         tc_fence_after();
-        if (!(p.dbg & 64)) {
-          const int m = 128 * (int)grp + row;
+        tmem_ld_wait();  // the prefetch of the first query job is in flight: one wait covers all loads
+        if (third < 2 && !(p.dbg & 64)) {
+          const int m = 128 * third + row;
           const uint32_t mc = (uint32_t)m & 63u;
           const uint32_t slab = s_ctx + (uint32_t)(m >> 6) * kCtxSlabBytes + (mc & 7u) * 2u;
 #pragma unroll
           for (int hlf = 0; hlf < 2; ++hlf) {
             uint32_t r[32];
-            tmem_ld_32x32(tmem + t_lane + kColCtx + 80u * grp + 32u * hlf, r);
+            tmem_ld_32x32(tmem + t_lane + kColCtx + 80u * third + 32u * hlf, r);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -725,26 +739,31 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
           }
           uint32_t r2[16];
-          tmem_ld_32x16(tmem + t_lane + kColCtx + 80u * grp + 64u, r2);
+          tmem_ld_32x16(tmem + t_lane + kColCtx + 80u * third + 64u, r2);
           tmem_ld_wait();
           st_shared_b16(slab + 8u * 1024u + (((mc >> 3) & 7u) << 4), __uint_as_float(r2[0]));  // n = 64
         }
-        if (lg == 0 && !(p.dbg & 64)) {
-          // block 2: features 256..271 live in lanes 0..15; group g takes columns [32 g, 32 g + 32)
-          uint32_t r[32], r2[16];
-          tmem_ld_32x32(tmem + kColCtx + 160u + 32u * grp, r);
-          if (grp == 1) tmem_ld_32x16(tmem + kColCtx + 160u + 64u, r2);
-          tmem_ld_wait();
-          if (lane < 16) {
-            const uint32_t mc = (uint32_t)lane;
-            const uint32_t slab = s_ctx + 4u * kCtxSlabBytes + (mc & 7u) * 2u;
+        if (third == 2 && lg == 0 && !(p.dbg & 64)) {
+          // block 2: features 256..271 live in lanes 0..15
+          const uint32_t mc = (uint32_t)lane;
+          const uint32_t slab = s_ctx + 4u * kCtxSlabBytes + (mc & 7u) * 2u;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const uint32_t n = 32u * grp + i;
-              st_shared_b16(slab + (n >> 3) * 1024u + (n & 7u) * 128u + ((((mc >> 3) ^ n) & 7u) << 4), __uint_as_float(r[i]));
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem + kColCtx + 160u + 32u * hlf, r);
+            tmem_ld_wait();
+            if (lane < 16) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const uint32_t n = 32u * hlf + i;
+                st_shared_b16(slab + (n >> 3) * 1024u + (n & 7u) * 128u + ((((mc >> 3) ^ n) & 7u) << 4), __uint_as_float(r[i]));
+              }
             }
-            if (grp == 1) st_shared_b16(slab + 8u * 1024u + (((mc >> 3) & 7u) << 4), __uint_as_float(r2[0]));
           }
+          uint32_t r2[16];
+          tmem_ld_32x16(tmem + kColCtx + 160u + 64u, r2);
+          tmem_ld_wait();
+          if (lane < 16) st_shared_b16(slab + 8u * 1024u + (((mc >> 3) & 7u) << 4), __uint_as_float(r2[0]));
         }
         fence_proxy_async_smem();
         tc_fence_before();
@@ -753,24 +772,26 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         TR(62);
       }
       // ---- queries: q' chunks feed the output MMAs; the out/den epilogue of tile t runs behind
-      //      this group's first job of tile t+1 ----
+      //      the first job of tile t+1 ----
       bool pending = false;
       for (int t = 0; t < nt; ++t) {
+        const bool more = t + 1 < nt || item != last_item;  // another job follows this tile
         if (KIND == 0) {
           diag = row_diag(tile_seq);
           float rmx = -INFINITY;
-          if ((mine ^= 1u)) max_job(C0{}, rmx);
-          if ((mine ^= 1u)) max_job(C1{}, rmx);
-          if ((mine ^= 1u)) max_job(C2{}, rmx);
+          max_job(C0{}, C1{}, true, rmx);
           if (pending) { epilogue(item, t - 1); pending = false; }
-          rmaxs[grp * 128 + row] = rmx;
+          max_job(C1{}, C2{}, true, rmx);
+          max_job(C2{}, C0{}, true, rmx);
+          rmaxs[third * 128 + row] = rmx;
           named_bar_sync(1, kFeatWarps * 32);
-          sub = (diag + fmaxf(rmaxs[row], rmaxs[128 + row])) * kLog2e;
+          sub = (diag + fmaxf(fmaxf(rmaxs[row], rmaxs[128 + row]), rmaxs[256 + row])) * kLog2e;
         }
         ++tile_seq;
-        if ((mine ^= 1u)) { feat_job(C0{}, false); if (pending) { epilogue(item, t - 1); pending = false; } }
-        if ((mine ^= 1u)) { feat_job(C1{}, false); if (pending) { epilogue(item, t - 1); pending = false; } }
-        if ((mine ^= 1u)) feat_job(C2{}, false);
+        feat_job(C0{}, C1{}, true, false);
+        if (pending) { epilogue(item, t - 1); pending = false; }
+        feat_job(C1{}, C2{}, true, false);
+        feat_job(C2{}, C0{}, more, false);
         pending = true;
       }
       epilogue(item, nt - 1);
