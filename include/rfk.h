@@ -162,17 +162,18 @@ int rfk_pair2att_logits(const float* pair, const float* Wf, const float* bf, flo
 
 /*
  * Per-(batch, channel) statistics over the L*L positions of a channels-last map
- * (nn.InstanceNorm2d, :453,:457): stats[b,0,c] = sum x, stats[b,1,c] = sum x^2 (f32, caller
- * zeroes `stats` first; accumulated with atomics).
+ * (nn.InstanceNorm2d, :453,:457): stats[b,0,c] = sum x, stats[b,1,c] = sum x^2 (f64, caller
+ * zeroes `stats` first; fixed-order f32 partial sums, f64 atomics across blocks, so the values
+ * narrowed to f32 are run-to-run reproducible).
  */
-int rfk_channel_stats(const void* x, int x_dtype, float* stats, int B, int64_t positions, int C,
+int rfk_channel_stats(const void* x, int x_dtype, double* stats, int B, int64_t positions, int C,
                       rfk_stream_t stream);
 
 /*
  * Apply InstanceNorm2d(affine, eps) + optional residual + ELU on a channels-last map (:453-462):
  *   y = (x - mean_c) * rsqrt(var_c + eps) * gamma_c + beta_c;  if (res) y += res;  if (elu) y = ELU(y)
  */
-int rfk_instnorm_apply(const void* x, int x_dtype, const float* stats, const float* gamma,
+int rfk_instnorm_apply(const void* x, int x_dtype, const double* stats, const float* gamma,
                        const float* beta, float eps, const void* res, int res_dtype, int elu,
                        void* y, int y_dtype, int B, int64_t positions, int C, rfk_stream_t stream);
 

@@ -336,7 +336,10 @@ pair2att_kernel(const float* __restrict__ pair, const float* __restrict__ Wf,
 // ----------------------------------------------------------------------------------------------
 // InstanceNorm statistics and apply (channels-last)
 // ----------------------------------------------------------------------------------------------
-__global__ void channel_stats_kernel(const void* __restrict__ x, int xdt, float* __restrict__ stats,
+// Partial sums over `chunk` positions are formed in a fixed order in fp32; the cross-block
+// accumulation uses fp64 atomics, whose order-dependent rounding (1e-16) vanishes when the
+// statistics are narrowed to fp32: the result is run-to-run reproducible in practice.
+__global__ void channel_stats_kernel(const void* __restrict__ x, int xdt, double* __restrict__ stats,
                                      int64_t positions, int C, int chunk) {
   const int b = blockIdx.y;
   const int64_t p0 = (int64_t)blockIdx.x * chunk;
@@ -348,13 +351,13 @@ __global__ void channel_stats_kernel(const void* __restrict__ x, int xdt, float*
       s += v;
       q = fmaf(v, v, q);
     }
-    atomicAdd(&stats[((int64_t)b * 2 + 0) * C + c], s);
-    atomicAdd(&stats[((int64_t)b * 2 + 1) * C + c], q);
+    atomicAdd(&stats[((int64_t)b * 2 + 0) * C + c], (double)s);
+    atomicAdd(&stats[((int64_t)b * 2 + 1) * C + c], (double)q);
   }
 }
 
 __global__ void __launch_bounds__(256)
-instnorm_apply_kernel(const void* __restrict__ x, int xdt, const float* __restrict__ stats,
+instnorm_apply_kernel(const void* __restrict__ x, int xdt, const double* __restrict__ stats,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                       const void* __restrict__ res, int rdt, int elu, void* __restrict__ y, int ydt,
                       int64_t positions, int C, int64_t total) {
@@ -362,9 +365,10 @@ instnorm_apply_kernel(const void* __restrict__ x, int xdt, const float* __restri
   if (idx >= total) return;
   const int c = (int)(idx % C);
   const int64_t b = idx / ((int64_t)C * positions);
-  const float inv_n = 1.f / (float)positions;
-  const float mean = stats[(b * 2 + 0) * C + c] * inv_n;
-  const float var = fmaxf(stats[(b * 2 + 1) * C + c] * inv_n - mean * mean, 0.f);
+  const double inv_n = 1.0 / (double)positions;
+  const double mean_d = stats[(b * 2 + 0) * C + c] * inv_n;
+  const float mean = (float)mean_d;
+  const float var = fmaxf((float)(stats[(b * 2 + 1) * C + c] * inv_n - mean_d * mean_d), 0.f);
   float v = (load_as_float(x, xdt, idx) - mean) * rsqrtf(var + eps) * gamma[c] + beta[c];
   if (res) v += load_as_float(res, rdt, idx);
   if (elu) v = v > 0.f ? v : expm1f(v);
@@ -485,7 +489,7 @@ extern "C" int rfk_pair2att_logits(const float* pair, const float* Wf, const flo
   return post_launch();
 }
 
-extern "C" int rfk_channel_stats(const void* x, int xdt, float* stats, int B, int64_t positions,
+extern "C" int rfk_channel_stats(const void* x, int xdt, double* stats, int B, int64_t positions,
                                  int C, rfk_stream_t stream) {
   if (!x || !stats) return RFK_ERR_NULL_POINTER;
   if (B <= 0 || positions <= 0 || C <= 0) return RFK_ERR_BAD_DIMS;
@@ -498,7 +502,7 @@ extern "C" int rfk_channel_stats(const void* x, int xdt, float* stats, int B, in
   return post_launch();
 }
 
-extern "C" int rfk_instnorm_apply(const void* x, int xdt, const float* stats, const float* gamma,
+extern "C" int rfk_instnorm_apply(const void* x, int xdt, const double* stats, const float* gamma,
                                   const float* beta, float eps, const void* res, int rdt, int elu,
                                   void* y, int ydt, int B, int64_t positions, int C,
                                   rfk_stream_t stream) {

@@ -1,5 +1,5 @@
 // rfk_favor_tc.cu — fused Performer FAVOR+ attention on tcgen05 / TMEM / TMA (bf16 operands,
-// fp32 accumulation), software-pipelined ("v4"). One persistent CTA per SM walks a stream of
+// fp32 accumulation), software-pipelined. One persistent CTA per SM walks a stream of
 // chunk JOBS; nothing of size tokens x m ever leaves the SM.
 //
 // A job is (item = (group, head), type, 128-token tile t, feature chunk c); the 272 (padded)
@@ -11,14 +11,27 @@
 // Per item: relu kernel  K(t,c)*, read-out of ctx, Q(t,c)*;
 //           softmax      KMAX(t,c)*, K(t,c)*, read-out, then per tile QMAX(t,c)*, Q(t,c)*.
 //
-// Three roles run decoupled and only meet at mbarriers:
-//   warp 0 lane 0  TMA producer: K/V/Q tiles into a 3-slot ring (runs ahead across items)
-//   warp 1 lane 0  MMA issuer:   U(j+1) is issued BEFORE the consumer MMA of job j, so the tensor
-//                  pipe always has [consumer(j), U(j+2)] queued while features(j+1) are computed
-//   warps 2..17    feature/epilogue warps in two groups of 8 that alternate jobs (group = job
-//                  parity = U slot = feature buffer; 2 warps per TMEM lane group, 64 columns each):
-//                  TMEM -> feature map -> bf16 smem; ctx read-out; out/den epilogue, deferred
-//                  behind the next tile's first job so it never waits for the tensor pipe
+// Four roles run decoupled and only meet at mbarriers:
+//   warp 0 lane 0  TMA producer: K/V/Q tiles into a 3-slot ring; a second cursor runs 6 tiles ahead
+//                  and pulls them into L2 (cp.async.bulk.prefetch.tensor), since two ring slots are
+//                  held by the K and V tile in use and one slot cannot cover the HBM latency
+//   warp 1         U issuer:  U = X.Omega_c'^T of every job, as far ahead as the two U slots allow
+//   warp 2         consumer issuer: context / output MMAs of the K and Q jobs
+//                  (both issuer warps run warp-uniform control flow and issue under elect.sync: a
+//                  lane-0-only branch makes the compiler wrap every UTCHMMA in a divergence waterfall,
+//                  and a single warp retires one dependent instruction per ~6-8 cycles, which is why
+//                  the per-job bookkeeping is split over two warps and uses precomputed descriptors)
+//   warps 3..14    12 feature/epilogue warps, all of them on every job: three warps share a TMEM lane
+//                  group and take the column ranges [0,48) | [40,88) | [80,128) of the chunk (uniform
+//                  x32+x16 TMEM loads; the 8-column overlaps are written twice with equal values).
+//                  Software-pipelined: while the packed features of job j are stored to shared memory,
+//                  fenced (fence.proxy.async) and published, the accumulator of job j+1 is already on
+//                  its way TMEM -> registers; the U slot is handed back as soon as the load lands.
+//                  15 warps leave 128 registers per thread (no spills, no per-job address recomputation).
+//                  ctx read-out; out/den epilogue deferred behind the next tile's first job.
+// Measured bounds (ncu + in-kernel timeline, profiles/): per 128x128 job ~130 KB of shared-memory
+// traffic (MMA operands from smem + feature stores + TMA) and the F2FP/HADD2 conversion pipes, not
+// the tensor pipe; the next step is to keep the features in TMEM (tcgen05.st, A-from-TMEM MMAs).
 //
 // TMEM (512 columns): ctx^T blocks b=0..2 (lanes = m - 128 b, 80 columns = d | 1) at [0,240);
 //   U ring 2 x 128 columns at [256,512); out|den accumulators D3[s] alias ctx blocks 0/1 (dead in
@@ -70,6 +83,11 @@ struct FavorTcParams {
   long long* trace;  // developer timeline (RFK_FAVOR_TRACE): [4 roles][kTraceMax][2] (event, clock) of CTA 0
 };
 constexpr int kTraceMax = 1024;
+#ifdef RFK_FAVOR_TRACE_BUILD  // developer builds only: the hooks cost ~10% of the kernel time
+constexpr bool kTraceBuild = true;
+#else
+constexpr bool kTraceBuild = false;
+#endif
 
 // MN-major SW128 descriptor: rows are K indices (128 B each, 8-row groups SBO=1024 apart),
 // 64-element MN chunks are `lbo_bytes` apart.
@@ -189,10 +207,11 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int nt = (p.tokens + kTile - 1) / kTile;
   const int64_t istride = gridDim.x;
   // developer timeline: role 0 = U issuer, 1 = consumer issuer, 2 / 3 = first warp of feature group 0 / 1
+  auto dbg_bits = [&]() { return kTraceBuild ? p.dbg : 0; };  // experiments exist in developer builds only
   int tr_n = 0;
   const int tr_role = warp == 1 ? 0 : warp == 2 ? 1 : warp == 3 ? 2 : warp == 7 ? 3 : -1;  // warps 3 / 7: lane group 3 of group 0 / 1
   auto TR = [&](int ev) {
-    if (p.trace && blockIdx.x == 0 && lane == 0 && tr_role >= 0 && tr_n < kTraceMax) {
+    if (kTraceBuild && p.trace && blockIdx.x == 0 && lane == 0 && tr_role >= 0 && tr_n < kTraceMax) {
       p.trace[((int64_t)tr_role * kTraceMax + tr_n) * 2] = ev;
       p.trace[((int64_t)tr_role * kTraceMax + tr_n) * 2 + 1] = clock64();
       ++tr_n;
@@ -298,12 +317,12 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       for (int i = 0; i < kPrefetch; ++i) prefetch_one();
       uint32_t slot = 0, par = 0;
       while (ld.item < p.items) {
-        if (!(p.dbg & 16)) prefetch_one();
+        if (!(dbg_bits() & 16)) prefetch_one();
         const CUtensorMap* tm; int t, h, g0, g1;
         cur_get(ld, tm, t);
         coords(ld.item, h, g0, g1);
         mbar_wait(bar_tempty(slot), par ^ 1u);
-        if (p.dbg & 16) {
+        if (dbg_bits() & 16) {
           mbar_arrive(bar_tfull(slot));
         } else {
           mbar_arrive_expect_tx(bar_tfull(slot), kSlabBytes);
@@ -343,7 +362,7 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (++r_slot == kRing) { r_slot = 0; r_par ^= 1u; }
       return x;
     };
-    auto commit_dbg = [&](uint32_t bar) { if (p.dbg & 128) mbar_arrive(bar); else umma_commit(bar); };
+    auto commit_dbg = [&](uint32_t bar) { umma_commit(bar); };
     using C0 = std::integral_constant<int, 0>;
     using C1 = std::integral_constant<int, 1>;
     using C2 = std::integral_constant<int, 2>;
@@ -363,7 +382,7 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint64_t db = d_omega + (uint64_t)(C * 1024);
         constexpr uint32_t idesc = C == 2 ? umma_idesc_bf16(128, 16) : umma_idesc_bf16(128, 128);
         if (elect_one()) {
-          if (!(p.dbg & 4)) {
+          if (!(dbg_bits() & 4)) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_bf16(tmem + kColU + us * 128u, da + 2 * k, db + 2 * k, idesc, k > 0);
           }
@@ -416,7 +435,7 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint64_t da = d_feat_mn + (uint64_t)(fs * 2048u);
         const uint64_t db = v.slot == 0 ? d_v0 : (v.slot == 1 ? d_v1 : d_v2);
         if (elect_one()) {
-          if (!(p.dbg & 1)) {
+          if (!(dbg_bits() & 1)) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)
               umma_bf16(tmem + kColCtx + 80u * C, da + 128 * k, db + 128 * k, idesc_bf16_major(128, 80, 1, 1), (t > 0 || k > 0));
@@ -451,7 +470,7 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint64_t da = d_feat_k + (uint64_t)(fs * 2048u);
         const uint64_t db = d_ctx + (uint64_t)(2 * C * 640);
         if (elect_one()) {
-          if (!(p.dbg & 2)) {
+          if (!(dbg_bits() & 2)) {
             constexpr int NK = C == 2 ? 1 : 8;
 #pragma unroll
             for (int k = 0; k < NK; ++k)
@@ -536,7 +555,7 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_d3free(ds));
       ++nD3;
-      if (t * kTile + row < p.tokens && !(p.dbg & 32)) {
+      if (t * kTile + row < p.tokens && !(dbg_bits() & 32)) {
         const int h = (int)(item % p.heads);
         const int64_t g = item / p.heads;
         const int64_t g0 = g % p.G0, g1 = g / p.G0;
@@ -723,7 +742,7 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         ++nItems;
         tc_fence_after();
         tmem_ld_wait();  // the prefetch of the first query job is in flight: one wait covers all loads
-        if (third < 2 && !(p.dbg & 64)) {
+        if (third < 2 && !(dbg_bits() & 64)) {
           const int m = 128 * third + row;
           const uint32_t mc = (uint32_t)m & 63u;
           const uint32_t slab = s_ctx + (uint32_t)(m >> 6) * kCtxSlabBytes + (mc & 7u) * 2u;
@@ -743,7 +762,7 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tmem_ld_wait();
           st_shared_b16(slab + 8u * 1024u + (((mc >> 3) & 7u) << 4), __uint_as_float(r2[0]));  // n = 64
         }
-        if (third == 2 && lg == 0 && !(p.dbg & 64)) {
+        if (third == 2 && lg == 0 && !(dbg_bits() & 64)) {
           // block 2: features 256..271 live in lanes 0..15
           const uint32_t mc = (uint32_t)lane;
           const uint32_t slab = s_ctx + 4u * kCtxSlabBytes + (mc & 7u) * 2u;

@@ -610,11 +610,11 @@ class PairUpdateWithMsa(nn.Module):
         fn = self.resnet[1].fn
         h_op = h if _MODE == 1 else ops.convert_rows(h.view(TP, P), _empty((TP, P), adt, msa)).view(B, L, L, P)
         c1 = self._conv(h_op, pk["conv1"]).view(B, L * L, P)
-        st = torch.zeros((B, 2, P), dtype=torch.float32, device=msa.device)
+        st = torch.zeros((B, 2, P), dtype=torch.float64, device=msa.device)
         ops.channel_stats(c1, st)
         a1 = ops.instnorm_apply(c1, st, pk["g1"], pk["b1"], fn[2].eps, _empty(c1.shape, adt, msa), elu=True)
         c2 = self._conv(a1.view(B, L, L, P), pk["conv2"]).view(B, L * L, P)
-        st2 = torch.zeros((B, 2, P), dtype=torch.float32, device=msa.device)
+        st2 = torch.zeros((B, 2, P), dtype=torch.float64, device=msa.device)
         ops.channel_stats(c2, st2)
         out = ops.instnorm_apply(c2, st2, pk["g2"], pk["b2"], fn[6].eps,
                                  _empty(c2.shape, torch.float32, msa), res=h.view(B, L * L, P), elu=True)

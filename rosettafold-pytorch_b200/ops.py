@@ -371,8 +371,8 @@ def pair2att_logits(pair, Wf, bf, eps, logits):
 
 def channel_stats(x, stats):
     B, P, Cn = x.shape
-    if not x.is_contiguous() or tuple(stats.shape) != (B, 2, Cn) or stats.dtype != torch.float32:
-        raise ValueError("channel_stats: x contiguous [B,P,C], stats f32 [B,2,C] (pre-zeroed)")
+    if not x.is_contiguous() or tuple(stats.shape) != (B, 2, Cn) or stats.dtype != torch.float64:
+        raise ValueError("channel_stats: x contiguous [B,P,C], stats f64 [B,2,C] (pre-zeroed)")
     backend().channel_stats(x, stats)
     return stats
 
@@ -382,6 +382,8 @@ def instnorm_apply(x, stats, gamma, beta, eps, out, *, res=None, elu=False):
         raise ValueError("instnorm_apply: x/out must be contiguous and equal-shaped")
     if res is not None and (res.shape != x.shape or not res.is_contiguous()):
         raise ValueError("instnorm_apply: res must match x")
+    if stats.dtype != torch.float64 or not stats.is_contiguous():
+        raise ValueError("instnorm_apply: stats must be the contiguous f64 [B,2,C] buffer of channel_stats")
     backend().instnorm_apply(x, stats, gamma, beta, float(eps), res, elu, out)
     return out
 

@@ -242,7 +242,7 @@ def test_instnorm(cuda_device, dtype):
     res = _rand((B, P, Cn), torch.float32, dev, 71)
     g = _rand((Cn,), torch.float32, dev, 72)
     b = _rand((Cn,), torch.float32, dev, 73)
-    stats = torch.zeros((B, 2, Cn), dtype=torch.float32, device=dev)
+    stats = torch.zeros((B, 2, Cn), dtype=torch.float64, device=dev)
     ops.channel_stats(x, stats)
     out = torch.empty((B, P, Cn), dtype=torch.float32, device=dev)
     ops.instnorm_apply(x, stats, g, b, 1e-6, out, res=res, elu=True)
