@@ -230,6 +230,79 @@ poswise_kernel(const void* __restrict__ pq, int64_t pqs, const void* __restrict_
   }
 }
 
+// Vectorised PositionWiseWeightFactor (bf16 operands, dh % 8 == 0): one block per (b, l). A thread
+// owns one 16-byte chunk (8 channels) of a row; `rows` MSA rows are processed per pass, so a warp
+// reads whole 128-byte lines of pk / q and writes whole lines of qt. Phase 1: logits[n][h] into
+// shared memory (the dh/8 threads of a head meet by shuffle); phase 2: softmax over n per head;
+// phase 3: qt[b,h,l,n,:] = q[b,n,l,h,:] * w[n,h] * q_scale.
+__device__ __forceinline__ void ld8_bf16(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__global__ void __launch_bounds__(256)
+poswise_vec_kernel(const __nv_bfloat16* __restrict__ pq, int64_t pqs, const __nv_bfloat16* __restrict__ pk,
+                   int64_t pks, float scale, float* __restrict__ w_out, const __nv_bfloat16* __restrict__ q,
+                   int64_t qs, float q_scale, __nv_bfloat16* __restrict__ qt, int N, int L, int H, int dh,
+                   int rows) {
+  extern __shared__ float lg[];  // [N][H]
+  const int CH = (H * dh) >> 3, gsz = dh >> 3;
+  const int c = threadIdx.x % CH, r = threadIdx.x / CH;
+  const int h = c / gsz;
+  const int l = blockIdx.x % L, b = blockIdx.x / L;
+  float pqv[8];
+  ld8_bf16(pq + ((int64_t)b * L + l) * pqs + c * 8, pqv);
+  for (int n0 = 0; n0 < N; n0 += rows) {
+    const int n = n0 + r;
+    float acc = 0.f;
+    if (n < N) {
+      float kv[8];
+      ld8_bf16(pk + (((int64_t)b * N + n) * L + l) * pks + c * 8, kv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc = fmaf(pqv[i], kv[i], acc);
+    }
+    for (int o = gsz >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (n < N && (c % gsz) == 0) lg[n * H + h] = acc * scale;
+  }
+  __syncthreads();
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int hh = warp; hh < H; hh += nw) {
+      float mx = -INFINITY;
+      for (int n = lane; n < N; n += 32) mx = fmaxf(mx, lg[n * H + hh]);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int n = lane; n < N; n += 32) {
+        const float e = __expf(lg[n * H + hh] - mx);
+        lg[n * H + hh] = e;
+        sum += e;
+      }
+      const float inv = 1.f / warp_sum(sum);
+      for (int n = lane; n < N; n += 32) {
+        const float w = lg[n * H + hh] * inv;
+        lg[n * H + hh] = w;
+        if (w_out) w_out[(((int64_t)b * N + n) * L + l) * H + hh] = w;
+      }
+    }
+  }
+  if (!qt) return;
+  __syncthreads();
+  const int64_t out_base = (((int64_t)b * H + h) * L + l) * ((int64_t)N * dh) + (c % gsz) * 8;
+  for (int n = r; n < N; n += rows) {
+    float qv[8];
+    ld8_bf16(q + (((int64_t)b * N + n) * L + l) * qs + c * 8, qv);
+    const float wn = lg[n * H + h] * q_scale;
+    uint4 u;
+    u.x = pack_bf16x2(qv[0] * wn, qv[1] * wn); u.y = pack_bf16x2(qv[2] * wn, qv[3] * wn);
+    u.z = pack_bf16x2(qv[4] * wn, qv[5] * wn); u.w = pack_bf16x2(qv[6] * wn, qv[7] * wn);
+    *reinterpret_cast<uint4*>(qt + out_base + (int64_t)n * dh) = u;
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // OPM operand preparation: block (32 x 8) per (b, l); transposes [n][u] -> [u][n] through smem.
 // ----------------------------------------------------------------------------------------------
@@ -375,6 +448,85 @@ instnorm_apply_kernel(const void* __restrict__ x, int xdt, const double* __restr
   store_from_float(y, ydt, idx, v);
 }
 
+// 128-bit vectorised InstanceNorm apply (C % 8 == 0): a thread owns 8 consecutive channels, derives
+// their (scale, shift) once and walks the positions of its block's chunk; loads/stores are 16-byte
+// (bf16) or 2 x 16-byte (f32) and a warp covers whole 128-byte lines.
+template <typename T>
+__device__ __forceinline__ void ld8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void ld8<float>(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void st8(T* p, const float (&v)[8]);
+template <>
+__device__ __forceinline__ void st8<float>(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <>
+__device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+template <typename TX, typename TR, typename TY>
+__global__ void __launch_bounds__(256)
+instnorm_apply_vec_kernel(const TX* __restrict__ x, const double* __restrict__ stats,
+                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                          const TR* __restrict__ res, int elu, TY* __restrict__ y, int64_t positions,
+                          int C, int chunk) {
+  const int groups = C >> 3;                       // 8-channel groups per position
+  const int rows_per_iter = blockDim.x / groups;   // positions covered by one pass of the block
+  const int g = threadIdx.x % groups, r = threadIdx.x / groups;
+  if (r >= rows_per_iter) return;
+  const int b = blockIdx.y;
+  const int c0 = g * 8;
+  float sc[8], sh[8];
+  const double inv_n = 1.0 / (double)positions;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const double mean_d = stats[((int64_t)b * 2 + 0) * C + c0 + i] * inv_n;
+    const float mean = (float)mean_d;
+    const float var = fmaxf((float)(stats[((int64_t)b * 2 + 1) * C + c0 + i] * inv_n - mean_d * mean_d), 0.f);
+    sc[i] = rsqrtf(var + eps) * gamma[c0 + i];
+    sh[i] = beta[c0 + i] - mean * sc[i];
+  }
+  const int64_t p0 = (int64_t)blockIdx.x * chunk;
+  const int64_t p1 = p0 + chunk < positions ? p0 + chunk : positions;
+  for (int64_t pos = p0 + r; pos < p1; pos += rows_per_iter) {
+    const int64_t off = ((int64_t)b * positions + pos) * C + c0;
+    float v[8];
+    ld8<TX>(x + off, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc[i], sh[i]);
+    if (res) {
+      float rr[8];
+      ld8<TR>(res + off, rr);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += rr[i];
+    }
+    if (elu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
+    }
+    st8<TY>(y + off, v);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 convert_rows_kernel(const void* __restrict__ x, int xdt, int64_t xs, void* __restrict__ y, int ydt,
                     int64_t ys, int64_t rows, int cols) {
@@ -452,6 +604,26 @@ extern "C" int rfk_poswise_weight(const void* pq, int64_t pqs, const void* pk, i
   if (qt && !q) return RFK_ERR_NULL_POINTER;
   if (B <= 0 || N <= 0 || L <= 0 || H <= 0 || dh <= 0) return RFK_ERR_BAD_DIMS;
   if (!dtype_ok(dt) || (qt && !dtype_ok(qtdt))) return RFK_ERR_BAD_DTYPE;
+  {
+    // vectorised path: bf16 operands, heads of 8k channels, everything 16-byte aligned
+    const int D = H * dh, gsz = dh / 8, CH = D / 8;
+    auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+    const bool pow2 = gsz > 0 && (gsz & (gsz - 1)) == 0 && gsz <= 32;
+    if (dt == RFK_BF16 && (!qt || qtdt == RFK_BF16) && dh % 8 == 0 && pow2 && CH <= 256 && pqs % 8 == 0 &&
+        pks % 8 == 0 && (!qt || qs % 8 == 0) && al16(pq) && al16(pk) && (!qt || (al16(q) && al16(qt))) &&
+        (size_t)N * H * sizeof(float) <= 48 * 1024) {
+      int rows = 256 / CH;
+      while (rows > 1 && (rows * CH) % 32 != 0) --rows;
+      if ((rows * CH) % 32 == 0) {
+        poswise_vec_kernel<<<(unsigned)(B * L), rows * CH, (size_t)N * H * sizeof(float),
+                             reinterpret_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const __nv_bfloat16*>(pq), pqs, reinterpret_cast<const __nv_bfloat16*>(pk), pks, scale,
+            w_out, reinterpret_cast<const __nv_bfloat16*>(q), qs, q_scale, reinterpret_cast<__nv_bfloat16*>(qt), N, L,
+            H, dh, rows);
+        return post_launch();
+      }
+    }
+  }
   const size_t smem = (size_t)4 * N * sizeof(float);
   if (smem > 48 * 1024) return RFK_ERR_BAD_DIMS;
   const int64_t items = (int64_t)B * L * H;
@@ -510,6 +682,27 @@ extern "C" int rfk_instnorm_apply(const void* x, int xdt, const double* stats, c
   if (B <= 0 || positions <= 0 || C <= 0) return RFK_ERR_BAD_DIMS;
   if (!dtype_ok(xdt) || !dtype_ok(ydt) || (res && !dtype_ok(rdt))) return RFK_ERR_BAD_DTYPE;
   const int64_t total = (int64_t)B * positions * C;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (C % 8 == 0 && C <= 2048 && al16(x) && al16(y) && (!res || al16(res)) && (!res || rdt == RFK_F32)) {
+    const int chunk = 256;
+    const int groups = C / 8;
+    const int threads = groups >= 256 ? 256 : (256 / groups) * groups;
+    if (threads >= groups) {
+      dim3 grid((unsigned)((positions + chunk - 1) / chunk), (unsigned)B);
+      cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+      const float* rf = reinterpret_cast<const float*>(res);
+#define RFK_IN_LAUNCH(TX, TY)                                                                       \
+  instnorm_apply_vec_kernel<TX, float, TY><<<grid, threads, 0, st>>>(                                \
+      reinterpret_cast<const TX*>(x), stats, gamma, beta, eps, rf, elu, reinterpret_cast<TY*>(y), \
+      positions, C, chunk)
+      if (xdt == RFK_BF16 && ydt == RFK_BF16) RFK_IN_LAUNCH(__nv_bfloat16, __nv_bfloat16);
+      else if (xdt == RFK_BF16) RFK_IN_LAUNCH(__nv_bfloat16, float);
+      else if (ydt == RFK_BF16) RFK_IN_LAUNCH(float, __nv_bfloat16);
+      else RFK_IN_LAUNCH(float, float);
+#undef RFK_IN_LAUNCH
+      return post_launch();
+    }
+  }
   instnorm_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0,
                           reinterpret_cast<cudaStream_t>(stream)>>>(
       x, xdt, stats, gamma, beta, eps, res, rdt, elu, y, ydt, positions, C, total);

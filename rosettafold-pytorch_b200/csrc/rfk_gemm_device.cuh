@@ -492,6 +492,19 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 2048 /*align*/ + kBarBytes + kStagingBytes;
 };
 
+// one lane of the (fully active) warp
+__device__ __forceinline__ bool gemm_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 template <int BN, int EPI, bool CONV = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -550,8 +563,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int64_t Z = p.Z0 * p.Z1 * p.Z2;
   const int64_t tiles = Z * m_blocks * n_blocks;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     // ===== TMA producer =====
+    // (this role and the MMA issuer run warp-uniform control flow with one elected lane issuing:
+    // under a lane-0-only branch the compiler treats every operand as divergent and wraps each
+    // UTMALDG / UTCHMMA in per-instruction election code)
     int stage = 0;
     uint32_t phase = 0;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
@@ -569,26 +585,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const int di = tap / 3 - 1, dj = tap % 3 - 1;
           for (int cb = 0; cb < p.conv_cblocks; ++cb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-            tma_load_5d(&tma_a, full_bar(stage), smem_a(stage), cb * kBlockK, j0 + dj, ii + di, bi, 0);
-            tma_load_5d(&tma_b, full_bar(stage), smem_b(stage), tap * p.conv_cpad + cb * kBlockK,
-                        (int)(nb * BN), 0, 0, 0);
+            if (gemm_elect_one()) {
+              mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+              tma_load_5d(&tma_a, full_bar(stage), smem_a(stage), cb * kBlockK, j0 + dj, ii + di, bi, 0);
+              tma_load_5d(&tma_b, full_bar(stage), smem_b(stage), tap * p.conv_cpad + cb * kBlockK,
+                          (int)(nb * BN), 0, 0, 0);
+            }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
       } else {
         for (int64_t kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          tma_load_5d(&tma_a, full_bar(stage), smem_a(stage), (int)(kb * kBlockK),
-                      (int)(mb * kBlockM), z0, z1, z2);
-          tma_load_5d(&tma_b, full_bar(stage), smem_b(stage), (int)(kb * kBlockK), (int)(nb * BN),
-                      z0 & p.bmask[0], z1 & p.bmask[1], z2 & p.bmask[2]);
+          if (gemm_elect_one()) {
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            tma_load_5d(&tma_a, full_bar(stage), smem_a(stage), (int)(kb * kBlockK),
+                        (int)(mb * kBlockM), z0, z1, z2);
+            tma_load_5d(&tma_b, full_bar(stage), smem_b(stage), (int)(kb * kBlockK), (int)(nb * BN),
+                        z0 & p.bmask[0], z1 & p.bmask[1], z2 & p.bmask[2]);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===== MMA issuer =====
     constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
     int stage = 0;
@@ -608,13 +630,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // (the K tail of a plain GEMM is zero-filled by TMA: skip the all-zero k16 steps too)
         const int nk16 = CONV ? (((int)(kb % p.conv_cblocks) == p.conv_cblocks - 1) ? p.conv_last_k16 : kBlockK / 16)
                               : ((kb == k_blocks - 1) ? (int)((p.K - kb * kBlockK + 15) / 16) : kBlockK / 16);
+        if (gemm_elect_one()) {
+          if (nk16 == kBlockK / 16) {
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k)
-          if (k < nk16)
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
-        umma_commit(empty_bar(stage));
-        if (kb == k_blocks - 1) umma_commit(tfull_bar(acc));
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              if (k < nk16)
+                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (kb == k_blocks - 1) umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }

@@ -182,7 +182,8 @@ def test_softmax_and_symmetrize(cuda_device):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
-@pytest.mark.parametrize("cfg", [(2, 7, 20, 12, 32), (1, 40, 16, 1, 32)])
+@pytest.mark.parametrize("cfg", [(2, 7, 20, 12, 32), (1, 40, 16, 1, 32), (1, 130, 33, 12, 32), (2, 64, 9, 3, 16),
+                                 (1, 5, 6, 2, 12)])
 def test_poswise_weight(cuda_device, dtype, cfg):
     dev = cuda_device
     B, N, L, H, dh = cfg
@@ -235,9 +236,12 @@ def test_pair2att_logits(cuda_device):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
-def test_instnorm(cuda_device, dtype):
+@pytest.mark.parametrize("shape", [(2, 900, 288), (1, 77, 72), (3, 333, 20)])
+def test_instnorm(cuda_device, dtype, shape):
+    """InstanceNorm2d + residual + ELU (:453-462): vectorised path (C % 8 == 0), ragged chunks, and
+    the scalar path (C = 20); both output dtypes."""
     dev = cuda_device
-    B, P, Cn = 2, 900, 288
+    B, P, Cn = shape
     x = _rand((B, P, Cn), dtype, dev, 70, 2.0) + 0.3
     res = _rand((B, P, Cn), torch.float32, dev, 71)
     g = _rand((Cn,), torch.float32, dev, 72)
@@ -250,6 +254,11 @@ def test_instnorm(cuda_device, dtype):
     ref = torch.nn.functional.elu(xn.permute(0, 2, 1) + res.double())
     torch.cuda.synchronize()
     assert rel_l2(out, ref) < 1e-4
+    out16 = torch.empty((B, P, Cn), dtype=torch.bfloat16, device=dev)
+    ops.instnorm_apply(x, stats, g, b, 1e-6, out16, elu=True)
+    ref16 = torch.nn.functional.elu(xn.permute(0, 2, 1))
+    torch.cuda.synchronize()
+    assert rel_l2(out16, ref16) < tol(torch.bfloat16)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
