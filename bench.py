@@ -202,13 +202,23 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
+    # The product path replays the trunk as ONE CUDA graph (rf.GraphedModule); the eager path is
+    # kept for the per-kernel-family device timing, whose events cannot live inside a graph.
+    gtrunk = rf.GraphedModule(trunk)
+    msa_s, pair_s = gtrunk.static_inputs(msa_d, pair_d)  # graph-owned input buffers
+    msa_s.copy_(msa_d)
+    pair_s.copy_(pair_d)
+
+    def step_eager():
         return trunk(msa_d, pair_d)
 
+    def step_resident():
+        return gtrunk(msa_s, pair_s)  # inputs already resident in HBM: no copy, one graph launch
+
     def step_e2e():
-        m = msa_h.to(dev, non_blocking=True)
-        p = pair_h.to(dev, non_blocking=True)
-        mo, po = trunk(m, p)
+        msa_s.copy_(msa_h, non_blocking=True)   # pinned host -> graph input buffers
+        pair_s.copy_(pair_h, non_blocking=True)
+        mo, po = gtrunk(msa_s, pair_s)
         msa_out_h.copy_(mo, non_blocking=True)
         pair_out_h.copy_(po, non_blocking=True)
 
@@ -226,15 +236,19 @@ def run_b200(args):
         return float(ms.item())
 
     for _ in range(max(3, args.warmup)):
+        step_eager()
+    for _ in range(max(3, args.warmup)):
         step_resident()
     clocks = Clocks(local)
     clocks.start()
+    # per-kernel-family device time: CUDA events on the launching stream around every librfk call
+    # of an eager pass over the same step (same kernels, same shapes as the graph replays)
     n0 = rf._lib.launch_count()
-    # per-kernel-family device timing on the launching stream, live in the timed region
     ops.start_timing(["gemm_bf16", "gemm_f32", "favor_attention", "conv3x3", "layernorm"])
-    total_ms = timed(step_resident, args.steps)
+    eager_ms = timed(step_eager, args.steps)
     fam = ops.stop_timing()
-    launches = rf._lib.launch_count() - n0
+    launches = (rf._lib.launch_count() - n0) // max(1, args.steps) * args.steps
+    total_ms = timed(step_resident, args.steps)
     step_e2e()  # warm the pinned-copy path
     e2e_ms = timed(step_e2e, args.steps)
     clk = clocks.stop()
@@ -265,7 +279,7 @@ def run_b200(args):
                     "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
                     "traffic": None, "peak_source": peak_src,
                     "launches_per_step": f["calls"] / args.steps, "avg_launch_ms": f["ms"] / max(1, f["calls"]),
-                    "share_of_step": f["ms"] / total_ms}
+                    "share_of_step": f["ms"] / eager_ms}
     families = {k: {"ms_per_step": v["ms"] / args.steps, "calls_per_step": v["calls"] / args.steps,
                     ("GB/s" if k == "layernorm" else "TFLOP/s"): (v["work"] / (v["ms"] * 1e-3) / (1e9 if k == "layernorm" else 1e12)) if v["ms"] > 0 else 0.0}
                 for k, v in fam.items() if v["calls"]}
@@ -279,7 +293,10 @@ def run_b200(args):
         "config": {"workload": f"trunk forward, {args.blocks} blocks x 4 encoder layers, B={B}/GPU, Nseq={N}, L={L}, d_msa 384, d_pair 288",
                    "parallelism": f"replicas x{world} (one sample per GPU, no data-path collective)",
                    "l2": "working set (msa 101 MB + pair 302 MB fp32 + intermediates) exceeds the 126 MB L2; no explicit flush",
-                   "ms_per_block": ms_per_step / args.blocks},
+                   "ms_per_block": ms_per_step / args.blocks,
+                   "execution": "timed region = CUDA-graph replays of the whole trunk (rf.GraphedModule, one launch per step); "
+                                "kernel-family durations and gpu_launches come from an eager pass of the same step",
+                   "eager_ms_per_step": eager_ms / args.steps},
         "e2e": {"value": e2e_value, "unit": "samples/s",
                 "h2d_bytes_per_step": int(msa_h.numel() * 4 + pair_h.numel() * 4),
                 "d2h_bytes_per_step": int(msa_out_h.numel() * 4 + pair_out_h.numel() * 4)},

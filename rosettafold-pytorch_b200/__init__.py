@@ -15,3 +15,4 @@ from .modules import (ColWise, EncoderLayer, FeedForward, MsaUpdateUsingSelfAtte
                       TwoTrackBlock, get_mode, load_reference_weights, set_mode)
 from . import replicas  # noqa: E402,F401
 from .integration import accelerate, accelerate_block  # noqa: E402,F401
+from .graphs import GraphedModule  # noqa: E402,F401

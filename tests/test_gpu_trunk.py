@@ -77,3 +77,27 @@ def test_block_is_deterministic_and_linear_in_batch(cuda_device):
     assert rel_l2(m[1:2], m1) < 1e-4 and rel_l2(p[1:2], p1) < 1e-4
     m2, p2 = blk(msa, pair)
     assert rel_l2(m2, m) < 1e-5 and rel_l2(p2, p) < 1e-5
+
+
+def test_cuda_graph_replay_matches_eager(cuda_device):
+    """GraphedModule: a captured TwoTrackBlock replays to the eager result, for new input values and
+    after a second shape has been captured (one graph per input shape)."""
+    cfg = dict(d_msa=96, d_pair=72, n_layers=1, B=1, N=9, L=40, seed=11)
+    blk, _, msa, pair = build_block(cfg, cuda_device)
+    gblk = rf.GraphedModule(blk)
+    for scale in (1.0, 0.5):
+        m_ref, p_ref = blk(msa * scale, pair * scale)
+        m, p = gblk(msa * scale, pair * scale)
+        torch.cuda.synchronize()
+        assert rel_l2(m, m_ref) < 1e-6 and rel_l2(p, p_ref) < 1e-6
+    msa2, pair2 = msa[:, :5, :24].contiguous(), pair[:, :24, :24].contiguous()
+    m2_ref, p2_ref = blk(msa2, pair2)
+    m2, p2 = gblk(msa2, pair2)
+    torch.cuda.synchronize()
+    assert rel_l2(m2, m2_ref) < 1e-6 and rel_l2(p2, p2_ref) < 1e-6
+    m_ref, p_ref = blk(msa, pair)
+    m, p = gblk(msa, pair)
+    torch.cuda.synchronize()
+    assert rel_l2(m, m_ref) < 1e-6 and rel_l2(p, p_ref) < 1e-6
+    with pytest.raises(RuntimeError):
+        gblk(msa.cpu(), pair.cpu())
