@@ -16,3 +16,5 @@ from .modules import (ColWise, EncoderLayer, FeedForward, MsaUpdateUsingSelfAtte
 from . import replicas  # noqa: E402,F401
 from .integration import accelerate, accelerate_block  # noqa: E402,F401
 from .graphs import GraphedModule  # noqa: E402,F401
+from . import sharded  # noqa: E402,F401
+from .sharded import ShardedPairAxialAttention, ShardedTrunkBlocks, ShardedTwoTrackBlock  # noqa: E402,F401

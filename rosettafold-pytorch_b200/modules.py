@@ -342,9 +342,9 @@ class PerformerSelfAttention(nn.Module):
             Wo=_w(self.to_out.weight), bo=_f(self.to_out.bias),
             proj=_f(self.fast_attention.projection_matrix)))
 
-    def _run(self, xn4, token_dim, res2):
+    def _run(self, xn4, token_dim, res2, out_dtype=torch.float32):
         """xn4: [A0,A1,A2,D] operand dtype; attention over axis `token_dim` (1 or 2), batched over
-        the other two axes. Returns to_out(attn) (+ res2) as float32 [T, D]."""
+        the other two axes. Returns to_out(attn) (+ res2) as `out_dtype` [T, D]."""
         pk = self._pack()
         A0, A1, A2, D = xn4.shape
         T = A0 * A1 * A2
@@ -360,7 +360,7 @@ class PerformerSelfAttention(nn.Module):
         ops.favor_attention(q4[..., :inner], q4[..., inner:2 * inner], q4[..., 2 * inner:], a4,
                             pk["proj"], kind=1 if self.fast_attention.generalized_attention else 0,
                             heads=self.heads)
-        out = _empty((T, D), torch.float32, xn4)
+        out = _empty((T, D), out_dtype, xn4)
         ops.gemm(ao, pk["Wo"], cview(out), bias=pk["bo"],
                  r0=None if res2 is None else cview(res2))
         return out
@@ -369,7 +369,7 @@ class PerformerSelfAttention(nn.Module):
         x4 = _as_f32(x4).contiguous()
         D = x4.shape[-1]
         xin = x4 if _MODE == 1 else ops.convert_rows(x4.view(-1, D), _empty((x4.numel() // D, D), _adt(), x4)).view(x4.shape)
-        return self._run(xin, token_dim).view(x4.shape)
+        return self._run(xin, token_dim, None).view(x4.shape)
 
     @torch.no_grad()
     def forward(self, x):

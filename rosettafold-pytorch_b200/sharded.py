@@ -1,0 +1,136 @@
+"""One long protein over several GPUs: pair row-sharding with an all-to-all transpose
+(BASELINE.json config 4).
+
+The pair tensor `pair[1, L, L, D]` is sharded on its first residue axis i: rank r owns rows
+[r L/P, (r+1) L/P). Inside `PairUpdateWithAxialAttention` (reference :501-547)
+
+  * column attention (tokens along j, one group per row i), every LayerNorm and the FeedForward are
+    local to a row shard;
+  * row attention (tokens along i, one group per column j) needs whole columns: the normalised
+    operand is transposed between ranks with ONE all-to-all (rank r receives columns
+    [r L/P, (r+1) L/P) of every row), attention + output projection run on the column shard, and a
+    second all-to-all brings the update back to the row shard where it is added to the fp32
+    residual stream. Only operand-dtype tensors (bf16 in the tensor-core mode) cross NVLink:
+    2 x L^2 D / P elements per rank and layer.
+
+`ShardedTwoTrackBlock` is the first stage of the long-protein path: the axial stage (62-75 % of a
+block) is sharded, the MSA track and `PairUpdateWithMsa` are still computed
+redundantly on every rank (their sharding - sequence-sharded MSA with an all-gather of the 32-channel
+OPM operands, a halo exchange for the 3x3 convolutions - is the next step).
+One process per GPU; `torch.distributed` (NCCL over NVLink on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import modules as M
+from . import ops
+
+
+def row_shard(L: int, rank: int, world: int):
+    if L % world:
+        raise ValueError(f"pair row-sharding needs L ({L}) divisible by the number of ranks ({world})")
+    n = L // world
+    return rank * n, (rank + 1) * n
+
+
+def all_to_all_rows_to_cols(x_rows: torch.Tensor, group=None) -> torch.Tensor:
+    """[Li, L, D] (my rows, all columns) -> [L, Lj, D] (all rows, my columns). One all-to-all."""
+    world = dist.get_world_size(group)
+    Li, L, D = x_rows.shape
+    Lj = L // world
+    # chunk p = my rows x the columns of rank p
+    send = x_rows.view(Li, world, Lj, D).permute(1, 0, 2, 3).contiguous()
+    recv = torch.empty_like(send)  # chunk p = rows of rank p x my columns: [P, Li, Lj, D] == [L, Lj, D]
+    dist.all_to_all_single(recv, send, group=group)
+    return recv.view(world * Li, Lj, D)
+
+
+def all_to_all_cols_to_rows(x_cols: torch.Tensor, group=None) -> torch.Tensor:
+    """[L, Lj, D] (all rows, my columns) -> [P, Li, Lj, D]: chunk p holds my rows x the columns of
+    rank p (the caller scatters it into its [Li, L, D] layout). One all-to-all, no packing."""
+    world = dist.get_world_size(group)
+    L, Lj, D = x_cols.shape
+    Li = L // world
+    send = x_cols.contiguous().view(world, Li, Lj, D)  # chunk p = rows of rank p
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    return recv
+
+
+class ShardedPairAxialAttention(nn.Module):
+    """`PairUpdateWithAxialAttention` on a row shard of the pair tensor (B = 1)."""
+
+    def __init__(self, module: M.PairUpdateWithAxialAttention, group=None):
+        super().__init__()
+        self.module = module
+        self.group = group
+
+    @torch.no_grad()
+    def forward(self, x_rows: torch.Tensor) -> torch.Tensor:
+        """x_rows: float32 [1, Li, L, D], rows [rank Li, (rank+1) Li) of the pair tensor."""
+        if x_rows.dim() != 4 or x_rows.shape[0] != 1:
+            raise ValueError("ShardedPairAxialAttention: expects one protein, x_rows [1, L/P, L, D]")
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world == 1:
+            return self.module(x_rows)
+        x = x_rows.float().clone(memory_format=torch.contiguous_format)  # updated in place below
+        _, Li, L, D = x.shape
+        if Li * world != L:
+            raise ValueError(f"row shard of {Li} rows x {world} ranks does not cover L = {L}")
+        adt = M._adt()
+        for layer in self.module.layers:
+            # ---- row attention (tokens along i): transpose the normalised operand between ranks ----
+            x2 = x.view(Li * L, D)
+            xn = M._ln_into(x2, layer.layer[0].fn[0], M._empty(x2.shape, adt, x2))
+            xt = all_to_all_rows_to_cols(xn.view(Li, L, D), self.group)            # [L, Lj, D]
+            upd = layer.row_attn._run(xt.view(1, L, L // world, D), 1, None, out_dtype=adt)  # [L*Lj, D]
+            back = all_to_all_cols_to_rows(upd.view(L, L // world, D), self.group)  # [P, Li, Lj, D]
+            # residual add in the row layout: x[i, p Lj + jj, :] += back[p, i, jj, :]
+            x.view(Li, world, L // world, D).add_(back.permute(1, 0, 2, 3))
+            # ---- column attention and feed-forward are local to the row shard ----
+            x = M._performer_block(layer.layer[1].fn[0], layer.col_attn, x, token_dim=2)
+            x = M._ff_block(layer.layer[2].fn[0], layer.ff, x.view(-1, D)).view(1, Li, L, D)
+        return x
+
+
+class ShardedTwoTrackBlock(nn.Module):
+    """A `TwoTrackBlock` for one long protein on `world` GPUs: replicated MSA track and
+    PairUpdateWithMsa, row-sharded pair axial attention, all-gather of the pair rows."""
+
+    def __init__(self, block: M.TwoTrackBlock, group=None):
+        super().__init__()
+        self.block = block
+        self.axial = ShardedPairAxialAttention(block.pair_update_with_axial_attention, group)
+        self.group = group
+
+    @torch.no_grad()
+    def forward(self, msa: torch.Tensor, pair: torch.Tensor):
+        """msa [1,N,L,d_msa], pair [1,L,L,d_pair] replicated on every rank -> same, replicated."""
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world == 1:
+            return self.block(msa, pair)
+        rank = dist.get_rank(self.group)
+        blk = self.block
+        msa, att = blk.msa_update_using_self_att(msa)
+        pair = blk.pair_update_with_msa(msa, pair, att)
+        lo, hi = row_shard(pair.shape[1], rank, world)
+        rows = self.axial(pair[:, lo:hi].contiguous())
+        full = torch.empty_like(pair)
+        dist.all_gather_into_tensor(full.view(-1), rows.reshape(-1), group=self.group)
+        msa = blk.msa_update_with_pair(msa, full)
+        return msa, full
+
+
+class ShardedTrunkBlocks(nn.Module):
+    def __init__(self, trunk: M.TrunkBlocks, group=None):
+        super().__init__()
+        self.blocks = nn.ModuleList([ShardedTwoTrackBlock(b, group) for b in trunk.blocks])
+
+    @torch.no_grad()
+    def forward(self, msa, pair):
+        for blk in self.blocks:
+            msa, pair = blk(msa, pair)
+        return msa, pair

@@ -1,0 +1,66 @@
+"""Long-protein path on CPU: world_size-2 gloo processes run the pair axial stage row-sharded with
+the all-to-all transpose (oracle-emulated ops) and must reproduce the single-process result."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import rosettafold_pytorch_b200 as rf
+    from oracle.ops_ref import RefBackend
+    from rosettafold_pytorch_b200 import ops
+    from rosettafold_pytorch_b200.sharded import (ShardedPairAxialAttention, ShardedTwoTrackBlock,
+                                                    all_to_all_cols_to_rows, all_to_all_rows_to_cols, row_shard)
+    from tests.helpers import build_block
+
+    ops._set_backend_for_tests(RefBackend())
+    rf.set_mode("fp32")
+    cfg = dict(d_msa=48, d_pair=40, n_layers=2, B=1, N=4, L=12, seed=13)
+    blk, _, msa, pair = build_block(cfg)
+    L = cfg["L"]
+    lo, hi = row_shard(L, rank, world)
+    # 1. the two transposes are inverse permutations of the pair tensor
+    x = pair[0, lo:hi].contiguous()                                   # [Li, L, D]
+    cols = all_to_all_rows_to_cols(x, None)                           # [L, Lj, D]
+    err_t = float((cols - pair[0][:, lo:hi]).abs().max())
+    back = all_to_all_cols_to_rows(cols, None)                        # [P, Li, Lj, D]
+    err_b = float((back.permute(1, 0, 2, 3).reshape(hi - lo, L, -1) - x).abs().max())
+    # 2. sharded axial stage == rows of the unsharded one
+    ax = ShardedPairAxialAttention(blk.pair_update_with_axial_attention)
+    rows = ax(pair[:, lo:hi].contiguous())
+    ref = blk.pair_update_with_axial_attention(pair)
+    err_ax = float((rows - ref[:, lo:hi]).abs().max())
+    # 3. whole block, outputs replicated on every rank
+    m, p = ShardedTwoTrackBlock(blk)(msa, pair)
+    m1, p1 = blk(msa, pair)
+    torch.save(dict(err_t=err_t, err_b=err_b, err_ax=err_ax, err_m=float((m - m1).abs().max()),
+                    err_p=float((p - p1).abs().max())), os.path.join(out_dir, f"res_{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_row_sharded_axial_matches_single_process(tmp_path):
+    port = 31500 + (os.getpid() % 2000)
+    os.environ["PYTHONPATH"] = ROOT + os.pathsep + os.environ.get("PYTHONPATH", "")
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for rank in range(2):
+        res = torch.load(os.path.join(tmp_path, f"res_{rank}.pt"))
+        assert res["err_t"] == 0.0 and res["err_b"] == 0.0, res
+        assert res["err_ax"] < 1e-4 and res["err_m"] < 1e-4 and res["err_p"] < 1e-4, res
+
+
+def test_row_shard_rejects_ragged():
+    from rosettafold_pytorch_b200.sharded import row_shard
+
+    assert row_shard(12, 1, 3) == (4, 8)
+    with pytest.raises(ValueError):
+        row_shard(10, 0, 4)
