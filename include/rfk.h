@@ -115,6 +115,21 @@ int rfk_layernorm(const void* x, int x_dtype, int64_t x_row_stride, const float*
                   const float* beta, float eps, void* y, int y_dtype, int64_t y_row_stride,
                   int64_t rows, int D, rfk_stream_t stream);
 
+/* y[r, :] = LayerNorm(x[r, :]) + res[r, :]  (res f32 with its own row stride): the
+ * `msa + ln_out(out)` of MsaUpdateWithPairAndCoord (:916) in one pass. */
+int rfk_layernorm_residual(const void* x, int x_dtype, int64_t x_row_stride, const float* gamma,
+                           const float* beta, float eps, const float* res, int64_t res_row_stride,
+                           void* y, int y_dtype, int64_t y_row_stride, int64_t rows, int D,
+                           rfk_stream_t stream);
+
+/*
+ * Distance mask of MsaUpdateWithPairAndCoord (:899-913): logits[b,h,i,j] += -1e9 wherever the
+ * C-alpha distance |ca[b,i] - ca[b,j]| is not below bins[h]. ca: f32, residue (b,i) at
+ * ca + (b*L+i)*ca_stride (3 coordinates); logits f32 [B,H,L,ld_logits], updated in place.
+ */
+int rfk_dist_mask_logits(const float* ca, int64_t ca_stride, const float* bins, int H, float* logits,
+                         int64_t ld_logits, int B, int L, rfk_stream_t stream);
+
 /* Row softmax over the last dimension (:255, :569): y[r,:] = softmax(x[r,:]); x fp32. */
 int rfk_softmax_rows(const float* x, int64_t x_row_stride, void* y, int y_dtype,
                      int64_t y_row_stride, int64_t rows, int cols, rfk_stream_t stream);

@@ -26,11 +26,48 @@ CONFIGS = {
 }
 
 
+COORD_CONFIGS = {
+    # MsaUpdateWithPairAndCoord (:865-920) as built by the three-track blocks (:1028-1035), ragged N / L
+    "msa_pair_coord": dict(d_msa=96, d_state=32, d_inner=32, d_ff=192, B=2, N=5, L=20, seed=6),
+}
+
+
+def synth_coords(B, L, d_state, seed):
+    """A random-walk backbone with ~3.8 A C-alpha spacing (so all four distance bins are exercised)
+    and a random state track."""
+    g = torch.Generator().manual_seed(seed)
+    steps = torch.randn((B, L, 3), generator=g)
+    ca = torch.cumsum(3.8 * steps / steps.norm(dim=-1, keepdim=True), dim=1)
+    xyz = torch.stack([ca + 1.46 * torch.randn((B, L, 3), generator=g) / 3 ** 0.5, ca,
+                       ca + 1.52 * torch.randn((B, L, 3), generator=g) / 3 ** 0.5], dim=2)
+    return xyz, torch.randn((B, L, d_state), generator=g)
+
+
+def make_coord(ref, rf):
+    for name, c in COORD_CONFIGS.items():
+        mine = rf.MsaUpdateWithPairAndCoord(c["d_msa"], c["d_state"], c["d_inner"], c["d_ff"])
+        sd = synth_state_dict(mine.state_dict(), seed=c["seed"])
+        rmod = ref.MsaUpdateWithPairAndCoord(c["d_msa"], c["d_state"], c["d_inner"], c["d_ff"])
+        rmod.load_state_dict(sd, strict=True)
+        rmod.eval()
+        msa, _ = synth_inputs(c["B"], c["N"], c["L"], c["d_msa"], 8, seed=c["seed"] + 100)
+        xyz, state = synth_coords(c["B"], c["L"], c["d_state"], c["seed"] + 200)
+        with torch.no_grad():
+            out = rmod(xyz, state, msa)
+        path = os.path.join(ROOT, "tests", "golden", f"{name}.pt")
+        torch.save(dict(config=c, weight_checksum=checksum(sd), xyz=xyz, state=state, msa_out=out,
+                        generator="oracle/make_golden.py on the unmodified reference (CPU fp32, eval)"), path)
+        print(name, tuple(out.shape), os.path.getsize(path))
+
+
 def main():
     import rosettafold_pytorch_b200 as rf
 
     ref = rl.load()
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    make_coord(ref, rf)
+    if "--coord-only" in sys.argv:
+        return
     for name, c in CONFIGS.items():
         mine = rf.TwoTrackBlock(c["d_msa"], c["d_pair"], n_encoder_layers=c["n_layers"])
         sd = synth_state_dict(mine.state_dict(), seed=c["seed"])

@@ -56,14 +56,23 @@ class RefBackend:
         c_view.copy_(acc.to(c_view.dtype))
 
     # nn.LayerNorm (:323 etc.)
-    def layernorm(self, x, gamma, beta, eps, out):
+    def layernorm(self, x, gamma, beta, eps, out, res=None):
         xf = x.to(self.acc)
         mean = xf.mean(-1, keepdim=True)
         var = xf.var(-1, unbiased=False, keepdim=True)
         y = (xf - mean) / torch.sqrt(var + eps)
         if gamma is not None:
             y = y * gamma.to(self.acc) + beta.to(self.acc)
+        if res is not None:
+            y = y + res.to(self.acc)
         out.copy_(y.to(out.dtype))
+
+    # distance mask of MsaUpdateWithPairAndCoord (:899-913)
+    def dist_mask_logits(self, ca, bins, logits):
+        L = logits.shape[2]
+        pdist = torch.cdist(ca.to(self.acc), ca.to(self.acc))
+        for h in range(bins.numel()):
+            logits[:, h, :, :L] += ((pdist < float(bins[h])).to(logits.dtype) - 1.0) * 1e9
 
     # softmax (:255, :569)
     def softmax_rows(self, x, out):

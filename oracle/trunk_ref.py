@@ -179,6 +179,25 @@ def msa_update_with_pair(msa, pair, w: W, n_layers):
     return msa
 
 
+def msa_update_with_pair_and_coord(xyz, state, msa, w: W, distance_bins=(8, 12, 16, 20), ca_idx=1):
+    """:889-920 — distance-masked attention from the state track applied to the normalised MSA."""
+    h = len(distance_bins)
+    b, n, l, d = msa.shape
+    state = layer_norm(state, w, "ln_state")
+    msa = layer_norm(msa, w, "ln_msa")
+    q = linear(state, w, "to_q").reshape(b, l, h, -1).permute(0, 2, 1, 3)
+    k = linear(state, w, "to_k").reshape(b, l, h, -1).permute(0, 2, 1, 3)
+    v = linear(msa, w, "to_v").reshape(b, n, l, h, d // h)
+    scale = (state.shape[-1] // h) ** -0.5
+    pdist = torch.cdist(xyz[:, :, ca_idx], xyz[:, :, ca_idx])
+    mask = torch.stack([(pdist < t).to(msa.dtype) for t in distance_bins], dim=1)
+    logits = torch.einsum("bhid,bhjd->bhij", q * scale, k) + (1.0 - mask) * -1e9
+    att = logits.softmax(dim=-1)
+    out = torch.einsum("bhij,bnjhd->bnihd", att, v).reshape(b, n, l, d)
+    msa = msa + layer_norm(out, w, "ln_out")
+    return msa + feed_forward(layer_norm(msa, w, "to_out.fn.0"), w.sub("to_out.fn.1"))
+
+
 def two_track_block(msa, pair, sd, n_layers, prefix="", stages=None):
     """:962-968. `stages`, if a dict, receives the intermediate tensors."""
     w = W(sd, prefix)

@@ -8,7 +8,7 @@ from . import _lib, ops  # noqa: F401
 __version__ = "0.1.0"
 from . import modules  # noqa: E402,F401
 from .modules import (ColWise, EncoderLayer, FeedForward, MsaUpdateUsingSelfAttention,  # noqa: E402,F401
-                      MsaUpdateWithPair, MsaUpdateWithPairLayer, OuterProductMean,
+                      MsaUpdateWithPair, MsaUpdateWithPairAndCoord, MsaUpdateWithPairLayer, OuterProductMean,
                       PairUpdateWithAxialAttention, PairUpdateWithAxialAttentionLayer,
                       PairUpdateWithMsa, PerformerSelfAttention, PositionWiseWeightFactor, Residual,
                       RowWise, SoftTiedAttentionOverResidues, Symmetrization, TrunkBlocks,

@@ -61,6 +61,8 @@ SYMBOLS = {
     "rfk_launch_count": (C.c_uint64, []),
     "rfk_gemm": (C.c_int, [C.POINTER(RfkGemmDesc), vp]),
     "rfk_layernorm": (C.c_int, [vp, C.c_int, i64, vp, vp, f32, vp, C.c_int, i64, i64, C.c_int, vp]),
+    "rfk_layernorm_residual": (C.c_int, [vp, C.c_int, i64, vp, vp, f32, vp, i64, vp, C.c_int, i64, i64, C.c_int, vp]),
+    "rfk_dist_mask_logits": (C.c_int, [vp, i64, vp, C.c_int, vp, i64, C.c_int, C.c_int, vp]),
     "rfk_softmax_rows": (C.c_int, [vp, i64, vp, C.c_int, i64, i64, C.c_int, vp]),
     "rfk_tied_att_symmetrize": (C.c_int, [vp, C.c_int, i64, vp, vp, i64, C.c_int, C.c_int, C.c_int, vp]),
     "rfk_poswise_weight": (C.c_int, [vp, i64, vp, i64, C.c_int, f32, vp, vp, i64, f32, vp, C.c_int,

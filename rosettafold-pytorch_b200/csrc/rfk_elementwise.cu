@@ -41,7 +41,7 @@ template <typename TI, typename TO, int VPL>
 __global__ void __launch_bounds__(256)
 layernorm_vec_kernel(const TI* __restrict__ x, int64_t xs, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float eps, TO* __restrict__ y, int64_t ys,
-                     int64_t rows, int D) {
+                     int64_t rows, int D, const float* __restrict__ res = nullptr, int64_t rs = 0) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -89,6 +89,10 @@ layernorm_vec_kernel(const TI* __restrict__ x, int64_t xs, const float* __restri
 #pragma unroll
         for (int j = 0; j < 4; ++j) o[j] = (v[i][j] - mean) * rstd;
       }
+      if (res) {  // y = LN(x) + res (f32 addend, rfk_layernorm_residual)
+        const float4 t = __ldg(reinterpret_cast<const float4*>(res + row * rs + c));
+        o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
+      }
       store4<TO>(yr + c, o);
     }
   }
@@ -98,7 +102,8 @@ layernorm_vec_kernel(const TI* __restrict__ x, int64_t xs, const float* __restri
 __global__ void __launch_bounds__(256)
 layernorm_generic_kernel(const void* __restrict__ x, int xdt, int64_t xs,
                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                         void* __restrict__ y, int ydt, int64_t ys, int64_t rows, int D) {
+                         void* __restrict__ y, int ydt, int64_t ys, int64_t rows, int D,
+                         const float* __restrict__ res = nullptr, int64_t rs = 0) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -114,24 +119,26 @@ layernorm_generic_kernel(const void* __restrict__ x, int xdt, int64_t xs,
   for (int c = lane; c < D; c += 32) {
     float o = (load_as_float(x, xdt, row * xs + c) - mean) * rstd;
     if (gamma) o = o * gamma[c] + beta[c];
+    if (res) o += res[row * rs + c];
     store_from_float(y, ydt, row * ys + c, o);
   }
 }
 
 template <typename TI, typename TO>
 static int launch_ln_vec(const void* x, int64_t xs, const float* g, const float* b, float eps,
-                         void* y, int64_t ys, int64_t rows, int D, cudaStream_t st) {
+                         void* y, int64_t ys, int64_t rows, int D, cudaStream_t st,
+                         const float* res = nullptr, int64_t rs = 0) {
   const int vecs = (D / 4 + 31) / 32;
   const unsigned blocks = (unsigned)((rows + 7) / 8);
   const TI* xi = reinterpret_cast<const TI*>(x);
   TO* yo = reinterpret_cast<TO*>(y);
   switch (vecs) {
-    case 1: layernorm_vec_kernel<TI, TO, 1><<<blocks, 256, 0, st>>>(xi, xs, g, b, eps, yo, ys, rows, D); break;
-    case 2: layernorm_vec_kernel<TI, TO, 2><<<blocks, 256, 0, st>>>(xi, xs, g, b, eps, yo, ys, rows, D); break;
-    case 3: layernorm_vec_kernel<TI, TO, 3><<<blocks, 256, 0, st>>>(xi, xs, g, b, eps, yo, ys, rows, D); break;
-    case 4: layernorm_vec_kernel<TI, TO, 4><<<blocks, 256, 0, st>>>(xi, xs, g, b, eps, yo, ys, rows, D); break;
+    case 1: layernorm_vec_kernel<TI, TO, 1><<<blocks, 256, 0, st>>>(xi, xs, g, b, eps, yo, ys, rows, D, res, rs); break;
+    case 2: layernorm_vec_kernel<TI, TO, 2><<<blocks, 256, 0, st>>>(xi, xs, g, b, eps, yo, ys, rows, D, res, rs); break;
+    case 3: layernorm_vec_kernel<TI, TO, 3><<<blocks, 256, 0, st>>>(xi, xs, g, b, eps, yo, ys, rows, D, res, rs); break;
+    case 4: layernorm_vec_kernel<TI, TO, 4><<<blocks, 256, 0, st>>>(xi, xs, g, b, eps, yo, ys, rows, D, res, rs); break;
     case 5: case 6: case 7: case 8:
-      layernorm_vec_kernel<TI, TO, 8><<<blocks, 256, 0, st>>>(xi, xs, g, b, eps, yo, ys, rows, D); break;
+      layernorm_vec_kernel<TI, TO, 8><<<blocks, 256, 0, st>>>(xi, xs, g, b, eps, yo, ys, rows, D, res, rs); break;
     default: return RFK_ERR_UNSUPPORTED;
   }
   return post_launch();
@@ -543,9 +550,9 @@ using namespace rfk;
 
 static inline bool dtype_ok(int d) { return d == RFK_F32 || d == RFK_BF16; }
 
-extern "C" int rfk_layernorm(const void* x, int xdt, int64_t xs, const float* gamma,
-                             const float* beta, float eps, void* y, int ydt, int64_t ys,
-                             int64_t rows, int D, rfk_stream_t stream) {
+static int layernorm_impl(const void* x, int xdt, int64_t xs, const float* gamma, const float* beta,
+                          float eps, const float* res, int64_t rs, void* y, int ydt, int64_t ys,
+                          int64_t rows, int D, rfk_stream_t stream) {
   if (!x || !y) return RFK_ERR_NULL_POINTER;
   if ((gamma == nullptr) != (beta == nullptr)) return RFK_ERR_NULL_POINTER;
   if (rows < 0 || D <= 0) return RFK_ERR_BAD_DIMS;
@@ -557,18 +564,60 @@ extern "C" int rfk_layernorm(const void* x, int xdt, int64_t xs, const float* ga
   const bool vec_ok = D % 4 == 0 && D <= 1024 && (reinterpret_cast<uintptr_t>(x) % xa) == 0 &&
                       (reinterpret_cast<uintptr_t>(y) % ya) == 0 && (xs * xe) % xa == 0 &&
                       (ys * ye) % ya == 0 &&
-                      (!gamma || (aligned16(gamma) && aligned16(beta)));
+                      (!gamma || (aligned16(gamma) && aligned16(beta))) &&
+                      (!res || (aligned16(res) && rs % 4 == 0));
   if (vec_ok) {
     if (xdt == RFK_F32 && ydt == RFK_F32)
-      return launch_ln_vec<float, float>(x, xs, gamma, beta, eps, y, ys, rows, D, st);
+      return launch_ln_vec<float, float>(x, xs, gamma, beta, eps, y, ys, rows, D, st, res, rs);
     if (xdt == RFK_F32 && ydt == RFK_BF16)
-      return launch_ln_vec<float, __nv_bfloat16>(x, xs, gamma, beta, eps, y, ys, rows, D, st);
+      return launch_ln_vec<float, __nv_bfloat16>(x, xs, gamma, beta, eps, y, ys, rows, D, st, res, rs);
     if (xdt == RFK_BF16 && ydt == RFK_BF16)
-      return launch_ln_vec<__nv_bfloat16, __nv_bfloat16>(x, xs, gamma, beta, eps, y, ys, rows, D, st);
-    return launch_ln_vec<__nv_bfloat16, float>(x, xs, gamma, beta, eps, y, ys, rows, D, st);
+      return launch_ln_vec<__nv_bfloat16, __nv_bfloat16>(x, xs, gamma, beta, eps, y, ys, rows, D, st, res, rs);
+    return launch_ln_vec<__nv_bfloat16, float>(x, xs, gamma, beta, eps, y, ys, rows, D, st, res, rs);
   }
   layernorm_generic_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, xdt, xs, gamma, beta, eps,
-                                                                      y, ydt, ys, rows, D);
+                                                                      y, ydt, ys, rows, D, res, rs);
+  return post_launch();
+}
+
+extern "C" int rfk_layernorm(const void* x, int xdt, int64_t xs, const float* gamma,
+                             const float* beta, float eps, void* y, int ydt, int64_t ys,
+                             int64_t rows, int D, rfk_stream_t stream) {
+  return layernorm_impl(x, xdt, xs, gamma, beta, eps, nullptr, 0, y, ydt, ys, rows, D, stream);
+}
+
+extern "C" int rfk_layernorm_residual(const void* x, int xdt, int64_t xs, const float* gamma,
+                                      const float* beta, float eps, const float* res, int64_t rs,
+                                      void* y, int ydt, int64_t ys, int64_t rows, int D,
+                                      rfk_stream_t stream) {
+  if (!res) return RFK_ERR_NULL_POINTER;
+  return layernorm_impl(x, xdt, xs, gamma, beta, eps, res, rs, y, ydt, ys, rows, D, stream);
+}
+
+// logits[b,h,i,j] += -1e9 where |ca_i - ca_j| >= bins[h] (MsaUpdateWithPairAndCoord, :899-913)
+__global__ void __launch_bounds__(256)
+dist_mask_logits_kernel(const float* __restrict__ ca, int64_t ca_stride, const float* __restrict__ bins,
+                        float* __restrict__ logits, int64_t ldl, int B, int H, int L) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)B * L * L) return;
+  const int j = (int)(idx % L);
+  const int i = (int)((idx / L) % L);
+  const int b = (int)(idx / ((int64_t)L * L));
+  const float* pi = ca + ((int64_t)b * L + i) * ca_stride;
+  const float* pj = ca + ((int64_t)b * L + j) * ca_stride;
+  const float dx = pi[0] - pj[0], dy = pi[1] - pj[1], dz = pi[2] - pj[2];
+  const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+  for (int h = 0; h < H; ++h)
+    if (!(d < bins[h])) logits[(((int64_t)b * H + h) * L + i) * ldl + j] += -1e9f;
+}
+
+extern "C" int rfk_dist_mask_logits(const float* ca, int64_t ca_stride, const float* bins, int H,
+                                    float* logits, int64_t ldl, int B, int L, rfk_stream_t stream) {
+  if (!ca || !bins || !logits) return RFK_ERR_NULL_POINTER;
+  if (B <= 0 || L <= 0 || H <= 0 || ldl < L || ca_stride < 3) return RFK_ERR_BAD_DIMS;
+  const int64_t total = (int64_t)B * L * L;
+  dist_mask_logits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      ca, ca_stride, bins, logits, ldl, B, H, L);
   return post_launch();
 }
 

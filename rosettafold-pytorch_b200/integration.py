@@ -36,12 +36,18 @@ def _make(name: str, ref: nn.Module) -> nn.Module:
         return M.MsaUpdateWithPair(
             d_msa=l0.msa2value[1].in_features, d_pair=l0.pair2att[1].normalized_shape[0],
             n_heads=l0.pair2att[2].out_features, n_encoder_layers=len(ref.encoder_layers))
+    if name == "msa_update_with_pair_and_coord":  # three-track / final blocks only (:1028-1035)
+        return M.MsaUpdateWithPairAndCoord(
+            d_msa=ref.ln_msa.normalized_shape[0], d_state=ref.ln_state.normalized_shape[0],
+            d_trfm_inner=ref.to_q.out_features // len(ref.distance_bins),
+            d_ff=ref.to_out.fn[1].net[0].out_features, distance_bins=list(ref.distance_bins))
     raise KeyError(name)
 
 
 def accelerate_block(block: nn.Module, device=None) -> nn.Module:
     """Replace the four trunk children of one reference block."""
-    for name in TRUNK_CHILDREN:
+    names = TRUNK_CHILDREN + (("msa_update_with_pair_and_coord",) if hasattr(block, "msa_update_with_pair_and_coord") else ())
+    for name in names:
         old = getattr(block, name)
         new = M.load_reference_weights(_make(name, old), old).eval()
         setattr(block, name, new.to(device) if device is not None else new)

@@ -762,6 +762,72 @@ class MsaUpdateWithPair(nn.Module):
 
 
 # ---------------------------------------------------------------------------------------------
+# MsaUpdateWithPairAndCoord (:865-920): the MSA update of the three-track blocks (:1044, :1123)
+# ---------------------------------------------------------------------------------------------
+CA_IDX = 1  # reference :15
+
+
+class MsaUpdateWithPairAndCoord(nn.Module):
+    def __init__(self, d_msa, d_state, d_trfm_inner, d_ff, distance_bins=[8, 12, 16, 20], p_dropout=0.1):
+        super().__init__()
+        self.distance_bins = distance_bins
+        self.n_heads = len(self.distance_bins)
+        self.scale = (d_state // self.n_heads) ** -0.5
+        self.d_inner = d_trfm_inner
+        self.ln_msa = nn.LayerNorm(d_msa)
+        self.ln_state = nn.LayerNorm(d_state)
+        self.to_q = nn.Linear(d_state, d_trfm_inner * self.n_heads)
+        self.to_k = nn.Linear(d_state, d_trfm_inner * self.n_heads)
+        self.to_v = nn.Linear(d_msa, d_msa)
+        self.ln_out = nn.LayerNorm(d_msa)
+        self.to_out = Residual(nn.Sequential(nn.LayerNorm(d_msa), FeedForward(d_msa, d_ff, p_dropout)))
+
+    def _pack(self):
+        return _packed(self, lambda: dict(
+            Wqk=_w(torch.cat([self.to_q.weight, self.to_k.weight], 0)),
+            bqk=_f(torch.cat([self.to_q.bias, self.to_k.bias], 0)),
+            Wv=_w(self.to_v.weight), bv=_f(self.to_v.bias),
+            bins=torch.tensor([float(b) for b in self.distance_bins], dtype=torch.float32,
+                              device=self.to_v.weight.device)))
+
+    @torch.no_grad()
+    def forward(self, xyz, state, msa):
+        """xyz: (B, L, 3, 3) backbone atoms, state: (B, L, d_state), msa: (B, N, L, d_msa) -> msa."""
+        msa, state = _as_f32(msa).contiguous(), _as_f32(state).contiguous()
+        xyz = _as_f32(xyz).contiguous()
+        pk = self._pack()
+        B, N, L, D = msa.shape
+        H, di = self.n_heads, self.d_inner
+        dh = D // H
+        T = B * N * L
+        adt = _adt()
+        Lp = _up8(L)
+        # distance-masked attention map from the state track (:892-913)
+        sn = _ln_into(state.view(B * L, -1), self.ln_state, _empty((B * L, state.shape[-1]), adt, msa))
+        qk = _empty((B * L, 2 * H * di), adt, msa)
+        ops.gemm(sn, pk["Wqk"], cview(qk), bias=pk["bqk"])
+        qk5 = qk.view(B, L, 2, H, di)
+        logits = _empty((B, H, L, Lp), torch.float32, msa)
+        ops.gemm(qk5[:, :, 0].permute(0, 2, 1, 3), qk5[:, :, 1].permute(0, 2, 1, 3),
+                 logits[..., :L].as_strided((1, B, H, 1, L, 1, L), (0, H * L * Lp, L * Lp, 0, Lp, 0, 1)),
+                 alpha=self.scale)
+        ops.dist_mask_logits(xyz[:, :, CA_IDX], pk["bins"], logits[..., :L])
+        att = _empty((B, H, L, Lp), adt, msa)
+        ops.softmax_rows(logits.view(B * H * L, Lp)[:, :L], att.view(B * H * L, Lp)[:, :L])
+        # values from the normalised MSA; the residual stream of this module is LN(msa) (:890, :916)
+        mn32 = _ln_into(msa.view(T, D), self.ln_msa, _empty((T, D), torch.float32, msa))
+        mn = mn32 if _MODE == 1 else ops.convert_rows(mn32, _empty((T, D), adt, msa))
+        vt = _empty((B, H, N * dh, Lp), adt, msa)  # b h (n d) j
+        ops.gemm(mn.view(B, N * L, D), pk["Wv"][None],
+                 vt.view(B, H, N, dh, Lp)[..., :L].permute(0, 2, 4, 1, 3)[None, None], bias=pk["bv"])
+        out = _empty((B, N, L, D), torch.float32, msa)
+        ops.gemm(att[..., :L], vt[..., :L], out.view(B, N, L, H, dh).permute(0, 3, 2, 1, 4).unsqueeze(2)[None])
+        y = _empty((T, D), torch.float32, msa)
+        ops.layernorm(out.view(T, D), _f(self.ln_out.weight), _f(self.ln_out.bias), self.ln_out.eps, y, res=mn32)
+        return _ff_block(self.to_out.fn[0], self.to_out.fn[1], y).view(B, N, L, D)
+
+
+# ---------------------------------------------------------------------------------------------
 # TwoTrackBlock (:923-968) and the trunk part of ThreeTrackBlock / FinalBlock (:1037-1041,
 # :1116-1120), which run the same four calls in the same order.
 # ---------------------------------------------------------------------------------------------

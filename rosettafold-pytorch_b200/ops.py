@@ -18,7 +18,7 @@ from ._lib import (ACT_ELU, ACT_NONE, ACT_RELU, EPI_BLOCKLN32, EPI_STD, RFK_BF16
 __all__ = [
     "ACT_NONE", "ACT_RELU", "ACT_ELU", "EPI_STD", "EPI_BLOCKLN32",
     "gemm", "layernorm", "softmax_rows", "tied_att_symmetrize", "poswise_weight", "opm_prep",
-    "pair2att_logits", "channel_stats", "instnorm_apply", "favor_attention", "convert_rows",
+    "pair2att_logits", "channel_stats", "instnorm_apply", "favor_attention", "convert_rows", "dist_mask_logits",
     "conv3x3", "pack_conv3x3_weight",
 ]
 
@@ -100,11 +100,22 @@ class _CudaBackend:
         d.ln_beta = None if ln_beta is None else ln_beta.data_ptr()
         _lib.check(self.lib.rfk_gemm(C.byref(d), self._stream(a)), "rfk_gemm")
 
-    def layernorm(self, x, gamma, beta, eps, out):
+    def layernorm(self, x, gamma, beta, eps, out, res=None):
+        if res is not None:
+            _lib.check(self.lib.rfk_layernorm_residual(
+                _ptr(x), _dt(x), x.stride(0), _f32ptr(gamma, "gamma"), _f32ptr(beta, "beta"), eps,
+                _ptr(res), res.stride(0), _ptr(out), _dt(out), out.stride(0), x.shape[0], x.shape[1],
+                self._stream(x)), "rfk_layernorm_residual")
+            return
         _lib.check(self.lib.rfk_layernorm(_ptr(x), _dt(x), x.stride(0), _f32ptr(gamma, "gamma"),
                                           _f32ptr(beta, "beta"), eps, _ptr(out), _dt(out),
                                           out.stride(0), x.shape[0], x.shape[1], self._stream(x)),
                    "rfk_layernorm")
+
+    def dist_mask_logits(self, ca, bins, logits):
+        B, H, L, ld = logits.shape[0], logits.shape[1], logits.shape[2], logits.stride(2)
+        _lib.check(self.lib.rfk_dist_mask_logits(_ptr(ca), ca.stride(1), _f32ptr(bins, "bins"), H, _ptr(logits),
+                                                 ld, B, L, self._stream(logits)), "rfk_dist_mask_logits")
 
     def softmax_rows(self, x, out):
         _lib.check(self.lib.rfk_softmax_rows(_ptr(x), x.stride(0), _ptr(out), _dt(out), out.stride(0),
@@ -288,14 +299,34 @@ def cview(t: torch.Tensor) -> torch.Tensor:
     return t.as_strided((1, 1, 1, 1, M, 1, N), (0, 0, 0, 0, t.stride(0), 0, t.stride(1)))
 
 
-def layernorm(x, gamma, beta, eps, out):
+def layernorm(x, gamma, beta, eps, out, res=None):
+    """out = LayerNorm(x) (+ res): `res` is an optional float32 addend of the same shape."""
     if x.dim() != 2 or out.dim() != 2 or x.shape != out.shape:
         raise ValueError("layernorm: x and out must be 2-D with equal shapes")
     if x.stride(1) != 1 or out.stride(1) != 1:
         raise ValueError("layernorm: last dim must be contiguous")
-    with _Timed("layernorm", float(x.numel() * x.element_size() + out.numel() * out.element_size())):  # bytes
-        backend().layernorm(x, gamma, beta, float(eps), out)
+    if res is not None and (res.shape != x.shape or res.dtype != torch.float32 or res.stride(1) != 1):
+        raise ValueError("layernorm: res must be float32, shaped like x, last dim contiguous")
+    nbytes = float(x.numel() * x.element_size() + out.numel() * out.element_size() + (0 if res is None else res.numel() * 4))
+    with _Timed("layernorm", nbytes):  # bytes
+        if res is None:
+            backend().layernorm(x, gamma, beta, float(eps), out)
+        else:
+            backend().layernorm(x, gamma, beta, float(eps), out, res)
     return out
+
+
+def dist_mask_logits(ca, bins, logits):
+    """logits[b,h,i,j] += -1e9 where |ca[b,i] - ca[b,j]| >= bins[h] (reference :899-913).
+    ca: float32 [B, L, 3] (any residue stride), bins: float32 [H], logits: float32 [B,H,L,>=L] view."""
+    if ca.dim() != 3 or ca.shape[2] != 3 or ca.dtype != torch.float32 or ca.stride(2) != 1 or ca.stride(0) != ca.shape[1] * ca.stride(1):
+        raise ValueError("dist_mask_logits: ca must be float32 [B, L, 3] with a uniform residue stride")
+    if logits.dim() != 4 or logits.dtype != torch.float32 or logits.stride(3) != 1 or logits.shape[1] != bins.numel():
+        raise ValueError("dist_mask_logits: logits must be float32 [B, H, L, L] rows")
+    if logits.stride(1) != logits.shape[2] * logits.stride(2) or logits.stride(0) != logits.shape[1] * logits.stride(1):
+        raise ValueError("dist_mask_logits: logits must be a row-padded contiguous [B,H,L,ld] buffer")
+    backend().dist_mask_logits(ca, bins, logits)
+    return logits
 
 
 def softmax_rows(x, out):

@@ -47,3 +47,16 @@ def run_stages(blk, msa, pair, teacher=None):
         p2 = teacher["pair_c"].to(msa.device)
     out["msa_d"] = blk.msa_update_with_pair(m, p2)
     return out
+
+
+def build_coord_module(gold, device="cpu"):
+    """The b200 MsaUpdateWithPairAndCoord with the fixture's synthetic weights, and its inputs."""
+    import rosettafold_pytorch_b200 as rf
+
+    c = gold["config"]
+    mod = rf.MsaUpdateWithPairAndCoord(c["d_msa"], c["d_state"], c["d_inner"], c["d_ff"]).eval()
+    sd = synth_state_dict(mod.state_dict(), seed=c["seed"])
+    assert abs(checksum(sd) - gold["weight_checksum"]) < 1e-6 * gold["weight_checksum"]
+    mod.load_state_dict(sd, strict=True)
+    msa, _ = synth_inputs(c["B"], c["N"], c["L"], c["d_msa"], 8, seed=c["seed"] + 100)
+    return mod.to(device), sd, gold["xyz"].to(device), gold["state"].to(device), msa.to(device)

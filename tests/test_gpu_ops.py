@@ -285,6 +285,40 @@ def test_favor_attention(cuda_device, dtype, kind, cfg):
     assert e < (1e-4 if dtype == torch.float32 else 1.5e-2), f"rel-l2 {e}"
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("D", [96, 384, 30])
+def test_layernorm_residual(cuda_device, dtype, D):
+    """y = LayerNorm(x) + res (:916): vector path (D % 4 == 0) and generic path (D = 30)."""
+    dev = cuda_device
+    x = _rand((77, D), torch.float32, dev, 110, 3.0) + 0.5
+    res = _rand((77, D), torch.float32, dev, 111)
+    g, b = _rand((D,), torch.float32, dev, 112) + 1.0, _rand((D,), torch.float32, dev, 113)
+    out = torch.empty((77, D), dtype=dtype, device=dev)
+    ops.layernorm(x, g, b, 1e-5, out, res=res)
+    ref = torch.nn.functional.layer_norm(x.double(), (D,), g.double(), b.double(), 1e-5) + res.double()
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) < tol(dtype)
+
+
+def test_dist_mask_logits(cuda_device):
+    """-1e9 wherever the C-alpha distance is not below the head's threshold (:899-913)."""
+    dev = cuda_device
+    B, H, L, Lp = 2, 4, 37, 40
+    g = torch.Generator().manual_seed(120)
+    xyz = (torch.randn((B, L, 3, 3), generator=g) * 8).to(dev)
+    bins = torch.tensor([8.0, 12.0, 16.0, 20.0], device=dev)
+    logits = _rand((B, H, L, Lp), torch.float32, dev, 121)
+    ref = logits.clone()
+    ops.dist_mask_logits(xyz[:, :, 1], bins, logits[..., :L])
+    pd = torch.cdist(xyz[:, :, 1], xyz[:, :, 1])
+    for h in range(H):
+        ref[:, h, :, :L] += (1.0 - (pd < bins[h]).float()) * -1e9
+    torch.cuda.synchronize()
+    assert torch.equal(logits[..., L:], ref[..., L:])  # padding untouched
+    assert rel_l2(logits[..., :L], ref[..., :L]) < 1e-6
+    assert int((logits[..., :L] < -1e8).sum()) == int((ref[..., :L] < -1e8).sum()) > 0
+
+
 def test_launch_counter_and_errors(cuda_device):
     n0 = rf._lib.launch_count()
     x = torch.randn(8, 32, device=cuda_device)

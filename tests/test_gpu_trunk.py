@@ -101,3 +101,18 @@ def test_cuda_graph_replay_matches_eager(cuda_device):
     assert rel_l2(m, m_ref) < 1e-6 and rel_l2(p, p_ref) < 1e-6
     with pytest.raises(RuntimeError):
         gblk(msa.cpu(), pair.cpu())
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_msa_update_with_pair_and_coord_vs_golden(cuda_device, mode, tol):
+    """MsaUpdateWithPairAndCoord (:865-920) through librfk vs the unmodified reference's output."""
+    from tests.helpers import build_coord_module
+
+    gold = load_golden("msa_pair_coord")
+    mod, _, xyz, state, msa = build_coord_module(gold, cuda_device)
+    rf.set_mode(mode)
+    out = mod(xyz, state, msa)
+    torch.cuda.synchronize()
+    e = rel_l2(out, gold["msa_out"])
+    print(mode, "MsaUpdateWithPairAndCoord rel-l2", e)
+    assert e < tol, e

@@ -130,3 +130,46 @@ def test_accelerate_swaps_trunk_of_reference_block(emulated_ops):
     with torch.no_grad():
         m, p = rblk(msa, pair)  # the reference's own forward (:962-968) on the b200 modules
     assert rel_l2(m, m_ref) < 1e-4 and rel_l2(p, p_ref) < 1e-4
+
+
+def test_msa_update_with_pair_and_coord_fp32_matches_golden(emulated_ops):
+    """Host logic of the three-track MSA update (:865-920) against the reference's golden output."""
+    from tests.helpers import build_coord_module
+
+    gold = load_golden("msa_pair_coord")
+    mod, _, xyz, state, msa = build_coord_module(gold)
+    rf.set_mode("fp32")
+    out = mod(xyz, state, msa)
+    assert out.shape == gold["msa_out"].shape
+    assert rel_l2(out, gold["msa_out"]) < 1e-4
+    assert set(mod.state_dict()) == {f"{m}.{p}" for m in ("ln_msa", "ln_state", "to_q", "to_k", "to_v", "ln_out",
+                                                          "to_out.fn.0", "to_out.fn.1.net.0", "to_out.fn.1.net.3")
+                                     for p in ("weight", "bias")}
+
+
+@pytest.mark.skipif(not __import__("oracle.reference_loader", fromlist=["x"]).available(),
+                    reason="reference source only exists in the build container")
+def test_accelerate_swaps_coord_update_of_three_track_block(emulated_ops):
+    """The MSA update of a reference ThreeTrackBlock (:1028-1035, called at :1044) is swapped too and
+    reproduces the reference module on the same inputs."""
+    import types
+
+    from oracle import reference_loader as rl
+    from oracle.make_golden import synth_coords
+    from oracle.weights import synth_inputs, synth_state_dict
+
+    ref = rl.load()
+    rmod = ref.MsaUpdateWithPairAndCoord(d_msa=48, d_state=16, d_trfm_inner=32, d_ff=96).eval()
+    rmod.load_state_dict(synth_state_dict(rmod.state_dict(), seed=41))
+    mine = rf.TwoTrackBlock(48, 40, n_encoder_layers=1)
+    rblk = rl.fix_eval(ref.TwoTrackBlock(48, 40, n_encoder_layers=1))
+    rblk.msa_update_with_pair_and_coord = rmod  # the attribute a ThreeTrackBlock carries
+    msa, _ = synth_inputs(1, 5, 12, 48, 8, seed=42)
+    xyz, state = synth_coords(1, 12, 16, 43)
+    with torch.no_grad():
+        want = rmod(xyz, state, msa)
+    rf.set_mode("fp32")
+    rf.accelerate_block(rblk)
+    got = rblk.msa_update_with_pair_and_coord
+    assert type(got).__module__.startswith("rosettafold_pytorch_b200")
+    assert rel_l2(got(xyz, state, msa), want) < 1e-4

@@ -60,3 +60,14 @@ def test_performer_restatement_properties():
     blocks = gaussian_orthogonal_random_matrix(128, 64, generator=g)
     unit = blocks / blocks.norm(dim=1, keepdim=True)
     assert torch.allclose(unit[:64] @ unit[:64].T, torch.eye(64), atol=1e-5)
+
+
+def test_coord_restatement_matches_golden():
+    """MsaUpdateWithPairAndCoord (:865-920): restatement vs the unmodified reference's output."""
+    from tests.helpers import build_coord_module
+
+    gold = load_golden("msa_pair_coord")
+    _, sd, xyz, state, msa = build_coord_module(gold)
+    with torch.no_grad():
+        out = trunk_ref.msa_update_with_pair_and_coord(xyz, state, msa, trunk_ref.W(sd))
+    assert rel_l2(out, gold["msa_out"]) < 2e-5
