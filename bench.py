@@ -265,21 +265,29 @@ def run_b200(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "MEASURED_PEAKS.json (sustained bf16)" if peaks else "fallback"
 
-    def tflops(f):
-        return f["work"] / (f["ms"] * 1e-3) / 1e12 if f["ms"] > 0 else 0.0
-
-    tensor_fams = {k: v for k, v in fam.items() if k in ("gemm_bf16", "favor_attention", "gemm_f32", "conv3x3") and v["calls"]}
-    dom = max(tensor_fams, key=lambda k: tensor_fams[k]["ms"]) if tensor_fams else None
+    # Dominant KERNEL = the (op, shape) bucket with the largest device time in the step: launches of one
+    # op with equal algorithmic work are one kernel at one shape (e.g. the 8 pair axial FAVOR calls
+    # of a block). achieved = algorithmic FLOPs per launch / average launch duration (CUDA events).
+    tensor_ops = ("gemm_bf16", "favor_attention", "gemm_f32", "conv3x3")
+    buckets = [(k, w, e) for k, v in fam.items() if k in tensor_ops for w, e in v["shapes"].items() if e["calls"]]
     roofline = None
-    if dom:
-        f = fam[dom]
-        ach = tflops(f)
-        roofline = {"kernel": {"gemm_bf16": "rfk::gemm_tc_kernel (tcgen05)", "favor_attention": "rfk::favor kernel",
-                               "gemm_f32": "rfk::gemm_f32_kernel", "conv3x3": "rfk::gemm_tc_kernel<CONV> (implicit GEMM)"}[dom],
-                    "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
-                    "traffic": None, "peak_source": peak_src,
-                    "launches_per_step": f["calls"] / args.steps, "avg_launch_ms": f["ms"] / max(1, f["calls"]),
-                    "share_of_step": f["ms"] / eager_ms}
+    if buckets:
+        dom, work, e = max(buckets, key=lambda t: t[2]["ms"])
+        avg_ms = e["ms"] / e["calls"]
+        ach = work / (avg_ms * 1e-3) / 1e12
+        kernel = {"gemm_bf16": "rfk::gemm_tc_kernel (tcgen05)", "favor_attention": "rfk::favor_tc_kernel (tcgen05 FAVOR+)",
+                  "gemm_f32": "rfk::gemm_f32_kernel", "conv3x3": "rfk::gemm_tc_kernel<CONV> (implicit GEMM)"}[dom]
+        # DRAM bytes per launch of that kernel from the round's `ncu --set full` capture (profiles/)
+        traffic = None
+        tr_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tr_path):
+            for ent in json.load(open(tr_path)):
+                if ent["op"] == dom and abs(ent["flops_per_launch"] - work) <= 1e-6 * work:
+                    traffic = ent["dram_bytes_per_launch"]
+        roofline = {"kernel": kernel, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
+                    "frac": ach / tf_peak, "traffic": traffic, "peak_source": peak_src,
+                    "flops_per_launch": work, "launches_per_step": e["calls"] / args.steps, "avg_launch_ms": avg_ms,
+                    "share_of_step": e["ms"] / eager_ms}
     families = {k: {"ms_per_step": v["ms"] / args.steps, "calls_per_step": v["calls"] / args.steps,
                     ("GB/s" if k == "layernorm" else "TFLOP/s"): (v["work"] / (v["ms"] * 1e-3) / (1e9 if k == "layernorm" else 1e12)) if v["ms"] > 0 else 0.0}
                 for k, v in fam.items() if v["calls"]}

@@ -208,8 +208,13 @@ def stop_timing():
     torch.cuda.synchronize()
     out = {}
     for name, items in (rec or {}).items():
-        out[name] = dict(ms=sum(a.elapsed_time(b) for a, b, _ in items), calls=len(items),
-                         work=float(sum(w for _, _, w in items)))
+        shapes = {}  # launches of one op with equal algorithmic work = one kernel shape
+        for a, b, w in items:
+            e = shapes.setdefault(float(w), dict(ms=0.0, calls=0))
+            e["ms"] += a.elapsed_time(b)
+            e["calls"] += 1
+        out[name] = dict(ms=sum(e["ms"] for e in shapes.values()), calls=len(items),
+                         work=float(sum(w for _, _, w in items)), shapes=shapes)
     return out
 
 
