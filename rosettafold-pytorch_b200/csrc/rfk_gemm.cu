@@ -247,6 +247,7 @@ extern "C" int rfk_gemm(const rfk_gemm_desc* d, rfk_stream_t stream_) {
 
   int bn = pick_bn(d->N);
   if (d->epi == RFK_EPI_BLOCKLN32) bn = 128;
+
   CUtensorMap ta, tb;
   rc = make_tmap_bf16(&ta, d->a, d->K, d->M, d->lda, d->Z, d->a_zs, kBlockM);
   if (rc != RFK_OK) return rc;

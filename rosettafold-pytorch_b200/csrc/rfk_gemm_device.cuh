@@ -713,7 +713,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           epilogue_warp_chunk<16>(p, stage, lane, z0, z1, z2, m_warp0, nb * BN + (BN / 32) * 32, v, c_row,
                                   r0_row, r1_row, bias);
         }
-      } else if constexpr (EPI >= 3) {
+      } else if constexpr (EPI == 3 || EPI == 4) {
         // ---- TMA-store epilogues: registers -> swizzled smem tile -> cp.async.bulk.tensor store.
         // No per-row address arithmetic, no transposing reads; partial tiles are clipped by TMA.
         static_assert(BN % 32 == 0, "TMA epilogues need 32-column chunks");
@@ -865,7 +865,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
-  if (EPI >= 3 && warp >= 2 && lane == 0) bulk_wait_all();  // smem tiles must outlive their bulk stores
+  if ((EPI == 3 || EPI == 4) && warp >= 2 && lane == 0) bulk_wait_all();  // smem tiles must outlive their bulk stores
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
