@@ -482,7 +482,7 @@ struct GemmCfg {
   static constexpr int kStageBytes = kBlockM * 128 + BN * 128;
   // epilogue staging: EPI 0-2 one [32][33] f32 transpose buffer per warp; EPI 3: two 2 KB bf16
   // tiles per warp; EPI 4: three 4 KB f32 tiles per warp (residual-in / result-out ring)
-  static constexpr int kStagingBytes = EPI == 3 ? kEpiWarps * 2 * 2048
+  static constexpr int kStagingBytes = EPI == 3 ? kEpiWarps * 4 * 2048
                                        : EPI == 4 ? kEpiWarps * 3 * 4096 : kEpiWarps * 32 * 33 * 4;
   static constexpr int kBarBytes = 512;
   static constexpr int kBudget = 232448 - 2048 - kBarBytes - kStagingBytes;
@@ -718,7 +718,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // No per-row address arithmetic, no transposing reads; partial tiles are clipped by TMA.
         static_assert(BN % 32 == 0, "TMA epilogues need 32-column chunks");
         constexpr uint32_t kBuf = EPI == 3 ? 2048u : 4096u;
-        constexpr int kRing = EPI == 3 ? 2 : 3;
+        constexpr int kRing = EPI == 3 ? 4 : 3;
         const int ew = warp - 2;
         const uint32_t ring = stg_base + (uint32_t)ew * kRing * kBuf;
         int lc[7];
@@ -785,8 +785,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
           if (!row_tile_ok) continue;  // ring slots / barrier parities only advance with real stores
           if constexpr (EPI == 3) {
-            // the store issued two chunks ago (same slot) must have finished reading the tile
-            if (lane == 0) bulk_wait_read<1>();
+            // the store issued four chunks ago (same slot) must have finished reading the tile
+            if (lane == 0) bulk_wait_read<3>();
             __syncwarp();
             const uint32_t rowb = buf + myrow * 64u, sw = (myrow >> 1) & 3u;
 #pragma unroll
