@@ -264,7 +264,7 @@ def test_instnorm(cuda_device, dtype, shape):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("kind", [0, 1])
 @pytest.mark.parametrize("cfg", [(1, 3, 40, 2), (2, 2, 128, 3), (1, 2, 200, 2), (1, 40, 512, 8), (2, 32, 128, 12),
-                                 (1, 70, 300, 3)])
+                                 (1, 70, 300, 3), (1, 200, 97, 4), (1, 300, 7, 2)])
 def test_favor_attention(cuda_device, dtype, kind, cfg):
     """FAVOR+ linear attention vs the performer restatement; strided token axis as in RowWise."""
     dev = cuda_device
