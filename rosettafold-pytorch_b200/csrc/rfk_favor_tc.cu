@@ -65,9 +65,7 @@ constexpr uint32_t kOffFeat = kOffCslab + kSlabBytes;
 constexpr uint32_t kOffCtx = kOffFeat + 4 * kSlabBytes;
 constexpr uint32_t kOffBar = kOffCtx + 5 * kCtxSlabBytes;
 constexpr uint32_t kOffScratch = kOffBar + 256;
-// scratch floats: diag partials [4][128] | row maxima [2][3][128] | per-chunk row maxima [3][128] | per-warp maxima
-// [2][16] | chunk stabilisers [4] | V column sums [80] | ctx column sums [80] | their per-warp partials [9][80]
-constexpr uint32_t kScratchFloats = 512 + 768 + 384 + 32 + 4 + 80 + 80 + 720;
+constexpr uint32_t kScratchFloats = 4 * 128 + 4 * 128 + 16;  // diag partials, row maxima, block max
 constexpr uint32_t kSmemBytes = kOffScratch + kScratchFloats * 4 + 1024;
 static_assert(kOffRing % 1024 == 0 && kOffCslab % 1024 == 0 && kOffFeat % 1024 == 0 && kOffCtx % 1024 == 0, "align");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
@@ -181,17 +179,7 @@ __device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
   return d;
 }
 
-// KIND 0: softmax kernel, two passes (stabiliser pass + feature pass), any number of tokens
-// KIND 1: generalized ReLU kernel
-// KIND 2: softmax kernel, SINGLE pass, tokens <= 128 (the MSA column attention): every feature chunk uses
-//         a provisional stabiliser (keys: max of the chunk; queries: per-row max of the chunk), and the
-//         exact arithmetic of the reference is restored afterwards in fp32:
-//           k'[t,m] = a_c e[t,m] + eps          a_c = exp(s_c - max_c s_c)       -> applied to ctx rows at read-out
-//           q'[t,m] = b_tc e[t,m] + eps         b_tc = exp(r_tc - max_c r_tc - diag_t) -> one out|den accumulator per
-//                                                                                   chunk, combined in the epilogue
-//         with the eps terms as rank-1 corrections (eps * sum_t [v_t|1] from a constant feature column,
-//         eps * sum_m ctx[m,:] from the read-out). Halves the jobs per item.
-template <int KIND>
+template <int KIND>  // 0: softmax kernel (exp features, stabilisers), 1: generalized ReLU kernel
 __global__ void __launch_bounds__(kThreads, 1)
 favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const FavorTcParams p) {
@@ -211,20 +199,13 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t bar_ctxfull = bars + 144u, bar_ctxready = bars + 152u;
   const uint32_t tmem_slot = bars + 160u;
   float* scratch = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + kOffScratch);
-  float* part = scratch;             // [4][128] partial |x|^2 of the column ranges
-  float* rmaxs = scratch + 512;      // [2][3][128] partial row maxima (double-buffered by job parity)
-  float* red = scratch + 1664;       // [2][16] per-warp maxima (double-buffered by job parity)
-  float* stab = scratch + 1696;      // [4] key stabiliser of every feature chunk
-  float* vsum_s = scratch + 1700;    // [80] sum_t [v_t | 1]
-  float* csum_s = scratch + 1780;    // [80] sum_m ctx[m, :]
-  float* cpart = scratch + 1860;     // [9][80] per-warp partials of csum
+  float* part = scratch;             // [4][128] partial |x|^2 of the four column quarters
+  float* rmaxs = scratch + 512;      // [4][128] partial row maxima
+  float* red = scratch + 1024;       // [16] per-warp maxima
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = (p.tokens + kTile - 1) / kTile;
   const int64_t istride = gridDim.x;
-  constexpr bool kTwoPass = KIND == 0;   // stabiliser passes exist
-  constexpr bool kSingle = KIND == 2;    // single-pass softmax kernel
-  constexpr bool kSoftmax = KIND != 1;
   // developer timeline: role 0 = U issuer, 1 = consumer issuer, 2 / 3 = first warp of feature group 0 / 1
   auto dbg_bits = [&]() { return kTraceBuild ? p.dbg : 0; };  // experiments exist in developer builds only
   int tr_n = 0;
@@ -304,7 +285,7 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         int64_t item;
         int ph, i;  // phase: 0 = key-max pass (softmax kernel), 1 = K/V pairs, 2 = Q
       };
-      auto cur_init = [&](Cursor& c) { c.item = blockIdx.x; c.ph = kTwoPass ? 0 : 1; c.i = 0; };
+      auto cur_init = [&](Cursor& c) { c.item = blockIdx.x; c.ph = KIND == 0 ? 0 : 1; c.i = 0; };
       auto cur_get = [&](const Cursor& c, const CUtensorMap*& tm, int& t) {
         if (c.ph == 1) { tm = (c.i & 1) ? &tm_v : &tm_k; t = c.i >> 1; }
         else { tm = c.ph == 0 ? &tm_k : &tm_q; t = c.i; }
@@ -313,7 +294,7 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const int n = c.ph == 1 ? 2 * nt : nt;
         if (++c.i < n) return;
         c.i = 0;
-        if (++c.ph == 3) { c.ph = kTwoPass ? 0 : 1; c.item += istride; }
+        if (++c.ph == 3) { c.ph = KIND == 0 ? 0 : 1; c.item += istride; }
       };
       auto coords = [&](int64_t item, int& h, int& g0, int& g1) {
         h = (int)(item % p.heads);
@@ -361,9 +342,9 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // instructions (a lane-0-only branch makes the compiler wrap every UTCHMMA in a divergence
     // waterfall). Both walk the same nest (item, pass = (kind, tile), chunk).
     constexpr int kPassM = 0, kPassK = 1, kPassX = 2, kPassQ = 3;  // key max, keys, query max, queries
-    const int P = kTwoPass ? 4 * nt : 2 * nt;
+    const int P = KIND == 0 ? 4 * nt : 2 * nt;
     auto decode = [&](int ps, int& t) -> int {
-      if (!kTwoPass) {
+      if (KIND == 1) {
         if (ps < nt) { t = ps; return kPassK; }
         t = ps - nt;
         return kPassQ;
@@ -417,7 +398,7 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int ps = 0; ps < P; ++ps) {
           int t;
           const int kind = decode(ps, t);
-          if (!(kTwoPass && kind == kPassQ)) a = alloc();  // a softmax Q pass reuses its QMAX tile
+          if (!(KIND == 0 && kind == kPassQ)) a = alloc();  // a softmax Q pass reuses its QMAX tile
           if (kind == kPassK) (void)alloc();                 // the V tile
           issue_u(a, C0{}, false);
           issue_u(a, C1{}, false);
@@ -445,11 +426,7 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t fs = nC & 1u;
         ++nC;
         const uint32_t nF = fs ? nF1++ : nF0++;
-        if (kSingle) {
-          if (C == 0) wait_d3_region(0);                     // the previous item's epilogue has read all three accumulators
-        } else if (t == 0 && C < 2) {
-          wait_d3_region((uint32_t)C);                       // ctx block c aliases D3[c]
-        }
+        if (t == 0 && C < 2) wait_d3_region((uint32_t)C);  // ctx block c aliases D3[c]
         if (C == 0) mbar_wait(bar_tfull(v.slot), v.par);
         TR(20 + C);
         mbar_wait(bar_fready(fs), nF & 1u);
@@ -478,13 +455,13 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t fs = nC & 1u;
         ++nC;
         const uint32_t nF = fs ? nF1++ : nF0++;
-        const uint32_t ds = kSingle ? 0u : (nD3 & 1u);
+        const uint32_t ds = nD3 & 1u;
         if (C == 0) {
           if (t == 0) {
             mbar_wait(bar_ctxready, nItems & 1u);
             ++nItems;
           }
-          if (!kSingle) wait_d3_region(ds);
+          wait_d3_region(ds);
         }
         TR(30 + C);
         mbar_wait(bar_fready(fs), nF & 1u);
@@ -497,8 +474,8 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             constexpr int NK = C == 2 ? 1 : 8;
 #pragma unroll
             for (int k = 0; k < NK; ++k)
-              umma_bf16(tmem + kColCtx + 80u * (kSingle ? (uint32_t)C : ds), da + (k >> 2) * 1024 + 2 * (k & 3),
-                        db + (k >> 2) * 640 + 2 * (k & 3), umma_idesc_bf16(128, 80), kSingle ? (k > 0) : (C > 0 || k > 0));
+              umma_bf16(tmem + kColCtx + 80u * ds, da + (k >> 2) * 1024 + 2 * (k & 3), db + (k >> 2) * 640 + 2 * (k & 3),
+                        umma_idesc_bf16(128, 80), (C > 0 || k > 0));
           }
           commit_dbg(bar_ffree(fs));
           if (C == 2) commit_dbg(bar_d3full(ds));
@@ -507,7 +484,7 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         TR(34);
         if (C == 2) {
           if (ds) ++d3u1; else ++d3u0;
-          if (!kSingle) ++nD3;
+          ++nD3;
         }
       };
       Tile v{0, 0};
@@ -515,7 +492,7 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int ps = 0; ps < P; ++ps) {
           int t;
           const int kind = decode(ps, t);
-          if (!(kTwoPass && kind == kPassQ)) (void)alloc();
+          if (!(KIND == 0 && kind == kPassQ)) (void)alloc();
           if (kind == kPassK) {
             v = alloc();
             consume_k(v, t, C0{});
@@ -543,7 +520,7 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int row = lg * 32 + lane;    // token row of the tile / TMEM lane
     const uint32_t t_lane = ((uint32_t)(lg * 32) << 16);
     constexpr float kLog2e = 1.4426950408889634f;
-    constexpr float kEps = kSoftmax ? 1e-4f : 1e-3f;
+    constexpr float kEps = KIND == 0 ? 1e-4f : 1e-3f;
     const uint32_t eps2 = pack_bf16x2(kEps, kEps);
     // column ranges [0,48) | [40,88) | [80,128): uniform x32 + x16 loads for every warp; the 8-column
     // overlaps are converted and stored twice with identical values
@@ -660,7 +637,7 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float x0 = __uint_as_float(r[2 * i]), x1 = __uint_as_float(r[2 * i + 1]);
-        if (kSoftmax)
+        if (KIND == 0)
           pk[i] = add_bf16x2(pack_bf16x2(ex2_approx(fmaf(x0, kLog2e, -sub)), ex2_approx(fmaf(x1, kLog2e, -sub))), eps2);
         else
           pk[i] = add_bf16x2(cvt_relu_bf16x2(x0, x1), eps2);
@@ -728,249 +705,9 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     using C1 = std::integral_constant<int, 1>;
     using C2 = std::integral_constant<int, 2>;
 
-    // ================= single-pass softmax kernel (KIND 2, one 128-token tile per item) =================
-    // column sums over the 32 rows of a warp: lane i returns sum_rows v[i] (transpose-reduce butterfly)
-    auto colsum32 = [&](float (&v)[32]) {
-#pragma unroll
-      for (int o = 16, n = 32; o >= 1; o >>= 1, n >>= 1) {
-        const bool up = (lane & o) != 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (i < n / 2) {
-            const float send = up ? v[i] : v[i + n / 2];
-            const float keep = up ? v[i + n / 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-          }
-        }
-      }
-      return v[0];
-    };
-    // store one chunk of packed features and publish it
-    auto publish = [&](auto cc, uint32_t us, uint32_t nF, const uint32_t* pk) {
-      constexpr int C = decltype(cc)::value;
-      constexpr int NC = C < 2 ? 48 : 16;
-      mbar_wait(bar_ffree(us), (nF & 1u) ^ 1u);
-      const uint32_t fb = frow + us * 2u * kSlabBytes;
-      if (C < 2 || third == 0) {
-        const int ch0 = C < 2 ? (col0 >> 3) : 0;
-#pragma unroll
-        for (int q = 0; q < NC / 8; ++q)
-          st_shared_v4(fb + fchunk(ch0 + q), make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]));
-        fence_proxy_async_smem();
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_fready(us));
-    };
-    // keys: e[t,m] = exp(u - diag_t - s_c), s_c = max of the chunk over the valid tokens; column p.m := 1
-    auto key_job_sp = [&](auto cc, auto next, bool zero_row) {
-      constexpr int C = decltype(cc)::value;
-      constexpr int NC = C < 2 ? 48 : 16;
-      const uint32_t us = nJ & 1u;
-      const uint32_t nF = us ? nF1++ : nF0++;
-      release_u();
-      const int m0 = C * 128 + (C < 2 ? col0 : 0);
-      const int lim = p.m - m0;  // columns >= lim are padding (column == lim is the constant feature)
-      float mx = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < NC; ++i)
-        if (i < lim && !zero_row) mx = fmaxf(mx, __uint_as_float(raw[i]));
-      mx = warp_max(mx);
-      float* rbuf = red + us * 16;
-      if (lane == 0) rbuf[fw] = mx;
-      named_bar_sync(1, kFeatWarps * 32);
-      float sc = rbuf[0];
-#pragma unroll
-      for (int i = 1; i < kFeatWarps; ++i) sc = fmaxf(sc, rbuf[i]);
-      if (fw == 0 && lane == 0) stab[C] = sc;
-      const float sb = (diag + sc) * kLog2e;
-      uint32_t pk[NC / 2];
-#pragma unroll
-      for (int i = 0; i < NC / 2; ++i) {
-        float a = ex2_approx(fmaf(__uint_as_float(raw[2 * i]), kLog2e, -sb));
-        float b = ex2_approx(fmaf(__uint_as_float(raw[2 * i + 1]), kLog2e, -sb));
-        if (zero_row || 2 * i > lim) a = 0.f; else if (2 * i == lim) a = 1.f;
-        if (zero_row || 2 * i + 1 > lim) b = 0.f; else if (2 * i + 1 == lim) b = 1.f;
-        pk[i] = pack_bf16x2(a, b);
-      }
-      ++nJ;
-      prefetch(next);
-      publish(cc, us, nF, pk);
-    };
-    float rq[3] = {0.f, 0.f, 0.f};  // per-chunk row maxima of the current query tile
-    // queries: e[t,m] = exp(u - r_tc), r_tc = max of row t over the chunk
-    auto query_job_sp = [&](auto cc, auto next, bool has_next) {
-      constexpr int C = decltype(cc)::value;
-      constexpr int NC = C < 2 ? 48 : 16;
-      const uint32_t us = nJ & 1u;
-      const uint32_t nF = us ? nF1++ : nF0++;
-      release_u();
-      const int m0 = C * 128 + (C < 2 ? col0 : 0);
-      const int lim = p.m - m0;
-      float mx = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < NC; ++i)
-        if (i < lim) mx = fmaxf(mx, __uint_as_float(raw[i]));
-      float* rb = rmaxs + us * 384;
-      rb[third * 128 + row] = mx;
-      named_bar_sync(1, kFeatWarps * 32);
-      const float r = fmaxf(fmaxf(rb[row], rb[128 + row]), rb[256 + row]);
-      rq[C] = r;  // every warp of the lane group holds the same value: no exchange needed later
-      const float sb = r * kLog2e;
-      uint32_t pk[NC / 2];
-#pragma unroll
-      for (int i = 0; i < NC / 2; ++i) {
-        float a = ex2_approx(fmaf(__uint_as_float(raw[2 * i]), kLog2e, -sb));
-        float b = ex2_approx(fmaf(__uint_as_float(raw[2 * i + 1]), kLog2e, -sb));
-        if (2 * i >= lim) a = 0.f;
-        if (2 * i + 1 >= lim) b = 0.f;
-        pk[i] = pack_bf16x2(a, b);
-      }
-      ++nJ;
-      if (has_next) prefetch(next);
-      publish(cc, us, nF, pk);
-    };
-    // context read-out with the stabiliser scales and the eps corrections; also sum_m ctx[m,:]
-    auto readout_sp = [&]() {
-      mbar_wait(bar_ctxfull, nItems & 1u);
-      ++nItems;
-      tc_fence_after();
-      tmem_ld_wait();
-      const int cm = p.m - 256;  // lane of the constant feature inside block 2
-      if (third == 2 && lg == 0) {
-        // sum_t [v_t | 1] = the context row of the constant feature
-        uint32_t r[32];
-#pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-          tmem_ld_32x32(tmem + kColCtx + 160u + 32u * hlf, r);
-          tmem_ld_wait();
-          if (lane == cm) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) vsum_s[32 * hlf + i] = __uint_as_float(r[i]);
-          }
-        }
-        uint32_t r2[16];
-        tmem_ld_32x16(tmem + kColCtx + 160u + 64u, r2);
-        tmem_ld_wait();
-        if (lane == cm) vsum_s[64] = __uint_as_float(r2[0]);
-      }
-      named_bar_sync(1, kFeatWarps * 32);
-      const float gm = fmaxf(fmaxf(stab[0], stab[1]), stab[2]);
-      const bool reader = third < 2 || lg == 0;           // block third, lane group lg (block 2: lanes 0..15 of lg 0)
-      const int unit = third < 2 ? third * 4 + lg : 8;
-      if (reader) {
-        const int m = 128 * third + row;
-        const bool live = m < p.m && (third < 2 || lane < 16);
-        const float alpha = ex2_approx((stab[third] - gm) * kLog2e);
-        const uint32_t mc = (uint32_t)m & 63u;
-        const uint32_t slab = s_ctx + (uint32_t)(m >> 6) * kCtxSlabBytes + (mc & 7u) * 2u;
-        const bool wr = third < 2 || lane < 16;
-#pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem + t_lane + kColCtx + 80u * third + 32u * hlf, r);
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const uint32_t n = 32u * hlf + i;
-            v[i] = live ? fmaf(alpha, __uint_as_float(r[i]), kEps * vsum_s[n]) : 0.f;
-            if (wr) st_shared_b16(slab + (n >> 3) * 1024u + (n & 7u) * 128u + ((((mc >> 3) ^ n) & 7u) << 4), v[i]);
-          }
-          const float cs = colsum32(v);
-          cpart[unit * 80 + 32 * hlf + lane] = cs;
-        }
-        uint32_t r2[16];
-        tmem_ld_32x16(tmem + t_lane + kColCtx + 80u * third + 64u, r2);
-        tmem_ld_wait();
-        const float v64 = live ? fmaf(alpha, __uint_as_float(r2[0]), kEps * vsum_s[64]) : 0.f;
-        if (wr) st_shared_b16(slab + 8u * 1024u + (((mc >> 3) & 7u) << 4), v64);  // n = 64
-        const float cs64 = warp_sum(v64);
-        if (lane == 0) cpart[unit * 80 + 64] = cs64;
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(1, kFeatWarps * 32);
-      {
-        const int tid = fw * 32 + lane;
-        if (tid < 65) {
-          float sm = 0.f;
-#pragma unroll
-          for (int u = 0; u < 9; ++u) sm += cpart[u * 80 + tid];
-          csum_s[tid] = sm;
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_ctxready);
-    };
-    // out = (sum_c b_c D_c[:, ch] + eps S[ch]) / (sum_c b_c D_c[:, 64] + eps S[64])
-    auto epilogue_sp = [&](int64_t item) {
-      mbar_wait(bar_d3full(0), nD3 & 1u);
-      tc_fence_after();
-      ++nD3;
-      const float r0m = rq[0], r1m = rq[1], r2m = rq[2];
-      const float rm = fmaxf(fmaxf(r0m, r1m), r2m) + diag;
-      const float beta[3] = {ex2_approx((r0m - rm) * kLog2e), ex2_approx((r1m - rm) * kLog2e), ex2_approx((r2m - rm) * kLog2e)};
-      const int ch0 = third * 24;
-      float num[24], den = kEps * csum_s[64];
-#pragma unroll
-      for (int i = 0; i < 24; ++i) num[i] = (third < 2 || i < 16) ? kEps * csum_s[ch0 + i] : 0.f;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        uint32_t rd[16], a0[16], a1[16];
-        tmem_ld_32x16(tmem + t_lane + kColCtx + 80u * c + 64, rd);
-        tmem_ld_32x16(tmem + t_lane + kColCtx + 80u * c + ch0, a0);
-        tmem_ld_32x16(tmem + t_lane + kColCtx + 80u * c + ch0 + 8, a1);
-        tmem_ld_wait();
-        den = fmaf(beta[c], __uint_as_float(rd[0]), den);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) num[i] = fmaf(beta[c], __uint_as_float(a0[i]), num[i]);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) num[8 + i] = fmaf(beta[c], __uint_as_float(a1[i]), num[8 + i]);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_d3free(0));
-      if (row < p.tokens && !(dbg_bits() & 32)) {
-        const int h = (int)(item % p.heads);
-        const int64_t g = item / p.heads;
-        const int64_t g0 = g % p.G0, g1 = g / p.G0;
-        const float inv = 1.f / den;
-        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + g1 * p.ogs1 + g0 * p.ogs0 +
-                                             (int64_t)row * p.ots + h * 64 + ch0);
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          if (q < 2 || third < 2) {
-            uint4 w;
-            w.x = pack_bf16x2(num[8 * q] * inv, num[8 * q + 1] * inv);
-            w.y = pack_bf16x2(num[8 * q + 2] * inv, num[8 * q + 3] * inv);
-            w.z = pack_bf16x2(num[8 * q + 4] * inv, num[8 * q + 5] * inv);
-            w.w = pack_bf16x2(num[8 * q + 6] * inv, num[8 * q + 7] * inv);
-            op[q] = w;
-          }
-        }
-      }
-    };
-
     if ((int64_t)blockIdx.x < p.items) prefetch(C0{});
-    if constexpr (kSingle) {
-      for (int64_t item = blockIdx.x; item < p.items; item += istride) {
-        diag = row_diag(tile_seq);            // keys
-        tile_seq += 2;
-        const bool zero_row = row >= p.tokens;
-        key_job_sp(C0{}, C1{}, zero_row);
-        key_job_sp(C1{}, C2{}, zero_row);
-        key_job_sp(C2{}, C0{}, zero_row);
-        readout_sp();
-        diag = row_diag(tile_seq);            // queries
-        ++tile_seq;
-        query_job_sp(C0{}, C1{}, true);
-        query_job_sp(C1{}, C2{}, true);
-        query_job_sp(C2{}, C0{}, item != last_item);
-        epilogue_sp(item);
-      }
-    } else
     for (int64_t item = blockIdx.x; item < p.items; item += istride) {
-      if (kTwoPass) {
+      if (KIND == 0) {
         // ---- key stabiliser: global max of K.Omega'^T over the valid tokens ----
         float kmx = -INFINITY;
         for (int t = 0; t < nt; ++t) {
@@ -990,7 +727,7 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       // ---- keys: k' chunks feed the context MMAs ----
       for (int t = 0; t < nt; ++t) {
-        if (kTwoPass) sub = (row_diag(tile_seq) + gmax) * kLog2e;
+        if (KIND == 0) sub = (row_diag(tile_seq) + gmax) * kLog2e;
         tile_seq += 2;
         const bool zero_row = t * kTile + row >= p.tokens;
         feat_job(C0{}, C1{}, true, zero_row);
@@ -1058,7 +795,7 @@ favor_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       bool pending = false;
       for (int t = 0; t < nt; ++t) {
         const bool more = t + 1 < nt || item != last_item;  // another job follows this tile
-        if (kTwoPass) {
+        if (KIND == 0) {
           diag = row_diag(tile_seq);
           float rmx = -INFINITY;
           max_job(C0{}, C1{}, true, rmx);
@@ -1160,7 +897,7 @@ int favor_tc_launch(const rfk_favor_desc* d, cudaStream_t stream) {
     const size_t bytes = sizeof(long long) * 4 * kTraceMax * 2;
     cudaMalloc(&p.trace, bytes);
     cudaMemsetAsync(p.trace, 0, bytes, stream);
-    rc = d->kind == 0 ? launch_kind<0>(tq, tk, tv, p, stream) : launch_kind<1>(tq, tk, tv, p, stream);  // (trace: two-pass kernels only)
+    rc = d->kind == 0 ? launch_kind<0>(tq, tk, tv, p, stream) : launch_kind<1>(tq, tk, tv, p, stream);
     cudaStreamSynchronize(stream);
     long long* h = (long long*)malloc(bytes);
     cudaMemcpy(h, p.trace, bytes, cudaMemcpyDeviceToHost);
@@ -1174,10 +911,7 @@ int favor_tc_launch(const rfk_favor_desc* d, cudaStream_t stream) {
     cudaFree(p.trace);
     return rc;
   }
-  if (d->kind != 0) return launch_kind<1>(tq, tk, tv, p, stream);
-  static const bool no_sp = getenv("RFK_FAVOR_TWO_PASS") != nullptr;  // A/B aid: force the two-pass softmax kernel
-  const bool single = !no_sp && d->tokens <= kTile && d->m_features >= 256 && d->m_features < kMP;
-  return single ? launch_kind<2>(tq, tk, tv, p, stream) : launch_kind<0>(tq, tk, tv, p, stream);
+  return d->kind == 0 ? launch_kind<0>(tq, tk, tv, p, stream) : launch_kind<1>(tq, tk, tv, p, stream);
 }
 
 }  // namespace rfk
