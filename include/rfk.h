@@ -230,6 +230,10 @@ int rfk_favor_attention(const rfk_favor_desc* d, rfk_stream_t stream);
  */
 int rfk_conv3x3_nhwc(const void* x, const void* w_packed, void* y, int y_dtype, int B, int L, int C,
                      int Cout, rfk_stream_t stream);
+/* Same on H x L images (x: [B][H][L][C]): a row shard of the pair map plus its halo rows
+ * (long-protein path). */
+int rfk_conv3x3_nhwc_hw(const void* x, const void* w_packed, void* y, int y_dtype, int B, int H, int L,
+                        int C, int Cout, rfk_stream_t stream);
 
 /* Cast / copy rows between dtypes with row strides (host-side plumbing for column slices). */
 int rfk_convert_rows(const void* x, int x_dtype, int64_t x_row_stride, void* y, int y_dtype,

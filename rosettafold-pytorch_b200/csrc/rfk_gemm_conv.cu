@@ -29,10 +29,10 @@ int launch_tc_conv(int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb
 
 using namespace rfk;
 
-extern "C" int rfk_conv3x3_nhwc(const void* x, const void* w_packed, void* y, int y_dtype, int B, int L,
-                                int C, int Cout, rfk_stream_t stream_) {
+extern "C" int rfk_conv3x3_nhwc_hw(const void* x, const void* w_packed, void* y, int y_dtype, int B, int H,
+                                   int L, int C, int Cout, rfk_stream_t stream_) {
   if (!x || !w_packed || !y) return RFK_ERR_NULL_POINTER;
-  if (B <= 0 || L <= 0 || C <= 0 || Cout <= 0) return RFK_ERR_BAD_DIMS;
+  if (B <= 0 || H <= 0 || L <= 0 || C <= 0 || Cout <= 0) return RFK_ERR_BAD_DIMS;
   if (C % 8) return RFK_ERR_BAD_DIMS;  // TMA stride rule (16-byte rows)
   if (y_dtype != RFK_BF16 && y_dtype != RFK_F32) return RFK_ERR_BAD_DTYPE;
   if (!aligned16(x) || !aligned16(w_packed) || !aligned16(y)) return RFK_ERR_MISALIGNED;
@@ -46,7 +46,7 @@ extern "C" int rfk_conv3x3_nhwc(const void* x, const void* w_packed, void* y, in
   const bool lean = Cout % 32 == 0 && (y_dtype == RFK_BF16 ? Cout % 8 == 0 : Cout % 4 == 0);
 
   GemmDev p{};
-  p.M = (int64_t)B * L * Lp;  // padded so that every tile lies inside one image row
+  p.M = (int64_t)B * H * Lp;  // padded so that every tile lies inside one image row
   p.N = Cout;
   p.K = (int64_t)9 * cpad;
   p.Z0 = p.Z1 = p.Z2 = 1;
@@ -56,14 +56,14 @@ extern "C" int rfk_conv3x3_nhwc(const void* x, const void* w_packed, void* y, in
   p.c_addr.ms[0] = Cout;                 // j
   p.c_addr.ms[1] = (int64_t)L * Cout;    // (b, i)
   p.c_addr.ns[0] = 1; p.c_addr.ns[1] = 0;
-  p.conv_L = L; p.conv_Lp = Lp; p.conv_cblocks = cblocks; p.conv_cpad = cpad;
+  p.conv_L = L; p.conv_H = H; p.conv_Lp = Lp; p.conv_cblocks = cblocks; p.conv_cpad = cpad;
   p.conv_last_k16 = (C - (cblocks - 1) * 64 + 15) / 16;
 
   CUtensorMap ta, tb;
   {
-    const uint64_t dims[5] = {(uint64_t)C, (uint64_t)L, (uint64_t)L, (uint64_t)B, 1};
-    const uint64_t strides[4] = {(uint64_t)C * 2, (uint64_t)L * C * 2, (uint64_t)L * L * C * 2,
-                                 (uint64_t)B * L * L * C * 2};
+    const uint64_t dims[5] = {(uint64_t)C, (uint64_t)L, (uint64_t)H, (uint64_t)B, 1};
+    const uint64_t strides[4] = {(uint64_t)C * 2, (uint64_t)L * C * 2, (uint64_t)H * L * C * 2,
+                                 (uint64_t)B * H * L * C * 2};
     const uint32_t box[5] = {64, (uint32_t)kBlockM, 1, 1, 1};
     if ((rc = make_tmap_bf16_raw(&ta, x, 5, dims, strides, box)) != RFK_OK) return rc;
   }
@@ -77,4 +77,9 @@ extern "C" int rfk_conv3x3_nhwc(const void* x, const void* w_packed, void* y, in
   const int64_t tiles = (p.M / kBlockM) * ((Cout + bn - 1) / bn);
   return launch_tc_conv(bn, !lean ? 0 : (y_dtype == RFK_BF16 ? 1 : 2), ta, tb, p, tiles,
                         reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int rfk_conv3x3_nhwc(const void* x, const void* w_packed, void* y, int y_dtype, int B, int L,
+                                int C, int Cout, rfk_stream_t stream_) {
+  return rfk_conv3x3_nhwc_hw(x, w_packed, y, y_dtype, B, L, L, C, Cout, stream_);
 }

@@ -25,7 +25,7 @@ struct GemmDev {
   int bmask[3];  // 0 -> broadcast B over that z level
   // implicit-GEMM 3x3 convolution mode (CONV kernels): A is the NHWC image [B][L][L][C]; a tile is
   // 128 consecutive columns j of one image row; K runs over 9 taps x conv_cblocks 64-channel blocks
-  int conv_L, conv_Lp, conv_cblocks, conv_last_k16, conv_cpad;
+  int conv_L, conv_H, conv_Lp, conv_cblocks, conv_last_k16, conv_cpad;  // conv_L = image width, conv_H = rows
   // TMA-store epilogues (EPI 3/4): tensor-map dimension d takes logical coordinate cmap[d] of
   // {0: n % NR, 1: n / NR, 2: m % MR, 3: m / MR, 4: z0, 5: z1, 6: z2}; -1 -> 0
   int cmap[5];
@@ -580,7 +580,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // columns are zero-filled by the TMA unit ('same' padding for free)
         const int64_t m0 = mb * kBlockM;
         const int img_row = (int)(m0 / p.conv_Lp), j0 = (int)(m0 % p.conv_Lp);
-        const int bi = img_row / p.conv_L, ii = img_row % p.conv_L;
+        const int bi = img_row / p.conv_H, ii = img_row % p.conv_H;
         for (int tap = 0; tap < 9; ++tap) {
           const int di = tap / 3 - 1, dj = tap % 3 - 1;
           for (int cb = 0; cb < p.conv_cblocks; ++cb) {

@@ -480,13 +480,15 @@ class OuterProductMean(nn.Module):
         return _packed(self, build)
 
     def _run(self, xt, yt, B, L):
-        """xt, yt: [B, L*P, N] K-major operands. Returns Linear(LN(outer-product sum)) f32 [B*L*L, out]."""
+        """xt: [B, Li*P, N], yt: [B, L*P, N] K-major operands (Li = L, or the rows of a row shard).
+        Returns Linear(LN(outer-product sum)) f32 [B*Li*L, out]."""
         pk = self._pack()
         P = self.in_features
         adt = _adt()
         ln = self.to_out[0]
-        o = _empty((B, L, L, P * P), adt, xt)
-        ov = o.view(B, L, L, P, P).permute(0, 1, 3, 2, 4)[None, None]  # [1,1,b,i,u,j,v]
+        Li = xt.shape[1] // P
+        o = _empty((B, Li, L, P * P), adt, xt)
+        ov = o.view(B, Li, L, P, P).permute(0, 1, 3, 2, 4)[None, None]  # [1,1,b,i,u,j,v]
         fused = _MODE == 0 and P == 32
         if fused:
             ops.gemm(xt, yt, ov, epi=EPI_BLOCKLN32, ln_eps=ln.eps)
@@ -494,7 +496,7 @@ class OuterProductMean(nn.Module):
             ops.gemm(xt, yt, ov)
             o2 = o.view(-1, P * P)
             ops.layernorm(o2, pk["g"], pk["b"], ln.eps, o2)
-        out = _empty((B * L * L, pk["W"].shape[0]), torch.float32, xt)
+        out = _empty((B * Li * L, pk["W"].shape[0]), torch.float32, xt)
         ops.gemm(o.view(-1, P * P), pk["Wfold" if fused else "W"], cview(out),
                  bias=pk["bfold" if fused else "bias"])
         return out
@@ -558,23 +560,39 @@ class PairUpdateWithMsa(nn.Module):
                 g1=_f(fn[2].weight), b1=_f(fn[2].bias), g2=_f(fn[6].weight), b2=_f(fn[6].bias))
         return _packed(self, build)
 
-    def _conv(self, x_bllc, w):
-        """3x3 'same' convolution on a channels-last [B,L,L,C] map: rfk_conv3x3_nhwc (tcgen05
+    def _conv(self, x_bhwc, w):
+        """3x3 'same' convolution on a channels-last [B,H,W,C] map: rfk_conv3x3_nhwc (tcgen05
         implicit GEMM) in bf16 mode; the fp32 validation mode uses the library convolution."""
         if _MODE == 0:
-            B, L, _, _ = x_bllc.shape
-            return ops.conv3x3(x_bllc, w, _empty((B, L, L, w.shape[0]), torch.bfloat16, x_bllc))
+            B, H, Wd, _ = x_bhwc.shape
+            return ops.conv3x3(x_bhwc, w, _empty((B, H, Wd, w.shape[0]), torch.bfloat16, x_bhwc))
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            y = F.conv2d(x_bllc.permute(0, 3, 1, 2), w, padding=1)
+            y = F.conv2d(x_bhwc.permute(0, 3, 1, 2), w, padding=1)
         return y.permute(0, 2, 3, 1).contiguous()
+
+    def _conv_rows(self, x_rows, w, halo):
+        """Convolution of a row shard [B, Li, L, C]: `halo(x)` returns the shard with one neighbour row
+        above and below ([B, Li+2, L, C], zeros at the image border); rows 1..Li of the result are exact."""
+        if halo is None:
+            return self._conv(x_rows, w)
+        y = self._conv(halo(x_rows), w)
+        return y[:, 1:-1].contiguous()
 
     @torch.no_grad()
     def forward(self, msa, pair, att):
-        msa, pair, att = _as_f32(msa).contiguous(), _as_f32(pair).contiguous(), _as_f32(att).contiguous()
+        return self._forward_rows(msa, pair, att, 0, pair.shape[1], None, None)
+
+    def _forward_rows(self, msa, pair_rows, att_rows, lo, hi, halo, allreduce):
+        """Rows [lo, hi) of the updated pair map. msa: the full MSA; pair_rows / att_rows: rows [lo, hi)
+        of pair and of the tied attention map. `halo` / `allreduce` (long-protein path, sharded.py):
+        neighbour-row exchange for the 3x3 convolutions and the sum of the InstanceNorm statistics over
+        the row shards; None for the whole map."""
+        msa, pair, att = _as_f32(msa).contiguous(), _as_f32(pair_rows).contiguous(), _as_f32(att_rows).contiguous()
         pk = self._pack()
         B, N, L, D = msa.shape
+        Li = hi - lo
         P, Q, H = self.d_pair, self.d_proj, self.n_heads
-        T, TP = B * N * L, B * L * L
+        T, TP = B * N * L, B * Li * L
         adt = _adt()
         # proj_msa: LN -> Linear -> LN (:434-438); m kept in float32 (tiny), operand copy for GEMMs
         xn = _ln_into(msa.view(T, D), self.proj_msa[0], _empty((T, D), adt, msa))
@@ -589,7 +607,7 @@ class PairUpdateWithMsa(nn.Module):
         yt = _empty((B, L * Q, Np), adt, msa)
         msa1d = _empty((B, L, 2 * Q), torch.float32, msa)
         ops.opm_prep(m32.view(B, N, L, Q), w.view(B, N, L), xt[..., :N], yt[..., :N], msa1d)
-        coevol = self.outer_product_mean._run(xt[..., :N], yt[..., :N], B, L)  # f32 [TP, P]
+        coevol = self.outer_product_mean._run(xt[:, lo * Q:hi * Q, :N], yt[..., :N], B, L)  # f32 [TP, P]
         # feature buffer [coevol_ln | ln_pair | att] — the 716-wide concat is never built (:487-496)
         KF = 2 * P + H
         feat = _empty((TP, _up8(KF)), adt, msa)
@@ -601,24 +619,30 @@ class PairUpdateWithMsa(nn.Module):
         colt = _empty((B, L, P), torch.float32, msa)
         ops.gemm(msa1d.view(B * L, 2 * Q), pk["Wr"], cview(rowt.view(B * L, P)))
         ops.gemm(msa1d.view(B * L, 2 * Q), pk["Wc"], cview(colt.view(B * L, P)))
-        h = _empty((B, L, L, P), torch.float32, msa)
-        ops.gemm(feat.view(B, L * L, -1)[..., :KF], pk["Wf"][None], h.view(1, 1, B, L, L, 1, P),
+        h = _empty((B, Li, L, P), torch.float32, msa)
+        ops.gemm(feat.view(B, Li * L, -1)[..., :KF], pk["Wf"][None], h.view(1, 1, B, Li, L, 1, P),
                  bias=pk["bf"],
-                 r0=rowt.view(1, 1, B, L, 1, 1, P).expand(1, 1, B, L, L, 1, P),
-                 r1=colt.view(1, 1, B, 1, L, 1, P).expand(1, 1, B, L, L, 1, P))
+                 r0=rowt[:, lo:hi].reshape(1, 1, B, Li, 1, 1, P).expand(1, 1, B, Li, L, 1, P),
+                 r1=colt.view(1, 1, B, 1, L, 1, P).expand(1, 1, B, Li, L, 1, P))
         # Residual(conv -> IN -> ELU -> conv -> IN) then ELU (:449-462)
         fn = self.resnet[1].fn
-        h_op = h if _MODE == 1 else ops.convert_rows(h.view(TP, P), _empty((TP, P), adt, msa)).view(B, L, L, P)
-        c1 = self._conv(h_op, pk["conv1"]).view(B, L * L, P)
-        st = torch.zeros((B, 2, P), dtype=torch.float64, device=msa.device)
-        ops.channel_stats(c1, st)
-        a1 = ops.instnorm_apply(c1, st, pk["g1"], pk["b1"], fn[2].eps, _empty(c1.shape, adt, msa), elu=True)
-        c2 = self._conv(a1.view(B, L, L, P), pk["conv2"]).view(B, L * L, P)
-        st2 = torch.zeros((B, 2, P), dtype=torch.float64, device=msa.device)
-        ops.channel_stats(c2, st2)
-        out = ops.instnorm_apply(c2, st2, pk["g2"], pk["b2"], fn[6].eps,
-                                 _empty(c2.shape, torch.float32, msa), res=h.view(B, L * L, P), elu=True)
-        return out.view(B, L, L, P)
+        scale = Li / L  # statistics are sums over the whole map: rescale so the kernels' 1/positions applies
+
+        def stats_of(c):
+            st = torch.zeros((B, 2, P), dtype=torch.float64, device=msa.device)
+            ops.channel_stats(c, st)
+            if allreduce is not None:
+                allreduce(st)
+                st.mul_(scale)
+            return st
+
+        h_op = h if _MODE == 1 else ops.convert_rows(h.view(TP, P), _empty((TP, P), adt, msa)).view(B, Li, L, P)
+        c1 = self._conv_rows(h_op, pk["conv1"], halo).view(B, Li * L, P)
+        a1 = ops.instnorm_apply(c1, stats_of(c1), pk["g1"], pk["b1"], fn[2].eps, _empty(c1.shape, adt, msa), elu=True)
+        c2 = self._conv_rows(a1.view(B, Li, L, P), pk["conv2"], halo).view(B, Li * L, P)
+        out = ops.instnorm_apply(c2, stats_of(c2), pk["g2"], pk["b2"], fn[6].eps,
+                                 _empty(c2.shape, torch.float32, msa), res=h.view(B, Li * L, P), elu=True)
+        return out.view(B, Li, L, P)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -178,9 +178,9 @@ class _CudaBackend:
         _lib.check(self.lib.rfk_favor_attention(C.byref(d), self._stream(q)), "rfk_favor_attention")
 
     def conv3x3(self, x, w_packed, out):
-        B, L, _, Cin = x.shape
-        _lib.check(self.lib.rfk_conv3x3_nhwc(_ptr(x), _ptr(w_packed), _ptr(out), _dt(out), B, L, Cin,
-                                             out.shape[3], self._stream(x)), "rfk_conv3x3_nhwc")
+        B, H, L, Cin = x.shape
+        _lib.check(self.lib.rfk_conv3x3_nhwc_hw(_ptr(x), _ptr(w_packed), _ptr(out), _dt(out), B, H, L, Cin,
+                                                out.shape[3], self._stream(x)), "rfk_conv3x3_nhwc_hw")
 
     def convert_rows(self, x, out):
         _lib.check(self.lib.rfk_convert_rows(_ptr(x), _dt(x), x.stride(0), _ptr(out), _dt(out),
@@ -455,10 +455,10 @@ def pack_conv3x3_weight(w: torch.Tensor) -> torch.Tensor:
 
 
 def conv3x3(x, w_packed, out):
-    """3x3 'same' convolution without bias on a channels-last map: x bf16 [B,L,L,Cin] contiguous,
-    w_packed from pack_conv3x3_weight, out bf16/f32 [B,L,L,Cout] contiguous."""
-    if x.dim() != 4 or x.shape[1] != x.shape[2] or not x.is_contiguous() or x.dtype != torch.bfloat16:
-        raise ValueError("conv3x3: x must be contiguous bf16 [B,L,L,C]")
+    """3x3 'same' convolution without bias on a channels-last map: x bf16 [B,H,W,Cin] contiguous,
+    w_packed from pack_conv3x3_weight, out bf16/f32 [B,H,W,Cout] contiguous."""
+    if x.dim() != 4 or not x.is_contiguous() or x.dtype != torch.bfloat16:
+        raise ValueError("conv3x3: x must be contiguous bf16 [B,H,W,C]")
     Cout, taps, cpad = w_packed.shape
     if taps != 9 or cpad != (x.shape[3] + 63) // 64 * 64 or w_packed.dtype != torch.bfloat16 or not w_packed.is_contiguous():
         raise ValueError("conv3x3: w_packed must come from pack_conv3x3_weight for this channel count")

@@ -13,10 +13,24 @@ The pair tensor `pair[1, L, L, D]` is sharded on its first residue axis i: rank 
     residual stream. Only operand-dtype tensors (bf16 in the tensor-core mode) cross NVLink:
     2 x L^2 D / P elements per rank and layer.
 
-`ShardedTwoTrackBlock` is the first stage of the long-protein path: the axial stage (62-75 % of a
-block) is sharded, the MSA track and `PairUpdateWithMsa` are still computed
-redundantly on every rank (their sharding - sequence-sharded MSA with an all-gather of the 32-channel
-OPM operands, a halo exchange for the 3x3 convolutions - is the next step).
+`ShardedTwoTrackBlock` shards three of the four stages of a block:
+
+  * pair axial attention: row-sharded as above;
+  * the Performer column layers of `MsaUpdateUsingSelfAttention` (tokens along n, one group per residue
+    l, every other op per token): each rank takes a slice of residues, no communication but the
+    all-gather of the MSA slices at the end;
+  * `MsaUpdateWithPair`: `u[n,h,i,:] = sum_j A[h,i,j] V[n,h,j,:]` and the FeedForward are independent
+    per MSA row n: each rank takes a slice of sequences (the pair-derived attention maps are recomputed
+    on every rank from the all-gathered pair), all-gather of the MSA slices at the end.
+
+  * `PairUpdateWithMsa`: the per-token MSA projections (32 channels) are cheap and stay replicated; the
+    outer-product sum, the 716-wide Linear and the convolution block run on the rank's pair rows. Each
+    3x3 convolution needs one neighbour row on either side (an all-gather of every rank's first and
+    last row: 2 L d_pair elements per rank) and the InstanceNorm statistics are all-reduced
+    (2 x d_pair doubles).
+
+Still replicated: the tied row layers (their logits contract over all sequences: needs an all-reduce
+of the 12 x L x L logits and a distributed softmax over n) - DESIGN.md section 7.
 One process per GPU; `torch.distributed` (NCCL over NVLink on GPUs, gloo in the CPU tests).
 """
 from __future__ import annotations
@@ -27,6 +41,10 @@ import torch.nn as nn
 
 from . import modules as M
 from . import ops
+
+
+def _as_like(t):
+    return t if t.dtype == torch.float32 else t.float()
 
 
 def row_shard(L: int, rank: int, world: int):
@@ -106,21 +124,70 @@ class ShardedTwoTrackBlock(nn.Module):
         self.axial = ShardedPairAxialAttention(block.pair_update_with_axial_attention, group)
         self.group = group
 
+    def _msa_self_attention(self, msa, rank, world):
+        """MsaUpdateUsingSelfAttention (:399-409): tied row layers replicated, Performer column layers
+        on a slice of residues."""
+        mod = self.block.msa_update_using_self_att
+        x = M._as_f32(msa).contiguous()
+        att = None
+        n = len(mod.residue_wise_encoder_layers)
+        for i, layer in enumerate(mod.residue_wise_encoder_layers):
+            x, a = layer._run(x, want_att=(i == n - 1))
+            att = a if a is not None else att
+        B, N, L, D = x.shape
+        lo, hi = row_shard(L, rank, world)
+        xs = x[:, :, lo:hi].contiguous()                      # [1, N, L/P, D]
+        for layer in mod.sequence_wise_encoder_layers:
+            xs, _ = layer._run(xs, token_dim=1)
+        gathered = torch.empty((world,) + tuple(xs.shape), dtype=xs.dtype, device=xs.device)
+        dist.all_gather_into_tensor(gathered.view(-1), xs.reshape(-1), group=self.group)
+        # [P, 1, N, L/P, D] -> [1, N, L, D]
+        return gathered.permute(1, 2, 0, 3, 4).reshape(B, N, L, D), att
+
+    def _pair_update_with_msa(self, msa, pair, att, rank, world):
+        """PairUpdateWithMsa (:465-498) for this rank's rows of the pair map."""
+        lo, hi = row_shard(pair.shape[1], rank, world)
+        group = self.group
+
+        def halo(x):  # [1, Li, L, C] -> [1, Li + 2, L, C]
+            edges = torch.stack([x[:, 0], x[:, -1]], 0).contiguous()            # my first / last row
+            allv = torch.empty((world,) + tuple(edges.shape), dtype=x.dtype, device=x.device)
+            dist.all_gather_into_tensor(allv.view(-1), edges.view(-1), group=group)
+            zero = torch.zeros_like(x[:, :1])
+            top = allv[rank - 1, 1].unsqueeze(1) if rank > 0 else zero          # last row of the rank above
+            bottom = allv[rank + 1, 0].unsqueeze(1) if rank + 1 < world else zero
+            return torch.cat([top, x, bottom], 1)
+
+        def allreduce(st):
+            dist.all_reduce(st, group=group)
+
+        return self.block.pair_update_with_msa._forward_rows(
+            msa, pair[:, lo:hi], att[:, lo:hi], lo, hi, halo, allreduce)
+
+    def _msa_update_with_pair(self, msa, pair, rank, world):
+        """MsaUpdateWithPair (:607-610) on a slice of MSA rows (every op is independent per sequence)."""
+        N = msa.shape[1]
+        lo, hi = row_shard(N, rank, world)
+        part = self.block.msa_update_with_pair(msa[:, lo:hi].contiguous(), pair)
+        full = torch.empty_like(msa)
+        dist.all_gather_into_tensor(full.view(-1), part.reshape(-1), group=self.group)
+        return full
+
     @torch.no_grad()
     def forward(self, msa: torch.Tensor, pair: torch.Tensor):
         """msa [1,N,L,d_msa], pair [1,L,L,d_pair] replicated on every rank -> same, replicated."""
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         if world == 1:
             return self.block(msa, pair)
+        if msa.shape[0] != 1:
+            raise ValueError("ShardedTwoTrackBlock: one protein per call (batches run as replicas)")
         rank = dist.get_rank(self.group)
-        blk = self.block
-        msa, att = blk.msa_update_using_self_att(msa)
-        pair = blk.pair_update_with_msa(msa, pair, att)
-        lo, hi = row_shard(pair.shape[1], rank, world)
-        rows = self.axial(pair[:, lo:hi].contiguous())
-        full = torch.empty_like(pair)
+        msa, att = self._msa_self_attention(msa, rank, world)
+        rows = self._pair_update_with_msa(msa, pair, att, rank, world)
+        rows = self.axial(rows)
+        full = torch.empty_like(_as_like(pair))
         dist.all_gather_into_tensor(full.view(-1), rows.reshape(-1), group=self.group)
-        msa = blk.msa_update_with_pair(msa, full)
+        msa = self._msa_update_with_pair(msa, full, rank, world)
         return msa, full
 
 

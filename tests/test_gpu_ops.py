@@ -319,6 +319,24 @@ def test_dist_mask_logits(cuda_device):
     assert int((logits[..., :L] < -1e8).sum()) == int((ref[..., :L] < -1e8).sum()) > 0
 
 
+def test_conv3x3_rectangular_row_shard(cuda_device):
+    """H x W images (a row shard of the pair map plus halo rows): rows 1..H-2 of the convolution of the
+    haloed shard equal the same rows of the convolution of the whole map."""
+    dev = cuda_device
+    B, L, Cin, Cout = 1, 40, 72, 96
+    x = _rand((B, L, L, Cin), torch.bfloat16, dev, 95)
+    w = _rand((Cout, Cin, 3, 3), torch.float32, dev, 96, (9 * Cin) ** -0.5)
+    wp = ops.pack_conv3x3_weight(w)
+    full = torch.empty((B, L, L, Cout), dtype=torch.float32, device=dev)
+    ops.conv3x3(x, wp, full)
+    lo, hi = 10, 23
+    shard = x[:, lo - 1:hi + 1].contiguous()          # 13 rows + one halo row on either side
+    part = torch.empty((B, hi - lo + 2, L, Cout), dtype=torch.float32, device=dev)
+    ops.conv3x3(shard, wp, part)
+    torch.cuda.synchronize()
+    assert rel_l2(part[:, 1:-1], full[:, lo:hi]) < 1e-6
+
+
 def test_launch_counter_and_errors(cuda_device):
     n0 = rf._lib.launch_count()
     x = torch.randn(8, 32, device=cuda_device)

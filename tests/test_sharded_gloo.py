@@ -24,7 +24,7 @@ def _worker(rank, world, port, out_dir):
 
     ops._set_backend_for_tests(RefBackend())
     rf.set_mode("fp32")
-    cfg = dict(d_msa=48, d_pair=40, n_layers=2, B=1, N=4, L=12, seed=13)
+    cfg = dict(d_msa=48, d_pair=40, n_layers=2, B=1, N=6, L=12, seed=13)
     blk, _, msa, pair = build_block(cfg)
     L = cfg["L"]
     lo, hi = row_shard(L, rank, world)
