@@ -173,3 +173,35 @@ def test_accelerate_swaps_coord_update_of_three_track_block(emulated_ops):
     got = rblk.msa_update_with_pair_and_coord
     assert type(got).__module__.startswith("rosettafold_pytorch_b200")
     assert rel_l2(got(xyz, state, msa), want) < 1e-4
+
+
+@pytest.mark.skipif(not __import__("oracle.reference_loader", fromlist=["x"]).available(),
+                    reason="reference source only exists in the build container")
+def test_accelerate_whole_reference_model(emulated_ops):
+    """Drop-in at the top: the unmodified reference `RoseTTAFold` (:1160-1271; two-track blocks, three-track
+    blocks with their SE(3) structure track on the oracle's dgl / lie_learn shims, output heads) gives the same
+    logits, coordinates and pLDDT before and after `rf.accelerate(model)` swaps the trunk under it."""
+    from oracle import reference_loader as rl
+
+    ref = rl.load()
+    torch.manual_seed(0)
+    model = rl.fix_eval(ref.RoseTTAFold(d_input=21, d_msa=48, d_pair=40, d_node=16, d_edge=16, d_state=16,
+                                        n_two_track_blocks=1, n_three_track_blocks=2, n_encoder_layers=1,
+                                        n_neighbors=[8, 8], p_dropout=0.1, max_len=64))
+    g = torch.Generator().manual_seed(1234)
+    B, N, L = 1, 4, 12
+    msa, seq = torch.randint(0, 21, (B, N, L), generator=g), torch.randint(0, 21, (B, L), generator=g)
+    aa_idx = torch.arange(L).repeat(B, 1)
+    with torch.no_grad():
+        logits, xyz, plddt = model(msa, seq, aa_idx)
+    rf.set_mode("fp32")
+    rf.accelerate(model)
+    swapped = [n for n, m in model.named_modules() if type(m).__module__.startswith("rosettafold_pytorch_b200")]
+    for stage in ("msa_update_using_self_att", "pair_update_with_msa", "pair_update_with_axial_attention",
+                  "msa_update_with_pair", "msa_update_with_pair_and_coord"):
+        assert any(n.endswith(stage) for n in swapped), stage
+    with torch.no_grad():
+        logits2, xyz2, plddt2 = model(msa, seq, aa_idx)
+    for k in logits:
+        assert rel_l2(logits2[k], logits[k]) < 1e-4, k
+    assert rel_l2(xyz2, xyz) < 1e-4 and rel_l2(plddt2, plddt) < 1e-4
