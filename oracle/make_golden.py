@@ -60,11 +60,74 @@ def make_coord(ref, rf):
         print(name, tuple(out.shape), os.path.getsize(path))
 
 
+TRACE_CONFIG = dict(d_msa=384, d_pair=288, d_node=32, d_edge=32, d_state=32, n_two_track_blocks=1,
+                    n_three_track_blocks=2, n_encoder_layers=1, n_neighbors=[8], B=1, N=5, L=20, seed=60)
+TRUNK_STAGES = ("msa_update_using_self_att", "pair_update_with_msa", "pair_update_with_axial_attention",
+                "msa_update_with_pair")
+
+
+def trace_blocks(model):
+    return [("two_track_blocks.0", model.two_track_blocks[0]), ("three_track_blocks.0", model.three_track_blocks[0]),
+            ("final_block", model.final_block)]
+
+
+def make_model_trace(ref, rf):
+    """The trunk IN SITU: the whole unmodified reference model (README widths; embeddings, SE(3) structure track
+    on the dgl / lie_learn shims, heads) runs once on integer MSA / sequence inputs (SURVEY.md section 8d recipe);
+    every trunk block's inputs and outputs are recorded by hooks, so the b200 blocks can be checked on the
+    activations and coordinates a real forward produces. Trunk weights are the re-derivable synthetic ones
+    (seed + block index); everything else keeps its `torch.manual_seed(0)` construction values."""
+    c = TRACE_CONFIG
+    torch.manual_seed(0)
+    model = ref.RoseTTAFold(d_input=21, d_msa=c["d_msa"], d_pair=c["d_pair"], d_node=c["d_node"], d_edge=c["d_edge"],
+                            d_state=c["d_state"], n_two_track_blocks=c["n_two_track_blocks"],
+                            n_three_track_blocks=c["n_three_track_blocks"], n_encoder_layers=c["n_encoder_layers"],
+                            n_neighbors=c["n_neighbors"], p_dropout=0.1, max_len=64)
+    rl.fix_eval(model)
+    rec, sums = {}, {}
+    for k, (name, blk) in enumerate(trace_blocks(model)):
+        mine = rf.TwoTrackBlock(c["d_msa"], c["d_pair"], n_encoder_layers=c["n_encoder_layers"])
+        sd = synth_state_dict(mine.state_dict(), seed=c["seed"] + k)
+        for st in TRUNK_STAGES:
+            push_to_reference(getattr(blk, st), {n[len(st) + 1:]: v for n, v in sd.items() if n.startswith(st + ".")})
+        sums[name] = checksum(sd)
+        r = rec.setdefault(name, {})
+        blk.register_forward_pre_hook(lambda m, a, r=r: r.update(msa_in=a[0].clone(), pair_in=a[1].clone()))
+        blk.msa_update_with_pair.register_forward_hook(lambda m, a, o, r=r: r.update(msa_trunk_out=o.clone()))
+        blk.pair_update_with_axial_attention.register_forward_hook(lambda m, a, o, r=r: r.update(pair_out=o.clone()))
+        coord = getattr(blk, "msa_update_with_pair_and_coord", None)
+        if coord is not None:
+            csd = synth_state_dict(coord.state_dict(), seed=c["seed"] + 10 + k)
+            coord.load_state_dict(csd, strict=True)
+            sums[name + ".coord"] = checksum(csd)
+            coord.register_forward_hook(lambda m, a, o, r=r: r.update(xyz=a[0].clone(), state=a[1].clone(),
+                                                                      msa_coord_in=a[2].clone(), msa_coord_out=o.clone()))
+    g = torch.Generator().manual_seed(1234)
+    B, N, L = c["B"], c["N"], c["L"]
+    msa, seq = torch.randint(0, 21, (B, N, L), generator=g), torch.randint(0, 21, (B, L), generator=g)
+    with torch.no_grad():
+        logits, xyz, plddt = model(msa, seq, torch.arange(L).repeat(B, 1))
+    assert all(torch.isfinite(v).all() for v in logits.values()) and torch.isfinite(xyz).all()
+    path = os.path.join(ROOT, "tests", "golden", "model_trace.pt")
+    torch.save(dict(config=c, weight_checksums=sums, blocks=rec,
+                    generator="oracle/make_golden.py --trace-only: hooks on the unmodified reference RoseTTAFold "
+                              "(CPU fp32, eval, dgl / lie_learn shims)"), path)
+    print("model_trace", {n: {k: tuple(v.shape) for k, v in r.items()} for n, r in rec.items()}, os.path.getsize(path))
+
+
 def main():
     import rosettafold_pytorch_b200 as rf
 
     ref = rl.load()
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    if "--trace-only" in sys.argv:
+        cwd = os.getcwd()
+        os.makedirs("/tmp/rfk_trace_cwd", exist_ok=True)
+        os.chdir("/tmp/rfk_trace_cwd")  # the reference caches its Q_J bases under ./cache
+        try:
+            return make_model_trace(ref, rf)
+        finally:
+            os.chdir(cwd)
     make_coord(ref, rf)
     if "--coord-only" in sys.argv:
         return

@@ -60,3 +60,35 @@ def build_coord_module(gold, device="cpu"):
     mod.load_state_dict(sd, strict=True)
     msa, _ = synth_inputs(c["B"], c["N"], c["L"], c["d_msa"], 8, seed=c["seed"] + 100)
     return mod.to(device), sd, gold["xyz"].to(device), gold["state"].to(device), msa.to(device)
+
+
+TRACE_BLOCKS = ("two_track_blocks.0", "three_track_blocks.0", "final_block")
+
+
+def build_trace_block(gold, name, device="cpu"):
+    """The b200 TwoTrackBlock (+ MsaUpdateWithPairAndCoord for a three-track block) carrying the synthetic
+    weights that block `name` of the traced reference model held (oracle/make_golden.py --trace-only)."""
+    import rosettafold_pytorch_b200 as rf
+
+    c = gold["config"]
+    k = TRACE_BLOCKS.index(name)
+    blk = rf.TwoTrackBlock(c["d_msa"], c["d_pair"], n_encoder_layers=c["n_encoder_layers"]).eval()
+    sd = synth_state_dict(blk.state_dict(), seed=c["seed"] + k)
+    assert abs(checksum(sd) - gold["weight_checksums"][name]) < 1e-6 * gold["weight_checksums"][name]
+    blk.load_state_dict(sd, strict=True)
+    coord = None
+    if "xyz" in gold["blocks"][name]:
+        coord = rf.MsaUpdateWithPairAndCoord(c["d_msa"], c["d_state"], 32, 4 * c["d_msa"]).eval()
+        coord.load_state_dict(synth_state_dict(coord.state_dict(), seed=c["seed"] + 10 + k), strict=True)
+        coord = coord.to(device)
+    return blk.to(device), coord, {n: v.to(device) for n, v in gold["blocks"][name].items()}
+
+
+def run_trace_block(blk, coord, rec):
+    """-> errors of the block's trunk outputs (and the coordinate-conditioned MSA update) against the trace."""
+    msa, pair = blk(rec["msa_in"], rec["pair_in"])
+    errs = dict(msa=rel_l2(msa, rec["msa_trunk_out"]), pair=rel_l2(pair, rec["pair_out"]))
+    if coord is not None:
+        errs["msa_coord"] = rel_l2(coord(rec["xyz"], rec["state"], rec["msa_coord_in"]), rec["msa_coord_out"])
+        errs["msa_coord_chain"] = rel_l2(coord(rec["xyz"], rec["state"], msa), rec["msa_coord_out"])
+    return errs

@@ -116,3 +116,18 @@ def test_msa_update_with_pair_and_coord_vs_golden(cuda_device, mode, tol):
     e = rel_l2(out, gold["msa_out"])
     print(mode, "MsaUpdateWithPairAndCoord rel-l2", e)
     assert e < tol, e
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+@pytest.mark.parametrize("name", ["two_track_blocks.0", "three_track_blocks.0", "final_block"])
+def test_blocks_in_situ_match_model_trace(cuda_device, name, mode, tol):
+    """The trunk blocks in situ: inputs, coordinates and outputs recorded by hooks during a forward of the whole
+    unmodified reference model (README widths; tests/golden/model_trace.pt), replayed through librfk."""
+    from tests.helpers import build_trace_block, run_trace_block
+
+    blk, coord, rec = build_trace_block(load_golden("model_trace"), name, cuda_device)
+    rf.set_mode(mode)
+    errs = run_trace_block(blk, coord, rec)
+    torch.cuda.synchronize()
+    print(mode, name, errs)
+    assert max(errs.values()) < tol, errs

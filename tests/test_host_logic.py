@@ -205,3 +205,14 @@ def test_accelerate_whole_reference_model(emulated_ops):
     for k in logits:
         assert rel_l2(logits2[k], logits[k]) < 1e-4, k
     assert rel_l2(xyz2, xyz) < 1e-4 and rel_l2(plddt2, plddt) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["two_track_blocks.0", "three_track_blocks.0", "final_block"])
+def test_blocks_in_situ_match_model_trace(emulated_ops, name):
+    """Host logic on the activations / coordinates of a whole reference-model forward (tests/golden/model_trace.pt)."""
+    from tests.helpers import build_trace_block, run_trace_block
+
+    blk, coord, rec = build_trace_block(load_golden("model_trace"), name)
+    rf.set_mode("fp32")
+    errs = run_trace_block(blk, coord, rec)
+    assert max(errs.values()) < 1e-4, errs
