@@ -505,6 +505,26 @@ __device__ __forceinline__ bool gemm_elect_one() {
   return pred != 0;
 }
 
+// tile index -> (n block, m block, z0, z1, z2), n fastest
+struct TileDecoder {
+  uint32_t n_blocks, m_blocks, Z0, Z1, Zn;
+  __device__ __forceinline__ void operator()(uint32_t t, uint32_t& nb, uint32_t& mb, uint32_t& z0, uint32_t& z1,
+                                             uint32_t& z2) const {
+    const uint32_t q = t / n_blocks;
+    nb = t - q * n_blocks;
+    if (Zn == 1) {
+      mb = q; z0 = z1 = z2 = 0;
+    } else {
+      const uint32_t z = q / m_blocks;
+      mb = q - z * m_blocks;
+      const uint32_t zq = z / Z0;
+      z0 = z - zq * Z0;
+      z2 = zq / Z1;
+      z1 = zq - z2 * Z1;
+    }
+  }
+};
+
 template <int BN, int EPI, bool CONV = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -528,7 +548,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   auto smem_a = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
   auto smem_b = [&](int s) { return smem_base + s * Cfg::kStageBytes + kBlockM * 128; };
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: the compiler then keeps it (and everything derived from it: TMEM lane
+  // group, staging slots, TMA-store coordinates) in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -557,11 +579,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int64_t m_blocks = (p.M + kBlockM - 1) / kBlockM;
-  const int64_t n_blocks = (p.N + BN - 1) / BN;
-  const int64_t k_blocks = CONV ? (int64_t)9 * p.conv_cblocks : (p.K + kBlockK - 1) / kBlockK;
-  const int64_t Z = p.Z0 * p.Z1 * p.Z2;
-  const int64_t tiles = Z * m_blocks * n_blocks;
+  // tile bookkeeping in 32 bits (the host checks that M, N and the tile count fit): a 64-bit division is a
+  // ~100-instruction subroutine, and every role decodes its tile index once per tile
+  const uint32_t m_blocks = (uint32_t)((p.M + kBlockM - 1) / kBlockM);
+  const uint32_t n_blocks = (uint32_t)((p.N + BN - 1) / BN);
+  const int k_blocks = CONV ? 9 * p.conv_cblocks : (int)((p.K + kBlockK - 1) / kBlockK);
+  const uint32_t Zn = (uint32_t)(p.Z0 * p.Z1 * p.Z2);
+  const uint32_t tiles = Zn * m_blocks * n_blocks;
+  const TileDecoder tdec{n_blocks, m_blocks, (uint32_t)p.Z0, (uint32_t)p.Z1, Zn};
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -570,16 +595,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // UTMALDG / UTCHMMA in per-instruction election code)
     int stage = 0;
     uint32_t phase = 0;
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-      const int64_t nb = t % n_blocks;
-      const int64_t mb = (t / n_blocks) % m_blocks;
-      const int64_t z = t / (n_blocks * m_blocks);
-      const int z0 = (int)(z % p.Z0), z1 = (int)((z / p.Z0) % p.Z1), z2 = (int)(z / (p.Z0 * p.Z1));
+    for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      uint32_t nb, mb, uz0, uz1, uz2;
+      tdec(t, nb, mb, uz0, uz1, uz2);
+      const int z0 = (int)uz0, z1 = (int)uz1, z2 = (int)uz2;
       if constexpr (CONV) {
         // tile -> (image b, row i, first column j0); taps shift the TMA box, out-of-image rows and
         // columns are zero-filled by the TMA unit ('same' padding for free)
-        const int64_t m0 = mb * kBlockM;
-        const int img_row = (int)(m0 / p.conv_Lp), j0 = (int)(m0 % p.conv_Lp);
+        const uint32_t m0 = mb * kBlockM;
+        const int img_row = (int)(m0 / (uint32_t)p.conv_Lp), j0 = (int)(m0 % (uint32_t)p.conv_Lp);
         const int bi = img_row / p.conv_H, ii = img_row % p.conv_H;
         for (int tap = 0; tap < 9; ++tap) {
           const int di = tap / 3 - 1, dj = tap % 3 - 1;
@@ -596,13 +620,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
         }
       } else {
-        for (int64_t kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           if (gemm_elect_one()) {
             mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-            tma_load_5d(&tma_a, full_bar(stage), smem_a(stage), (int)(kb * kBlockK),
+            tma_load_5d(&tma_a, full_bar(stage), smem_a(stage), kb * kBlockK,
                         (int)(mb * kBlockM), z0, z1, z2);
-            tma_load_5d(&tma_b, full_bar(stage), smem_b(stage), (int)(kb * kBlockK), (int)(nb * BN),
+            tma_load_5d(&tma_b, full_bar(stage), smem_b(stage), kb * kBlockK, (int)(nb * BN),
                         z0 & p.bmask[0], z1 & p.bmask[1], z2 & p.bmask[2]);
           }
           __syncwarp();
@@ -617,19 +641,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-      for (int64_t kb = 0; kb < k_blocks; ++kb) {
+      for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         const uint64_t adesc = umma_desc_sw128(smem_a(stage));
         const uint64_t bdesc = umma_desc_sw128(smem_b(stage));
         // conv: the last channel block of a tap may hold fewer than 64 real channels
         // (the K tail of a plain GEMM is zero-filled by TMA: skip the all-zero k16 steps too)
-        const int nk16 = CONV ? (((int)(kb % p.conv_cblocks) == p.conv_cblocks - 1) ? p.conv_last_k16 : kBlockK / 16)
-                              : ((kb == k_blocks - 1) ? (int)((p.K - kb * kBlockK + 15) / 16) : kBlockK / 16);
+        const int nk16 = CONV ? ((kb % p.conv_cblocks == p.conv_cblocks - 1) ? p.conv_last_k16 : kBlockK / 16)
+                              : ((kb == k_blocks - 1) ? ((int)p.K - kb * kBlockK + 15) / 16 : kBlockK / 16);
         if (gemm_elect_one()) {
           if (nk16 == kBlockK / 16) {
 #pragma unroll
@@ -657,11 +681,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint32_t epi_count = 0;  // chunks stored so far by this warp (ring slot / residual barrier parity)
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-      const int64_t nb = t % n_blocks;
-      const int64_t mb = (t / n_blocks) % m_blocks;
-      const int64_t z = t / (n_blocks * m_blocks);
-      const int64_t z0 = z % p.Z0, z1 = (z / p.Z0) % p.Z1, z2 = z / (p.Z0 * p.Z1);
+    for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      uint32_t unb, umb, uz0, uz1, uz2;
+      tdec(t, unb, umb, uz0, uz1, uz2);
+      const int64_t nb = unb, mb = umb, z0 = uz0, z1 = uz1, z2 = uz2;
       const int64_t m_warp0 = mb * kBlockM + lg * 32;
       const float* bias = p.bias ? p.bias + z0 * p.bias_zs[0] + z1 * p.bias_zs[1] + z2 * p.bias_zs[2] : nullptr;
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BN);
@@ -721,72 +744,86 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         constexpr int kRing = EPI == 3 ? 4 : 3;
         const int ew = warp - 2;
         const uint32_t ring = stg_base + (uint32_t)ew * kRing * kBuf;
-        int lc[7];
+        // Everything the TMA instructions take is warp-uniform and lives in registers: the per-dimension
+        // fixed coordinates are resolved once per tile (select chains, no indexed local array), the column
+        // pair (n % NR, n / NR) is advanced incrementally (no division per chunk), and the instructions are
+        // issued by an elected lane under warp-uniform control flow. (The same code under `if (lane == 0)`
+        // with a division and a cmap-indexed array per chunk kept the epilogue warps busy for ~1800 cycles per
+        // 32x32 chunk - more than the main loop needs per tile: profiles/r01_gemm_epilogue_notes.md.)
+        const uint32_t nr = (uint32_t)p.NR;
+        int fx[5];
         {
           const uint32_t mu = (uint32_t)m_warp0, mr = (uint32_t)p.MR;
-          lc[3] = (int)(mu / mr); lc[2] = (int)(mu - (uint32_t)lc[3] * mr);
-          lc[4] = (int)z0; lc[5] = (int)z1; lc[6] = (int)z2;
+          const int l3 = (int)(mu / mr), l2 = (int)(mu - (uint32_t)l3 * mr);
+#pragma unroll
+          for (int d = 0; d < 5; ++d) {
+            const int cm = p.cmap[d];
+            fx[d] = cm == 2 ? l2 : cm == 3 ? l3 : cm == 4 ? (int)uz0 : cm == 5 ? (int)uz1 : cm == 6 ? (int)uz2 : 0;
+          }
         }
-        auto coord = [&](int d) { return p.cmap[d] < 0 ? 0 : lc[p.cmap[d]]; };
-        auto set_n = [&](int64_t n0) {
-          const uint32_t nu = (uint32_t)n0, nr = (uint32_t)p.NR;
-          lc[1] = (int)(nu / nr); lc[0] = (int)(nu - (uint32_t)lc[1] * nr);
+#define RFK_COORDS(lo, hi)                                                                                   \
+  (p.cmap[0] == 0 ? (int)(lo) : p.cmap[0] == 1 ? (int)(hi) : fx[0]),                                         \
+      (p.cmap[1] == 0 ? (int)(lo) : p.cmap[1] == 1 ? (int)(hi) : fx[1]),                                     \
+      (p.cmap[2] == 0 ? (int)(lo) : p.cmap[2] == 1 ? (int)(hi) : fx[2]),                                     \
+      (p.cmap[3] == 0 ? (int)(lo) : p.cmap[3] == 1 ? (int)(hi) : fx[3]),                                     \
+      (p.cmap[4] == 0 ? (int)(lo) : p.cmap[4] == 1 ? (int)(hi) : fx[4])
+        auto advance = [&](uint32_t& lo, uint32_t& hi) {  // next chunk of this warp: 64 columns on
+          lo += 64u;
+          while (lo >= nr) { lo -= nr; ++hi; }
         };
-        const bool row_tile_ok = m_warp0 < p.M;
-        int nch = 0;  // chunks of this tile owned by this warp: c = chalf + 2 i
-        for (int c = chalf; c < BN / 32 && nb * BN + c * 32 < p.N; c += 2) ++nch;
+        const uint32_t n_tile0 = unb * (uint32_t)BN;
+        const uint32_t n_first = n_tile0 + (uint32_t)chalf * 32u;
+        uint32_t nhi = n_first / nr, nlo = n_first - nhi * nr;   // columns of the chunk being stored
+        uint32_t phi = nhi, plo = nlo;                           // columns of the next residual tile to fetch
+        // chunks of this tile owned by this warp: c = chalf + 2 i
+        const int ct = min(BN / 32, (int)(((uint32_t)p.N - n_tile0 + 31u) >> 5));
+        const int nch = (m_warp0 < p.M && ct > chalf) ? (ct - chalf + 1) >> 1 : 0;
         const bool use_res = EPI == 4 && p.has_rmap != 0;
-        if (use_res && row_tile_ok) {
+        if (use_res && nch > 0) {
           // every earlier store of this warp has been read out of the ring: prefetch two residual tiles
-          if (lane == 0) {
-            bulk_wait_read<0>();
-            for (int i = 0; i < 2 && i < nch; ++i) {
-              set_n(nb * BN + (chalf + 2 * i) * 32);
-              mbar_arrive_expect_tx(res_bar(ew, (int)((epi_count + i) % 3)), kBuf);
-              tma_load_5d(&tma_r, res_bar(ew, (int)((epi_count + i) % 3)), ring + (uint32_t)((epi_count + i) % 3) * kBuf,
-                          coord(0), coord(1), coord(2), coord(3), coord(4));
+          // (bulk async-groups belong to the issuing lane; elect.sync picks the same lane every time, the
+          // other lanes' waits return at once)
+          bulk_wait_read<0>();
+          for (int i = 0; i < 2 && i < nch; ++i) {
+            const int s = (int)((epi_count + i) % 3);
+            if (gemm_elect_one()) {
+              mbar_arrive_expect_tx(res_bar(ew, s), kBuf);
+              tma_load_5d(&tma_r, res_bar(ew, s), ring + (uint32_t)s * kBuf, RFK_COORDS(plo, phi));
             }
+            advance(plo, phi);
           }
           __syncwarp();
         }
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t myrow = (uint32_t)lane;
-#pragma unroll 1
-        for (int i = 0; i < nch; ++i) {
-          const int c = chalf + 2 * i;
-          const int64_t n0 = nb * BN + c * 32;
+        // one chunk: accumulator registers -> bias / LN / activation (/ residual) -> swizzled tile -> TMA store
+        auto process = [&](uint32_t (&r)[32], int i) {
+          const uint32_t n0 = n_tile0 + (uint32_t)(chalf + 2 * i) * 32u;
           const int slot = (int)(epi_count % kRing);
           const uint32_t buf = ring + (uint32_t)slot * kBuf;
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c * 32, r);
-          // bias of the 32 columns (same addresses in every lane: broadcast loads)
-          float4 bq[8];
-          if (bias) {
+          float v[32];
+          if (bias) {  // same addresses in every lane: broadcast loads
 #pragma unroll
-            for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(bias + n0) + j);
+            for (int j = 0; j < 8; ++j) {
+              const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + n0) + j);
+              v[4 * j] = __uint_as_float(r[4 * j]) + bq.x;
+              v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bq.y;
+              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bq.z;
+              v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bq.w;
+            }
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) bq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[4 * j] = __uint_as_float(r[4 * j]) + bq[j].x;
-            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bq[j].y;
-            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bq[j].z;
-            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bq[j].w;
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           }
           if (EPI == 3 && p.epi == RFK_EPI_BLOCKLN32) blockln32(p, lane, v);
           if (p.act == RFK_ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
-          if (!row_tile_ok) continue;  // ring slots / barrier parities only advance with real stores
           if constexpr (EPI == 3) {
             // the store issued four chunks ago (same slot) must have finished reading the tile
-            if (lane == 0) bulk_wait_read<3>();
+            bulk_wait_read<3>();
             __syncwarp();
             const uint32_t rowb = buf + myrow * 64u, sw = (myrow >> 1) & 3u;
 #pragma unroll
@@ -800,11 +837,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               mbar_wait(res_bar(ew, slot), (uint32_t)((epi_count / 3) & 1));
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
-                const float4 t = ld_shared_f4(rowb + ((((uint32_t)q) ^ sw) << 4));
-                v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+                const float4 t4 = ld_shared_f4(rowb + ((((uint32_t)q) ^ sw) << 4));
+                v[4 * q] += t4.x; v[4 * q + 1] += t4.y; v[4 * q + 2] += t4.z; v[4 * q + 3] += t4.w;
               }
             } else {
-              if (lane == 0) bulk_wait_read<2>();
+              bulk_wait_read<2>();
               __syncwarp();
             }
 #pragma unroll
@@ -815,23 +852,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
-            set_n(n0);
-            tma_store_5d(&tma_c, buf, coord(0), coord(1), coord(2), coord(3), coord(4));
+          if (gemm_elect_one()) {
+            tma_store_5d(&tma_c, buf, RFK_COORDS(nlo, nhi));
             bulk_commit();
-            if (use_res && i + 2 < nch) {
-              // slot of chunk i+2 was last used by chunk i-1: its store may still be in flight
-              bulk_wait_read<1>();
-              set_n(nb * BN + (chalf + 2 * (i + 2)) * 32);
-              const int s2 = (int)((epi_count + 2) % 3);
+          }
+          if (use_res && i + 2 < nch) {
+            // slot of chunk i+2 was last used by chunk i-1: its store may still be in flight
+            bulk_wait_read<1>();
+            const int s2 = (int)((epi_count + 2) % 3);
+            if (gemm_elect_one()) {
               mbar_arrive_expect_tx(res_bar(ew, s2), kBuf);
-              tma_load_5d(&tma_r, res_bar(ew, s2), ring + (uint32_t)s2 * kBuf, coord(0), coord(1), coord(2),
-                          coord(3), coord(4));
+              tma_load_5d(&tma_r, res_bar(ew, s2), ring + (uint32_t)s2 * kBuf, RFK_COORDS(plo, phi));
             }
+            advance(plo, phi);
           }
           __syncwarp();
+          advance(nlo, nhi);
           ++epi_count;
+        };
+        if (nch > 0) {
+          // the accumulator chunk after the one being processed is already on its way out of TMEM
+          // (a prefetch past the last owned chunk re-reads the first one: always inside the accumulator)
+          uint32_t ra[32], rb[32];
+          auto chunk_addr = [&](int i) {
+            const int c = chalf + 2 * i;
+            return taddr + (uint32_t)((c < BN / 32 ? c : chalf) * 32);
+          };
+          tmem_ld_32x32(chunk_addr(0), ra);
+#pragma unroll 1
+          for (int i = 0; i < nch; i += 2) {
+            tmem_ld_wait();
+            tmem_ld_32x32(chunk_addr(i + 1), rb);
+            process(ra, i);
+            if (i + 1 < nch) {
+              tmem_ld_wait();
+              tmem_ld_32x32(chunk_addr(i + 2), ra);
+              process(rb, i + 1);
+            }
+          }
+          tmem_ld_wait();  // the trailing prefetch must land before the accumulator is handed back
         }
+#undef RFK_COORDS
       } else {
         static_assert(EPI == 0 || BN % 32 == 0, "lean epilogues need 32-column chunks");
         // rows of this warp are affine in memory: offset(row) = base + row * ms[0]
@@ -865,7 +926,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
-  if ((EPI == 3 || EPI == 4) && warp >= 2 && lane == 0) bulk_wait_all();  // smem tiles must outlive their bulk stores
+  if ((EPI == 3 || EPI == 4) && warp >= 2) bulk_wait_all();  // smem tiles must outlive their bulk stores
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -885,6 +946,8 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev
   using Cfg = GemmCfg<BN, EPI>;
   static const EpiMaps kNoMaps{};
   if (!em) em = &kNoMaps;
+  // the kernel decodes tiles and splits m / n in 32-bit arithmetic
+  if (tiles > 0x7fffffffLL || p.M > 0x7fffffffLL || p.N > 0x7fffffffLL || p.K > 0x7fffffffLL) return RFK_ERR_BAD_DIMS;
   static bool configured = false;  // benign race: the attribute call is idempotent
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, CONV>,
