@@ -246,6 +246,8 @@ extern "C" int rfk_gemm(const rfk_gemm_desc* d, rfk_stream_t stream_) {
   if (rc != RFK_OK) return rc;
 
   int bn = pick_bn(d->N);
+  static const char* force_bn = getenv("RFK_GEMM_BN");  // A/B debugging aid: one of 256/192/128/96/64/32
+  if (force_bn && atoi(force_bn) >= 32 && atoi(force_bn) % 32 == 0 && atoi(force_bn) <= 256) bn = atoi(force_bn);
   if (d->epi == RFK_EPI_BLOCKLN32) bn = 128;
 
   CUtensorMap ta, tb;

@@ -473,6 +473,9 @@ __device__ __forceinline__ void epilogue_fast_chunk(const GemmDev& p, float4* st
 // tcgen05 kernel
 // ----------------------------------------------------------------------------------------------
 constexpr int kBlockM = 128;
+#ifndef RFK_EPI3_RING
+#define RFK_EPI3_RING 4
+#endif
 constexpr int kBlockK = 64;
 constexpr int kGemmThreads = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kEpiWarps = 8;
@@ -482,7 +485,8 @@ struct GemmCfg {
   static constexpr int kStageBytes = kBlockM * 128 + BN * 128;
   // epilogue staging: EPI 0-2 one [32][33] f32 transpose buffer per warp; EPI 3: two 2 KB bf16
   // tiles per warp; EPI 4: three 4 KB f32 tiles per warp (residual-in / result-out ring)
-  static constexpr int kStagingBytes = EPI == 3 ? kEpiWarps * 4 * 2048
+  static constexpr int kRing3 = RFK_EPI3_RING;
+  static constexpr int kStagingBytes = EPI == 3 ? kEpiWarps * kRing3 * 2048
                                        : EPI == 4 ? kEpiWarps * 3 * 4096 : kEpiWarps * 32 * 33 * 4;
   static constexpr int kBarBytes = 512;
   static constexpr int kBudget = 232448 - 2048 - kBarBytes - kStagingBytes;
@@ -641,7 +645,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    // the last column block may be narrower than BN: its MMAs only cover the real columns (rounded up to the
+    // instruction granularity of 16), so a wide BN costs no tensor time on the ragged edge
+    const uint32_t n_tail = (uint32_t)p.N - (n_blocks - 1) * (uint32_t)BN;
+    const uint32_t idesc_tail = umma_idesc_bf16(kBlockM, (int)((n_tail + 15u) & ~15u));
     for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const uint32_t idesc_t = (t % n_blocks == n_blocks - 1) ? idesc_tail : idesc;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -658,12 +667,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (nk16 == kBlockK / 16) {
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
-              umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_t, (kb > 0 || k > 0) ? 1u : 0u);
           } else {
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
               if (k < nk16)
-                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_t, (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));
           if (kb == k_blocks - 1) umma_commit(tfull_bar(acc));
@@ -741,7 +750,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // No per-row address arithmetic, no transposing reads; partial tiles are clipped by TMA.
         static_assert(BN % 32 == 0, "TMA epilogues need 32-column chunks");
         constexpr uint32_t kBuf = EPI == 3 ? 2048u : 4096u;
-        constexpr int kRing = EPI == 3 ? 4 : 3;
+        constexpr int kRing = EPI == 3 ? Cfg::kRing3 : 3;
         const int ew = warp - 2;
         const uint32_t ring = stg_base + (uint32_t)ew * kRing * kBuf;
         // Everything the TMA instructions take is warp-uniform and lives in registers: the per-dimension
@@ -823,7 +832,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
           if constexpr (EPI == 3) {
             // the store issued four chunks ago (same slot) must have finished reading the tile
-            bulk_wait_read<3>();
+            bulk_wait_read<Cfg::kRing3 - 1>();
             __syncwarp();
             const uint32_t rowb = buf + myrow * 64u, sw = (myrow >> 1) & 3u;
 #pragma unroll
