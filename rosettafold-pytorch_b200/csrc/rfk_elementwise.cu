@@ -413,6 +413,70 @@ pair2att_kernel(const float* __restrict__ pair, const float* __restrict__ Wf,
   }
 }
 
+// D = 32 NT: eight lanes per (i <= j) pair of positions, 16-byte loads, all 2 NT loads of a lane in flight
+// before the first use; a warp covers four consecutive j, a block 32; blocks below the diagonal exit.
+template <int NT>
+__global__ void __launch_bounds__(256)
+pair2att_vec_kernel(const float* __restrict__ pair, const float* __restrict__ Wf,
+                    const float* __restrict__ bf, float eps, float* __restrict__ logits, int64_t ldl,
+                    int L, int C) {
+  constexpr int D = NT * 32;
+  extern __shared__ float sw[];  // [C][D]
+  const int i = blockIdx.y, b = blockIdx.z;
+  const int j0 = blockIdx.x * 32;
+  if (j0 + 31 < i) return;
+  for (int t = threadIdx.x; t < C * (D / 4); t += blockDim.x)
+    reinterpret_cast<float4*>(sw)[t] = __ldg(reinterpret_cast<const float4*>(Wf) + t);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l8 = lane & 7;
+  const int j = j0 + warp * 4 + (lane >> 3);
+  const bool active = j < L && j >= i;
+  const int jj = active ? j : i;  // idle groups shadow the diagonal element (they take part in the shuffles)
+  const float4* pij = reinterpret_cast<const float4*>(pair + (((int64_t)b * L + i) * L + jj) * D) + l8;
+  const float4* pji = reinterpret_cast<const float4*>(pair + (((int64_t)b * L + jj) * L + i) * D) + l8;
+  float4 u[NT], w[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) { u[t] = __ldg(pij + 8 * t); w[t] = __ldg(pji + 8 * t); }
+  auto sum8 = [](float x) {
+    x += __shfl_xor_sync(0xffffffffu, x, 4);
+    x += __shfl_xor_sync(0xffffffffu, x, 2);
+    x += __shfl_xor_sync(0xffffffffu, x, 1);
+    return x;
+  };
+  float s = 0.f;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    u[t].x = 0.5f * (u[t].x + w[t].x); u[t].y = 0.5f * (u[t].y + w[t].y);
+    u[t].z = 0.5f * (u[t].z + w[t].z); u[t].w = 0.5f * (u[t].w + w[t].w);
+    s += (u[t].x + u[t].y) + (u[t].z + u[t].w);
+  }
+  const float mean = sum8(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    u[t].x -= mean; u[t].y -= mean; u[t].z -= mean; u[t].w -= mean;
+    q = fmaf(u[t].x, u[t].x, q); q = fmaf(u[t].y, u[t].y, q);
+    q = fmaf(u[t].z, u[t].z, q); q = fmaf(u[t].w, u[t].w, q);
+  }
+  const float rstd = rsqrtf(sum8(q) / (float)D + eps);
+  for (int c = 0; c < C; ++c) {
+    const float4* wc = reinterpret_cast<const float4*>(sw + c * D) + l8;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const float4 ww = wc[8 * t];
+      acc = fmaf(u[t].x, ww.x, acc); acc = fmaf(u[t].y, ww.y, acc);
+      acc = fmaf(u[t].z, ww.z, acc); acc = fmaf(u[t].w, ww.w, acc);
+    }
+    acc = sum8(acc) * rstd + bf[c];
+    if (active && l8 == 0) {
+      const int64_t base = ((int64_t)b * C + c) * L;
+      logits[(base + i) * ldl + j] = acc;
+      logits[(base + j) * ldl + i] = acc;
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // InstanceNorm statistics and apply (channels-last)
 // ----------------------------------------------------------------------------------------------
@@ -514,23 +578,46 @@ instnorm_apply_vec_kernel(const TX* __restrict__ x, const double* __restrict__ s
   }
   const int64_t p0 = (int64_t)blockIdx.x * chunk;
   const int64_t p1 = p0 + chunk < positions ? p0 + chunk : positions;
-  for (int64_t pos = p0 + r; pos < p1; pos += rows_per_iter) {
-    const int64_t off = ((int64_t)b * positions + pos) * C + c0;
-    float v[8];
-    ld8<TX>(x + off, v);
+  auto finish = [&](float (&v)[8], const float (&rr)[8], int64_t off) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc[i], sh[i]);
-    if (res) {
-      float rr[8];
-      ld8<TR>(res + off, rr);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] += rr[i];
-    }
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc[i], sh[i]) + rr[i];
     if (elu) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
     }
     st8<TY>(y + off, v);
+  };
+  const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int64_t row0 = (int64_t)b * positions;
+  int64_t pos = p0 + r;
+  // two positions in flight per thread (all loads issued before the first use)
+  for (; pos + rows_per_iter < p1; pos += 2 * rows_per_iter) {
+    const int64_t off0 = (row0 + pos) * C + c0, off1 = (row0 + pos + rows_per_iter) * C + c0;
+    float v0[8], v1[8];
+    ld8<TX>(x + off0, v0);
+    ld8<TX>(x + off1, v1);
+    if (res) {
+      float r0[8], r1[8];
+      ld8<TR>(res + off0, r0);
+      ld8<TR>(res + off1, r1);
+      finish(v0, r0, off0);
+      finish(v1, r1, off1);
+    } else {
+      finish(v0, zero8, off0);
+      finish(v1, zero8, off1);
+    }
+  }
+  if (pos < p1) {
+    const int64_t off0 = (row0 + pos) * C + c0;
+    float v0[8];
+    ld8<TX>(x + off0, v0);
+    if (res) {
+      float r0[8];
+      ld8<TR>(res + off0, r0);
+      finish(v0, r0, off0);
+    } else {
+      finish(v0, zero8, off0);
+    }
   }
 }
 
@@ -542,6 +629,75 @@ convert_rows_kernel(const void* __restrict__ x, int xdt, int64_t xs, void* __res
   const int64_t r = idx / cols;
   const int c = (int)(idx % cols);
   store_from_float(y, ydt, r * ys + c, load_as_float(x, xdt, r * xs + c));
+}
+
+// 8 elements per thread (two 16-byte accesses on the f32 side, one on the bf16 side); cols % 8 == 0
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(256)
+convert_rows_vec_kernel(const TX* __restrict__ x, int64_t xs, TY* __restrict__ y, int64_t ys, int64_t rows,
+                        int groups) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * groups) return;
+  const int64_t r = idx / groups;
+  const int c = (int)(idx - r * groups) * 8;
+  float v[8];
+  ld8<TX>(x + r * xs + c, v);
+  st8<TY>(y + r * ys + c, v);
+}
+
+// InstanceNorm statistics, 8 channels per thread: a block covers `chunk` positions, its threads form
+// (rows_per_iter x C/8) and each keeps 16 fp32 partial sums; the rows are folded in shared memory (fixed
+// order) and one thread per channel group issues the fp64 atomics.
+template <typename TX>
+__global__ void __launch_bounds__(256)
+channel_stats_vec_kernel(const TX* __restrict__ x, double* __restrict__ stats, int64_t positions, int C,
+                         int chunk) {
+  extern __shared__ float red[];  // [rows_per_iter][C][2]
+  const int groups = C >> 3;
+  const int rows_per_iter = blockDim.x / groups;
+  const int g = threadIdx.x % groups, r = threadIdx.x / groups;
+  const int b = blockIdx.y;
+  const int64_t p0 = (int64_t)blockIdx.x * chunk;
+  const int64_t p1 = p0 + chunk < positions ? p0 + chunk : positions;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  if (r < rows_per_iter) {
+    const TX* base = x + (int64_t)b * positions * C + g * 8;
+    int64_t pos = p0 + r;
+    // two rows in flight per thread
+    for (; pos + rows_per_iter < p1; pos += 2 * rows_per_iter) {
+      float v0[8], v1[8];
+      ld8<TX>(base + pos * C, v0);
+      ld8<TX>(base + (pos + rows_per_iter) * C, v1);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += v0[i]; q[i] = fmaf(v0[i], v0[i], q[i]);
+        s[i] += v1[i]; q[i] = fmaf(v1[i], v1[i], q[i]);
+      }
+    }
+    if (pos < p1) {
+      float v0[8];
+      ld8<TX>(base + pos * C, v0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += v0[i]; q[i] = fmaf(v0[i], v0[i], q[i]); }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      red[((int64_t)r * C + g * 8 + i) * 2 + 0] = s[i];
+      red[((int64_t)r * C + g * 8 + i) * 2 + 1] = q[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float ss = 0.f, qq = 0.f;
+    for (int rr = 0; rr < rows_per_iter; ++rr) {
+      ss += red[((int64_t)rr * C + c) * 2 + 0];
+      qq += red[((int64_t)rr * C + c) * 2 + 1];
+    }
+    atomicAdd(&stats[((int64_t)b * 2 + 0) * C + c], (double)ss);
+    atomicAdd(&stats[((int64_t)b * 2 + 1) * C + c], (double)qq);
+  }
 }
 
 }  // namespace rfk
@@ -704,6 +860,13 @@ extern "C" int rfk_pair2att_logits(const float* pair, const float* Wf, const flo
     cudaFuncSetAttribute(pair2att_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     configured = true;
   }
+  if (D == 288 && (reinterpret_cast<uintptr_t>(pair) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wf) & 15) == 0 &&
+      L <= 65535 && B <= 65535) {
+    dim3 grid((unsigned)((L + 31) / 32), (unsigned)L, (unsigned)B);
+    pair2att_vec_kernel<9><<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(pair, Wf, bf, eps, logits,
+                                                                                        ldl, L, C);
+    return post_launch();
+  }
   const int64_t items = (int64_t)B * L * L;
   pair2att_kernel<<<(unsigned)((items + 7) / 8), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       pair, Wf, bf, eps, logits, ldl, B, L, D, C);
@@ -715,6 +878,24 @@ extern "C" int rfk_channel_stats(const void* x, int xdt, double* stats, int B, i
   if (!x || !stats) return RFK_ERR_NULL_POINTER;
   if (B <= 0 || positions <= 0 || C <= 0) return RFK_ERR_BAD_DIMS;
   if (!dtype_ok(xdt)) return RFK_ERR_BAD_DTYPE;
+  if (C % 8 == 0 && C <= 2048 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int groups = C / 8;
+    const int threads = groups >= 256 ? 256 : (256 / groups) * groups;
+    const int rows_per_iter = threads / groups;
+    const size_t smem = (size_t)rows_per_iter * C * 2 * sizeof(float);
+    if (threads >= groups && smem <= 48 * 1024) {
+      const int vchunk = 256;
+      dim3 vgrid((unsigned)((positions + vchunk - 1) / vchunk), (unsigned)B);
+      cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+      if (xdt == RFK_BF16)
+        channel_stats_vec_kernel<__nv_bfloat16><<<vgrid, threads, smem, st>>>(
+            reinterpret_cast<const __nv_bfloat16*>(x), stats, positions, C, vchunk);
+      else
+        channel_stats_vec_kernel<float><<<vgrid, threads, smem, st>>>(reinterpret_cast<const float*>(x), stats,
+                                                                      positions, C, vchunk);
+      return post_launch();
+    }
+  }
   const int chunk = 128;
   dim3 grid((unsigned)((positions + chunk - 1) / chunk), (unsigned)B);
   const int threads = C >= 256 ? 256 : ((C + 31) / 32) * 32;
@@ -765,6 +946,24 @@ extern "C" int rfk_convert_rows(const void* x, int xdt, int64_t xs, void* y, int
   if (!dtype_ok(xdt) || !dtype_ok(ydt)) return RFK_ERR_BAD_DTYPE;
   if (rows == 0) return RFK_OK;
   const int64_t total = rows * cols;
+  {
+    const int xe = xdt == RFK_F32 ? 4 : 2, ye = ydt == RFK_F32 ? 4 : 2;
+    auto ok = [](const void* q, int64_t stride, int es) {
+      return (reinterpret_cast<uintptr_t>(q) & 15) == 0 && (stride * es) % 16 == 0;
+    };
+    if (cols % 8 == 0 && ok(x, xs, xe) && ok(y, ys, ye) && xdt != ydt) {
+      const int groups = cols / 8;
+      const int64_t work = rows * groups;
+      cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+      if (xdt == RFK_F32)
+        convert_rows_vec_kernel<float, __nv_bfloat16><<<(unsigned)((work + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const float*>(x), xs, reinterpret_cast<__nv_bfloat16*>(y), ys, rows, groups);
+      else
+        convert_rows_vec_kernel<__nv_bfloat16, float><<<(unsigned)((work + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const __nv_bfloat16*>(x), xs, reinterpret_cast<float*>(y), ys, rows, groups);
+      return post_launch();
+    }
+  }
   convert_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0,
                         reinterpret_cast<cudaStream_t>(stream)>>>(x, xdt, xs, y, ydt, ys, rows, cols);
   return post_launch();

@@ -363,3 +363,20 @@ def test_conv3x3_implicit_gemm(cuda_device, cfg):
         torch.cuda.synchronize()
         e = rel_l2(out, ref.permute(0, 2, 3, 1))
         assert e < tol(odt), f"{odt}: rel-l2 {e}"
+
+
+@pytest.mark.parametrize("cols,ys", [(288, 584), (288, 288), (12, 584), (100, 100)])
+def test_convert_rows(cuda_device, cols, ys):
+    """Row-wise dtype conversion into a strided destination: 8-wide vector path and the scalar path."""
+    dev = cuda_device
+    rows = 1000
+    x = _rand((rows, cols), torch.float32, dev, 90)
+    y = torch.zeros((rows, ys), dtype=torch.bfloat16, device=dev)
+    ops.convert_rows(x, y[:, ys - cols:] if (ys - cols) % 8 == 0 else y[:, :cols])
+    torch.cuda.synchronize()
+    got = y[:, ys - cols:] if (ys - cols) % 8 == 0 else y[:, :cols]
+    assert torch.equal(got, x.to(torch.bfloat16))
+    back = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+    ops.convert_rows(got, back)
+    torch.cuda.synchronize()
+    assert torch.equal(back, got.float())
