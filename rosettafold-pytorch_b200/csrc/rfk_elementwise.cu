@@ -583,7 +583,7 @@ instnorm_apply_vec_kernel(const TX* __restrict__ x, const double* __restrict__ s
     for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc[i], sh[i]) + rr[i];
     if (elu) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
+      for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.f ? v[i] : __expf(v[i]) - 1.f;  // abs error ~1e-7
     }
     st8<TY>(y + off, v);
   };

@@ -285,7 +285,8 @@ extern "C" int rfk_gemm(const rfk_gemm_desc* d, rfk_stream_t stream_) {
   static const bool no_tma_epi = getenv("RFK_GEMM_NO_TMA_EPILOGUE") != nullptr;  // A/B debugging aid
   // flavour 4 pays for its 96 KB residual/result ring with pipeline stages: only worth it for the
   // short-K GEMMs that are bound by the fp32 residual stream, not by the tensor pipe
-  if ((epi == 1 || (epi == 2 && d->r0 && !d->r1 && d->K <= 768)) && !no_tma_epi) {
+  static const bool epi4_any_k = getenv("RFK_GEMM_EPI4_ANYK") != nullptr;              // A/B debugging aid
+  if ((epi == 1 || (epi == 2 && d->r0 && !d->r1 && (d->K <= 768 || epi4_any_k))) && !no_tma_epi) {
     const bool n_split = d->NR < d->N, m_split = d->MR < d->M;
     if ((!n_split || d->N % d->NR == 0) && (!m_split || d->M % d->MR == 0)) {
       const int64_t ext[7] = {n_split ? d->NR : d->N, n_split ? d->N / d->NR : 1,

@@ -2,6 +2,7 @@
 // tcgen05 GEMM kernel (CONV instances): nn.Conv2d(d_pair, d_pair, 3, padding="same", bias=False) of
 // PairUpdateWithMsa (rosettafold_pytorch.py:451-457). The im2col matrix is never built: each of the
 // 9 taps is a TMA box shifted by (di, dj) over the NHWC tensor, with the border zero-filled by TMA.
+#include <cstdlib>
 #include "rfk_gemm_device.cuh"
 
 namespace rfk {
@@ -43,6 +44,8 @@ extern "C" int rfk_conv3x3_nhwc_hw(const void* x, const void* w_packed, void* y,
   int bn = 32;
   for (int cand : {256, 128, 96, 64, 32})
     if (Cout % cand == 0) { bn = cand; break; }
+  static const char* force_bn = getenv("RFK_CONV_BN");  // A/B debugging aid: 256 / 128 / 96 / 64 / 32
+  if (force_bn && atoi(force_bn) >= 32 && Cout % 32 == 0) bn = atoi(force_bn);
   const bool lean = Cout % 32 == 0 && (y_dtype == RFK_BF16 ? Cout % 8 == 0 : Cout % 4 == 0);
 
   GemmDev p{};
