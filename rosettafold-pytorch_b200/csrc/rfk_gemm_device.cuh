@@ -30,6 +30,7 @@ struct GemmDev {
   // {0: n % NR, 1: n / NR, 2: m % MR, 3: m / MR, 4: z0, 5: z1, 6: z2}; -1 -> 0
   int cmap[5];
   int has_rmap;  // residual r0 is fetched with TMA (map tma_r)
+  int wide;      // EPI 3: the store box is 64 columns (full 128-byte lines) instead of 32
   // SIMT path only
   const float* a32;
   const float* b32;
@@ -480,9 +481,11 @@ constexpr int kBlockK = 64;
 constexpr int kGemmThreads = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kEpiWarps = 8;
 
-template <int BN, int EPI = 0>
+// CTAS = 2: CTA pair (cta_group::2) - a 256-row tile over two SMs, each CTA stages its 128 rows of A and
+// BN/2 rows of B per k-block (half the B traffic through shared memory per SM)
+template <int BN, int EPI = 0, int CTAS = 1>
 struct GemmCfg {
-  static constexpr int kStageBytes = kBlockM * 128 + BN * 128;
+  static constexpr int kStageBytes = kBlockM * 128 + (BN / CTAS) * 128;
   // epilogue staging: EPI 0-2 one [32][33] f32 transpose buffer per warp; EPI 3: two 2 KB bf16
   // tiles per warp; EPI 4: three 4 KB f32 tiles per warp (residual-in / result-out ring)
   static constexpr int kRing3 = RFK_EPI3_RING;
@@ -529,13 +532,15 @@ struct TileDecoder {
   }
 };
 
-template <int BN, int EPI, bool CONV = false>
+template <int BN, int EPI, bool CONV = false, int CTAS = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r,
                const GemmDev p) {
-  using Cfg = GemmCfg<BN, EPI>;
+  using Cfg = GemmCfg<BN, EPI, CTAS>;
+  static_assert(CTAS == 1 || (!CONV && BN % 32 == 0), "CTA pairs: plain GEMM only");
   constexpr int STAGES = Cfg::kStages;
+  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * Cfg::kStageBytes;
@@ -564,7 +569,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kEpiWarps);
+      mbar_init(tempty_bar(a), kEpiWarps * CTAS);  // pair: the epilogue warps of both CTAs release the leader's
     }
     if constexpr (EPI == 4)
       for (int w = 0; w < kEpiWarps; ++w)
@@ -574,18 +579,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     tma_prefetch_desc(&tma_b);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (CTAS == 2) {
+      tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive
+  else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   // tile bookkeeping in 32 bits (the host checks that M, N and the tile count fit): a 64-bit division is a
   // ~100-instruction subroutine, and every role decodes its tile index once per tile
-  const uint32_t m_blocks = (uint32_t)((p.M + kBlockM - 1) / kBlockM);
+  constexpr int kTileM = kBlockM * CTAS;
+  const uint32_t m_blocks = (uint32_t)((p.M + kTileM - 1) / kTileM);
   const uint32_t n_blocks = (uint32_t)((p.N + BN - 1) / BN);
   const int k_blocks = CONV ? 9 * p.conv_cblocks : (int)((p.K + kBlockK - 1) / kBlockK);
   const uint32_t Zn = (uint32_t)(p.Z0 * p.Z1 * p.Z2);
@@ -599,7 +611,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // UTMALDG / UTCHMMA in per-instruction election code)
     int stage = 0;
     uint32_t phase = 0;
-    for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const uint32_t full0 = CTAS == 2 ? mapa_u32(full_bar(0), 0) : 0u;  // the leader's full barriers (cluster address)
+    for (uint32_t t = blockIdx.x / CTAS; t < tiles; t += gridDim.x / CTAS) {
       uint32_t nb, mb, uz0, uz1, uz2;
       tdec(t, nb, mb, uz0, uz1, uz2);
       const int z0 = (int)uz0, z1 = (int)uz1, z2 = (int)uz2;
@@ -627,20 +640,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           if (gemm_elect_one()) {
-            mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-            tma_load_5d(&tma_a, full_bar(stage), smem_a(stage), kb * kBlockK,
-                        (int)(mb * kBlockM), z0, z1, z2);
-            tma_load_5d(&tma_b, full_bar(stage), smem_b(stage), kb * kBlockK, (int)(nb * BN),
-                        z0 & p.bmask[0], z1 & p.bmask[1], z2 & p.bmask[2]);
+            if constexpr (CTAS == 2) {
+              // both CTAs' loads are counted on the leader's barrier, which the leader arms for the pair
+              if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+              const uint32_t fb = full0 + 8u * (uint32_t)stage;
+              tma_load_5d_2sm(&tma_a, fb, smem_a(stage), kb * kBlockK,
+                              (int)(mb * kTileM + cta_rank * kBlockM), z0, z1, z2);
+              tma_load_5d_2sm(&tma_b, fb, smem_b(stage), kb * kBlockK, (int)(nb * BN + cta_rank * (BN / 2)),
+                              z0 & p.bmask[0], z1 & p.bmask[1], z2 & p.bmask[2]);
+            } else {
+              mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+              tma_load_5d(&tma_a, full_bar(stage), smem_a(stage), kb * kBlockK,
+                          (int)(mb * kBlockM), z0, z1, z2);
+              tma_load_5d(&tma_b, full_bar(stage), smem_b(stage), kb * kBlockK, (int)(nb * BN),
+                          z0 & p.bmask[0], z1 & p.bmask[1], z2 & p.bmask[2]);
+            }
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
+  } else if (warp == 1 && cta_rank == 0) {
+    // ===== MMA issuer (pair: the leader CTA only) =====
+    constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -648,8 +671,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // the last column block may be narrower than BN: its MMAs only cover the real columns (rounded up to the
     // instruction granularity of 16), so a wide BN costs no tensor time on the ragged edge
     const uint32_t n_tail = (uint32_t)p.N - (n_blocks - 1) * (uint32_t)BN;
-    const uint32_t idesc_tail = umma_idesc_bf16(kBlockM, (int)((n_tail + 15u) & ~15u));
-    for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const uint32_t idesc_tail = umma_idesc_bf16(kTileM, (int)((n_tail + 15u) & ~15u));
+    auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t accumulate) {
+      if constexpr (CTAS == 2) umma_bf16_2sm(d, a, b, id, accumulate);
+      else umma_bf16(d, a, b, id, accumulate);
+    };
+    auto commit = [&](uint32_t bar) {
+      if constexpr (CTAS == 2) umma_commit_2sm(bar);
+      else umma_commit(bar);
+    };
+    for (uint32_t t = blockIdx.x / CTAS; t < tiles; t += gridDim.x / CTAS) {
       const uint32_t idesc_t = (t % n_blocks == n_blocks - 1) ? idesc_tail : idesc;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
@@ -667,15 +698,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (nk16 == kBlockK / 16) {
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
-              umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_t, (kb > 0 || k > 0) ? 1u : 0u);
+              mma(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_t, (kb > 0 || k > 0) ? 1u : 0u);
           } else {
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
               if (k < nk16)
-                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_t, (kb > 0 || k > 0) ? 1u : 0u);
+                mma(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_t, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));
-          if (kb == k_blocks - 1) umma_commit(tfull_bar(acc));
+          commit(empty_bar(stage));
+          if (kb == k_blocks - 1) commit(tfull_bar(acc));
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -690,11 +721,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint32_t epi_count = 0;  // chunks stored so far by this warp (ring slot / residual barrier parity)
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const uint32_t tempty0 = CTAS == 2 ? mapa_u32(tempty_bar(0), 0) : 0u;  // the leader's (cluster address)
+    for (uint32_t t = blockIdx.x / CTAS; t < tiles; t += gridDim.x / CTAS) {
       uint32_t unb, umb, uz0, uz1, uz2;
       tdec(t, unb, umb, uz0, uz1, uz2);
       const int64_t nb = unb, mb = umb, z0 = uz0, z1 = uz1, z2 = uz2;
-      const int64_t m_warp0 = mb * kBlockM + lg * 32;
+      const int64_t m_warp0 = mb * kTileM + cta_rank * kBlockM + lg * 32;
       const float* bias = p.bias ? p.bias + z0 * p.bias_zs[0] + z1 * p.bias_zs[1] + z2 * p.bias_zs[2] : nullptr;
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BN);
       if constexpr (EPI == 0 && CONV) {
@@ -776,8 +808,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       (p.cmap[2] == 0 ? (int)(lo) : p.cmap[2] == 1 ? (int)(hi) : fx[2]),                                     \
       (p.cmap[3] == 0 ? (int)(lo) : p.cmap[3] == 1 ? (int)(hi) : fx[3]),                                     \
       (p.cmap[4] == 0 ? (int)(lo) : p.cmap[4] == 1 ? (int)(hi) : fx[4])
-        auto advance = [&](uint32_t& lo, uint32_t& hi) {  // next chunk of this warp: 64 columns on
-          lo += 64u;
+        auto advance = [&](uint32_t& lo, uint32_t& hi, uint32_t by = 64u) {  // next chunk of this warp
+          lo += by;
           while (lo >= nr) { lo -= nr; ++hi; }
         };
         const uint32_t n_tile0 = unb * (uint32_t)BN;
@@ -808,6 +840,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const uint32_t myrow = (uint32_t)lane;
         // one chunk: accumulator registers -> bias / LN / activation (/ residual) -> swizzled tile -> TMA store
         auto process = [&](uint32_t (&r)[32], int i) {
+#if defined(RFK_GEMM_DBG) && RFK_GEMM_DBG >= 3
+          asm volatile("" ::"r"(r[0]), "r"(r[31]));
+          return;
+#endif
           const uint32_t n0 = n_tile0 + (uint32_t)(chalf + 2 * i) * 32u;
           const int slot = (int)(epi_count % kRing);
           const uint32_t buf = ring + (uint32_t)slot * kBuf;
@@ -830,6 +866,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
+#if defined(RFK_GEMM_DBG) && RFK_GEMM_DBG >= 2
+          asm volatile("" ::"f"(v[0]), "f"(v[5]), "f"(v[17]), "f"(v[31]));
+          return;
+#endif
           if constexpr (EPI == 3) {
             // the store issued four chunks ago (same slot) must have finished reading the tile
             bulk_wait_read<Cfg::kRing3 - 1>();
@@ -861,10 +901,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
           fence_proxy_async_smem();
           __syncwarp();
+#if !defined(RFK_GEMM_DBG) || RFK_GEMM_DBG < 1
           if (gemm_elect_one()) {
             tma_store_5d(&tma_c, buf, RFK_COORDS(nlo, nhi));
             bulk_commit();
           }
+#endif
           if (use_res && i + 2 < nch) {
             // slot of chunk i+2 was last used by chunk i-1: its store may still be in flight
             bulk_wait_read<1>();
@@ -879,7 +921,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           advance(nlo, nhi);
           ++epi_count;
         };
-        if (nch > 0) {
+        if (EPI == 3 && p.wide) {
+          // ---- 64-column stores: every row of the box is a whole 128-byte line (half as many TMA stores,
+          // no partial-line writes; the 32-column form spent ~1/3 of the kernel on its stores) ----
+          const int ct64 = min(BN / 64, (int)(((uint32_t)p.N - n_tile0 + 63u) >> 6));
+          const int ngr = (m_warp0 < p.M && ct64 > chalf) ? (ct64 - chalf + 1) >> 1 : 0;
+          const uint32_t g_first = n_tile0 + (uint32_t)chalf * 64u;
+          nhi = g_first / nr; nlo = g_first - nhi * nr;
+#pragma unroll 1
+          for (int i = 0; i < ngr; ++i) {
+            const int g = chalf + 2 * i;
+            const uint32_t n0 = n_tile0 + (uint32_t)g * 64u;
+            const uint32_t buf = ring + (uint32_t)(epi_count & 1u) * 4096u;
+            uint32_t ra[32], rb[32];
+            tmem_ld_32x32(taddr + (uint32_t)(g * 64), ra);
+            tmem_ld_32x32(taddr + (uint32_t)(g * 64 + 32), rb);
+            tmem_ld_wait();
+            bulk_wait_read<1>();  // the store that last used this slot (two groups ago) has read it
+            __syncwarp();
+            const uint32_t rowb = buf + myrow * 128u, sw = myrow & 7u;
+            auto half = [&](uint32_t (&r)[32], uint32_t h) {
+              float v[32];
+              if (bias) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + n0 + 32u * h) + j);
+                  v[4 * j] = __uint_as_float(r[4 * j]) + bq.x;
+                  v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bq.y;
+                  v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bq.z;
+                  v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bq.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+              }
+              if (p.epi == RFK_EPI_BLOCKLN32) blockln32(p, lane, v);
+              if (p.act == RFK_ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
+#pragma unroll
+              for (uint32_t q = 0; q < 4; ++q)
+                st_shared_v4u(rowb + (((4u * h + q) ^ sw) << 4), pack_bf16x2(v[8 * q], v[8 * q + 1]),
+                              pack_bf16x2(v[8 * q + 2], v[8 * q + 3]), pack_bf16x2(v[8 * q + 4], v[8 * q + 5]),
+                              pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+            };
+            half(ra, 0u);
+            half(rb, 1u);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (gemm_elect_one()) {
+              tma_store_5d(&tma_c, buf, RFK_COORDS(nlo, nhi));
+              bulk_commit();
+            }
+            __syncwarp();
+            advance(nlo, nhi, 128u);
+            ++epi_count;
+          }
+        } else if (nch > 0) {
           // the accumulator chunk after the one being processed is already on its way out of TMEM
           // (a prefetch past the last owned chunk re-reads the first one: always inside the accumulator)
           uint32_t ra[32], rb[32];
@@ -931,16 +1030,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if constexpr (CTAS == 2) mbar_arrive_cluster(tempty0 + 8u * (uint32_t)acc);
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
   if ((EPI == 3 || EPI == 4) && warp >= 2) bulk_wait_all();  // smem tiles must outlive their bulk stores
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();  // neither CTA may free TMEM (or exit) while the pair still works
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (CTAS == 2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -970,6 +1074,38 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev
   return post_launch();
 }
 
+// CTA-pair launch: clusters of two CTAs (one TPC), grid = an even number of SMs, 256-row tiles
+template <int BN, int EPI>
+static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb_half, const GemmDev& p, int64_t tiles,
+                          cudaStream_t stream, const EpiMaps* em) {
+  using Cfg = GemmCfg<BN, EPI, 2>;
+  if (tiles > 0x7fffffffLL || p.M > 0x7fffffffLL || p.N > 0x7fffffffLL || p.K > 0x7fffffffLL) return RFK_ERR_BAD_DIMS;
+  auto kernel = gemm_tc_kernel<BN, EPI, false, 2>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return cuda_status(e);
+    configured = true;
+  }
+  int64_t pairs = num_sms() / 2;
+  if (tiles < pairs) pairs = tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ta, tb_half, em->c, em->r, p);
+  if (e != cudaSuccess) return cuda_status(e);
+  return post_launch();
+}
+
 template <int EPI>
 static int launch_tc_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p,
                         int64_t tiles, cudaStream_t stream, const EpiMaps* em = nullptr) {
@@ -989,6 +1125,7 @@ int launch_tc_epi0(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const G
 int launch_tc_epi1(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s);
 int launch_tc_epi2(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s);
 int launch_tc_epi3(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s, const EpiMaps* em);
+int launch_tc_pair_epi3(int bn, const CUtensorMap& ta, const CUtensorMap& tb_half, const GemmDev& p, int64_t tiles, cudaStream_t s, const EpiMaps* em);
 int launch_tc_epi4(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s, const EpiMaps* em);
 int launch_tc_conv(int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s);
 int make_tmap_bf16_raw(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
