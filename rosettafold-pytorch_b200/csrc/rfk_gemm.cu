@@ -138,7 +138,7 @@ static int make_tmap_raw(CUtensorMap* map, const void* ptr, int rank, const uint
 // {n%NR, n/NR, m%MR, m/MR, z0, z1, z2} with size-1 dims dropped; box = 32 x 32 over (n%NR, m%MR).
 // Returns RFK_ERR_UNSUPPORTED when the view needs more than 5 dims or breaks a TMA rule.
 int make_epi_tmap(CUtensorMap* map, int cmap[5], const void* ptr, int dtype, const rfk_addr& a,
-                  const int64_t ext[7], int box_n = 32) {
+                  const int64_t ext[7]) {
   const int es = dtype == RFK_BF16 ? 2 : 4;
   if (!aligned16(ptr) || a.ns[0] != 1) return RFK_ERR_UNSUPPORTED;
   const int64_t strides[7] = {a.ns[0], a.ns[1], a.ms[0], a.ms[1], a.zs[0], a.zs[1], a.zs[2]};
@@ -155,14 +155,14 @@ int make_epi_tmap(CUtensorMap* map, int cmap[5], const void* ptr, int dtype, con
       sb[nd - 1] = (uint64_t)st * es;
     }
     dims[nd] = (uint64_t)ext[l];
-    box[nd] = l == 0 ? box_n : (l == 2 ? 32 : 1);
+    box[nd] = (l == 0 || l == 2) ? 32 : 1;
     cmap[nd] = l;
     ++nd;
   }
   for (int d = nd; d < 5; ++d) cmap[d] = -1;
   return make_tmap_raw(map, ptr, 5, dims, sb, box,
                        dtype == RFK_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
-                       (dtype == RFK_BF16 && box_n == 32) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+                       dtype == RFK_BF16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 int make_tmap_bf16_raw(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims,
@@ -246,6 +246,17 @@ extern "C" int rfk_gemm(const rfk_gemm_desc* d, rfk_stream_t stream_) {
   if (rc != RFK_OK) return rc;
 
   int bn = pick_bn(d->N);
+  // B-stationary form for the short-K, wide-N, bf16-output projections (q|k|v, FeedForward up-projection):
+  // decided here because it fixes the column-block width; the epilogue checks further down must agree
+  static const bool no_bstat = getenv("RFK_GEMM_NO_BSTAT") != nullptr;  // A/B debugging aid
+  int bstat_kb = 0;
+  if (!no_bstat && Z == 1 && d->K <= 384 && d->c_dtype == RFK_BF16 && !d->r0 && !d->r1 && d->M >= 16384 &&
+      d->N >= 512 && d->epi == RFK_EPI_STD) {
+    const int kb = d->K <= 320 ? 5 : 6;
+    const int first = kb == 5 ? 192 : 128, second = kb == 5 ? 128 : 192;
+    if (d->N % first == 0) { bstat_kb = kb; bn = first; }
+    else if (d->N % second == 0) { bstat_kb = kb; bn = second; }
+  }
   static const char* force_bn = getenv("RFK_GEMM_BN");  // A/B debugging aid: one of 256/192/128/96/64/32
   if (force_bn && atoi(force_bn) >= 32 && atoi(force_bn) % 32 == 0 && atoi(force_bn) <= 256) bn = atoi(force_bn);
   if (d->epi == RFK_EPI_BLOCKLN32) bn = 128;
@@ -294,11 +305,7 @@ extern "C" int rfk_gemm(const rfk_gemm_desc* d, rfk_stream_t stream_) {
                               d->Z[0], d->Z[1], d->Z[2]};
       EpiMaps em{};
       int cmap_c[5], cmap_r[5];
-      // bf16 stores go out in 64-column boxes (whole 128-byte lines) when the column blocks allow it
-      static const bool no_wide = getenv("RFK_GEMM_NO_WIDE_STORE") != nullptr;  // A/B debugging aid
-      const bool wide = epi == 1 && !no_wide && ext[0] % 64 == 0 && bn % 64 == 0 && d->N % 64 == 0;
-      p.wide = wide ? 1 : 0;
-      bool ok = make_epi_tmap(&em.c, cmap_c, d->c, d->c_dtype, d->c_addr, ext, wide ? 64 : 32) == RFK_OK;
+      bool ok = make_epi_tmap(&em.c, cmap_c, d->c, d->c_dtype, d->c_addr, ext) == RFK_OK;
       bool res_tma = false;
       if (ok && epi == 2 && d->r0) {
         res_tma = make_epi_tmap(&em.r, cmap_r, d->r0, RFK_F32, d->r0_addr, ext) == RFK_OK;
@@ -317,6 +324,7 @@ extern "C" int rfk_gemm(const rfk_gemm_desc* d, rfk_stream_t stream_) {
           const int64_t tiles2 = Z * ((d->M + 2 * kBlockM - 1) / (2 * kBlockM)) * (d->N / bn);
           return launch_tc_pair_epi3(bn, ta, tb_half, p, tiles2, stream, &em);
         }
+        if (bstat_kb && epi == 1) return launch_tc_bstat_epi3(bn, bstat_kb, ta, tb, p, tiles, stream, &em);
         return epi == 1 ? launch_tc_epi3(bn, ta, tb, p, tiles, stream, &em)
                         : launch_tc_epi4(bn, ta, tb, p, tiles, stream, &em);
       }

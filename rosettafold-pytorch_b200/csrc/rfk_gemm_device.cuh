@@ -30,7 +30,6 @@ struct GemmDev {
   // {0: n % NR, 1: n / NR, 2: m % MR, 3: m / MR, 4: z0, 5: z1, 6: z2}; -1 -> 0
   int cmap[5];
   int has_rmap;  // residual r0 is fetched with TMA (map tma_r)
-  int wide;      // EPI 3: the store box is 64 columns (full 128-byte lines) instead of 32
   // SIMT path only
   const float* a32;
   const float* b32;
@@ -483,20 +482,25 @@ constexpr int kEpiWarps = 8;
 
 // CTAS = 2: CTA pair (cta_group::2) - a 256-row tile over two SMs, each CTA stages its 128 rows of A and
 // BN/2 rows of B per k-block (half the B traffic through shared memory per SM)
-template <int BN, int EPI = 0, int CTAS = 1>
+// KB > 0: B-stationary - the whole [BN x K] weight block (KB k-blocks of 64) stays in shared memory while the CTA
+// walks a contiguous range of row blocks; only A streams through the ring. For the short-K projections the
+// weight re-reads are 2/3 of the L2 -> SM operand traffic that bounds the streaming form.
+template <int BN, int EPI = 0, int CTAS = 1, int KB = 0>
 struct GemmCfg {
-  static constexpr int kStageBytes = kBlockM * 128 + (BN / CTAS) * 128;
+  static constexpr int kStageBytes = kBlockM * 128 + (KB > 0 ? 0 : (BN / CTAS) * 128);
+  static constexpr int kBResident = KB * BN * 128;
   // epilogue staging: EPI 0-2 one [32][33] f32 transpose buffer per warp; EPI 3: two 2 KB bf16
   // tiles per warp; EPI 4: three 4 KB f32 tiles per warp (residual-in / result-out ring)
-  static constexpr int kRing3 = RFK_EPI3_RING;
+  static constexpr int kRing3 = KB > 0 ? 2 : RFK_EPI3_RING;
   static constexpr int kStagingBytes = EPI == 3 ? kEpiWarps * kRing3 * 2048
                                        : EPI == 4 ? kEpiWarps * 3 * 4096 : kEpiWarps * 32 * 33 * 4;
   static constexpr int kBarBytes = 512;
-  static constexpr int kBudget = 232448 - 2048 - kBarBytes - kStagingBytes;
+  static constexpr int kBudget = 232448 - 2048 - kBarBytes - kStagingBytes - kBResident;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128
                                    : 2 * BN <= 256 ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 2048 /*align*/ + kBarBytes + kStagingBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBResident + 2048 /*align*/ + kBarBytes + kStagingBytes;
+  static_assert(kStages >= 2, "shared memory budget");
 };
 
 // one lane of the (fully active) warp
@@ -532,24 +536,27 @@ struct TileDecoder {
   }
 };
 
-template <int BN, int EPI, bool CONV = false, int CTAS = 1>
+template <int BN, int EPI, bool CONV = false, int CTAS = 1, int KB = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r,
                const GemmDev p) {
-  using Cfg = GemmCfg<BN, EPI, CTAS>;
+  using Cfg = GemmCfg<BN, EPI, CTAS, KB>;
   static_assert(CTAS == 1 || (!CONV && BN % 32 == 0), "CTA pairs: plain GEMM only");
+  static_assert(KB == 0 || (!CONV && CTAS == 1), "B-stationary: plain single-CTA GEMM only");
   constexpr int STAGES = Cfg::kStages;
   const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * Cfg::kStageBytes;
+  const uint32_t bres_base = smem_base + STAGES * Cfg::kStageBytes;  // resident weight block (KB > 0), 1024-aligned
+  const uint32_t bar_base = bres_base + Cfg::kBResident;
   // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  const uint32_t bfull_bar = bar_base + 8u * (2 * STAGES + 5);  // resident weight block landed (KB > 0)
   // EPI 4: one residual-arrival barrier per (epilogue warp, ring slot)
   auto res_bar = [&](int w, int slot) { return bar_base + 256u + 8u * (w * 3 + slot); };
   // staging area, 1024-byte aligned (TMA-store swizzle patterns are address based)
@@ -567,6 +574,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
+    mbar_init(bfull_bar, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kEpiWarps * CTAS);  // pair: the epilogue warps of both CTAs release the leader's
@@ -603,6 +611,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const uint32_t Zn = (uint32_t)(p.Z0 * p.Z1 * p.Z2);
   const uint32_t tiles = Zn * m_blocks * n_blocks;
   const TileDecoder tdec{n_blocks, m_blocks, (uint32_t)p.Z0, (uint32_t)p.Z1, Zn};
+  // tile walk of this CTA. Streaming form: tiles blockIdx, blockIdx + grid, ... with n fastest (CTAs running side by
+  // side share A rows in L2). B-stationary form (Z = 1): a contiguous range of the column-block-major tile list, so
+  // the column block - and with it the resident weights - changes at most a few times per CTA.
+  const uint32_t t_begin = KB > 0 ? (uint32_t)((uint64_t)blockIdx.x * tiles / gridDim.x) : blockIdx.x / CTAS;
+  const uint32_t t_end = KB > 0 ? (uint32_t)((uint64_t)(blockIdx.x + 1) * tiles / gridDim.x) : tiles;
+  const uint32_t t_step = KB > 0 ? 1u : gridDim.x / CTAS;
+  auto decode = [&](uint32_t t, uint32_t& nb, uint32_t& mb, uint32_t& z0, uint32_t& z1, uint32_t& z2) {
+    if constexpr (KB > 0) {
+      nb = t / m_blocks; mb = t - nb * m_blocks; z0 = z1 = z2 = 0;
+    } else {
+      tdec(t, nb, mb, z0, z1, z2);
+    }
+  };
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -612,10 +633,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t full0 = CTAS == 2 ? mapa_u32(full_bar(0), 0) : 0u;  // the leader's full barriers (cluster address)
-    for (uint32_t t = blockIdx.x / CTAS; t < tiles; t += gridDim.x / CTAS) {
+    uint32_t cur_nb = 0xffffffffu;
+    for (uint32_t t = t_begin; t < t_end; t += t_step) {
       uint32_t nb, mb, uz0, uz1, uz2;
-      tdec(t, nb, mb, uz0, uz1, uz2);
+      decode(t, nb, mb, uz0, uz1, uz2);
       const int z0 = (int)uz0, z1 = (int)uz1, z2 = (int)uz2;
+      if constexpr (KB > 0) {
+        if (nb != cur_nb) {
+          // new column block: every MMA that reads the old weights has completed once the most recently filled
+          // A stage has been released (MMAs retire in order); then fetch the new [BN x K] block
+          if (cur_nb != 0xffffffffu) {
+            const int prev = stage == 0 ? STAGES - 1 : stage - 1;
+            mbar_wait(empty_bar(prev), stage == 0 ? (phase ^ 1u) : phase);
+          }
+          if (gemm_elect_one()) {
+            mbar_arrive_expect_tx(bfull_bar, (uint32_t)k_blocks * (uint32_t)(BN * 128));
+            for (int kb = 0; kb < k_blocks; ++kb)
+              tma_load_5d(&tma_b, bfull_bar, bres_base + (uint32_t)kb * (uint32_t)(BN * 128), kb * kBlockK,
+                          (int)(nb * BN), 0, 0, 0);
+          }
+          __syncwarp();
+          cur_nb = nb;
+        }
+      }
       if constexpr (CONV) {
         // tile -> (image b, row i, first column j0); taps shift the TMA box, out-of-image rows and
         // columns are zero-filled by the TMA unit ('same' padding for free)
@@ -652,8 +692,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
               tma_load_5d(&tma_a, full_bar(stage), smem_a(stage), kb * kBlockK,
                           (int)(mb * kBlockM), z0, z1, z2);
-              tma_load_5d(&tma_b, full_bar(stage), smem_b(stage), kb * kBlockK, (int)(nb * BN),
-                          z0 & p.bmask[0], z1 & p.bmask[1], z2 & p.bmask[2]);
+              if constexpr (KB == 0)
+                tma_load_5d(&tma_b, full_bar(stage), smem_b(stage), kb * kBlockK, (int)(nb * BN),
+                            z0 & p.bmask[0], z1 & p.bmask[1], z2 & p.bmask[2]);
             }
           }
           __syncwarp();
@@ -680,8 +721,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       if constexpr (CTAS == 2) umma_commit_2sm(bar);
       else umma_commit(bar);
     };
-    for (uint32_t t = blockIdx.x / CTAS; t < tiles; t += gridDim.x / CTAS) {
-      const uint32_t idesc_t = (t % n_blocks == n_blocks - 1) ? idesc_tail : idesc;
+    uint32_t cur_nb = 0xffffffffu, bphase = 0;
+    for (uint32_t t = t_begin; t < t_end; t += t_step) {
+      uint32_t idesc_t;
+      if constexpr (KB > 0) {
+        const uint32_t nb = t / m_blocks;
+        idesc_t = nb == n_blocks - 1 ? idesc_tail : idesc;
+        if (nb != cur_nb) {  // wait for the resident weights of this column block
+          mbar_wait(bfull_bar, bphase);
+          bphase ^= 1u;
+          cur_nb = nb;
+        }
+      } else {
+        idesc_t = (t % n_blocks == n_blocks - 1) ? idesc_tail : idesc;
+      }
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -689,7 +742,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         const uint64_t adesc = umma_desc_sw128(smem_a(stage));
-        const uint64_t bdesc = umma_desc_sw128(smem_b(stage));
+        const uint64_t bdesc = umma_desc_sw128(KB > 0 ? bres_base + (uint32_t)kb * (uint32_t)(BN * 128) : smem_b(stage));
         // conv: the last channel block of a tap may hold fewer than 64 real channels
         // (the K tail of a plain GEMM is zero-filled by TMA: skip the all-zero k16 steps too)
         const int nk16 = CONV ? ((kb % p.conv_cblocks == p.conv_cblocks - 1) ? p.conv_last_k16 : kBlockK / 16)
@@ -722,9 +775,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t tempty0 = CTAS == 2 ? mapa_u32(tempty_bar(0), 0) : 0u;  // the leader's (cluster address)
-    for (uint32_t t = blockIdx.x / CTAS; t < tiles; t += gridDim.x / CTAS) {
+    for (uint32_t t = t_begin; t < t_end; t += t_step) {
       uint32_t unb, umb, uz0, uz1, uz2;
-      tdec(t, unb, umb, uz0, uz1, uz2);
+      decode(t, unb, umb, uz0, uz1, uz2);
       const int64_t nb = unb, mb = umb, z0 = uz0, z1 = uz1, z2 = uz2;
       const int64_t m_warp0 = mb * kTileM + cta_rank * kBlockM + lg * 32;
       const float* bias = p.bias ? p.bias + z0 * p.bias_zs[0] + z1 * p.bias_zs[1] + z2 * p.bias_zs[2] : nullptr;
@@ -808,8 +861,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       (p.cmap[2] == 0 ? (int)(lo) : p.cmap[2] == 1 ? (int)(hi) : fx[2]),                                     \
       (p.cmap[3] == 0 ? (int)(lo) : p.cmap[3] == 1 ? (int)(hi) : fx[3]),                                     \
       (p.cmap[4] == 0 ? (int)(lo) : p.cmap[4] == 1 ? (int)(hi) : fx[4])
-        auto advance = [&](uint32_t& lo, uint32_t& hi, uint32_t by = 64u) {  // next chunk of this warp
-          lo += by;
+        auto advance = [&](uint32_t& lo, uint32_t& hi) {  // next chunk of this warp: 64 columns on
+          lo += 64u;
           while (lo >= nr) { lo -= nr; ++hi; }
         };
         const uint32_t n_tile0 = unb * (uint32_t)BN;
@@ -840,10 +893,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const uint32_t myrow = (uint32_t)lane;
         // one chunk: accumulator registers -> bias / LN / activation (/ residual) -> swizzled tile -> TMA store
         auto process = [&](uint32_t (&r)[32], int i) {
-#if defined(RFK_GEMM_DBG) && RFK_GEMM_DBG >= 3
-          asm volatile("" ::"r"(r[0]), "r"(r[31]));
-          return;
-#endif
           const uint32_t n0 = n_tile0 + (uint32_t)(chalf + 2 * i) * 32u;
           const int slot = (int)(epi_count % kRing);
           const uint32_t buf = ring + (uint32_t)slot * kBuf;
@@ -866,10 +915,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
-#if defined(RFK_GEMM_DBG) && RFK_GEMM_DBG >= 2
-          asm volatile("" ::"f"(v[0]), "f"(v[5]), "f"(v[17]), "f"(v[31]));
-          return;
-#endif
           if constexpr (EPI == 3) {
             // the store issued four chunks ago (same slot) must have finished reading the tile
             bulk_wait_read<Cfg::kRing3 - 1>();
@@ -901,12 +946,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
           fence_proxy_async_smem();
           __syncwarp();
-#if !defined(RFK_GEMM_DBG) || RFK_GEMM_DBG < 1
           if (gemm_elect_one()) {
             tma_store_5d(&tma_c, buf, RFK_COORDS(nlo, nhi));
             bulk_commit();
           }
-#endif
           if (use_res && i + 2 < nch) {
             // slot of chunk i+2 was last used by chunk i-1: its store may still be in flight
             bulk_wait_read<1>();
@@ -921,64 +964,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           advance(nlo, nhi);
           ++epi_count;
         };
-        if (EPI == 3 && p.wide) {
-          // ---- 64-column stores: every row of the box is a whole 128-byte line (half as many TMA stores,
-          // no partial-line writes; the 32-column form spent ~1/3 of the kernel on its stores) ----
-          const int ct64 = min(BN / 64, (int)(((uint32_t)p.N - n_tile0 + 63u) >> 6));
-          const int ngr = (m_warp0 < p.M && ct64 > chalf) ? (ct64 - chalf + 1) >> 1 : 0;
-          const uint32_t g_first = n_tile0 + (uint32_t)chalf * 64u;
-          nhi = g_first / nr; nlo = g_first - nhi * nr;
-#pragma unroll 1
-          for (int i = 0; i < ngr; ++i) {
-            const int g = chalf + 2 * i;
-            const uint32_t n0 = n_tile0 + (uint32_t)g * 64u;
-            const uint32_t buf = ring + (uint32_t)(epi_count & 1u) * 4096u;
-            uint32_t ra[32], rb[32];
-            tmem_ld_32x32(taddr + (uint32_t)(g * 64), ra);
-            tmem_ld_32x32(taddr + (uint32_t)(g * 64 + 32), rb);
-            tmem_ld_wait();
-            bulk_wait_read<1>();  // the store that last used this slot (two groups ago) has read it
-            __syncwarp();
-            const uint32_t rowb = buf + myrow * 128u, sw = myrow & 7u;
-            auto half = [&](uint32_t (&r)[32], uint32_t h) {
-              float v[32];
-              if (bias) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + n0 + 32u * h) + j);
-                  v[4 * j] = __uint_as_float(r[4 * j]) + bq.x;
-                  v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bq.y;
-                  v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bq.z;
-                  v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bq.w;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-              }
-              if (p.epi == RFK_EPI_BLOCKLN32) blockln32(p, lane, v);
-              if (p.act == RFK_ACT_RELU) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-              }
-#pragma unroll
-              for (uint32_t q = 0; q < 4; ++q)
-                st_shared_v4u(rowb + (((4u * h + q) ^ sw) << 4), pack_bf16x2(v[8 * q], v[8 * q + 1]),
-                              pack_bf16x2(v[8 * q + 2], v[8 * q + 3]), pack_bf16x2(v[8 * q + 4], v[8 * q + 5]),
-                              pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
-            };
-            half(ra, 0u);
-            half(rb, 1u);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (gemm_elect_one()) {
-              tma_store_5d(&tma_c, buf, RFK_COORDS(nlo, nhi));
-              bulk_commit();
-            }
-            __syncwarp();
-            advance(nlo, nhi, 128u);
-            ++epi_count;
-          }
-        } else if (nch > 0) {
+        if (nch > 0) {
           // the accumulator chunk after the one being processed is already on its way out of TMEM
           // (a prefetch past the last owned chunk re-reads the first one: always inside the accumulator)
           uint32_t ra[32], rb[32];
@@ -1106,6 +1092,25 @@ static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb_half, con
   return post_launch();
 }
 
+// B-stationary launch (flavour 3, Z = 1): one CTA per SM, each walking a contiguous range of the tile list
+template <int BN, int KB>
+static int launch_tc_bstat(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles,
+                           cudaStream_t stream, const EpiMaps* em) {
+  using Cfg = GemmCfg<BN, 3, 1, KB>;
+  if (tiles > 0x7fffffffLL || p.M > 0x7fffffffLL || p.N > 0x7fffffffLL || p.K > (int64_t)KB * kBlockK) return RFK_ERR_BAD_DIMS;
+  auto kernel = gemm_tc_kernel<BN, 3, false, 1, KB>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return cuda_status(e);
+    configured = true;
+  }
+  int grid = num_sms();
+  if (tiles < grid) grid = (int)tiles;
+  kernel<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, em->c, em->r, p);
+  return post_launch();
+}
+
 template <int EPI>
 static int launch_tc_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p,
                         int64_t tiles, cudaStream_t stream, const EpiMaps* em = nullptr) {
@@ -1126,6 +1131,7 @@ int launch_tc_epi1(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const G
 int launch_tc_epi2(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s);
 int launch_tc_epi3(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s, const EpiMaps* em);
 int launch_tc_pair_epi3(int bn, const CUtensorMap& ta, const CUtensorMap& tb_half, const GemmDev& p, int64_t tiles, cudaStream_t s, const EpiMaps* em);
+int launch_tc_bstat_epi3(int bn, int kb, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s, const EpiMaps* em);
 int launch_tc_epi4(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s, const EpiMaps* em);
 int launch_tc_conv(int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s);
 int make_tmap_bf16_raw(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);

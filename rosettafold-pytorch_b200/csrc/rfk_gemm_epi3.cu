@@ -15,4 +15,13 @@ int launch_tc_pair_epi3(int bn, const CUtensorMap& ta, const CUtensorMap& tb_hal
     default: return RFK_ERR_UNSUPPORTED;
   }
 }
+// B-stationary instances: short-K projections with bf16 output (K <= 320: five k-blocks, K <= 384: six)
+int launch_tc_bstat_epi3(int bn, int kb, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles,
+                         cudaStream_t s, const EpiMaps* em) {
+  if (bn == 192 && kb == 5) return launch_tc_bstat<192, 5>(ta, tb, p, tiles, s, em);
+  if (bn == 128 && kb == 5) return launch_tc_bstat<128, 5>(ta, tb, p, tiles, s, em);
+  if (bn == 192 && kb == 6) return launch_tc_bstat<192, 6>(ta, tb, p, tiles, s, em);
+  if (bn == 128 && kb == 6) return launch_tc_bstat<128, 6>(ta, tb, p, tiles, s, em);
+  return RFK_ERR_UNSUPPORTED;
+}
 }  // namespace rfk
