@@ -246,17 +246,6 @@ extern "C" int rfk_gemm(const rfk_gemm_desc* d, rfk_stream_t stream_) {
   if (rc != RFK_OK) return rc;
 
   int bn = pick_bn(d->N);
-  // B-stationary form for the short-K, wide-N, bf16-output projections (q|k|v, FeedForward up-projection):
-  // decided here because it fixes the column-block width; the epilogue checks further down must agree
-  static const bool no_bstat = getenv("RFK_GEMM_NO_BSTAT") != nullptr;  // A/B debugging aid
-  int bstat_kb = 0;
-  if (!no_bstat && Z == 1 && d->K <= 384 && d->c_dtype == RFK_BF16 && !d->r0 && !d->r1 && d->M >= 16384 &&
-      d->N >= 512 && d->epi == RFK_EPI_STD) {
-    const int kb = d->K <= 320 ? 5 : 6;
-    const int first = kb == 5 ? 192 : 128, second = kb == 5 ? 128 : 192;
-    if (d->N % first == 0) { bstat_kb = kb; bn = first; }
-    else if (d->N % second == 0) { bstat_kb = kb; bn = second; }
-  }
   static const char* force_bn = getenv("RFK_GEMM_BN");  // A/B debugging aid: one of 256/192/128/96/64/32
   if (force_bn && atoi(force_bn) >= 32 && atoi(force_bn) % 32 == 0 && atoi(force_bn) <= 256) bn = atoi(force_bn);
   if (d->epi == RFK_EPI_BLOCKLN32) bn = 128;
@@ -315,16 +304,6 @@ extern "C" int rfk_gemm(const rfk_gemm_desc* d, rfk_stream_t stream_) {
       if (ok) {
         for (int i = 0; i < 5; ++i) p.cmap[i] = cmap_c[i];
         p.has_rmap = res_tma ? 1 : 0;
-        // CTA pairs for the big bf16-output GEMMs (opt-in while it is being measured)
-        static const bool pair_on = getenv("RFK_GEMM_PAIR") != nullptr;
-        if (pair_on && epi == 1 && bn >= 128 && d->N % bn == 0 && d->M >= 4096) {
-          CUtensorMap tb_half;
-          rc = make_tmap_bf16(&tb_half, d->b, d->K, d->N, d->ldb, d->Z, d->b_zs, bn / 2);
-          if (rc != RFK_OK) return rc;
-          const int64_t tiles2 = Z * ((d->M + 2 * kBlockM - 1) / (2 * kBlockM)) * (d->N / bn);
-          return launch_tc_pair_epi3(bn, ta, tb_half, p, tiles2, stream, &em);
-        }
-        if (bstat_kb && epi == 1) return launch_tc_bstat_epi3(bn, bstat_kb, ta, tb, p, tiles, stream, &em);
         return epi == 1 ? launch_tc_epi3(bn, ta, tb, p, tiles, stream, &em)
                         : launch_tc_epi4(bn, ta, tb, p, tiles, stream, &em);
       }

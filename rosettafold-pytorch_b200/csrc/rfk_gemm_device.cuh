@@ -480,27 +480,20 @@ constexpr int kBlockK = 64;
 constexpr int kGemmThreads = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kEpiWarps = 8;
 
-// CTAS = 2: CTA pair (cta_group::2) - a 256-row tile over two SMs, each CTA stages its 128 rows of A and
-// BN/2 rows of B per k-block (half the B traffic through shared memory per SM)
-// KB > 0: B-stationary - the whole [BN x K] weight block (KB k-blocks of 64) stays in shared memory while the CTA
-// walks a contiguous range of row blocks; only A streams through the ring. For the short-K projections the
-// weight re-reads are 2/3 of the L2 -> SM operand traffic that bounds the streaming form.
-template <int BN, int EPI = 0, int CTAS = 1, int KB = 0>
+template <int BN, int EPI = 0>
 struct GemmCfg {
-  static constexpr int kStageBytes = kBlockM * 128 + (KB > 0 ? 0 : (BN / CTAS) * 128);
-  static constexpr int kBResident = KB * BN * 128;
+  static constexpr int kStageBytes = kBlockM * 128 + BN * 128;
   // epilogue staging: EPI 0-2 one [32][33] f32 transpose buffer per warp; EPI 3: two 2 KB bf16
   // tiles per warp; EPI 4: three 4 KB f32 tiles per warp (residual-in / result-out ring)
-  static constexpr int kRing3 = KB > 0 ? 2 : RFK_EPI3_RING;
+  static constexpr int kRing3 = RFK_EPI3_RING;
   static constexpr int kStagingBytes = EPI == 3 ? kEpiWarps * kRing3 * 2048
                                        : EPI == 4 ? kEpiWarps * 3 * 4096 : kEpiWarps * 32 * 33 * 4;
   static constexpr int kBarBytes = 512;
-  static constexpr int kBudget = 232448 - 2048 - kBarBytes - kStagingBytes - kBResident;
+  static constexpr int kBudget = 232448 - 2048 - kBarBytes - kStagingBytes;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128
                                    : 2 * BN <= 256 ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBResident + 2048 /*align*/ + kBarBytes + kStagingBytes;
-  static_assert(kStages >= 2, "shared memory budget");
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2048 /*align*/ + kBarBytes + kStagingBytes;
 };
 
 // one lane of the (fully active) warp
@@ -536,27 +529,22 @@ struct TileDecoder {
   }
 };
 
-template <int BN, int EPI, bool CONV = false, int CTAS = 1, int KB = 0>
+template <int BN, int EPI, bool CONV = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r,
                const GemmDev p) {
-  using Cfg = GemmCfg<BN, EPI, CTAS, KB>;
-  static_assert(CTAS == 1 || (!CONV && BN % 32 == 0), "CTA pairs: plain GEMM only");
-  static_assert(KB == 0 || (!CONV && CTAS == 1), "B-stationary: plain single-CTA GEMM only");
+  using Cfg = GemmCfg<BN, EPI>;
   constexpr int STAGES = Cfg::kStages;
-  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bres_base = smem_base + STAGES * Cfg::kStageBytes;  // resident weight block (KB > 0), 1024-aligned
-  const uint32_t bar_base = bres_base + Cfg::kBResident;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::kStageBytes;
   // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
-  const uint32_t bfull_bar = bar_base + 8u * (2 * STAGES + 5);  // resident weight block landed (KB > 0)
   // EPI 4: one residual-arrival barrier per (epilogue warp, ring slot)
   auto res_bar = [&](int w, int slot) { return bar_base + 256u + 8u * (w * 3 + slot); };
   // staging area, 1024-byte aligned (TMA-store swizzle patterns are address based)
@@ -574,10 +562,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(bfull_bar, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kEpiWarps * CTAS);  // pair: the epilogue warps of both CTAs release the leader's
+      mbar_init(tempty_bar(a), kEpiWarps);
     }
     if constexpr (EPI == 4)
       for (int w = 0; w < kEpiWarps; ++w)
@@ -587,43 +574,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     tma_prefetch_desc(&tma_b);
   }
   if (warp == 1) {
-    if constexpr (CTAS == 2) {
-      tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
-      tmem_relinquish_2sm();
-    } else {
-      tmem_alloc(tmem_slot, Cfg::kTmemCols);
-      tmem_relinquish();
-    }
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
   }
   tc_fence_before();
-  if constexpr (CTAS == 2) cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive
-  else __syncthreads();
+  __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   // tile bookkeeping in 32 bits (the host checks that M, N and the tile count fit): a 64-bit division is a
   // ~100-instruction subroutine, and every role decodes its tile index once per tile
-  constexpr int kTileM = kBlockM * CTAS;
-  const uint32_t m_blocks = (uint32_t)((p.M + kTileM - 1) / kTileM);
+  const uint32_t m_blocks = (uint32_t)((p.M + kBlockM - 1) / kBlockM);
   const uint32_t n_blocks = (uint32_t)((p.N + BN - 1) / BN);
   const int k_blocks = CONV ? 9 * p.conv_cblocks : (int)((p.K + kBlockK - 1) / kBlockK);
   const uint32_t Zn = (uint32_t)(p.Z0 * p.Z1 * p.Z2);
   const uint32_t tiles = Zn * m_blocks * n_blocks;
   const TileDecoder tdec{n_blocks, m_blocks, (uint32_t)p.Z0, (uint32_t)p.Z1, Zn};
-  // tile walk of this CTA. Streaming form: tiles blockIdx, blockIdx + grid, ... with n fastest (CTAs running side by
-  // side share A rows in L2). B-stationary form (Z = 1): a contiguous range of the column-block-major tile list, so
-  // the column block - and with it the resident weights - changes at most a few times per CTA.
-  const uint32_t t_begin = KB > 0 ? (uint32_t)((uint64_t)blockIdx.x * tiles / gridDim.x) : blockIdx.x / CTAS;
-  const uint32_t t_end = KB > 0 ? (uint32_t)((uint64_t)(blockIdx.x + 1) * tiles / gridDim.x) : tiles;
-  const uint32_t t_step = KB > 0 ? 1u : gridDim.x / CTAS;
-  auto decode = [&](uint32_t t, uint32_t& nb, uint32_t& mb, uint32_t& z0, uint32_t& z1, uint32_t& z2) {
-    if constexpr (KB > 0) {
-      nb = t / m_blocks; mb = t - nb * m_blocks; z0 = z1 = z2 = 0;
-    } else {
-      tdec(t, nb, mb, z0, z1, z2);
-    }
-  };
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -632,30 +599,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // UTMALDG / UTCHMMA in per-instruction election code)
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t full0 = CTAS == 2 ? mapa_u32(full_bar(0), 0) : 0u;  // the leader's full barriers (cluster address)
-    uint32_t cur_nb = 0xffffffffu;
-    for (uint32_t t = t_begin; t < t_end; t += t_step) {
+    for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
       uint32_t nb, mb, uz0, uz1, uz2;
-      decode(t, nb, mb, uz0, uz1, uz2);
+      tdec(t, nb, mb, uz0, uz1, uz2);
       const int z0 = (int)uz0, z1 = (int)uz1, z2 = (int)uz2;
-      if constexpr (KB > 0) {
-        if (nb != cur_nb) {
-          // new column block: every MMA that reads the old weights has completed once the most recently filled
-          // A stage has been released (MMAs retire in order); then fetch the new [BN x K] block
-          if (cur_nb != 0xffffffffu) {
-            const int prev = stage == 0 ? STAGES - 1 : stage - 1;
-            mbar_wait(empty_bar(prev), stage == 0 ? (phase ^ 1u) : phase);
-          }
-          if (gemm_elect_one()) {
-            mbar_arrive_expect_tx(bfull_bar, (uint32_t)k_blocks * (uint32_t)(BN * 128));
-            for (int kb = 0; kb < k_blocks; ++kb)
-              tma_load_5d(&tma_b, bfull_bar, bres_base + (uint32_t)kb * (uint32_t)(BN * 128), kb * kBlockK,
-                          (int)(nb * BN), 0, 0, 0);
-          }
-          __syncwarp();
-          cur_nb = nb;
-        }
-      }
       if constexpr (CONV) {
         // tile -> (image b, row i, first column j0); taps shift the TMA box, out-of-image rows and
         // columns are zero-filled by the TMA unit ('same' padding for free)
@@ -680,31 +627,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           if (gemm_elect_one()) {
-            if constexpr (CTAS == 2) {
-              // both CTAs' loads are counted on the leader's barrier, which the leader arms for the pair
-              if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
-              const uint32_t fb = full0 + 8u * (uint32_t)stage;
-              tma_load_5d_2sm(&tma_a, fb, smem_a(stage), kb * kBlockK,
-                              (int)(mb * kTileM + cta_rank * kBlockM), z0, z1, z2);
-              tma_load_5d_2sm(&tma_b, fb, smem_b(stage), kb * kBlockK, (int)(nb * BN + cta_rank * (BN / 2)),
-                              z0 & p.bmask[0], z1 & p.bmask[1], z2 & p.bmask[2]);
-            } else {
-              mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-              tma_load_5d(&tma_a, full_bar(stage), smem_a(stage), kb * kBlockK,
-                          (int)(mb * kBlockM), z0, z1, z2);
-              if constexpr (KB == 0)
-                tma_load_5d(&tma_b, full_bar(stage), smem_b(stage), kb * kBlockK, (int)(nb * BN),
-                            z0 & p.bmask[0], z1 & p.bmask[1], z2 & p.bmask[2]);
-            }
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            tma_load_5d(&tma_a, full_bar(stage), smem_a(stage), kb * kBlockK,
+                        (int)(mb * kBlockM), z0, z1, z2);
+            tma_load_5d(&tma_b, full_bar(stage), smem_b(stage), kb * kBlockK, (int)(nb * BN),
+                        z0 & p.bmask[0], z1 & p.bmask[1], z2 & p.bmask[2]);
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
-  } else if (warp == 1 && cta_rank == 0) {
-    // ===== MMA issuer (pair: the leader CTA only) =====
-    constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -712,29 +648,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // the last column block may be narrower than BN: its MMAs only cover the real columns (rounded up to the
     // instruction granularity of 16), so a wide BN costs no tensor time on the ragged edge
     const uint32_t n_tail = (uint32_t)p.N - (n_blocks - 1) * (uint32_t)BN;
-    const uint32_t idesc_tail = umma_idesc_bf16(kTileM, (int)((n_tail + 15u) & ~15u));
-    auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t accumulate) {
-      if constexpr (CTAS == 2) umma_bf16_2sm(d, a, b, id, accumulate);
-      else umma_bf16(d, a, b, id, accumulate);
-    };
-    auto commit = [&](uint32_t bar) {
-      if constexpr (CTAS == 2) umma_commit_2sm(bar);
-      else umma_commit(bar);
-    };
-    uint32_t cur_nb = 0xffffffffu, bphase = 0;
-    for (uint32_t t = t_begin; t < t_end; t += t_step) {
-      uint32_t idesc_t;
-      if constexpr (KB > 0) {
-        const uint32_t nb = t / m_blocks;
-        idesc_t = nb == n_blocks - 1 ? idesc_tail : idesc;
-        if (nb != cur_nb) {  // wait for the resident weights of this column block
-          mbar_wait(bfull_bar, bphase);
-          bphase ^= 1u;
-          cur_nb = nb;
-        }
-      } else {
-        idesc_t = (t % n_blocks == n_blocks - 1) ? idesc_tail : idesc;
-      }
+    const uint32_t idesc_tail = umma_idesc_bf16(kBlockM, (int)((n_tail + 15u) & ~15u));
+    for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const uint32_t idesc_t = (t % n_blocks == n_blocks - 1) ? idesc_tail : idesc;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -742,7 +658,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         const uint64_t adesc = umma_desc_sw128(smem_a(stage));
-        const uint64_t bdesc = umma_desc_sw128(KB > 0 ? bres_base + (uint32_t)kb * (uint32_t)(BN * 128) : smem_b(stage));
+        const uint64_t bdesc = umma_desc_sw128(smem_b(stage));
         // conv: the last channel block of a tap may hold fewer than 64 real channels
         // (the K tail of a plain GEMM is zero-filled by TMA: skip the all-zero k16 steps too)
         const int nk16 = CONV ? ((kb % p.conv_cblocks == p.conv_cblocks - 1) ? p.conv_last_k16 : kBlockK / 16)
@@ -751,15 +667,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (nk16 == kBlockK / 16) {
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
-              mma(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_t, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_t, (kb > 0 || k > 0) ? 1u : 0u);
           } else {
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
               if (k < nk16)
-                mma(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_t, (kb > 0 || k > 0) ? 1u : 0u);
+                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_t, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          commit(empty_bar(stage));
-          if (kb == k_blocks - 1) commit(tfull_bar(acc));
+          umma_commit(empty_bar(stage));
+          if (kb == k_blocks - 1) umma_commit(tfull_bar(acc));
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -774,12 +690,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint32_t epi_count = 0;  // chunks stored so far by this warp (ring slot / residual barrier parity)
     int acc = 0;
     uint32_t acc_phase = 0;
-    const uint32_t tempty0 = CTAS == 2 ? mapa_u32(tempty_bar(0), 0) : 0u;  // the leader's (cluster address)
-    for (uint32_t t = t_begin; t < t_end; t += t_step) {
+    for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
       uint32_t unb, umb, uz0, uz1, uz2;
-      decode(t, unb, umb, uz0, uz1, uz2);
+      tdec(t, unb, umb, uz0, uz1, uz2);
       const int64_t nb = unb, mb = umb, z0 = uz0, z1 = uz1, z2 = uz2;
-      const int64_t m_warp0 = mb * kTileM + cta_rank * kBlockM + lg * 32;
+      const int64_t m_warp0 = mb * kBlockM + lg * 32;
       const float* bias = p.bias ? p.bias + z0 * p.bias_zs[0] + z1 * p.bias_zs[1] + z2 * p.bias_zs[2] : nullptr;
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BN);
       if constexpr (EPI == 0 && CONV) {
@@ -1016,21 +931,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        if constexpr (CTAS == 2) mbar_arrive_cluster(tempty0 + 8u * (uint32_t)acc);
-        else mbar_arrive(tempty_bar(acc));
-      }
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
   if ((EPI == 3 || EPI == 4) && warp >= 2) bulk_wait_all();  // smem tiles must outlive their bulk stores
   tc_fence_before();
-  if constexpr (CTAS == 2) cluster_sync_all();  // neither CTA may free TMEM (or exit) while the pair still works
-  else __syncthreads();
+  __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    if constexpr (CTAS == 2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
-    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -1060,57 +970,6 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev
   return post_launch();
 }
 
-// CTA-pair launch: clusters of two CTAs (one TPC), grid = an even number of SMs, 256-row tiles
-template <int BN, int EPI>
-static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb_half, const GemmDev& p, int64_t tiles,
-                          cudaStream_t stream, const EpiMaps* em) {
-  using Cfg = GemmCfg<BN, EPI, 2>;
-  if (tiles > 0x7fffffffLL || p.M > 0x7fffffffLL || p.N > 0x7fffffffLL || p.K > 0x7fffffffLL) return RFK_ERR_BAD_DIMS;
-  auto kernel = gemm_tc_kernel<BN, EPI, false, 2>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return cuda_status(e);
-    configured = true;
-  }
-  int64_t pairs = num_sms() / 2;
-  if (tiles < pairs) pairs = tiles;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(2 * pairs));
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ta, tb_half, em->c, em->r, p);
-  if (e != cudaSuccess) return cuda_status(e);
-  return post_launch();
-}
-
-// B-stationary launch (flavour 3, Z = 1): one CTA per SM, each walking a contiguous range of the tile list
-template <int BN, int KB>
-static int launch_tc_bstat(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles,
-                           cudaStream_t stream, const EpiMaps* em) {
-  using Cfg = GemmCfg<BN, 3, 1, KB>;
-  if (tiles > 0x7fffffffLL || p.M > 0x7fffffffLL || p.N > 0x7fffffffLL || p.K > (int64_t)KB * kBlockK) return RFK_ERR_BAD_DIMS;
-  auto kernel = gemm_tc_kernel<BN, 3, false, 1, KB>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return cuda_status(e);
-    configured = true;
-  }
-  int grid = num_sms();
-  if (tiles < grid) grid = (int)tiles;
-  kernel<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, em->c, em->r, p);
-  return post_launch();
-}
-
 template <int EPI>
 static int launch_tc_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p,
                         int64_t tiles, cudaStream_t stream, const EpiMaps* em = nullptr) {
@@ -1130,8 +989,6 @@ int launch_tc_epi0(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const G
 int launch_tc_epi1(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s);
 int launch_tc_epi2(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s);
 int launch_tc_epi3(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s, const EpiMaps* em);
-int launch_tc_pair_epi3(int bn, const CUtensorMap& ta, const CUtensorMap& tb_half, const GemmDev& p, int64_t tiles, cudaStream_t s, const EpiMaps* em);
-int launch_tc_bstat_epi3(int bn, int kb, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s, const EpiMaps* em);
 int launch_tc_epi4(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s, const EpiMaps* em);
 int launch_tc_conv(int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int64_t tiles, cudaStream_t s);
 int make_tmap_bf16_raw(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);

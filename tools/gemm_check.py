@@ -1,5 +1,5 @@
-"""CTA-pair GEMM (RFK_GEMM_PAIR=1) vs a float32 matmul of the same bf16 operands, plus timing.
-usage: [RFK_GEMM_PAIR=1] python tools/pair_gemm_check.py"""
+"""bf16-output GEMMs (ragged M, K tails, the big projection shapes) vs a float32 matmul of the same bf16 operands on
+sampled rows, plus timing. usage: python tools/gemm_check.py  (A/B: RFK_GEMM_BN, RFK_GEMM_NO_TMA_EPILOGUE)"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -7,7 +7,6 @@ from rosettafold_pytorch_b200 import ops
 from rosettafold_pytorch_b200.ops import cview
 
 dev = torch.device("cuda:0")
-print("pair", os.environ.get("RFK_GEMM_PAIR"))
 for T, N, K, act in [(4096, 256, 64, 0), (4224, 256, 104, 1), (8192 + 128, 512, 288, 0), (65536, 768, 384, 0),
                      (65536, 2304, 384, 0), (262144, 1536, 288, 0), (262144, 1152, 288, 1)]:
     torch.manual_seed(T + N)
