@@ -156,6 +156,17 @@ int rfk_poswise_weight(const void* pq, int64_t pq_stride, const void* pk, int64_
                        rfk_stream_t stream);
 
 /*
+ * Same, for an MSA whose sequences are sharded over devices (the softmax of :213 runs over ALL sequences):
+ * additionally writes stats[b,l,h,0..1] = (max_n logit, sum_n exp(logit - max)) of the N sequences given, so
+ * that the caller can merge the shards: with M = max over shards of max_r and S = sum_r sum_r exp(max_r - M),
+ * the globally normalised weights are w_r * (sum_r exp(max_r - M) / S). stats may be NULL.
+ */
+int rfk_poswise_weight_stats(const void* pq, int64_t pq_stride, const void* pk, int64_t pk_stride,
+                             int in_dtype, float scale, float* w_out, const void* q, int64_t q_stride,
+                             float q_scale, void* qt, int qt_dtype, float* stats, int B, int N, int L,
+                             int H, int dh, rfk_stream_t stream);
+
+/*
  * Operand preparation for the outer-product sum (:469-482): from m = proj_msa(msa) [B,N,L,P]
  * (f32) and w [B,N,L] (f32) write
  *   xt[b, l*P+u, n] = m[b,n,l,u]            yt[b, l*P+v, n] = m[b,n,l,v] * w[b,n,l]

@@ -88,12 +88,15 @@ class RefBackend:
             att16.copy_(s.to(att16.dtype))
 
     # PositionWiseWeightFactor (:205-217) + q scaling (:252) + relayout for :254
-    def poswise_weight(self, pq, pk, scale, w_out, q, q_scale, qt, H, dh):
+    def poswise_weight(self, pq, pk, scale, w_out, q, q_scale, qt, H, dh, stats=None):
         B, N, L, D = pk.shape
         pqh = pq.to(self.acc).reshape(B, L, H, dh)
         pkh = pk.to(self.acc).reshape(B, N, L, H, dh)
         logits = torch.einsum("blhd,bnlhd->blhn", pqh, pkh) * scale
         w = torch.softmax(logits, dim=-1)  # [B,L,H,N]
+        if stats is not None:  # (max, sum of exp) over the sequences given: merges sequence shards
+            mx = logits.max(dim=-1).values
+            stats.copy_(torch.stack([mx, torch.exp(logits - mx.unsqueeze(-1)).sum(-1)], dim=-1).to(stats.dtype))
         if w_out is not None:
             w_out.copy_(w.permute(0, 3, 1, 2).to(w_out.dtype))
         if qt is not None:

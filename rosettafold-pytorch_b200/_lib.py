@@ -67,6 +67,8 @@ SYMBOLS = {
     "rfk_tied_att_symmetrize": (C.c_int, [vp, C.c_int, i64, vp, vp, i64, C.c_int, C.c_int, C.c_int, vp]),
     "rfk_poswise_weight": (C.c_int, [vp, i64, vp, i64, C.c_int, f32, vp, vp, i64, f32, vp, C.c_int,
                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "rfk_poswise_weight_stats": (C.c_int, [vp, i64, vp, i64, C.c_int, f32, vp, vp, i64, f32, vp, C.c_int, vp,
+                                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "rfk_opm_prep": (C.c_int, [vp, vp, vp, vp, C.c_int, i64, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "rfk_pair2att_logits": (C.c_int, [vp, vp, vp, f32, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "rfk_channel_stats": (C.c_int, [vp, C.c_int, vp, C.c_int, i64, C.c_int, vp]),

@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(128)
 poswise_kernel(const void* __restrict__ pq, int64_t pqs, const void* __restrict__ pk, int64_t pks,
                int dt, float scale, float* __restrict__ w_out, const void* __restrict__ q,
                int64_t qs, float q_scale, void* __restrict__ qt, int qtdt, int B, int N, int L,
-               int H, int dh) {
+               int H, int dh, float* __restrict__ stats) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t item = (int64_t)blockIdx.x * 4 + warp;
@@ -220,7 +220,12 @@ poswise_kernel(const void* __restrict__ pq, int64_t pqs, const void* __restrict_
     lg[n] = e;
     s += e;
   }
-  const float inv = 1.f / warp_sum(s);
+  s = warp_sum(s);
+  const float inv = 1.f / s;
+  if (stats && lane == 0) {  // (max, sum of exp) of this sequence shard: lets the caller merge softmaxes across shards
+    stats[(((int64_t)b * L + l) * H + h) * 2 + 0] = mx;
+    stats[(((int64_t)b * L + l) * H + h) * 2 + 1] = s;
+  }
   __syncwarp();
   if (w_out)
     for (int n = lane; n < N; n += 32)
@@ -255,7 +260,7 @@ __global__ void __launch_bounds__(256)
 poswise_vec_kernel(const __nv_bfloat16* __restrict__ pq, int64_t pqs, const __nv_bfloat16* __restrict__ pk,
                    int64_t pks, float scale, float* __restrict__ w_out, const __nv_bfloat16* __restrict__ q,
                    int64_t qs, float q_scale, __nv_bfloat16* __restrict__ qt, int N, int L, int H, int dh,
-                   int rows) {
+                   int rows, float* __restrict__ stats) {
   extern __shared__ float lg[];  // [N][H]
   const int CH = (H * dh) >> 3, gsz = dh >> 3;
   const int c = threadIdx.x % CH, r = threadIdx.x / CH;
@@ -288,7 +293,12 @@ poswise_vec_kernel(const __nv_bfloat16* __restrict__ pq, int64_t pqs, const __nv
         lg[n * H + hh] = e;
         sum += e;
       }
-      const float inv = 1.f / warp_sum(sum);
+      sum = warp_sum(sum);
+      const float inv = 1.f / sum;
+      if (stats && lane == 0) {
+        stats[(((int64_t)b * L + l) * H + hh) * 2 + 0] = mx;
+        stats[(((int64_t)b * L + l) * H + hh) * 2 + 1] = sum;
+      }
       for (int n = lane; n < N; n += 32) {
         const float w = lg[n * H + hh] * inv;
         lg[n * H + hh] = w;
@@ -805,6 +815,14 @@ extern "C" int rfk_poswise_weight(const void* pq, int64_t pqs, const void* pk, i
                                   float scale, float* w_out, const void* q, int64_t qs,
                                   float q_scale, void* qt, int qtdt, int B, int N, int L, int H,
                                   int dh, rfk_stream_t stream) {
+  return rfk_poswise_weight_stats(pq, pqs, pk, pks, dt, scale, w_out, q, qs, q_scale, qt, qtdt, nullptr, B, N, L, H,
+                                  dh, stream);
+}
+
+extern "C" int rfk_poswise_weight_stats(const void* pq, int64_t pqs, const void* pk, int64_t pks, int dt,
+                                        float scale, float* w_out, const void* q, int64_t qs,
+                                        float q_scale, void* qt, int qtdt, float* stats, int B, int N,
+                                        int L, int H, int dh, rfk_stream_t stream) {
   if (!pq || !pk) return RFK_ERR_NULL_POINTER;
   if (qt && !q) return RFK_ERR_NULL_POINTER;
   if (B <= 0 || N <= 0 || L <= 0 || H <= 0 || dh <= 0) return RFK_ERR_BAD_DIMS;
@@ -824,7 +842,7 @@ extern "C" int rfk_poswise_weight(const void* pq, int64_t pqs, const void* pk, i
                              reinterpret_cast<cudaStream_t>(stream)>>>(
             reinterpret_cast<const __nv_bfloat16*>(pq), pqs, reinterpret_cast<const __nv_bfloat16*>(pk), pks, scale,
             w_out, reinterpret_cast<const __nv_bfloat16*>(q), qs, q_scale, reinterpret_cast<__nv_bfloat16*>(qt), N, L,
-            H, dh, rows);
+            H, dh, rows, stats);
         return post_launch();
       }
     }
@@ -833,7 +851,7 @@ extern "C" int rfk_poswise_weight(const void* pq, int64_t pqs, const void* pk, i
   if (smem > 48 * 1024) return RFK_ERR_BAD_DIMS;
   const int64_t items = (int64_t)B * L * H;
   poswise_kernel<<<(unsigned)((items + 3) / 4), 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      pq, pqs, pk, pks, dt, scale, w_out, q, qs, q_scale, qt, qtdt, B, N, L, H, dh);
+      pq, pqs, pk, pks, dt, scale, w_out, q, qs, q_scale, qt, qtdt, B, N, L, H, dh, stats);
   return post_launch();
 }
 

@@ -249,9 +249,15 @@ class SoftTiedAttentionOverResidues(nn.Module):
                 Wo=_w(self.to_out.weight), bo=_f(self.to_out.bias))
         return _packed(self, build)
 
-    def _attend(self, xn4, res2, want_att):
+    def _attend(self, xn4, res2, want_att, shard=None):
         """xn4: [B,N,L,D] operand dtype (already normalised by the caller).
-        Returns (to_out(attention) (+ res2) as float32 [T, D], symmetrised att or None)."""
+        Returns (to_out(attention) (+ res2) as float32 [T, D], symmetrised att or None).
+
+        With `shard` (rosettafold_pytorch_b200.sharded.SequenceShard) xn4 holds this rank's slice of the
+        sequences: projections, q scaling, A.V and to_out are per sequence and stay local; the three places
+        where :205-257 couple the sequences go through the context - the query row (sequence 0 of the whole
+        MSA, :207), the softmax over ALL sequences of the position-wise weights (:213: merged from per-shard
+        (max, sum) statistics) and the logits, which sum over all sequences (:254: all-reduce)."""
         pk = self._pack()
         B, N, L, D = xn4.shape
         H, dh = self.n_heads, self.d_head
@@ -269,13 +275,19 @@ class SoftTiedAttentionOverResidues(nn.Module):
         vt = _empty((B, H, N * dh, Lp), adt, xn4)  # b h (n d) j: K-major operand of A.V
         ops.gemm(xb, pk["Wv"][None],
                  vt.view(B, H, N, dh, Lp)[..., :L].permute(0, 2, 4, 1, 3)[None, None], bias=pk["bv"])
-        pq = self.poswise_weight._project_query(xn4)
+        pq = self.poswise_weight._project_query(xn4 if shard is None else shard.first_sequence(xn4))
         qp4 = qp.view(B, N, L, 2 * D)
         qt = _empty((B, H, L, N * dh), adt, xn4)  # q * w * scale, b h i (n d)
+        stats = None if shard is None else _empty((B, L, H, 2), torch.float32, xn4)
         ops.poswise_weight(pq, qp4[..., D:], self.poswise_weight.scale, q=qp4[..., :D],
-                           q_scale=self.scale, qt=qt, heads=H, d_head=dh)
+                           q_scale=self.scale, qt=qt, heads=H, d_head=dh, stats=stats)
         logits = _empty((B, H, L, L), torch.float32, xn4)
         ops.gemm(qt, kt, logits.view(1, B, H, 1, L, 1, L))
+        if shard is not None:
+            # this shard's weights were normalised over its own sequences: rescale row (h, i) of the partial
+            # logits to the global normalisation, then sum the partial logits over the shards
+            logits.mul_(shard.softmax_correction(stats).permute(0, 2, 1).unsqueeze(-1))
+            shard.allreduce(logits)
         A = _empty((B, H, L, Lp), adt, xn4)
         ops.softmax_rows(logits.view(B * H * L, L), A.view(B * H * L, Lp)[:, :L])
         att = None
@@ -410,16 +422,17 @@ class EncoderLayer(nn.Module):
                                          FeedForward(d_msa, d_ff, p_dropout=p_dropout),
                                          nn.Dropout(p_dropout)))
 
-    def _run(self, x4, token_dim=2, want_att=None):
+    def _run(self, x4, token_dim=2, want_att=None, shard=None):
         """x4: float32 [B,N,L,D]. Tied: attention over residues with logits tied over N.
-        Performer: attention over axis `token_dim`."""
+        Performer: attention over axis `token_dim`. `shard`: sequence-shard context (tied layers only,
+        see SoftTiedAttentionOverResidues._attend)."""
         D = x4.shape[-1]
         x2 = x4.view(-1, D)
         att = None
         if self.tied:
             xn = _ln_into(x2, self.ln, _empty(x2.shape, _adt(), x2))
             want = self.return_att if want_att is None else want_att
-            x1, att = self.attn._attend(xn.view(x4.shape), x2, want)
+            x1, att = self.attn._attend(xn.view(x4.shape), x2, want, shard)
         else:
             x1 = _performer_block(self.ln, self.attn, x4, token_dim).view(-1, D)
         out = _ff_block(self.ff.fn[0], self.ff.fn[1], x1).view(x4.shape)

@@ -129,12 +129,12 @@ class _CudaBackend:
             0 if att16 is None else att16.stride(2), B, H, L, self._stream(A)),
             "rfk_tied_att_symmetrize")
 
-    def poswise_weight(self, pq, pk, scale, w_out, q, q_scale, qt, H, dh):
+    def poswise_weight(self, pq, pk, scale, w_out, q, q_scale, qt, H, dh, stats=None):
         B, N, L, _ = pk.shape
-        _lib.check(self.lib.rfk_poswise_weight(
+        _lib.check(self.lib.rfk_poswise_weight_stats(
             _ptr(pq), pq.stride(1), _ptr(pk), pk.stride(2), _dt(pk), scale, _ptr(w_out), _ptr(q),
-            0 if q is None else q.stride(2), q_scale, _ptr(qt), 0 if qt is None else _dt(qt),
-            B, N, L, H, dh, self._stream(pk)), "rfk_poswise_weight")
+            0 if q is None else q.stride(2), q_scale, _ptr(qt), 0 if qt is None else _dt(qt), _ptr(stats),
+            B, N, L, H, dh, self._stream(pk)), "rfk_poswise_weight_stats")
 
     def opm_prep(self, m, w, xt, yt, msa1d):
         B, N, L, P = m.shape
@@ -355,9 +355,10 @@ def tied_att_symmetrize(A, att, att16=None):
     return att
 
 
-def poswise_weight(pq, pk, scale, *, w_out=None, q=None, q_scale=1.0, qt=None, heads, d_head):
+def poswise_weight(pq, pk, scale, *, w_out=None, q=None, q_scale=1.0, qt=None, heads, d_head, stats=None):
     """pq: [B,L,H*dh] view, pk/q: [B,N,L,H*dh] views (last dim contiguous, rows packed over
-    (b,n,l)); w_out: contiguous f32 [B,N,L,H]; qt: contiguous [B,H,L,N*dh]."""
+    (b,n,l)); w_out: contiguous f32 [B,N,L,H]; qt: contiguous [B,H,L,N*dh]; stats: optional contiguous f32
+    [B,L,H,2] receiving (max, sum of exp) of the logits over the N sequences given (sequence-sharded MSAs)."""
     B, N, L, D = pk.shape
     if D != heads * d_head or tuple(pq.shape) != (B, L, D):
         raise ValueError("poswise_weight: bad shapes")
@@ -372,7 +373,13 @@ def poswise_weight(pq, pk, scale, *, w_out=None, q=None, q_scale=1.0, qt=None, h
         raise ValueError("poswise_weight: w_out must be contiguous [B,N,L,H]")
     if qt is not None and (tuple(qt.shape) != (B, heads, L, N * d_head) or not qt.is_contiguous()):
         raise ValueError("poswise_weight: qt must be contiguous [B,H,L,N*dh]")
-    backend().poswise_weight(pq, pk, float(scale), w_out, q, float(q_scale), qt, heads, d_head)
+    if stats is not None and (tuple(stats.shape) != (B, L, heads, 2) or not stats.is_contiguous() or
+                              stats.dtype != torch.float32):
+        raise ValueError("poswise_weight: stats must be contiguous f32 [B,L,H,2]")
+    if stats is None:
+        backend().poswise_weight(pq, pk, float(scale), w_out, q, float(q_scale), qt, heads, d_head)
+    else:
+        backend().poswise_weight(pq, pk, float(scale), w_out, q, float(q_scale), qt, heads, d_head, stats)
 
 
 def opm_prep(m, w, xt, yt, msa1d):

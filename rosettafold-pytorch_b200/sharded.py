@@ -29,8 +29,14 @@ The pair tensor `pair[1, L, L, D]` is sharded on its first residue axis i: rank 
     last row: 2 L d_pair elements per rank) and the InstanceNorm statistics are all-reduced
     (2 x d_pair doubles).
 
-Still replicated: the tied row layers (their logits contract over all sequences: needs an all-reduce
-of the 12 x L x L logits and a distributed softmax over n) - DESIGN.md section 7.
+  * the tied row layers of `MsaUpdateUsingSelfAttention`: each rank takes a slice of sequences. Projections,
+    the q scaling, A.V, to_out and the FeedForward are per sequence; the layer couples sequences in three
+    places only (`SequenceShard`): the query row of the position-wise weights is sequence 0 of the whole MSA
+    (broadcast from rank 0: L x d_msa operand-dtype elements), their softmax runs over all sequences (merged
+    from per-rank (max, sum) statistics: an all-gather of 2 x L x 12 floats) and the logits sum over all
+    sequences (all-reduce of 12 x L x L floats). One all-to-all then turns the sequence shards into the
+    residue shards the Performer column layers work on.
+
 One process per GPU; `torch.distributed` (NCCL over NVLink on GPUs, gloo in the CPU tests).
 """
 from __future__ import annotations
@@ -76,6 +82,46 @@ def all_to_all_cols_to_rows(x_cols: torch.Tensor, group=None) -> torch.Tensor:
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv, send, group=group)
     return recv
+
+
+class SequenceShard:
+    """The collectives of a tied row layer whose sequences are split over the ranks of `group`
+    (hooks called by `SoftTiedAttentionOverResidues._attend`)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.root = dist.get_global_rank(group, 0) if group is not None else 0
+
+    def first_sequence(self, xn4: torch.Tensor) -> torch.Tensor:
+        """[B, N/P, L, D] -> [B, 1, L, D]: sequence 0 of the whole MSA (rank 0's first row)."""
+        row = xn4[:, :1].contiguous()
+        dist.broadcast(row, src=self.root, group=self.group)
+        return row
+
+    def softmax_correction(self, stats: torch.Tensor) -> torch.Tensor:
+        """stats [B, L, H, 2] = (max, sum of exp) of this rank's position-wise logits -> the factor [B, L, H]
+        that turns weights normalised over this rank's sequences into weights normalised over all of them."""
+        allst = torch.empty((self.world,) + tuple(stats.shape), dtype=stats.dtype, device=stats.device)
+        dist.all_gather_into_tensor(allst.view(-1), stats.reshape(-1), group=self.group)
+        gmax = allst[..., 0].max(dim=0).values
+        gsum = (allst[..., 1] * torch.exp(allst[..., 0] - gmax)).sum(dim=0)
+        return stats[..., 1] * torch.exp(stats[..., 0] - gmax) / gsum
+
+    def allreduce(self, t: torch.Tensor) -> None:
+        dist.all_reduce(t, group=self.group)
+
+
+def all_to_all_seqs_to_residues(x_seqs: torch.Tensor, group=None) -> torch.Tensor:
+    """[1, N/P, L, D] (my sequences, all residues) -> [1, N, L/P, D] (all sequences, my residues)."""
+    world = dist.get_world_size(group)
+    _, Nl, L, D = x_seqs.shape
+    Ll = L // world
+    send = x_seqs.view(Nl, world, Ll, D).permute(1, 0, 2, 3).contiguous()  # chunk p = my sequences x residues of p
+    recv = torch.empty_like(send)                                           # chunk q = sequences of q x my residues
+    dist.all_to_all_single(recv, send, group=group)
+    return recv.view(1, world * Nl, Ll, D)
 
 
 class ShardedPairAxialAttention(nn.Module):
@@ -125,18 +171,21 @@ class ShardedTwoTrackBlock(nn.Module):
         self.group = group
 
     def _msa_self_attention(self, msa, rank, world):
-        """MsaUpdateUsingSelfAttention (:399-409): tied row layers replicated, Performer column layers
-        on a slice of residues."""
+        """MsaUpdateUsingSelfAttention (:399-409): tied row layers on a slice of sequences, one all-to-all,
+        Performer column layers on a slice of residues."""
         mod = self.block.msa_update_using_self_att
         x = M._as_f32(msa).contiguous()
+        B, N, L, D = x.shape
         att = None
         n = len(mod.residue_wise_encoder_layers)
+        row_shard(L, rank, world)                             # both axes must divide
+        n_lo, n_hi = row_shard(N, rank, world)
+        shard = SequenceShard(self.group)
+        xq = x[:, n_lo:n_hi].contiguous()                     # [1, N/P, L, D]
         for i, layer in enumerate(mod.residue_wise_encoder_layers):
-            x, a = layer._run(x, want_att=(i == n - 1))
+            xq, a = layer._run(xq, want_att=(i == n - 1), shard=shard)
             att = a if a is not None else att
-        B, N, L, D = x.shape
-        lo, hi = row_shard(L, rank, world)
-        xs = x[:, :, lo:hi].contiguous()                      # [1, N, L/P, D]
+        xs = all_to_all_seqs_to_residues(xq, self.group)      # [1, N, L/P, D]
         for layer in mod.sequence_wise_encoder_layers:
             xs, _ = layer._run(xs, token_dim=1)
         gathered = torch.empty((world,) + tuple(xs.shape), dtype=xs.dtype, device=xs.device)

@@ -203,6 +203,38 @@ def test_poswise_weight(cuda_device, dtype, cfg):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_poswise_weight_sequence_shards_merge(cuda_device, dtype):
+    """The (max, sum) statistics of rfk_poswise_weight_stats merge two sequence shards into the softmax over
+    all sequences (the identity the sequence-sharded tied row layers rely on)."""
+    dev = cuda_device
+    B, N, L, H, dh = 2, 12, 9, 12, 32
+    D = H * dh
+    pq = _rand((B, L, D), dtype, dev, 45, 2.0)
+    pk = _rand((B, N, L, D), dtype, dev, 46, 2.0)
+    w_full = torch.empty((B, N, L, H), dtype=torch.float32, device=dev)
+    st_full = torch.empty((B, L, H, 2), dtype=torch.float32, device=dev)
+    ops.poswise_weight(pq, pk, dh ** -0.5, w_out=w_full, heads=H, d_head=dh, stats=st_full)
+    st_ref, w_ref = torch.empty_like(st_full), torch.empty_like(w_full)
+    REF.poswise_weight(pq, pk, dh ** -0.5, w_ref, None, 1.0, None, H, dh, st_ref)
+    parts, stats = [], []
+    for lo, hi in ((0, 5), (5, 12)):  # ragged split
+        pk_s = pk[:, lo:hi].contiguous()
+        w = torch.empty((B, hi - lo, L, H), dtype=torch.float32, device=dev)
+        st = torch.empty((B, L, H, 2), dtype=torch.float32, device=dev)
+        ops.poswise_weight(pq, pk_s, dh ** -0.5, w_out=w, heads=H, d_head=dh, stats=st)
+        parts.append(w)
+        stats.append(st)
+    torch.cuda.synchronize()
+    assert rel_l2(st_full, st_ref) < 1e-5
+    allst = torch.stack(stats)
+    gmax = allst[..., 0].max(0).values
+    gsum = (allst[..., 1] * torch.exp(allst[..., 0] - gmax)).sum(0)
+    merged = torch.cat([w * (st[..., 1] * torch.exp(st[..., 0] - gmax) / gsum).unsqueeze(1)
+                        for w, st in zip(parts, stats)], dim=1)
+    assert rel_l2(merged, w_full) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_opm_prep(cuda_device, dtype):
     dev = cuda_device
     B, N, L, P = 2, 37, 9, 32

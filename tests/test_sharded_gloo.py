@@ -1,5 +1,6 @@
-"""Long-protein path on CPU: world_size-2 gloo processes run the pair axial stage row-sharded with
-the all-to-all transpose (oracle-emulated ops) and must reproduce the single-process result."""
+"""Long-protein path on CPU: world_size-2 gloo processes run the sharded stages (pair axial attention with the
+all-to-all transpose, sequence-sharded tied row layers, whole block; oracle-emulated ops) and must reproduce
+the single-process result."""
 import os
 import sys
 
@@ -39,10 +40,16 @@ def _worker(rank, world, port, out_dir):
     rows = ax(pair[:, lo:hi].contiguous())
     ref = blk.pair_update_with_axial_attention(pair)
     err_ax = float((rows - ref[:, lo:hi]).abs().max())
-    # 3. whole block, outputs replicated on every rank
-    m, p = ShardedTwoTrackBlock(blk)(msa, pair)
+    # 3. MSA self-attention: tied row layers sequence-sharded (broadcast query row, merged position-wise softmax,
+    #    all-reduced logits), all-to-all, Performer column layers residue-sharded
+    sblk = ShardedTwoTrackBlock(blk)
+    ms, atts = sblk._msa_self_attention(msa, rank, world)
+    mr, attr = blk.msa_update_using_self_att(msa)
+    err_sa = max(float((ms - mr).abs().max()), float((atts - attr).abs().max()))
+    # 4. whole block, outputs replicated on every rank
+    m, p = sblk(msa, pair)
     m1, p1 = blk(msa, pair)
-    torch.save(dict(err_t=err_t, err_b=err_b, err_ax=err_ax, err_m=float((m - m1).abs().max()),
+    torch.save(dict(err_t=err_t, err_b=err_b, err_ax=err_ax, err_sa=err_sa, err_m=float((m - m1).abs().max()),
                     err_p=float((p - p1).abs().max())), os.path.join(out_dir, f"res_{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
@@ -55,7 +62,7 @@ def test_two_rank_row_sharded_axial_matches_single_process(tmp_path):
     for rank in range(2):
         res = torch.load(os.path.join(tmp_path, f"res_{rank}.pt"))
         assert res["err_t"] == 0.0 and res["err_b"] == 0.0, res
-        assert res["err_ax"] < 1e-4 and res["err_m"] < 1e-4 and res["err_p"] < 1e-4, res
+        assert res["err_ax"] < 1e-4 and res["err_sa"] < 1e-4 and res["err_m"] < 1e-4 and res["err_p"] < 1e-4, res
 
 
 def test_row_shard_rejects_ragged():
