@@ -43,7 +43,7 @@ def timed(fn):
     return float(ms), out
 
 ms_sh, (m_sh, p_sh) = timed(lambda: sblk(msa, pair))
-res = {"config": f"TwoTrackBlock (1,{args.N},{args.L}), {args.layers} encoder layers, row-/sequence-sharded x{world} (tied row layers replicated)",
+res = {"config": f"TwoTrackBlock (1,{args.N},{args.L}), {args.layers} encoder layers, row-/sequence-sharded x{world} (tied row layers by sequence, Performer column layers by residue, pair stages by row)",
        "n_gpus": world, "ms_per_block_sharded": ms_sh}
 if rank == 0:
     ms_1, (m_1, p_1) = timed(lambda: blk(msa, pair)) if world == 1 else (None, blk(msa, pair))
