@@ -187,6 +187,16 @@ int rfk_pair2att_logits(const float* pair, const float* Wf, const float* bf, flo
                         rfk_stream_t stream);
 
 /*
+ * Same for a ROW-SHARDED pair map (one long protein over several devices): this device holds rows
+ * [i0, i0+Li) as rows[b,il,j,:] = pair[b,i0+il,j,:] and the transposed shard cols_t[b,j,il,:] = pair[b,j,i0+il,:]
+ * (what an all-to-all of the row shards delivers); writes logits[b, c, il, j] for its rows and every j
+ * (f32 [B,C,Li,ld_logits]). The symmetrisation (:555-556) is the only place the pair rows meet their columns.
+ */
+int rfk_pair2att_logits_rows(const float* rows, const float* cols_t, const float* Wf, const float* bf,
+                             float eps, float* logits, int64_t ld_logits, int B, int Li, int L, int D,
+                             int C, rfk_stream_t stream);
+
+/*
  * Per-(batch, channel) statistics over the L*L positions of a channels-last map
  * (nn.InstanceNorm2d, :453,:457): stats[b,0,c] = sum x, stats[b,1,c] = sum x^2 (f64, caller
  * zeroes `stats` first; fixed-order f32 partial sums, f64 atomics across blocks, so the values

@@ -124,6 +124,14 @@ class RefBackend:
         lg = torch.einsum("bijd,cd->bcij", xh, Wf.to(self.acc)) + bf.to(self.acc).reshape(1, -1, 1, 1)
         logits.copy_(lg.to(logits.dtype))
 
+    def pair2att_logits_rows(self, rows, cols_t, Wf, bf, eps, logits):
+        s = 0.5 * (rows.to(self.acc) + cols_t.to(self.acc).transpose(1, 2))
+        mean = s.mean(-1, keepdim=True)
+        var = s.var(-1, unbiased=False, keepdim=True)
+        xh = (s - mean) / torch.sqrt(var + eps)
+        lg = torch.einsum("bijd,cd->bcij", xh, Wf.to(self.acc)) + bf.to(self.acc).reshape(1, -1, 1, 1)
+        logits.copy_(lg.to(logits.dtype))
+
     # InstanceNorm2d statistics / apply (:453, :457) and the ELUs (:454, :462)
     def channel_stats(self, x, stats):
         xf = x.to(self.acc)

@@ -71,6 +71,8 @@ SYMBOLS = {
                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "rfk_opm_prep": (C.c_int, [vp, vp, vp, vp, C.c_int, i64, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "rfk_pair2att_logits": (C.c_int, [vp, vp, vp, f32, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "rfk_pair2att_logits_rows": (C.c_int, [vp, vp, vp, vp, f32, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           vp]),
     "rfk_channel_stats": (C.c_int, [vp, C.c_int, vp, C.c_int, i64, C.c_int, vp]),
     "rfk_instnorm_apply": (C.c_int, [vp, C.c_int, vp, vp, vp, f32, vp, C.c_int, C.c_int, vp, C.c_int,
                                      C.c_int, i64, C.c_int, vp]),

@@ -487,6 +487,113 @@ pair2att_vec_kernel(const float* __restrict__ pair, const float* __restrict__ Wf
   }
 }
 
+// Row-sharded pair map (one long protein over several GPUs): this device holds rows [i0, i0 + Li) of the pair
+// map, `rows[b, il, j, :] = pair[b, i0 + il, j, :]`, and the transposed shard it received by all-to-all,
+// `cols_t[b, j, il, :] = pair[b, j, i0 + il, :]`; it produces logits[b, c, il, j] for its rows and every j.
+// Generic D (<= 512): one warp per (il, j).
+__global__ void __launch_bounds__(256)
+pair2att_rows_kernel(const float* __restrict__ rows, const float* __restrict__ cols_t,
+                     const float* __restrict__ Wf, const float* __restrict__ bf, float eps,
+                     float* __restrict__ logits, int64_t ldl, int B, int Li, int L, int D, int C) {
+  extern __shared__ float sw[];  // [C][D]
+  for (int i = threadIdx.x; i < C * D; i += blockDim.x) sw[i] = Wf[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= (int64_t)B * Li * L) return;
+  const int j = (int)(item % L);
+  const int il = (int)((item / L) % Li);
+  const int b = (int)(item / ((int64_t)L * Li));
+  const float* pij = rows + (((int64_t)b * Li + il) * L + j) * D;
+  const float* pji = cols_t + (((int64_t)b * L + j) * Li + il) * D;
+  float v[16];
+  float s = 0.f;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    const int d = t * 32 + lane;
+    v[t] = d < D ? 0.5f * (pij[d] + pji[d]) : 0.f;
+    s += v[t];
+  }
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    const int d = t * 32 + lane;
+    const float dd = d < D ? v[t] - mean : 0.f;
+    v[t] = dd;
+    q += dd * dd;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+  for (int c = 0; c < C; ++c) {
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const int d = t * 32 + lane;
+      if (d < D) acc = fmaf(v[t], sw[c * D + d], acc);
+    }
+    acc = warp_sum(acc) * rstd + bf[c];
+    if (lane == 0) logits[(((int64_t)b * C + c) * Li + il) * ldl + j] = acc;
+  }
+}
+
+// D = 32 NT: eight lanes per (il, j), 16-byte loads (as pair2att_vec_kernel, without the triangle)
+template <int NT>
+__global__ void __launch_bounds__(256)
+pair2att_rows_vec_kernel(const float* __restrict__ rows, const float* __restrict__ cols_t,
+                         const float* __restrict__ Wf, const float* __restrict__ bf, float eps,
+                         float* __restrict__ logits, int64_t ldl, int Li, int L, int C) {
+  constexpr int D = NT * 32;
+  extern __shared__ float sw[];  // [C][D]
+  const int il = blockIdx.y, b = blockIdx.z;
+  const int j0 = blockIdx.x * 32;
+  for (int t = threadIdx.x; t < C * (D / 4); t += blockDim.x)
+    reinterpret_cast<float4*>(sw)[t] = __ldg(reinterpret_cast<const float4*>(Wf) + t);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l8 = lane & 7;
+  const int j = j0 + warp * 4 + (lane >> 3);
+  const bool active = j < L;
+  const int jj = active ? j : L - 1;
+  const float4* pij = reinterpret_cast<const float4*>(rows + (((int64_t)b * Li + il) * L + jj) * D) + l8;
+  const float4* pji = reinterpret_cast<const float4*>(cols_t + (((int64_t)b * L + jj) * Li + il) * D) + l8;
+  float4 u[NT], w[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) { u[t] = __ldg(pij + 8 * t); w[t] = __ldg(pji + 8 * t); }
+  auto sum8 = [](float x) {
+    x += __shfl_xor_sync(0xffffffffu, x, 4);
+    x += __shfl_xor_sync(0xffffffffu, x, 2);
+    x += __shfl_xor_sync(0xffffffffu, x, 1);
+    return x;
+  };
+  float s = 0.f;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    u[t].x = 0.5f * (u[t].x + w[t].x); u[t].y = 0.5f * (u[t].y + w[t].y);
+    u[t].z = 0.5f * (u[t].z + w[t].z); u[t].w = 0.5f * (u[t].w + w[t].w);
+    s += (u[t].x + u[t].y) + (u[t].z + u[t].w);
+  }
+  const float mean = sum8(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    u[t].x -= mean; u[t].y -= mean; u[t].z -= mean; u[t].w -= mean;
+    q = fmaf(u[t].x, u[t].x, q); q = fmaf(u[t].y, u[t].y, q);
+    q = fmaf(u[t].z, u[t].z, q); q = fmaf(u[t].w, u[t].w, q);
+  }
+  const float rstd = rsqrtf(sum8(q) / (float)D + eps);
+  for (int c = 0; c < C; ++c) {
+    const float4* wc = reinterpret_cast<const float4*>(sw + c * D) + l8;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const float4 ww = wc[8 * t];
+      acc = fmaf(u[t].x, ww.x, acc); acc = fmaf(u[t].y, ww.y, acc);
+      acc = fmaf(u[t].z, ww.z, acc); acc = fmaf(u[t].w, ww.w, acc);
+    }
+    acc = sum8(acc) * rstd + bf[c];
+    if (active && l8 == 0) logits[(((int64_t)b * C + c) * Li + il) * ldl + j] = acc;
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // InstanceNorm statistics and apply (channels-last)
 // ----------------------------------------------------------------------------------------------
@@ -888,6 +995,31 @@ extern "C" int rfk_pair2att_logits(const float* pair, const float* Wf, const flo
   const int64_t items = (int64_t)B * L * L;
   pair2att_kernel<<<(unsigned)((items + 7) / 8), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       pair, Wf, bf, eps, logits, ldl, B, L, D, C);
+  return post_launch();
+}
+
+extern "C" int rfk_pair2att_logits_rows(const float* rows, const float* cols_t, const float* Wf, const float* bf,
+                                        float eps, float* logits, int64_t ldl, int B, int Li, int L, int D,
+                                        int C, rfk_stream_t stream) {
+  if (!rows || !cols_t || !Wf || !bf || !logits) return RFK_ERR_NULL_POINTER;
+  if (B <= 0 || Li <= 0 || L <= 0 || Li > L || D <= 0 || D > 512 || C <= 0 || C > kP2AMaxC || ldl < L)
+    return RFK_ERR_BAD_DIMS;
+  const size_t smem = (size_t)C * D * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(pair2att_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    configured = true;
+  }
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (D == 288 && al16(rows) && al16(cols_t) && al16(Wf) && Li <= 65535 && B <= 65535) {
+    dim3 grid((unsigned)((L + 31) / 32), (unsigned)Li, (unsigned)B);
+    pair2att_rows_vec_kernel<9><<<grid, 256, smem, st>>>(rows, cols_t, Wf, bf, eps, logits, ldl, Li, L, C);
+    return post_launch();
+  }
+  const int64_t items = (int64_t)B * Li * L;
+  pair2att_rows_kernel<<<(unsigned)((items + 7) / 8), 256, smem, st>>>(rows, cols_t, Wf, bf, eps, logits, ldl, B, Li,
+                                                                       L, D, C);
   return post_launch();
 }
 

@@ -777,6 +777,23 @@ def _pair2att(layers, pair):
     return att_p
 
 
+def _pair2att_rows(layers, rows, cols_t, gather_rows):
+    """`_pair2att` for a row-sharded pair map: rows [B,Li,L,P] / cols_t [B,L,Li,P] as in ops.pair2att_logits_rows;
+    `gather_rows(x [B,C,Li,L]) -> [B,C,L,L]` concatenates every rank's logit rows (softmax_j needs whole rows
+    only, but the attention maps are applied to every MSA row shard, so all ranks need all rows)."""
+    B, Li, L, P = rows.shape
+    Wf = torch.cat([l._pack()["Wf"] for l in layers], 0)
+    bf = torch.cat([l._pack()["bf"] for l in layers], 0)
+    Cn = Wf.shape[0]
+    part = _empty((B, Cn, Li, L), torch.float32, rows)
+    ops.pair2att_logits_rows(rows, cols_t, Wf, bf, layers[0].pair2att[1].eps, part)
+    logits = gather_rows(part)
+    Lp = _up8(L)
+    att_p = _empty((B, Cn, L, Lp), _adt(), rows)
+    ops.softmax_rows(logits.view(B * Cn * L, L), att_p.view(B * Cn * L, Lp)[:, :L])
+    return att_p
+
+
 class MsaUpdateWithPair(nn.Module):
     def __init__(self, d_msa, d_pair, n_heads, n_encoder_layers=4, p_dropout=0.1):
         super().__init__()
@@ -786,13 +803,18 @@ class MsaUpdateWithPair(nn.Module):
     @torch.no_grad()
     def forward(self, msa, pair):
         msa, pair = _as_f32(msa).contiguous(), _as_f32(pair).contiguous()
+        return self._run(msa, lambda chunk: _pair2att(chunk, pair))
+
+    def _run(self, msa, att_of):
+        """att_of(layers) -> the attention maps [B, len(layers)*H, L, Lp] of those layers (from the whole pair map,
+        or from a row shard: rosettafold_pytorch_b200.sharded)."""
         layers = list(self.encoder_layers)
         # chunks of <= 32 output channels per pass over pair (kernel limit)
         H = layers[0].n_heads
         per = max(1, 32 // H)
         for c0 in range(0, len(layers), per):
             chunk = layers[c0:c0 + per]
-            att_p = _pair2att(chunk, pair)
+            att_p = att_of(chunk)
             for i, layer in enumerate(chunk):
                 msa = layer._run(msa, att_p[:, i * H:(i + 1) * H])
         return msa

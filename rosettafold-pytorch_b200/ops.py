@@ -148,6 +148,12 @@ class _CudaBackend:
                                                 logits.stride(2), B, L, D, Cn, self._stream(pair)),
                    "rfk_pair2att_logits")
 
+    def pair2att_logits_rows(self, rows, cols_t, Wf, bf, eps, logits):
+        B, Li, L, D = rows.shape
+        _lib.check(self.lib.rfk_pair2att_logits_rows(_ptr(rows), _ptr(cols_t), _ptr(Wf), _ptr(bf), eps, _ptr(logits),
+                                                     logits.stride(2), B, Li, L, D, Wf.shape[0],
+                                                     self._stream(rows)), "rfk_pair2att_logits_rows")
+
     def channel_stats(self, x, stats):
         B, P, Cn = x.shape
         _lib.check(self.lib.rfk_channel_stats(_ptr(x), _dt(x), _ptr(stats), B, P, Cn, self._stream(x)),
@@ -409,6 +415,23 @@ def pair2att_logits(pair, Wf, bf, eps, logits):
             or logits.stride(1) != L * logits.stride(2) or logits.stride(0) != Cn * logits.stride(1):
         raise ValueError("pair2att_logits: logits must be a packed [B,C,L,ld] f32 view")
     backend().pair2att_logits(pair, Wf, bf, float(eps), logits)
+    return logits
+
+
+def pair2att_logits_rows(rows, cols_t, Wf, bf, eps, logits):
+    """Row-sharded form of pair2att_logits: rows f32 [B,Li,L,D] = this rank's rows of the pair map, cols_t f32
+    [B,L,Li,D] = the same rows' columns (cols_t[b,j,il] = pair[b,j,i0+il]); logits f32 [B,C,Li,ld] view."""
+    B, Li, L, D = rows.shape
+    Cn = Wf.shape[0]
+    if not rows.is_contiguous() or rows.dtype != torch.float32 or not cols_t.is_contiguous() \
+            or cols_t.dtype != torch.float32 or tuple(cols_t.shape) != (B, L, Li, D):
+        raise ValueError("pair2att_logits_rows: rows [B,Li,L,D] and cols_t [B,L,Li,D] must be contiguous f32")
+    if tuple(Wf.shape) != (Cn, D) or tuple(bf.shape) != (Cn,) or not Wf.is_contiguous():
+        raise ValueError("pair2att_logits_rows: bad weight shapes")
+    if tuple(logits.shape) != (B, Cn, Li, L) or logits.dtype != torch.float32 or logits.stride(3) != 1 \
+            or logits.stride(1) != Li * logits.stride(2) or logits.stride(0) != Cn * logits.stride(1):
+        raise ValueError("pair2att_logits_rows: logits must be a packed [B,C,Li,ld] f32 view")
+    backend().pair2att_logits_rows(rows, cols_t, Wf, bf, float(eps), logits)
     return logits
 
 

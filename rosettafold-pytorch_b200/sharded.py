@@ -193,9 +193,9 @@ class ShardedTwoTrackBlock(nn.Module):
         # [P, 1, N, L/P, D] -> [1, N, L, D]
         return gathered.permute(1, 2, 0, 3, 4).reshape(B, N, L, D), att
 
-    def _pair_update_with_msa(self, msa, pair, att, rank, world):
-        """PairUpdateWithMsa (:465-498) for this rank's rows of the pair map."""
-        lo, hi = row_shard(pair.shape[1], rank, world)
+    def _pair_update_with_msa(self, msa, rows, att, rank, world):
+        """PairUpdateWithMsa (:465-498) for this rank's rows [1, L/P, L, d_pair] of the pair map."""
+        lo, hi = row_shard(rows.shape[2], rank, world)
         group = self.group
 
         def halo(x):  # [1, Li, L, C] -> [1, Li + 2, L, C]
@@ -210,17 +210,44 @@ class ShardedTwoTrackBlock(nn.Module):
         def allreduce(st):
             dist.all_reduce(st, group=group)
 
-        return self.block.pair_update_with_msa._forward_rows(
-            msa, pair[:, lo:hi], att[:, lo:hi], lo, hi, halo, allreduce)
+        return self.block.pair_update_with_msa._forward_rows(msa, rows, att[:, lo:hi], lo, hi, halo, allreduce)
 
-    def _msa_update_with_pair(self, msa, pair, rank, world):
-        """MsaUpdateWithPair (:607-610) on a slice of MSA rows (every op is independent per sequence)."""
+    def _msa_update_with_pair(self, msa, rows, rank, world):
+        """MsaUpdateWithPair (:607-610) on a slice of MSA rows (every op is independent per sequence). The
+        attention maps come from the row-sharded pair map: the symmetrisation (:555-556) needs each row's
+        columns, which one all-to-all of the row shards delivers (L^2 d_pair / P floats per rank instead of an
+        all-gather of the whole map); every rank then computes the logits of its rows and the ranks all-gather
+        the 16 x L x L logits."""
         N = msa.shape[1]
         lo, hi = row_shard(N, rank, world)
-        part = self.block.msa_update_with_pair(msa[:, lo:hi].contiguous(), pair)
+        group = self.group
+        rows = rows.contiguous()
+        cols_t = all_to_all_rows_to_cols(rows[0], group).unsqueeze(0)          # [1, L, L/P, D]
+
+        def gather_rows(part):  # [1, C, Li, L] -> [1, C, L, L]
+            allp = torch.empty((world,) + tuple(part.shape), dtype=part.dtype, device=part.device)
+            dist.all_gather_into_tensor(allp.view(-1), part.reshape(-1), group=group)
+            return allp.permute(1, 2, 0, 3, 4).reshape(part.shape[0], part.shape[1], -1, part.shape[3])
+
+        mod = self.block.msa_update_with_pair
+        part = mod._run(msa[:, lo:hi].contiguous(), lambda chunk: M._pair2att_rows(chunk, rows, cols_t, gather_rows))
         full = torch.empty_like(msa)
         dist.all_gather_into_tensor(full.view(-1), part.reshape(-1), group=self.group)
         return full
+
+    @torch.no_grad()
+    def forward_rows(self, msa: torch.Tensor, rows: torch.Tensor):
+        """msa [1,N,L,d_msa] replicated, rows [1,L/P,L,d_pair] = this rank's rows of the pair map ->
+        (msa replicated, this rank's rows of the new pair map). The pair map is never gathered: consecutive
+        blocks hand the row shards to each other (`ShardedTrunkBlocks`)."""
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if msa.shape[0] != 1:
+            raise ValueError("ShardedTwoTrackBlock: one protein per call (batches run as replicas)")
+        msa, att = self._msa_self_attention(msa, rank, world)
+        rows = self._pair_update_with_msa(msa, _as_like(rows), att, rank, world)
+        rows = self.axial(rows)
+        msa = self._msa_update_with_pair(msa, rows, rank, world)
+        return msa, rows
 
     @torch.no_grad()
     def forward(self, msa: torch.Tensor, pair: torch.Tensor):
@@ -228,16 +255,18 @@ class ShardedTwoTrackBlock(nn.Module):
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         if world == 1:
             return self.block(msa, pair)
-        if msa.shape[0] != 1:
-            raise ValueError("ShardedTwoTrackBlock: one protein per call (batches run as replicas)")
-        rank = dist.get_rank(self.group)
-        msa, att = self._msa_self_attention(msa, rank, world)
-        rows = self._pair_update_with_msa(msa, pair, att, rank, world)
-        rows = self.axial(rows)
-        full = torch.empty_like(_as_like(pair))
-        dist.all_gather_into_tensor(full.view(-1), rows.reshape(-1), group=self.group)
-        msa = self._msa_update_with_pair(msa, full, rank, world)
-        return msa, full
+        lo, hi = row_shard(pair.shape[1], dist.get_rank(self.group), world)
+        msa, rows = self.forward_rows(msa, pair[:, lo:hi].contiguous())
+        return msa, gather_pair_rows(rows, self.group)
+
+
+def gather_pair_rows(rows: torch.Tensor, group=None) -> torch.Tensor:
+    """[1, L/P, L, D] on every rank -> the whole [1, L, L, D] map on every rank."""
+    world = dist.get_world_size(group)
+    full = torch.empty((rows.shape[0], rows.shape[1] * world) + tuple(rows.shape[2:]), dtype=rows.dtype,
+                       device=rows.device)
+    dist.all_gather_into_tensor(full.view(-1), rows.reshape(-1), group=group)
+    return full
 
 
 class ShardedTrunkBlocks(nn.Module):
@@ -247,6 +276,17 @@ class ShardedTrunkBlocks(nn.Module):
 
     @torch.no_grad()
     def forward(self, msa, pair):
+        """Replicated in, replicated out; between the blocks the pair map stays row-sharded."""
+        if not self.blocks:
+            return msa, pair
+        group = self.blocks[0].group
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world == 1:
+            for blk in self.blocks:
+                msa, pair = blk(msa, pair)
+            return msa, pair
+        lo, hi = row_shard(pair.shape[1], dist.get_rank(group), world)
+        rows = pair[:, lo:hi].contiguous()
         for blk in self.blocks:
-            msa, pair = blk(msa, pair)
-        return msa, pair
+            msa, rows = blk.forward_rows(msa, rows)
+        return msa, gather_pair_rows(rows, group)

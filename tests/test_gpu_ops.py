@@ -267,6 +267,30 @@ def test_pair2att_logits(cuda_device):
     assert rel_l2(lg[..., :L], ref) < 1e-5
 
 
+@pytest.mark.parametrize("D", [288, 72])
+def test_pair2att_logits_rows(cuda_device, D):
+    """Row-sharded pair2att (long-protein path): rows + transposed shard of two ragged row ranges reproduce the
+    whole-map kernel (vectorised D = 288 path and the generic one)."""
+    dev = cuda_device
+    B, L, Cn = 2, 33, 16
+    pair = _rand((B, L, L, D), torch.float32, dev, 63, 2.0)
+    Wf = _rand((Cn, D), torch.float32, dev, 64, 0.1)
+    bf = _rand((Cn,), torch.float32, dev, 65)
+    full = torch.empty((B, Cn, L, L), dtype=torch.float32, device=dev)
+    ops.pair2att_logits(pair, Wf, bf, 1e-5, full)
+    for lo, hi in ((0, 13), (13, 33)):
+        rows = pair[:, lo:hi].contiguous()
+        cols_t = pair[:, :, lo:hi].contiguous()
+        Lp = 40
+        part = torch.zeros((B, Cn, hi - lo, Lp), dtype=torch.float32, device=dev)
+        ops.pair2att_logits_rows(rows, cols_t, Wf, bf, 1e-5, part[..., :L])
+        ref = torch.empty((B, Cn, hi - lo, L), dtype=torch.float32, device=dev)
+        REF.pair2att_logits_rows(rows, cols_t, Wf, bf, 1e-5, ref)
+        torch.cuda.synchronize()
+        assert rel_l2(part[..., :L], ref) < 1e-5
+        assert rel_l2(part[..., :L], full[:, :, lo:hi]) < 1e-5
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 @pytest.mark.parametrize("shape", [(2, 900, 288), (1, 77, 72), (3, 333, 20)])
 def test_instnorm(cuda_device, dtype, shape):

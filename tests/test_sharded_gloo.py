@@ -49,8 +49,17 @@ def _worker(rank, world, port, out_dir):
     # 4. whole block, outputs replicated on every rank
     m, p = sblk(msa, pair)
     m1, p1 = blk(msa, pair)
+    # 5. two blocks: the pair map stays row-sharded between them (MsaUpdateWithPair's attention maps come from the
+    #    row shard + its all-to-all transpose)
+    from rosettafold_pytorch_b200.sharded import ShardedTrunkBlocks
+    from oracle.weights import synth_state_dict
+    trunk = rf.TrunkBlocks(cfg["d_msa"], cfg["d_pair"], n_blocks=2, n_encoder_layers=1).eval()
+    trunk.load_state_dict(synth_state_dict(trunk.state_dict(), seed=17), strict=True)
+    mt, pt = ShardedTrunkBlocks(trunk)(msa, pair)
+    mt1, pt1 = trunk(msa, pair)
+    err_trunk = max(float((mt - mt1).abs().max()), float((pt - pt1).abs().max()))
     torch.save(dict(err_t=err_t, err_b=err_b, err_ax=err_ax, err_sa=err_sa, err_m=float((m - m1).abs().max()),
-                    err_p=float((p - p1).abs().max())), os.path.join(out_dir, f"res_{rank}.pt"))
+                    err_p=float((p - p1).abs().max()), err_trunk=err_trunk), os.path.join(out_dir, f"res_{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -63,6 +72,7 @@ def test_two_rank_row_sharded_axial_matches_single_process(tmp_path):
         res = torch.load(os.path.join(tmp_path, f"res_{rank}.pt"))
         assert res["err_t"] == 0.0 and res["err_b"] == 0.0, res
         assert res["err_ax"] < 1e-4 and res["err_sa"] < 1e-4 and res["err_m"] < 1e-4 and res["err_p"] < 1e-4, res
+        assert res["err_trunk"] < 1e-4, res
 
 
 def test_row_shard_rejects_ragged():

@@ -17,6 +17,8 @@ ap.add_argument("--L", type=int, default=1024)
 ap.add_argument("--N", type=int, default=256)
 ap.add_argument("--layers", type=int, default=4)
 ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--blocks", type=int, default=1, help="> 1: a trunk of that many blocks; the pair map stays "
+                "row-sharded between blocks (ShardedTrunkBlocks), reported per block")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -24,11 +26,14 @@ dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 torch.manual_seed(0)  # identical weights (and FAVOR projections) on every rank
-blk = rf.TwoTrackBlock(384, 288, n_encoder_layers=args.layers).eval().to(dev)
+if args.blocks > 1:
+    blk = rf.TrunkBlocks(384, 288, n_blocks=args.blocks, n_encoder_layers=args.layers).eval().to(dev)
+else:
+    blk = rf.TwoTrackBlock(384, 288, n_encoder_layers=args.layers).eval().to(dev)
 g = torch.Generator().manual_seed(5)
 msa = torch.randn((1, args.N, args.L, 384), generator=g).to(dev)
 pair = torch.randn((1, args.L, args.L, 288), generator=g).to(dev)
-sblk = rf.ShardedTwoTrackBlock(blk)
+sblk = rf.ShardedTrunkBlocks(blk) if args.blocks > 1 else rf.ShardedTwoTrackBlock(blk)
 
 def timed(fn):
     for _ in range(2): fn()
@@ -40,10 +45,10 @@ def timed(fn):
     b.record(); torch.cuda.synchronize()
     ms = torch.tensor([a.elapsed_time(b) / args.steps], device=dev)
     if world > 1: dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    return float(ms), out
+    return float(ms) / args.blocks, out
 
 ms_sh, (m_sh, p_sh) = timed(lambda: sblk(msa, pair))
-res = {"config": f"TwoTrackBlock (1,{args.N},{args.L}), {args.layers} encoder layers, row-/sequence-sharded x{world} (tied row layers by sequence, Performer column layers by residue, pair stages by row)",
+res = {"config": f"{args.blocks} x TwoTrackBlock (1,{args.N},{args.L}), {args.layers} encoder layers, row-/sequence-sharded x{world} (tied row layers by sequence, Performer column layers by residue, pair stages by row)",
        "n_gpus": world, "ms_per_block_sharded": ms_sh}
 if rank == 0:
     ms_1, (m_1, p_1) = timed(lambda: blk(msa, pair)) if world == 1 else (None, blk(msa, pair))
