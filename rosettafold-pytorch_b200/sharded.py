@@ -41,12 +41,17 @@ One process per GPU; `torch.distributed` (NCCL over NVLink on GPUs, gloo in the 
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
 
 from . import modules as M
 from . import ops
+
+
+_STAGE_TIMING = bool(os.environ.get("RFK_SHARD_TIMING"))  # developer aid: per-stage device times of every block
 
 
 def _as_like(t):
@@ -243,10 +248,27 @@ class ShardedTwoTrackBlock(nn.Module):
         world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         if msa.shape[0] != 1:
             raise ValueError("ShardedTwoTrackBlock: one protein per call (batches run as replicas)")
+        marks = [] if _STAGE_TIMING and msa.is_cuda else None
+
+        def mark(name):
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+
+        mark("start")
         msa, att = self._msa_self_attention(msa, rank, world)
+        mark("msa_self_attention")
         rows = self._pair_update_with_msa(msa, _as_like(rows), att, rank, world)
+        mark("pair_update_with_msa")
         rows = self.axial(rows)
+        mark("pair_axial_attention")
         msa = self._msa_update_with_pair(msa, rows, rank, world)
+        mark("msa_update_with_pair")
+        if marks is not None:
+            torch.cuda.synchronize()
+            print(f"[rank {rank}] " + ", ".join(f"{n} {a.elapsed_time(b):.2f} ms"
+                                                for (_, a), (n, b) in zip(marks[:-1], marks[1:])), flush=True)
         return msa, rows
 
     @torch.no_grad()
