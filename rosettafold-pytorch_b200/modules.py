@@ -595,22 +595,35 @@ class PairUpdateWithMsa(nn.Module):
     def forward(self, msa, pair, att):
         return self._forward_rows(msa, pair, att, 0, pair.shape[1], None, None)
 
-    def _forward_rows(self, msa, pair_rows, att_rows, lo, hi, halo, allreduce):
-        """Rows [lo, hi) of the updated pair map. msa: the full MSA; pair_rows / att_rows: rows [lo, hi)
-        of pair and of the tied attention map. `halo` / `allreduce` (long-protein path, sharded.py):
-        neighbour-row exchange for the 3x3 convolutions and the sum of the InstanceNorm statistics over
-        the row shards; None for the whole map."""
-        msa, pair, att = _as_f32(msa).contiguous(), _as_f32(pair_rows).contiguous(), _as_f32(att_rows).contiguous()
+    def _project(self, msa):
+        """The first two steps of proj_msa (LN -> Linear, :434-437) on any slice of the MSA: [B,n,l,D] ->
+        float32 [B,n,l,d_proj]. Per token, so the long-protein path runs it on residue shards and gathers the
+        32-channel result instead of the 384-channel MSA."""
+        msa = _as_f32(msa).contiguous()
         pk = self._pack()
-        B, N, L, D = msa.shape
+        T, D = msa.numel() // msa.shape[-1], msa.shape[-1]
+        xn = _ln_into(msa.view(T, D), self.proj_msa[0], _empty((T, D), _adt(), msa))
+        mraw = _empty((T, self.d_proj), torch.float32, msa)
+        ops.gemm(xn, pk["Wproj"], cview(mraw), bias=pk["bproj"])
+        return mraw.view(*msa.shape[:-1], self.d_proj)
+
+    def _forward_rows(self, msa, pair_rows, att_rows, lo, hi, halo, allreduce, mraw=None):
+        """Rows [lo, hi) of the updated pair map. msa: the full MSA (or None with `mraw` = `_project` of the
+        full MSA); pair_rows / att_rows: rows [lo, hi) of pair and of the tied attention map. `halo` /
+        `allreduce` (long-protein path, sharded.py): neighbour-row exchange for the 3x3 convolutions and the
+        sum of the InstanceNorm statistics over the row shards; None for the whole map."""
+        pair, att = _as_f32(pair_rows).contiguous(), _as_f32(att_rows).contiguous()
+        pk = self._pack()
+        if mraw is None:
+            mraw = self._project(msa)
+        msa = mraw  # device / dtype template for the buffers below
+        B, N, L, Q = mraw.shape
+        mraw = mraw.reshape(B * N * L, Q)
         Li = hi - lo
-        P, Q, H = self.d_pair, self.d_proj, self.n_heads
+        P, H = self.d_pair, self.n_heads
         T, TP = B * N * L, B * Li * L
         adt = _adt()
-        # proj_msa: LN -> Linear -> LN (:434-438); m kept in float32 (tiny), operand copy for GEMMs
-        xn = _ln_into(msa.view(T, D), self.proj_msa[0], _empty((T, D), adt, msa))
-        mraw = _empty((T, Q), torch.float32, msa)
-        ops.gemm(xn, pk["Wproj"], cview(mraw), bias=pk["bproj"])
+        # third step of proj_msa (LN, :438); m kept in float32 (tiny), operand copy for GEMMs
         m32 = _ln_into(mraw, self.proj_msa[2], _empty((T, Q), torch.float32, msa))
         m_op = m32 if _MODE == 1 else _ln_into(mraw, self.proj_msa[2], _empty((T, Q), adt, msa))
         w = self.poswise_weight._weights(m_op.view(B, N, L, Q))  # [B,N,L,1] (:469-470)

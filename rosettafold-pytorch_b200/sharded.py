@@ -1,43 +1,37 @@
-"""One long protein over several GPUs: pair row-sharding with an all-to-all transpose
-(BASELINE.json config 4).
+"""One long protein over several GPUs (BASELINE.json config 4).
 
-The pair tensor `pair[1, L, L, D]` is sharded on its first residue axis i: rank r owns rows
-[r L/P, (r+1) L/P). Inside `PairUpdateWithAxialAttention` (reference :501-547)
+Between the stages of a block - and between the blocks of a trunk (`ShardedTrunkBlocks`) - no tensor of the
+size of the MSA or of the pair map is ever replicated: the MSA lives as sequence shards `[1, N/P, L, D]` or
+residue shards `[1, N, L/P, D]`, the pair map as row shards `[1, L/P, L, D]` (rank r owns rows
+[r L/P, (r+1) L/P)). Per block (reference :962-968):
 
-  * column attention (tokens along j, one group per row i), every LayerNorm and the FeedForward are
-    local to a row shard;
-  * row attention (tokens along i, one group per column j) needs whole columns: the normalised
-    operand is transposed between ranks with ONE all-to-all (rank r receives columns
-    [r L/P, (r+1) L/P) of every row), attention + output projection run on the column shard, and a
-    second all-to-all brings the update back to the row shard where it is added to the fp32
-    residual stream. Only operand-dtype tensors (bf16 in the tensor-core mode) cross NVLink:
-    2 x L^2 D / P elements per rank and layer.
-
-`ShardedTwoTrackBlock` shards three of the four stages of a block:
-
-  * pair axial attention: row-sharded as above;
-  * the Performer column layers of `MsaUpdateUsingSelfAttention` (tokens along n, one group per residue
-    l, every other op per token): each rank takes a slice of residues, no communication but the
-    all-gather of the MSA slices at the end;
-  * `MsaUpdateWithPair`: `u[n,h,i,:] = sum_j A[h,i,j] V[n,h,j,:]` and the FeedForward are independent
-    per MSA row n: each rank takes a slice of sequences (the pair-derived attention maps are recomputed
-    on every rank from the all-gathered pair), all-gather of the MSA slices at the end.
-
-  * `PairUpdateWithMsa`: the per-token MSA projections (32 channels) are cheap and stay replicated; the
-    outer-product sum, the 716-wide Linear and the convolution block run on the rank's pair rows. Each
-    3x3 convolution needs one neighbour row on either side (an all-gather of every rank's first and
-    last row: 2 L d_pair elements per rank) and the InstanceNorm statistics are all-reduced
+  A `MsaUpdateUsingSelfAttention`
+    * tied row layers on the sequence shard. Projections, the q scaling, A.V, to_out and the FeedForward are
+      per sequence; the layer couples sequences in three places only (`SequenceShard`): the query row of the
+      position-wise weights is sequence 0 of the whole MSA (broadcast from rank 0: L x d_msa operand-dtype
+      elements), their softmax runs over all sequences (merged from per-rank (max, sum) statistics: an
+      all-gather of 2 x L x 12 floats) and the logits sum over all sequences (all-reduce of 12 x L x L floats);
+    * one all-to-all turns sequence shards into residue shards;
+    * Performer column layers (tokens along n, one group per residue) on the residue shard: local.
+  B `PairUpdateWithMsa` on the pair rows: the MSA enters through its 32-channel projection only, computed on the
+    residue shard and all-gathered (N L 32 floats); outer-product sum, 716-wide Linear and the convolution block
+    run on the rank's rows. Each 3x3 convolution needs one neighbour row on either side (an all-gather of every
+    rank's first and last row: 2 L d_pair elements per rank), the InstanceNorm statistics are all-reduced
     (2 x d_pair doubles).
+  C `PairUpdateWithAxialAttention` on the pair rows: column attention (tokens along j), every LayerNorm and the
+    FeedForward are local; row attention (tokens along i) needs whole columns: the normalised operand is
+    transposed between ranks with ONE all-to-all (rank r receives columns [r L/P, (r+1) L/P) of every row),
+    attention + output projection run on the column shard, and a second all-to-all brings the update back to the
+    row shard where it is added to the fp32 residual stream. Only operand-dtype tensors (bf16 in the tensor-core
+    mode) cross NVLink: 2 x L^2 D / P elements per rank and layer.
+  D `MsaUpdateWithPair`: one all-to-all turns the residue shards back into sequence shards (every op is
+    independent per sequence). The attention maps need the symmetrised pair map (:555-556), the one place where
+    pair rows meet their columns: one all-to-all delivers each rank the columns of its rows, it computes the
+    logits of its rows (`rfk_pair2att_logits_rows`) and the ranks all-gather the 16 x L x L logits.
 
-  * the tied row layers of `MsaUpdateUsingSelfAttention`: each rank takes a slice of sequences. Projections,
-    the q scaling, A.V, to_out and the FeedForward are per sequence; the layer couples sequences in three
-    places only (`SequenceShard`): the query row of the position-wise weights is sequence 0 of the whole MSA
-    (broadcast from rank 0: L x d_msa operand-dtype elements), their softmax runs over all sequences (merged
-    from per-rank (max, sum) statistics: an all-gather of 2 x L x 12 floats) and the logits sum over all
-    sequences (all-reduce of 12 x L x L floats). One all-to-all then turns the sequence shards into the
-    residue shards the Performer column layers work on.
-
-One process per GPU; `torch.distributed` (NCCL over NVLink on GPUs, gloo in the CPU tests).
+`ShardedTwoTrackBlock.forward` / `ShardedTrunkBlocks.forward` take and return replicated tensors (they shard at
+entry and all-gather once at exit); `forward_rows` is the shard-to-shard form. N and L must be divisible by the
+number of ranks. One process per GPU; `torch.distributed` (NCCL over NVLink on GPUs, gloo in the CPU tests).
 """
 from __future__ import annotations
 
@@ -129,6 +123,17 @@ def all_to_all_seqs_to_residues(x_seqs: torch.Tensor, group=None) -> torch.Tenso
     return recv.view(1, world * Nl, Ll, D)
 
 
+def all_to_all_residues_to_seqs(x_res: torch.Tensor, group=None) -> torch.Tensor:
+    """[1, N, L/P, D] (all sequences, my residues) -> [1, N/P, L, D] (my sequences, all residues)."""
+    world = dist.get_world_size(group)
+    _, N, Ll, D = x_res.shape
+    Nl = N // world
+    send = x_res.contiguous().view(world, Nl, Ll, D)       # chunk p = sequences of rank p x my residues
+    recv = torch.empty_like(send)                          # chunk q = my sequences x residues of rank q
+    dist.all_to_all_single(recv, send, group=group)
+    return recv.permute(1, 0, 2, 3).reshape(1, Nl, world * Ll, D)
+
+
 class ShardedPairAxialAttention(nn.Module):
     """`PairUpdateWithAxialAttention` on a row shard of the pair tensor (B = 1)."""
 
@@ -175,33 +180,35 @@ class ShardedTwoTrackBlock(nn.Module):
         self.axial = ShardedPairAxialAttention(block.pair_update_with_axial_attention, group)
         self.group = group
 
-    def _msa_self_attention(self, msa, rank, world):
-        """MsaUpdateUsingSelfAttention (:399-409): tied row layers on a slice of sequences, one all-to-all,
-        Performer column layers on a slice of residues."""
+    def _msa_self_attention(self, msa_seq, rank, world):
+        """MsaUpdateUsingSelfAttention (:399-409): msa_seq [1, N/P, L, D] = this rank's sequences -> the updated
+        MSA as this rank's residues [1, N, L/P, D], and the (replicated) symmetrised tied attention map. Tied row
+        layers on the sequence shard, one all-to-all, Performer column layers on the residue shard."""
         mod = self.block.msa_update_using_self_att
-        x = M._as_f32(msa).contiguous()
-        B, N, L, D = x.shape
+        xq = M._as_f32(msa_seq).contiguous()
+        row_shard(xq.shape[2], rank, world)                   # L must divide too
         att = None
         n = len(mod.residue_wise_encoder_layers)
-        row_shard(L, rank, world)                             # both axes must divide
-        n_lo, n_hi = row_shard(N, rank, world)
         shard = SequenceShard(self.group)
-        xq = x[:, n_lo:n_hi].contiguous()                     # [1, N/P, L, D]
         for i, layer in enumerate(mod.residue_wise_encoder_layers):
             xq, a = layer._run(xq, want_att=(i == n - 1), shard=shard)
             att = a if a is not None else att
         xs = all_to_all_seqs_to_residues(xq, self.group)      # [1, N, L/P, D]
         for layer in mod.sequence_wise_encoder_layers:
             xs, _ = layer._run(xs, token_dim=1)
-        gathered = torch.empty((world,) + tuple(xs.shape), dtype=xs.dtype, device=xs.device)
-        dist.all_gather_into_tensor(gathered.view(-1), xs.reshape(-1), group=self.group)
-        # [P, 1, N, L/P, D] -> [1, N, L, D]
-        return gathered.permute(1, 2, 0, 3, 4).reshape(B, N, L, D), att
+        return xs, att
 
-    def _pair_update_with_msa(self, msa, rows, att, rank, world):
-        """PairUpdateWithMsa (:465-498) for this rank's rows [1, L/P, L, d_pair] of the pair map."""
+    def _pair_update_with_msa(self, msa_res, rows, att, rank, world):
+        """PairUpdateWithMsa (:465-498) for this rank's rows [1, L/P, L, d_pair] of the pair map. msa_res
+        [1, N, L/P, D]: the MSA enters through its 32-channel projection only (per token), which is computed on
+        the residue shard and all-gathered (N L 32 floats instead of N L 384)."""
         lo, hi = row_shard(rows.shape[2], rank, world)
         group = self.group
+        mod = self.block.pair_update_with_msa
+        part = mod._project(msa_res)                                             # [1, N, L/P, Q]
+        allm = torch.empty((world,) + tuple(part.shape), dtype=part.dtype, device=part.device)
+        dist.all_gather_into_tensor(allm.view(-1), part.reshape(-1), group=group)
+        mraw = allm.permute(1, 2, 0, 3, 4).reshape(part.shape[0], part.shape[1], -1, part.shape[3])  # [1, N, L, Q]
 
         def halo(x):  # [1, Li, L, C] -> [1, Li + 2, L, C]
             edges = torch.stack([x[:, 0], x[:, -1]], 0).contiguous()            # my first / last row
@@ -215,17 +222,17 @@ class ShardedTwoTrackBlock(nn.Module):
         def allreduce(st):
             dist.all_reduce(st, group=group)
 
-        return self.block.pair_update_with_msa._forward_rows(msa, rows, att[:, lo:hi], lo, hi, halo, allreduce)
+        return mod._forward_rows(None, rows, att[:, lo:hi], lo, hi, halo, allreduce, mraw=mraw)
 
-    def _msa_update_with_pair(self, msa, rows, rank, world):
-        """MsaUpdateWithPair (:607-610) on a slice of MSA rows (every op is independent per sequence). The
-        attention maps come from the row-sharded pair map: the symmetrisation (:555-556) needs each row's
-        columns, which one all-to-all of the row shards delivers (L^2 d_pair / P floats per rank instead of an
-        all-gather of the whole map); every rank then computes the logits of its rows and the ranks all-gather
-        the 16 x L x L logits."""
-        N = msa.shape[1]
-        lo, hi = row_shard(N, rank, world)
+    def _msa_update_with_pair(self, msa_res, rows, rank, world):
+        """MsaUpdateWithPair (:607-610): msa_res [1, N, L/P, D] -> this rank's sequences [1, N/P, L, D] of the
+        updated MSA (every op is independent per sequence; one all-to-all turns residue shards into sequence
+        shards). The attention maps come from the row-sharded pair map: the symmetrisation (:555-556) needs each
+        row's columns, which one all-to-all of the row shards delivers (L^2 d_pair / P floats per rank instead
+        of an all-gather of the whole map); every rank then computes the logits of its rows and the ranks
+        all-gather the 16 x L x L logits."""
         group = self.group
+        msa_seq = all_to_all_residues_to_seqs(msa_res, group)
         rows = rows.contiguous()
         cols_t = all_to_all_rows_to_cols(rows[0], group).unsqueeze(0)          # [1, L, L/P, D]
 
@@ -235,20 +242,17 @@ class ShardedTwoTrackBlock(nn.Module):
             return allp.permute(1, 2, 0, 3, 4).reshape(part.shape[0], part.shape[1], -1, part.shape[3])
 
         mod = self.block.msa_update_with_pair
-        part = mod._run(msa[:, lo:hi].contiguous(), lambda chunk: M._pair2att_rows(chunk, rows, cols_t, gather_rows))
-        full = torch.empty_like(msa)
-        dist.all_gather_into_tensor(full.view(-1), part.reshape(-1), group=self.group)
-        return full
+        return mod._run(msa_seq, lambda chunk: M._pair2att_rows(chunk, rows, cols_t, gather_rows))
 
     @torch.no_grad()
-    def forward_rows(self, msa: torch.Tensor, rows: torch.Tensor):
-        """msa [1,N,L,d_msa] replicated, rows [1,L/P,L,d_pair] = this rank's rows of the pair map ->
-        (msa replicated, this rank's rows of the new pair map). The pair map is never gathered: consecutive
-        blocks hand the row shards to each other (`ShardedTrunkBlocks`)."""
+    def forward_rows(self, msa_seq: torch.Tensor, rows: torch.Tensor):
+        """msa_seq [1,N/P,L,d_msa] = this rank's sequences, rows [1,L/P,L,d_pair] = this rank's rows of the pair
+        map -> the same shards of the block's outputs. Neither tensor is ever gathered: consecutive blocks hand
+        the shards to each other (`ShardedTrunkBlocks`)."""
         world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-        if msa.shape[0] != 1:
+        if msa_seq.shape[0] != 1:
             raise ValueError("ShardedTwoTrackBlock: one protein per call (batches run as replicas)")
-        marks = [] if _STAGE_TIMING and msa.is_cuda else None
+        marks = [] if _STAGE_TIMING and msa_seq.is_cuda else None
 
         def mark(name):
             if marks is not None:
@@ -257,19 +261,19 @@ class ShardedTwoTrackBlock(nn.Module):
                 marks.append((name, ev))
 
         mark("start")
-        msa, att = self._msa_self_attention(msa, rank, world)
+        msa_res, att = self._msa_self_attention(msa_seq, rank, world)
         mark("msa_self_attention")
-        rows = self._pair_update_with_msa(msa, _as_like(rows), att, rank, world)
+        rows = self._pair_update_with_msa(msa_res, _as_like(rows), att, rank, world)
         mark("pair_update_with_msa")
         rows = self.axial(rows)
         mark("pair_axial_attention")
-        msa = self._msa_update_with_pair(msa, rows, rank, world)
+        msa_seq = self._msa_update_with_pair(msa_res, rows, rank, world)
         mark("msa_update_with_pair")
         if marks is not None:
             torch.cuda.synchronize()
             print(f"[rank {rank}] " + ", ".join(f"{n} {a.elapsed_time(b):.2f} ms"
                                                 for (_, a), (n, b) in zip(marks[:-1], marks[1:])), flush=True)
-        return msa, rows
+        return msa_seq, rows
 
     @torch.no_grad()
     def forward(self, msa: torch.Tensor, pair: torch.Tensor):
@@ -277,17 +281,24 @@ class ShardedTwoTrackBlock(nn.Module):
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         if world == 1:
             return self.block(msa, pair)
-        lo, hi = row_shard(pair.shape[1], dist.get_rank(self.group), world)
-        msa, rows = self.forward_rows(msa, pair[:, lo:hi].contiguous())
-        return msa, gather_pair_rows(rows, self.group)
+        msa_seq, rows = shard_inputs(msa, pair, self.group)
+        msa_seq, rows = self.forward_rows(msa_seq, rows)
+        return gather_shards(msa_seq, self.group), gather_shards(rows, self.group)
 
 
-def gather_pair_rows(rows: torch.Tensor, group=None) -> torch.Tensor:
-    """[1, L/P, L, D] on every rank -> the whole [1, L, L, D] map on every rank."""
+def shard_inputs(msa: torch.Tensor, pair: torch.Tensor, group=None):
+    """Replicated msa [1,N,L,D], pair [1,L,L,P] -> (this rank's sequences, this rank's pair rows)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_lo, n_hi = row_shard(msa.shape[1], rank, world)
+    lo, hi = row_shard(pair.shape[1], rank, world)
+    return msa[:, n_lo:n_hi].contiguous(), pair[:, lo:hi].contiguous()
+
+
+def gather_shards(x: torch.Tensor, group=None) -> torch.Tensor:
+    """[1, X/P, ...] shards of axis 1 on every rank -> the whole [1, X, ...] tensor on every rank."""
     world = dist.get_world_size(group)
-    full = torch.empty((rows.shape[0], rows.shape[1] * world) + tuple(rows.shape[2:]), dtype=rows.dtype,
-                       device=rows.device)
-    dist.all_gather_into_tensor(full.view(-1), rows.reshape(-1), group=group)
+    full = torch.empty((x.shape[0], x.shape[1] * world) + tuple(x.shape[2:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(full.view(-1), x.reshape(-1), group=group)
     return full
 
 
@@ -298,7 +309,8 @@ class ShardedTrunkBlocks(nn.Module):
 
     @torch.no_grad()
     def forward(self, msa, pair):
-        """Replicated in, replicated out; between the blocks the pair map stays row-sharded."""
+        """Replicated in, replicated out; between the blocks the MSA stays sequence-sharded and the pair map
+        row-sharded."""
         if not self.blocks:
             return msa, pair
         group = self.blocks[0].group
@@ -307,8 +319,7 @@ class ShardedTrunkBlocks(nn.Module):
             for blk in self.blocks:
                 msa, pair = blk(msa, pair)
             return msa, pair
-        lo, hi = row_shard(pair.shape[1], dist.get_rank(group), world)
-        rows = pair[:, lo:hi].contiguous()
+        msa_seq, rows = shard_inputs(msa, pair, group)
         for blk in self.blocks:
-            msa, rows = blk.forward_rows(msa, rows)
-        return msa, gather_pair_rows(rows, group)
+            msa_seq, rows = blk.forward_rows(msa_seq, rows)
+        return gather_shards(msa_seq, group), gather_shards(rows, group)

@@ -43,9 +43,10 @@ def _worker(rank, world, port, out_dir):
     # 3. MSA self-attention: tied row layers sequence-sharded (broadcast query row, merged position-wise softmax,
     #    all-reduced logits), all-to-all, Performer column layers residue-sharded
     sblk = ShardedTwoTrackBlock(blk)
-    ms, atts = sblk._msa_self_attention(msa, rank, world)
+    n_lo, n_hi = row_shard(cfg["N"], rank, world)
+    ms, atts = sblk._msa_self_attention(msa[:, n_lo:n_hi].contiguous(), rank, world)   # -> residue shard
     mr, attr = blk.msa_update_using_self_att(msa)
-    err_sa = max(float((ms - mr).abs().max()), float((atts - attr).abs().max()))
+    err_sa = max(float((ms - mr[:, :, lo:hi]).abs().max()), float((atts - attr).abs().max()))
     # 4. whole block, outputs replicated on every rank
     m, p = sblk(msa, pair)
     m1, p1 = blk(msa, pair)
