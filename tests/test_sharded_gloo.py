@@ -65,11 +65,12 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_rank_row_sharded_axial_matches_single_process(tmp_path):
-    port = 31500 + (os.getpid() % 2000)
+@pytest.mark.parametrize("world", [2, 3])  # with three ranks the middle one has a halo neighbour on both sides
+def test_sharded_stages_match_single_process(tmp_path, world):
+    port = 31500 + (os.getpid() % 2000) + world
     os.environ["PYTHONPATH"] = ROOT + os.pathsep + os.environ.get("PYTHONPATH", "")
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    for rank in range(2):
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for rank in range(world):
         res = torch.load(os.path.join(tmp_path, f"res_{rank}.pt"))
         assert res["err_t"] == 0.0 and res["err_b"] == 0.0, res
         assert res["err_ax"] < 1e-4 and res["err_sa"] < 1e-4 and res["err_m"] < 1e-4 and res["err_p"] < 1e-4, res
