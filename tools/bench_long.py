@@ -1,10 +1,11 @@
 #!/usr/bin/env python
-"""Long-protein path (BASELINE.json config 4): one TwoTrackBlock at (1, N, L) with the pair axial
-stage row-sharded over the ranks (NCCL all-to-all transposes), checked against the single-GPU block
-on rank 0 and timed on the device (max over ranks).
+"""Long-protein path (BASELINE.json config 4): one TwoTrackBlock (or, with --blocks K, a trunk of K blocks) at
+(1, N, L), sharded over the ranks as described in rosettafold_pytorch_b200/sharded.py, checked against the
+single-GPU run on rank 0 and timed on the device (CUDA events, max over ranks).
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-      --master-port 29533 tools/bench_long.py --L 1024 --N 256
+      --master-port 29533 tools/bench_long.py --L 1024 --N 256 [--blocks 2]
+  RFK_SHARD_TIMING=1 ... prints the device time of every stage of every block (adds a synchronize per block).
 """
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
