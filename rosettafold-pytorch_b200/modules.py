@@ -593,6 +593,10 @@ class PairUpdateWithMsa(nn.Module):
 
     @torch.no_grad()
     def forward(self, msa, pair, att):
+        if pair.shape[1] * pair.shape[2] <= 1:
+            # the reference's InstanceNorm2d (:453) refuses a 1 x 1 map with exactly this error
+            raise ValueError(f"Expected more than 1 spatial element when training, got input size "
+                             f"{torch.Size([pair.shape[0], pair.shape[3], pair.shape[1], pair.shape[2]])}")
         return self._forward_rows(msa, pair, att, 0, pair.shape[1], None, None)
 
     def _project(self, msa):

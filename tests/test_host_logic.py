@@ -216,3 +216,33 @@ def test_blocks_in_situ_match_model_trace(emulated_ops, name):
     rf.set_mode("fp32")
     errs = run_trace_block(blk, coord, rec)
     assert max(errs.values()) < 1e-4, errs
+
+
+def test_single_residue_is_refused_like_the_reference(emulated_ops):
+    """L = 1: the reference's InstanceNorm2d (:453) raises ValueError on a 1 x 1 map; so does the replacement."""
+    from oracle import trunk_ref
+
+    cfg = dict(d_msa=48, d_pair=40, n_layers=1, B=2, N=3, L=1, seed=23)
+    blk, sd, msa, pair = build_block(cfg)
+    rf.set_mode("fp32")
+    with pytest.raises(ValueError, match="more than 1 spatial element"):
+        trunk_ref.two_track_block(msa, pair, sd, 1)
+    with pytest.raises(ValueError, match="more than 1 spatial element"):
+        blk(msa, pair)
+
+
+@pytest.mark.parametrize("B,N,L", [(1, 1, 9), (2, 3, 2), (1, 2, 8), (3, 9, 17)])
+def test_block_degenerate_shapes_match_restatement(emulated_ops, B, N, L):
+    """Host logic at the edges the reference accepts: a single sequence (the query row of the position-wise
+    weights is the only row), two residues (3x3 convolution on a 2 x 2 map), batches > 1, sizes below / across the
+    8-element padding of the operand buffers."""
+    from oracle import trunk_ref
+
+    cfg = dict(d_msa=48, d_pair=40, n_layers=1, B=B, N=N, L=L, seed=23)
+    blk, sd, msa, pair = build_block(cfg)
+    rf.set_mode("fp32")
+    m, p = blk(msa, pair)
+    with torch.no_grad():
+        m_ref, p_ref = trunk_ref.two_track_block(msa, pair, sd, cfg["n_layers"])
+    assert m.shape == msa.shape and p.shape == pair.shape
+    assert rel_l2(m, m_ref) < 1e-4 and rel_l2(p, p_ref) < 1e-4
