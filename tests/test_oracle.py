@@ -71,3 +71,32 @@ def test_coord_restatement_matches_golden():
     with torch.no_grad():
         out = trunk_ref.msa_update_with_pair_and_coord(xyz, state, msa, trunk_ref.W(sd))
     assert rel_l2(out, gold["msa_out"]) < 2e-5
+
+
+def test_performer_restatement_is_an_unbiased_softmax_attention_estimator():
+    """`performer_pytorch` itself is absent (parity unpinned), so the restatement is anchored on what the published
+    algorithm IS: a Monte-Carlo estimator of exp(q.k / sqrt(d)) attention. With the restated constants (inputs
+    scaled by d^-1/4, the ||x||^2 / 2 term, Gaussian-orthogonal features) the result must converge to exact
+    softmax attention like 1/sqrt(m); a wrong scale, sign or normaliser converges to something else (plateau)."""
+    from oracle import performer_ref as P
+
+    g = torch.Generator().manual_seed(1)
+    B, H, T, d = 2, 3, 40, 64
+    q = torch.randn(B, H, T, d, generator=g, dtype=torch.float64) * 0.3
+    k = torch.randn(B, H, T, d, generator=g, dtype=torch.float64) * 0.3
+    v = torch.randn(B, H, T, d, generator=g, dtype=torch.float64)
+    exact = torch.softmax(q @ k.transpose(-1, -2) * d ** -0.5, -1) @ v
+    errs = []
+    for m in (64, 256, 1024, 4096):
+        e = []
+        for s in range(6):
+            proj = P.gaussian_orthogonal_random_matrix(m, d, generator=torch.Generator().manual_seed(10 + s)).double()
+            e.append(float((P.favor_attention(q, k, v, proj, False) - exact).norm() / exact.norm()))
+        errs.append(sum(e) / len(e))
+    assert errs[-1] < 0.03, errs
+    for a, b in zip(errs[:-1], errs[1:]):       # 4x the features -> about half the error
+        assert 1.5 < a / b < 2.7, errs
+    # the ReLU ("generalized") kernel is NOT a softmax estimator: it must not be confused with it
+    proj = P.gaussian_orthogonal_random_matrix(4096, d, generator=torch.Generator().manual_seed(3)).double()
+    gen = P.favor_attention(q, k, v, proj, True)
+    assert float((gen - exact).norm() / exact.norm()) > 0.05
