@@ -22,7 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .ops import ACT_NONE, ACT_RELU, EPI_BLOCKLN32, cview
+from .ops import ACT_RELU, EPI_BLOCKLN32, cview
 
 _MODE = 0  # 0 = bf16 tensor-core mode, 1 = fp32 validation mode
 

@@ -42,7 +42,6 @@ import torch.distributed as dist
 import torch.nn as nn
 
 from . import modules as M
-from . import ops
 
 
 _STAGE_TIMING = bool(os.environ.get("RFK_SHARD_TIMING"))  # developer aid: per-stage device times of every block

@@ -152,8 +152,6 @@ def test_msa_update_with_pair_and_coord_fp32_matches_golden(emulated_ops):
 def test_accelerate_swaps_coord_update_of_three_track_block(emulated_ops):
     """The MSA update of a reference ThreeTrackBlock (:1028-1035, called at :1044) is swapped too and
     reproduces the reference module on the same inputs."""
-    import types
-
     from oracle import reference_loader as rl
     from oracle.make_golden import synth_coords
     from oracle.weights import synth_inputs, synth_state_dict
