@@ -7,6 +7,7 @@ reference keeps in plain lists), everything else of the model is left untouched.
 """
 from __future__ import annotations
 
+import torch
 import torch.nn as nn
 
 from . import modules as M
@@ -44,23 +45,73 @@ def _make(name: str, ref: nn.Module) -> nn.Module:
     raise KeyError(name)
 
 
-def accelerate_block(block: nn.Module, device=None) -> nn.Module:
-    """Replace the four trunk children of one reference block."""
+def _home_device(module: nn.Module):
+    for t in list(module.parameters(recurse=True)) + list(module.buffers(recurse=True)):
+        return t.device
+    return None
+
+
+def _move_inputs_hook(module: nn.Module, args, kwargs):
+    """Forward pre-hook: tensor arguments that live elsewhere are copied to the device of `module`'s weights."""
+    dev = _home_device(module)
+    if dev is None:
+        return None
+
+    def mv(x):
+        if isinstance(x, torch.Tensor) and x.device != dev:
+            # host -> device may overlap; device -> host must have landed before the CPU code reads it
+            return x.to(dev, non_blocking=dev.type == "cuda")
+        if isinstance(x, (tuple, list)):
+            return type(x)(mv(y) for y in x)
+        return x
+
+    return tuple(mv(a) for a in args), {k: mv(v) for k, v in kwargs.items()}
+
+
+def _add_hop(module: nn.Module) -> None:
+    if not getattr(module, "_rfk_hop", False):
+        module.register_forward_pre_hook(_move_inputs_hook, with_kwargs=True)
+        module._rfk_hop = True
+
+
+def accelerate_block(block: nn.Module, device=None, hop: bool = False) -> nn.Module:
+    """Replace the trunk children of one reference block. `hop`: see `accelerate`."""
     names = TRUNK_CHILDREN + (("msa_update_with_pair_and_coord",) if hasattr(block, "msa_update_with_pair_and_coord") else ())
     for name in names:
         old = getattr(block, name)
         new = M.load_reference_weights(_make(name, old), old).eval()
         setattr(block, name, new.to(device) if device is not None else new)
+    if hop:
+        # every direct child gets its tensor arguments on its own device: the swapped modules pull msa / pair / xyz
+        # onto the GPU, the reference's structure track and heads pull what they consume back to the CPU
+        for child in block.children():
+            _add_hop(child)
     return block
 
 
-def accelerate(model: nn.Module, device=None) -> nn.Module:
-    """Replace the trunk of every block of a reference RoseTTAFold (rosettafold_pytorch.py:1220-1267)."""
+def accelerate(model: nn.Module, device=None, hop: bool = False) -> nn.Module:
+    """Replace the trunk of every block of a reference RoseTTAFold (rosettafold_pytorch.py:1220-1267).
+
+    `hop=True` is for the UNMODIFIED reference model, which only runs on the CPU (its embeddings index CPU tables
+    with Python loops and its list-held layers ignore `.to()`): the swapped trunk
+    modules live on `device`, everything else stays where it is, and forward pre-hooks copy tensor arguments to the
+    device of the module that consumes them. Tensors then cross PCIe only where the trunk meets the reference's own
+    code: embeddings -> first block, trunk -> SE(3) structure track (msa, pair), structure track -> coordinate-
+    conditioned MSA update (xyz, state), last block -> prediction head. No structure (attribute names,
+    `state_dict` keys) changes."""
     blocks = list(getattr(model, "two_track_blocks", [])) + list(getattr(model, "three_track_blocks", []))
     if hasattr(model, "final_block"):
         blocks.append(model.final_block)
+    whole_model = bool(blocks)
     if not blocks and all(hasattr(model, n) for n in TRUNK_CHILDREN):
         blocks = [model]
     for blk in blocks:
-        accelerate_block(blk, device)
+        accelerate_block(blk, device, hop)
+    if hop and whole_model:
+        # the model's own direct children (embeddings, initial coordinates, prediction head); the block containers
+        # are skipped, their blocks were handled above
+        for child in model.children():
+            holds_blocks = isinstance(child, nn.ModuleList) and any(c in blocks for c in child)
+            if not holds_blocks and child not in blocks:
+                _add_hop(child)
     return model

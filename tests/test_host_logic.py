@@ -244,3 +244,42 @@ def test_block_degenerate_shapes_match_restatement(emulated_ops, B, N, L):
         m_ref, p_ref = trunk_ref.two_track_block(msa, pair, sd, cfg["n_layers"])
     assert m.shape == msa.shape and p.shape == pair.shape
     assert rel_l2(m, m_ref) < 1e-4 and rel_l2(p, p_ref) < 1e-4
+
+
+@pytest.mark.skipif(not __import__("oracle.reference_loader", fromlist=["x"]).available(),
+                    reason="reference source only exists in the build container")
+def test_accelerate_with_device_hops_keeps_structure_and_results(emulated_ops, tmp_path, monkeypatch):
+    """`rf.accelerate(model, device, hop=True)` (for the CPU-only reference model with the trunk on a GPU): the
+    forward pre-hooks sit on the swapped modules and on the reference modules that consume their outputs, the
+    module tree and `state_dict` keys are untouched, results are unchanged. (Here both devices are the CPU: this
+    checks the wiring, not a transfer.)"""
+    from oracle import reference_loader as rl
+
+    monkeypatch.chdir(tmp_path)  # the reference caches its SE(3) bases under ./cache
+    ref = rl.load()
+    torch.manual_seed(0)
+    model = rl.fix_eval(ref.RoseTTAFold(d_input=21, d_msa=48, d_pair=40, d_node=16, d_edge=16, d_state=16,
+                                        n_two_track_blocks=1, n_three_track_blocks=2, n_encoder_layers=1,
+                                        n_neighbors=[8, 8], p_dropout=0.1, max_len=64))
+    g = torch.Generator().manual_seed(1234)
+    msa, seq = torch.randint(0, 21, (1, 4, 12), generator=g), torch.randint(0, 21, (1, 12), generator=g)
+    aa_idx = torch.arange(12).repeat(1, 1)
+    with torch.no_grad():
+        logits, xyz, plddt = model(msa, seq, aa_idx)
+    rf.set_mode("fp32")
+    rf.accelerate(model, device="cpu")
+    keys = set(model.state_dict())
+    rf.accelerate_block(model.final_block, device="cpu", hop=True)   # idempotent per module
+    rf.accelerate(model, device="cpu", hop=True)
+    assert set(model.state_dict()) == keys
+    hopped = {n for n, m in model.named_modules() if getattr(m, "_rfk_hop", False)}
+    assert {"msa_emb", "pair_emb", "initial_coord_generation_with_msa_and_pair", "prediction_head",
+            "final_block.plddt_head", "final_block.coord_update_with_msa_and_pair",
+            "three_track_blocks.0.coord_update_with_msa_and_pair", "three_track_blocks.0.msa_update_with_pair_and_coord",
+            "two_track_blocks.0.msa_update_using_self_att", "two_track_blocks.0.msa_update_with_pair"} <= hopped
+    assert not any(n in hopped for n in ("two_track_blocks", "three_track_blocks", "final_block", ""))
+    with torch.no_grad():
+        logits2, xyz2, plddt2 = model(msa, seq, aa_idx)
+    for k in logits:
+        assert rel_l2(logits2[k], logits[k]) < 1e-4
+    assert rel_l2(xyz2, xyz) < 1e-4 and rel_l2(plddt2, plddt) < 1e-4
