@@ -59,42 +59,40 @@ class _CudaBackend:
 
     # -- gemm ---------------------------------------------------------------------------------
     def gemm(self, a, b, c_view, bias, act, alpha, r0, r1, epi, ln_gamma, ln_beta, ln_eps):
+        # (one shape / stride tuple per tensor and slice assignments into the ctypes arrays: this runs ~100 times
+        # per block on the host)
         d = RfkGemmDesc()
-        Z = list(a.shape[:3])
-        M, K = a.shape[3], a.shape[4]
-        N = b.shape[3]
+        ash, ast, bsh, bst = a.shape, a.stride(), b.shape, b.stride()
         d.a, d.b = a.data_ptr(), b.data_ptr()
         d.ab_dtype = _dt(a)
         d.act = act
-        d.M, d.N, d.K = M, N, K
-        for i in range(3):  # Z[0] is the fastest level = tensor dim 2
-            d.Z[i] = Z[2 - i]
-            d.a_zs[i] = a.stride(2 - i) if Z[2 - i] > 1 else 0
-            d.b_zs[i] = b.stride(2 - i) if b.shape[2 - i] > 1 else 0
-            d.bias_zs[i] = 0
-        d.lda, d.ldb = a.stride(3), b.stride(3)
+        d.M, d.N, d.K = ash[3], bsh[3], ash[4]
+        # Z[0] is the fastest level = tensor dim 2
+        d.Z[0:3] = (ash[2], ash[1], ash[0])
+        d.a_zs[0:3] = (ast[2] if ash[2] > 1 else 0, ast[1] if ash[1] > 1 else 0, ast[0] if ash[0] > 1 else 0)
+        d.b_zs[0:3] = (bst[2] if bsh[2] > 1 else 0, bst[1] if bsh[1] > 1 else 0, bst[0] if bsh[0] > 1 else 0)
+        d.lda, d.ldb = ast[3], bst[3]
         d.bias = None if bias is None else bias.data_ptr()
         d.alpha = alpha
         d.epi = epi
-        d.MR, d.NR = c_view.shape[4], c_view.shape[6]
+        csh = c_view.shape
+        d.MR, d.NR = csh[4], csh[6]
         d.c = c_view.data_ptr()
         d.c_dtype = _dt(c_view)
 
-        def fill(addr: RfkAddr, t):
-            for i in range(3):
-                addr.zs[i] = t.stride(2 - i) if t.shape[2 - i] > 1 else 0
-            addr.ms[0] = t.stride(4) if t.shape[4] > 1 else 0
-            addr.ms[1] = t.stride(3) if t.shape[3] > 1 else 0
-            addr.ns[0] = t.stride(6) if t.shape[6] > 1 else 0
-            addr.ns[1] = t.stride(5) if t.shape[5] > 1 else 0
+        def fill(addr: RfkAddr, t, sh):
+            st = t.stride()
+            addr.zs[0:3] = (st[2] if sh[2] > 1 else 0, st[1] if sh[1] > 1 else 0, st[0] if sh[0] > 1 else 0)
+            addr.ms[0:2] = (st[4] if sh[4] > 1 else 0, st[3] if sh[3] > 1 else 0)
+            addr.ns[0:2] = (st[6] if sh[6] > 1 else 0, st[5] if sh[5] > 1 else 0)
 
-        fill(d.c_addr, c_view)
+        fill(d.c_addr, c_view, csh)
         if r0 is not None:
             d.r0, d.r0_dtype = r0.data_ptr(), _dt(r0)
-            fill(d.r0_addr, r0)
+            fill(d.r0_addr, r0, r0.shape)
         if r1 is not None:
             d.r1, d.r1_dtype = r1.data_ptr(), _dt(r1)
-            fill(d.r1_addr, r1)
+            fill(d.r1_addr, r1, r1.shape)
         d.ln_eps = ln_eps
         d.ln_gamma = None if ln_gamma is None else ln_gamma.data_ptr()
         d.ln_beta = None if ln_beta is None else ln_beta.data_ptr()
@@ -262,9 +260,9 @@ def _set_backend_for_tests(b):
 # public wrappers (shape / stride validation common to every backend)
 # ---------------------------------------------------------------------------------------------
 def _lead(t: torch.Tensor, nd: int) -> torch.Tensor:
-    while t.dim() < nd:
-        t = t.unsqueeze(0)
-    return t
+    """Pad with leading size-1 dims (one view op: this wrapper runs ~100 times per block on the host)."""
+    k = nd - t.dim()
+    return t.view((1,) * k + tuple(t.shape)) if k > 0 else t
 
 
 def gemm(a, b, c_view, *, bias=None, act=ACT_NONE, alpha=1.0, r0=None, r1=None, epi=EPI_STD,
@@ -276,30 +274,32 @@ def gemm(a, b, c_view, *, bias=None, act=ACT_NONE, alpha=1.0, r0=None, r1=None, 
     indexed [Z2, Z1, Z0, M1, MR, N1, NR] with m = M1*MR + mr, n = N1*NR + nr (use .expand for
     broadcast addends): the kernel writes/reads exactly those strides.
     """
-    a, b = _lead(a, 5), _lead(b, 5)
-    if a.dim() != 5 or b.dim() != 5 or c_view.dim() != 7:
+    if a.dim() > 5 or b.dim() > 5 or c_view.dim() != 7:
         raise ValueError("gemm: a, b must be <=5-D and c_view 7-D")
+    a, b = _lead(a, 5), _lead(b, 5)
     if a.dtype != b.dtype:
         raise TypeError("gemm: a and b dtypes differ")
     if a.stride(4) != 1 or b.stride(4) != 1:
         raise ValueError("gemm: K must be the contiguous dimension of a and b")
-    if a.shape[4] != b.shape[4]:
+    ash, bsh, csh = tuple(a.shape), tuple(b.shape), tuple(c_view.shape)
+    if ash[4] != bsh[4]:
         raise ValueError(f"gemm: K mismatch {a.shape} vs {b.shape}")
     for i in range(3):
-        if b.shape[i] not in (1, a.shape[i]):
+        if bsh[i] != 1 and bsh[i] != ash[i]:
             raise ValueError("gemm: b batch dims must match a or be 1")
-    Zs, M, N = tuple(a.shape[:3]), a.shape[3], b.shape[3]
+    Zs, M, N = ash[:3], ash[3], bsh[3]
     for name, t in (("c_view", c_view), ("r0", r0), ("r1", r1)):
         if t is None:
             continue
-        if tuple(t.shape[:3]) != Zs or t.shape[3] * t.shape[4] != M or t.shape[5] * t.shape[6] != N:
-            raise ValueError(f"gemm: {name} shape {tuple(t.shape)} does not match Z={Zs} M={M} N={N}")
-        if tuple(t.shape[3:]) != tuple(c_view.shape[3:]):
+        tsh = csh if t is c_view else tuple(t.shape)
+        if tsh[:3] != Zs or tsh[3] * tsh[4] != M or tsh[5] * tsh[6] != N:
+            raise ValueError(f"gemm: {name} shape {tsh} does not match Z={Zs} M={M} N={N}")
+        if tsh[3:] != csh[3:]:
             raise ValueError("gemm: residual views must share c_view's (M1,MR,N1,NR) split")
     if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
         raise ValueError("gemm: bias must be contiguous float32 of length N")
     name = "gemm_bf16" if a.dtype == torch.bfloat16 else "gemm_f32"
-    with _Timed(name, 2.0 * Zs[0] * Zs[1] * Zs[2] * M * N * a.shape[4]):  # algorithmic FLOPs
+    with _Timed(name, 2.0 * Zs[0] * Zs[1] * Zs[2] * M * N * ash[4]):  # algorithmic FLOPs
         backend().gemm(a, b, c_view, bias, act, float(alpha), r0, r1, epi, ln_gamma, ln_beta, float(ln_eps))
     return c_view
 
