@@ -175,12 +175,13 @@ def test_accelerate_swaps_coord_update_of_three_track_block(emulated_ops):
 
 @pytest.mark.skipif(not __import__("oracle.reference_loader", fromlist=["x"]).available(),
                     reason="reference source only exists in the build container")
-def test_accelerate_whole_reference_model(emulated_ops):
+def test_accelerate_whole_reference_model(emulated_ops, tmp_path, monkeypatch):
     """Drop-in at the top: the unmodified reference `RoseTTAFold` (:1160-1271; two-track blocks, three-track
     blocks with their SE(3) structure track on the oracle's dgl / lie_learn shims, output heads) gives the same
     logits, coordinates and pLDDT before and after `rf.accelerate(model)` swaps the trunk under it."""
     from oracle import reference_loader as rl
 
+    monkeypatch.chdir(tmp_path)  # the reference caches its SE(3) bases under ./cache
     ref = rl.load()
     torch.manual_seed(0)
     model = rl.fix_eval(ref.RoseTTAFold(d_input=21, d_msa=48, d_pair=40, d_node=16, d_edge=16, d_state=16,
