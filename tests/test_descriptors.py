@@ -72,3 +72,70 @@ def test_gemm_descriptors_of_a_block_forward_match_the_plain_restatement():
         ops._set_backend_for_tests(prev)
         rf.set_mode("bf16")
     assert count["n"] > 100
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every prototype of include/rfk.h against the ctypes binding: same number of parameters, pointers bound as
+    pointers, 64-bit integers as 64-bit, floats as floats (a drift here corrupts arguments silently)."""
+    import os
+    import re
+
+    from rosettafold_pytorch_b200 import _lib
+
+    hdr = open(os.path.join(os.path.dirname(_lib.LIB_PATH), "..", "include", "rfk.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = re.findall(r"\b(?:int|const char\*|uint64_t|unsigned long long)\s+(rfk_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr)
+    assert {n for n, _ in protos} == set(_lib.SYMBOLS)
+    for name, params in protos:
+        params = params.strip()
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        _, argtypes = _lib.SYMBOLS[name]
+        assert len(plist) == len(argtypes), (name, plist, argtypes)
+        for p, t in zip(plist, argtypes):
+            if "*" in p or "rfk_stream_t" in p:
+                assert t is C.c_void_p or issubclass(t, C._Pointer), (name, p, t)
+            elif p.startswith("int64_t"):
+                assert t is C.c_int64, (name, p, t)
+            elif p.startswith("float"):
+                assert t is C.c_float, (name, p, t)
+            elif p.startswith("int"):
+                assert t is C.c_int, (name, p, t)
+            else:
+                raise AssertionError(f"{name}: unhandled parameter type '{p}'")
+
+
+def test_ctypes_struct_layouts_match_a_c_compiler(tmp_path):
+    """sizeof / offsetof of rfk_gemm_desc, rfk_favor_desc and rfk_addr as gcc lays them out from include/rfk.h vs the
+    ctypes Structures of the binding (same field names on both sides)."""
+    import os
+    import shutil
+    import subprocess
+
+    import pytest
+
+    from rosettafold_pytorch_b200 import _lib
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    inc = os.path.abspath(os.path.join(os.path.dirname(_lib.LIB_PATH), "..", "include"))
+    structs = {"rfk_gemm_desc": _lib.RfkGemmDesc, "rfk_favor_desc": _lib.RfkFavorDesc, "rfk_addr": _lib.RfkAddr}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "rfk.h"', 'int main(void) {']
+    for cname, ct in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-I", inc, str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        cname, field, value = line.split()
+        ct = structs[cname]
+        want = C.sizeof(ct) if field == "size" else getattr(ct, field).offset
+        assert int(value) == want, (cname, field, value, want)
+        seen += 1
+    assert seen == sum(len(ct._fields_) + 1 for ct in structs.values())
