@@ -38,68 +38,47 @@ def parse():
     ap.add_argument("--batch", type=int, default=1, help="samples per GPU per step")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-slice", type=int, default=8,
-                    help="CPU legs evaluate batch-separable stages on 1/slice of their batch axis")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU reference leg (oracle port of the reference's trunk, timed on the host cores)
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(args, torch, threads):
-    """One bounded sample of the trunk workload on the CPU: one encoder layer of each stage of one
-    block at the full (1, N, L) shape; batch-separable stages (Performer column attention, pair
-    axial layer) run on 1/slice of their batch axis and are scaled back (they are exactly linear in
-    that axis). Returns seconds per full trunk forward (blocks x (4 layers x stages + MSA->pair))."""
-    from oracle import trunk_ref
-    from oracle.weights import synth_inputs, synth_state_dict
-    import rosettafold_pytorch_b200 as rf
+def workload_desc(args):
+    """config.workload: the same string in both arms."""
+    return (f"trunk forward, {args.blocks} blocks x {N_LAYERS} encoder layers, B={args.batch}/GPU, Nseq={args.N}, "
+            f"L={args.L}, d_msa {D_MSA}, d_pair {D_PAIR}")
 
-    torch.set_num_threads(threads)
-    L, N, s = args.L, args.N, max(1, args.cpu_slice)
-    blk = rf.TwoTrackBlock(D_MSA, D_PAIR, n_encoder_layers=1)
-    sd = synth_state_dict(blk.state_dict(), seed=1)
-    del blk
-    W = trunk_ref.W
-    msa, pair = synth_inputs(1, N, L, D_MSA, D_PAIR, seed=2)
-    att = torch.softmax(torch.randn(1, L, L, 12), dim=2)
-    t = {}
 
-    def timed(name, fn):
+class CpuBlock:
+    """One whole TwoTrackBlock of the workload (all four stages, all N_LAYERS encoder layers of each, full
+    (B, N, L) shape, no slicing) on the CPU oracle port: what a timed CPU step runs. The trunk is `blocks`
+    such blocks of identical cost in sequence, so the only scale factor is x blocks."""
+
+    def __init__(self, args, torch, shape=None):
+        from oracle import trunk_ref
+        from oracle.weights import synth_inputs, synth_state_dict
+        import rosettafold_pytorch_b200 as rf
+
+        self.torch, self.trunk_ref = torch, trunk_ref
+        B, N, L = shape or (args.batch, args.N, args.L)
+        blk = rf.TwoTrackBlock(D_MSA, D_PAIR, n_encoder_layers=N_LAYERS)
+        self.sd = synth_state_dict(blk.state_dict(), seed=1)
+        self.msa, self.pair = synth_inputs(B, N, L, D_MSA, D_PAIR, seed=2)
+
+    def step(self):
         t0 = time.perf_counter()
-        with torch.no_grad():
-            out = fn()
-        t[name] = time.perf_counter() - t0
-        return out
-
-    wA = W(sd, "msa_update_using_self_att.")
-    timed("tied_row_layer", lambda: trunk_ref.encoder_layer_tied(msa, wA.sub("residue_wise_encoder_layers.0"), 12))
-    ls = max(1, L // s)
-    x_cols = msa.transpose(1, 2)[:, :ls].contiguous()  # (b, l/s, n, d): attention over n
-    timed("performer_col_layer", lambda: trunk_ref.encoder_layer_performer(x_cols, wA.sub("sequence_wise_encoder_layers.0"), 12))
-    timed("pair_update_with_msa", lambda: trunk_ref.pair_update_with_msa(msa, pair, att, W(sd, "pair_update_with_msa.")))
-    wC = W(sd, "pair_update_with_axial_attention.layers.0.")
-    # row attention batches over columns j, column attention over rows i: slice each batch axis
-    pr = pair[:, :, :ls].contiguous()
-    pc = pair[:, :ls].contiguous()
-    xn = trunk_ref.layer_norm(pr, wC, "layer.0.fn.0").transpose(1, 2).reshape(ls, L, D_PAIR)
-    timed("pair_row_attn", lambda: trunk_ref.performer_attention(xn, wC.sub("row_attn"), 8, True))
-    xn2 = trunk_ref.layer_norm(pc, wC, "layer.1.fn.0").reshape(ls, L, D_PAIR)
-    timed("pair_col_attn", lambda: trunk_ref.performer_attention(xn2, wC.sub("col_attn"), 8, True))
-    timed("pair_ff", lambda: pc + trunk_ref.feed_forward(trunk_ref.layer_norm(pc, wC, "layer.2.fn.0"), wC.sub("ff")))
-    timed("msa_update_with_pair_layer", lambda: trunk_ref.msa_update_with_pair_layer(
-        msa, pair, W(sd, "msa_update_with_pair.encoder_layers.0.")))
-    scale = L / ls
-    per_layer = (t["tied_row_layer"] + scale * t["performer_col_layer"] +
-                 scale * (t["pair_row_attn"] + t["pair_col_attn"] + t["pair_ff"]) + t["msa_update_with_pair_layer"])
-    block_s = N_LAYERS * per_layer + t["pair_update_with_msa"]
-    return args.blocks * block_s, t
+        with self.torch.no_grad():
+            m, p = self.trunk_ref.two_track_block(self.msa, self.pair, self.sd, N_LAYERS)
+        assert bool(self.torch.isfinite(m).all()) and bool(self.torch.isfinite(p).all())
+        return time.perf_counter() - t0
 
 
 def sample_desc(args):
-    return (f"oracle port (oracle/trunk_ref.py), fp32: 1 of {N_LAYERS} encoder layers of each stage of 1 of "
-            f"{args.blocks} blocks at (1,{args.N},{args.L}); Performer column / pair axial stages on 1/{args.cpu_slice} "
-            f"of their batch axis; scaled linearly to the full trunk")
+    return (f"oracle port (oracle/trunk_ref.py), fp32, torch CPU kernels: one WHOLE TwoTrackBlock (all four stages, "
+            f"all {N_LAYERS} encoder layers of each) at the full ({args.batch},{args.N},{args.L}) shape per timed step, nothing "
+            f"sliced; the trunk is {args.blocks} such blocks of identical cost in sequence, so seconds per trunk = "
+            f"{args.blocks} x the mean timed block")
 
 
 def run_reference(args):
@@ -109,21 +88,23 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    warm = argparse.Namespace(**{**vars(args), "L": 64, "N": 16})
-    cpu_sample(warm, torch, threads)  # first-call overheads (thread pools, oneDNN primitives)
+    torch.set_num_threads(threads)
+    CpuBlock(args, torch, shape=(1, 16, 64)).step()  # first-call overheads (thread pools, oneDNN primitives)
+    blk = CpuBlock(args, torch)
     for _ in range(args.warmup):
-        cpu_sample(args, torch, threads)
-    times = []
-    for _ in range(max(1, args.steps)):
-        sec, _ = cpu_sample(args, torch, threads)
-        times.append(sec)
-    sec = sum(times) / len(times)
-    value = 1.0 / sec
+        blk.step()
+    times = [blk.step() for _ in range(max(1, args.steps))]
+    block_s = sum(times) / len(times)
+    trunk_s = args.blocks * block_s
+    value = args.batch / trunk_s
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": block_s * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"trunk forward, {args.blocks} blocks, B=1, Nseq={args.N}, L={args.L}, d_msa 384, d_pair 288"},
+        "config": {"workload": workload_desc(args),
+                   "timed_step": f"one TwoTrackBlock = 1/{args.blocks} of the workload (ms_per_step is the mean of the "
+                                 f"{max(1, args.steps)} timed blocks; value = batch / ({args.blocks} x that))",
+                   "ms_per_trunk": trunk_s * 1e3, "block_s_min": min(times), "block_s_max": max(times)},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port",
                          "sample": sample_desc(args)},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -346,7 +327,7 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": f"trunk forward, {args.blocks} blocks x 4 encoder layers, B={B}/GPU, Nseq={N}, L={L}, d_msa 384, d_pair 288",
+        "config": {"workload": workload_desc(args),
                    "parallelism": f"replicas x{world} (one sample per GPU, no data-path collective)",
                    "l2": "working set (msa 101 MB + pair 302 MB fp32 + intermediates) exceeds the 126 MB L2; no explicit flush",
                    "ms_per_block": ms_per_step / args.blocks,
@@ -365,11 +346,12 @@ def run_b200(args):
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        warm = argparse.Namespace(**{**vars(args), "L": 64, "N": 16})
-        cpu_sample(warm, torch, threads)  # first-call overheads (thread pools, oneDNN primitives)
-        sec, parts = cpu_sample(args, torch, threads)
-        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "samples/s", "cores": threads, "kind": "port",
-                                "sample": sample_desc(args), "parts_s": {k: round(v, 3) for k, v in parts.items()}}
+        torch.set_num_threads(threads)
+        CpuBlock(args, torch, shape=(1, 16, 64)).step()  # first-call overheads (thread pools, oneDNN primitives)
+        block_s = CpuBlock(args, torch).step()
+        line["cpu_baseline"] = {"value": B / (args.blocks * block_s), "unit": "samples/s", "cores": threads, "kind": "port",
+                                "sample": sample_desc(args) + " (one timed block here; `--impl reference` averages K)",
+                                "block_s": round(block_s, 2)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -8,25 +8,33 @@ namespace rfk {
 static std::atomic<uint64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// Device probes are cached PER DEVICE (index = cudaGetDevice()): a host process may drive several GPUs.
+static std::atomic<int> g_arch[kMaxDevices];  // 0 = unknown, 1 = sm_10x, 2 = anything else
+static std::atomic<int> g_sms[kMaxDevices];
+
 int check_arch() {
-  static int cached = -1;
-  if (cached >= 0) return cached;
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return RFK_ERR_UNSUPPORTED_ARCH;
+  const bool cacheable = dev >= 0 && dev < kMaxDevices;
+  if (cacheable) {
+    const int c = g_arch[dev].load(std::memory_order_relaxed);
+    if (c) return c == 1 ? RFK_OK : RFK_ERR_UNSUPPORTED_ARCH;
+  }
   if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
     return RFK_ERR_UNSUPPORTED_ARCH;
-  cached = (major == 10) ? RFK_OK : RFK_ERR_UNSUPPORTED_ARCH;
-  return cached;
+  if (cacheable) g_arch[dev].store(major == 10 ? 1 : 2, std::memory_order_relaxed);
+  return major == 10 ? RFK_OK : RFK_ERR_UNSUPPORTED_ARCH;
 }
 
 int num_sms() {
-  static int cached = 0;
-  if (cached > 0) return cached;
   int dev = 0, n = 0;
-  cudaGetDevice(&dev);
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  const bool cacheable = dev >= 0 && dev < kMaxDevices;
+  if (cacheable && (n = g_sms[dev].load(std::memory_order_relaxed)) > 0) return n;
   cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  cached = n > 0 ? n : 148;
-  return cached;
+  n = n > 0 ? n : 148;
+  if (cacheable) g_sms[dev].store(n, std::memory_order_relaxed);
+  return n;
 }
 
 }  // namespace rfk

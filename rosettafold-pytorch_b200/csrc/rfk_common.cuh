@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "../../include/rfk.h"
 
 namespace rfk {
@@ -19,8 +21,25 @@ inline int post_launch() {
   count_launch();
   return cuda_status(cudaGetLastError());
 }
-int check_arch();  // RFK_OK iff the current device is compute capability 10.x
-int num_sms();
+int check_arch();  // RFK_OK iff the CURRENT device is compute capability 10.x (cached per device)
+int num_sms();     // SM count of the current device (cached per device)
+
+// One-time kernel configuration PER DEVICE: cudaFuncSetAttribute (opt-in shared memory) applies to the device
+// that is current when it is called, so a process that drives several GPUs must repeat it on each one.
+// `f()` returns an RFK status; it runs once per device (std::call_once), later calls return its result.
+constexpr int kMaxDevices = 64;
+struct PerDeviceOnce {
+  std::once_flag flag[kMaxDevices];
+  int status[kMaxDevices];
+};
+template <class F>
+inline int per_device_once(PerDeviceOnce& st, F&& f) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return RFK_ERR_UNSUPPORTED_ARCH;
+  if (dev < 0 || dev >= kMaxDevices) return f();  // beyond the table: configure on every launch
+  std::call_once(st.flag[dev], [&]() { st.status[dev] = f(); });
+  return st.status[dev];
+}
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 

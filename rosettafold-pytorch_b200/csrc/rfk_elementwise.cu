@@ -980,11 +980,11 @@ extern "C" int rfk_pair2att_logits(const float* pair, const float* Wf, const flo
   if (B <= 0 || L <= 0 || D <= 0 || D > 512 || C <= 0 || C > kP2AMaxC || ldl < L)
     return RFK_ERR_BAD_DIMS;
   const size_t smem = (size_t)C * D * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(pair2att_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    configured = true;
-  }
+  static rfk::PerDeviceOnce once;
+  const int cfg_rc = rfk::per_device_once(once, []() {
+    return rfk::cuda_status(cudaFuncSetAttribute(pair2att_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  });
+  if (cfg_rc != RFK_OK) return cfg_rc;
   if (D == 288 && (reinterpret_cast<uintptr_t>(pair) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wf) & 15) == 0 &&
       L <= 65535 && B <= 65535) {
     dim3 grid((unsigned)((L + 31) / 32), (unsigned)L, (unsigned)B);
@@ -1005,11 +1005,11 @@ extern "C" int rfk_pair2att_logits_rows(const float* rows, const float* cols_t, 
   if (B <= 0 || Li <= 0 || L <= 0 || Li > L || D <= 0 || D > 512 || C <= 0 || C > kP2AMaxC || ldl < L)
     return RFK_ERR_BAD_DIMS;
   const size_t smem = (size_t)C * D * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(pair2att_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    configured = true;
-  }
+  static rfk::PerDeviceOnce once;
+  const int cfg_rc = rfk::per_device_once(once, []() {
+    return rfk::cuda_status(cudaFuncSetAttribute(pair2att_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  });
+  if (cfg_rc != RFK_OK) return cfg_rc;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (D == 288 && al16(rows) && al16(cols_t) && al16(Wf) && Li <= 65535 && B <= 65535) {

@@ -219,13 +219,11 @@ extern "C" int rfk_favor_attention(const rfk_favor_desc* d, rfk_stream_t stream_
   p.ogs0 = d->out_gs[0]; p.ogs1 = d->out_gs[1]; p.ots = d->out_ts;
   const size_t smem = sizeof(float) * (size_t)(kFavorMaxM * 65 + kFavorMaxM * 64 + kFavorMaxM +
                                                2 * kTokTile * 64 + kTokTile * kFavorMaxM + 256);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(favor_simt_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_status(e);
-    configured = true;
-  }
+  static PerDeviceOnce once;
+  const int cfg_rc = per_device_once(once, [smem]() {
+    return cuda_status(cudaFuncSetAttribute(favor_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  });
+  if (cfg_rc != RFK_OK) return cfg_rc;
   const int64_t blocks = d->G[0] * d->G[1] * d->heads;
   if (blocks > 0x7fffffffLL) return RFK_ERR_BAD_DIMS;
   favor_simt_kernel<<<(unsigned)blocks, 256, smem, stream>>>(p);

@@ -855,12 +855,11 @@ int make_head_tmap(CUtensorMap* map, const void* ptr, const rfk_favor_desc* d) {
 template <int KIND>
 int launch_kind(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const FavorTcParams& p,
                 cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(favor_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e != cudaSuccess) return cuda_status(e);
-    configured = true;
-  }
+  static PerDeviceOnce once;
+  const int cfg_rc = per_device_once(once, []() {
+    return cuda_status(cudaFuncSetAttribute(favor_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  });
+  if (cfg_rc != RFK_OK) return cfg_rc;
   int grid = num_sms();
   if (p.items < grid) grid = (int)p.items;
   favor_tc_kernel<KIND><<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, p);

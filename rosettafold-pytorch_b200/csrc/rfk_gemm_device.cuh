@@ -957,13 +957,12 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev
   if (!em) em = &kNoMaps;
   // the kernel decodes tiles and splits m / n in 32-bit arithmetic
   if (tiles > 0x7fffffffLL || p.M > 0x7fffffffLL || p.N > 0x7fffffffLL || p.K > 0x7fffffffLL) return RFK_ERR_BAD_DIMS;
-  static bool configured = false;  // benign race: the attribute call is idempotent
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, CONV>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return cuda_status(e);
-    configured = true;
-  }
+  static PerDeviceOnce once;  // one per template instance
+  const int cfg_rc = per_device_once(once, []() {
+    return cuda_status(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            Cfg::kSmemBytes));
+  });
+  if (cfg_rc != RFK_OK) return cfg_rc;
   int grid = num_sms();
   if (tiles < grid) grid = (int)tiles;
   gemm_tc_kernel<BN, EPI, CONV><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, em->c, em->r, p);

@@ -1,12 +1,17 @@
 """Tensor-level wrappers over the C ABI (include/rfk.h).
 
 Every function takes CUDA tensors (or strided views of them), validates shapes/strides, and
-enqueues exactly one librfk kernel on the current CUDA stream. Nothing here computes with
-PyTorch: torch is used for device memory and streams only. Calling any op without librfk.so or
-on a non-CUDA tensor raises.
+enqueues exactly one librfk kernel on the current CUDA stream of the tensors' device. Nothing here
+computes with PyTorch: torch is used for device memory and streams only. Calling any op without
+librfk.so or on a non-CUDA tensor raises.
+
+Call path: public wrapper (validation) -> `_call` (all tensor arguments on ONE device, that device made
+current for the launch) -> `torch.ops.rfk.<op>` (torch custom op, `_torch_ops.py`) -> `_CudaBackend.<op>`
+(ctypes marshalling) -> `extern "C" rfk_<op>` in librfk.so.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 
 import torch
@@ -98,7 +103,7 @@ class _CudaBackend:
         d.ln_beta = None if ln_beta is None else ln_beta.data_ptr()
         _lib.check(self.lib.rfk_gemm(C.byref(d), self._stream(a)), "rfk_gemm")
 
-    def layernorm(self, x, gamma, beta, eps, out, res=None):
+    def layernorm(self, x, gamma, beta, eps, out, res):
         if res is not None:
             _lib.check(self.lib.rfk_layernorm_residual(
                 _ptr(x), _dt(x), x.stride(0), _f32ptr(gamma, "gamma"), _f32ptr(beta, "beta"), eps,
@@ -127,7 +132,7 @@ class _CudaBackend:
             0 if att16 is None else att16.stride(2), B, H, L, self._stream(A)),
             "rfk_tied_att_symmetrize")
 
-    def poswise_weight(self, pq, pk, scale, w_out, q, q_scale, qt, H, dh, stats=None):
+    def poswise_weight(self, pq, pk, scale, w_out, q, q_scale, qt, H, dh, stats):
         B, N, L, _ = pk.shape
         _lib.check(self.lib.rfk_poswise_weight_stats(
             _ptr(pq), pq.stride(1), _ptr(pk), pk.stride(2), _dt(pk), scale, _ptr(w_out), _ptr(q),
@@ -242,10 +247,40 @@ class _Timed:
 
 
 def backend():
-    global _backend
+    global _backend, _ops
     if _backend is None:
         _backend = _CudaBackend()
+        from . import _torch_ops
+
+        _ops = _torch_ops.register(_backend)  # torch.ops.rfk.* -> this backend
     return _backend
+
+
+_ops = {}
+_no_guard = contextlib.nullcontext()
+
+
+def _call(name, *args):
+    """Launch op `name`: every tensor argument must live on the same device (a module left on the CPU with CUDA
+    inputs would otherwise hand host pointers to a kernel), and that device is made current for the launch (the
+    C side configures kernels and reads the SM count of the CURRENT device). With the librfk backend the call
+    goes through the torch custom op `torch.ops.rfk.<name>`; a test backend is called directly."""
+    dev = None
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            if dev is None:
+                dev = a.device
+            elif a.device != dev:
+                raise RuntimeError(f"rfk.{name}: tensor arguments live on different devices ({dev} and {a.device}); "
+                                   "move the module and its inputs to one CUDA device")
+    b = backend()
+    if b.name != "librfk":
+        return getattr(b, name)(*args)
+    if dev is None or dev.type != "cuda":
+        raise RuntimeError("rfk ops run on CUDA tensors only (no CPU path exists)")
+    guard = _no_guard if dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+    with guard:
+        return _ops[name](*args)
 
 
 def _set_backend_for_tests(b):
@@ -300,7 +335,7 @@ def gemm(a, b, c_view, *, bias=None, act=ACT_NONE, alpha=1.0, r0=None, r1=None, 
         raise ValueError("gemm: bias must be contiguous float32 of length N")
     name = "gemm_bf16" if a.dtype == torch.bfloat16 else "gemm_f32"
     with _Timed(name, 2.0 * Zs[0] * Zs[1] * Zs[2] * M * N * ash[4]):  # algorithmic FLOPs
-        backend().gemm(a, b, c_view, bias, act, float(alpha), r0, r1, epi, ln_gamma, ln_beta, float(ln_eps))
+        _call("gemm", a, b, c_view, bias, act, float(alpha), r0, r1, epi, ln_gamma, ln_beta, float(ln_eps))
     return c_view
 
 
@@ -320,10 +355,7 @@ def layernorm(x, gamma, beta, eps, out, res=None):
         raise ValueError("layernorm: res must be float32, shaped like x, last dim contiguous")
     nbytes = float(x.numel() * x.element_size() + out.numel() * out.element_size() + (0 if res is None else res.numel() * 4))
     with _Timed("layernorm", nbytes):  # bytes
-        if res is None:
-            backend().layernorm(x, gamma, beta, float(eps), out)
-        else:
-            backend().layernorm(x, gamma, beta, float(eps), out, res)
+        _call("layernorm", x, gamma, beta, float(eps), out, res)
     return out
 
 
@@ -336,7 +368,7 @@ def dist_mask_logits(ca, bins, logits):
         raise ValueError("dist_mask_logits: logits must be float32 [B, H, L, L] rows")
     if logits.stride(1) != logits.shape[2] * logits.stride(2) or logits.stride(0) != logits.shape[1] * logits.stride(1):
         raise ValueError("dist_mask_logits: logits must be a row-padded contiguous [B,H,L,ld] buffer")
-    backend().dist_mask_logits(ca, bins, logits)
+    _call("dist_mask_logits", ca, bins, logits)
     return logits
 
 
@@ -345,7 +377,7 @@ def softmax_rows(x, out):
         raise ValueError("softmax_rows: x must be 2-D float32 and out the same shape")
     if x.stride(1) != 1 or out.stride(1) != 1:
         raise ValueError("softmax_rows: last dim must be contiguous")
-    backend().softmax_rows(x, out)
+    _call("softmax_rows", x, out)
     return out
 
 
@@ -357,7 +389,7 @@ def tied_att_symmetrize(A, att, att16=None):
         raise ValueError("tied_att_symmetrize: bad shapes")
     if A.stride(3) != 1 or A.stride(1) != L * A.stride(2) or A.stride(0) != H * A.stride(1):
         raise ValueError("tied_att_symmetrize: A must be [B,H,L,ld] packed")
-    backend().tied_att_symmetrize(A, att, att16)
+    _call("tied_att_symmetrize", A, att, att16)
     return att
 
 
@@ -382,10 +414,7 @@ def poswise_weight(pq, pk, scale, *, w_out=None, q=None, q_scale=1.0, qt=None, h
     if stats is not None and (tuple(stats.shape) != (B, L, heads, 2) or not stats.is_contiguous() or
                               stats.dtype != torch.float32):
         raise ValueError("poswise_weight: stats must be contiguous f32 [B,L,H,2]")
-    if stats is None:
-        backend().poswise_weight(pq, pk, float(scale), w_out, q, float(q_scale), qt, heads, d_head)
-    else:
-        backend().poswise_weight(pq, pk, float(scale), w_out, q, float(q_scale), qt, heads, d_head, stats)
+    _call("poswise_weight", pq, pk, float(scale), w_out, q, float(q_scale), qt, heads, d_head, stats)
 
 
 def opm_prep(m, w, xt, yt, msa1d):
@@ -401,7 +430,7 @@ def opm_prep(m, w, xt, yt, msa1d):
             raise ValueError("opm_prep: xt/yt must be [B, L*P, N] views with packed rows")
     if xt.stride(1) != yt.stride(1) or xt.dtype != yt.dtype:
         raise ValueError("opm_prep: xt and yt must share leading dimension and dtype")
-    backend().opm_prep(m, w, xt, yt, msa1d)
+    _call("opm_prep", m, w, xt, yt, msa1d)
 
 
 def pair2att_logits(pair, Wf, bf, eps, logits):
@@ -414,7 +443,7 @@ def pair2att_logits(pair, Wf, bf, eps, logits):
     if tuple(logits.shape) != (B, Cn, L, L) or logits.dtype != torch.float32 or logits.stride(3) != 1 \
             or logits.stride(1) != L * logits.stride(2) or logits.stride(0) != Cn * logits.stride(1):
         raise ValueError("pair2att_logits: logits must be a packed [B,C,L,ld] f32 view")
-    backend().pair2att_logits(pair, Wf, bf, float(eps), logits)
+    _call("pair2att_logits", pair, Wf, bf, float(eps), logits)
     return logits
 
 
@@ -431,7 +460,7 @@ def pair2att_logits_rows(rows, cols_t, Wf, bf, eps, logits):
     if tuple(logits.shape) != (B, Cn, Li, L) or logits.dtype != torch.float32 or logits.stride(3) != 1 \
             or logits.stride(1) != Li * logits.stride(2) or logits.stride(0) != Cn * logits.stride(1):
         raise ValueError("pair2att_logits_rows: logits must be a packed [B,C,Li,ld] f32 view")
-    backend().pair2att_logits_rows(rows, cols_t, Wf, bf, float(eps), logits)
+    _call("pair2att_logits_rows", rows, cols_t, Wf, bf, float(eps), logits)
     return logits
 
 
@@ -439,7 +468,7 @@ def channel_stats(x, stats):
     B, P, Cn = x.shape
     if not x.is_contiguous() or tuple(stats.shape) != (B, 2, Cn) or stats.dtype != torch.float64:
         raise ValueError("channel_stats: x contiguous [B,P,C], stats f64 [B,2,C] (pre-zeroed)")
-    backend().channel_stats(x, stats)
+    _call("channel_stats", x, stats)
     return stats
 
 
@@ -450,7 +479,7 @@ def instnorm_apply(x, stats, gamma, beta, eps, out, *, res=None, elu=False):
         raise ValueError("instnorm_apply: res must match x")
     if stats.dtype != torch.float64 or not stats.is_contiguous():
         raise ValueError("instnorm_apply: stats must be the contiguous f64 [B,2,C] buffer of channel_stats")
-    backend().instnorm_apply(x, stats, gamma, beta, float(eps), res, elu, out)
+    _call("instnorm_apply", x, stats, gamma, beta, float(eps), res, bool(elu), out)
     return out
 
 
@@ -470,7 +499,7 @@ def favor_attention(q, k, v, out, proj, *, kind, heads):
     # algorithmic FLOPs: feature maps 2*(2*T*h*64*m) + context/output 2*(2*T*h*64*m)
     tokens_total = q.shape[0] * q.shape[1] * q.shape[2]
     with _Timed("favor_attention", 8.0 * tokens_total * heads * 64 * proj.shape[0]):
-        backend().favor_attention(q, k, v, out, proj, int(kind), int(heads))
+        _call("favor_attention", q, k, v, out, proj, int(kind), int(heads))
     return out
 
 
@@ -495,12 +524,12 @@ def conv3x3(x, w_packed, out):
     if tuple(out.shape) != (x.shape[0], x.shape[1], x.shape[2], Cout) or not out.is_contiguous():
         raise ValueError("conv3x3: bad output shape")
     with _Timed("conv3x3", 2.0 * x.shape[0] * x.shape[1] * x.shape[2] * 9 * x.shape[3] * Cout):
-        backend().conv3x3(x, w_packed, out)
+        _call("conv3x3", x, w_packed, out)
     return out
 
 
 def convert_rows(x, out):
     if x.dim() != 2 or x.shape != out.shape or x.stride(1) != 1 or out.stride(1) != 1:
         raise ValueError("convert_rows: 2-D views with contiguous last dim")
-    backend().convert_rows(x, out)
+    _call("convert_rows", x, out)
     return out

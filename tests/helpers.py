@@ -18,6 +18,18 @@ def load_golden(name):
     return torch.load(os.path.join(GOLDEN_DIR, f"{name}.pt"), weights_only=False)
 
 
+def subset_stages(stages, cfg):
+    """Restrict full stage outputs to the rows a subset fixture holds (oracle/make_golden.py SUBSET_CONFIGS);
+    a config without row lists keeps the whole tensors."""
+    if "msa_rows" not in cfg:
+        return stages
+    out = {}
+    for k, v in stages.items():
+        idx = torch.tensor(cfg["msa_rows"] if k.startswith("msa") else cfg["pair_rows"], device=v.device)
+        out[k] = v.index_select(1, idx)
+    return out
+
+
 def build_block(cfg, device="cpu"):
     """A b200 TwoTrackBlock carrying the fixture's synthetic weights, and the fixture inputs."""
     import rosettafold_pytorch_b200 as rf

@@ -64,6 +64,26 @@ def test_gemm_plain(cuda_device, dtype, shape):
     assert e < 2e-5, f"rel-l2 {e}"
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_gemm_long_k_tied_logits(cuda_device, dtype):
+    """The tied-logit contraction at the metric shape (1, 128, 512): per head 512 x 512 with K = N*32 = 4096
+    (64 k-blocks through the TMA ring), and the A.V shape 512 x 4096 x 512, f32 and bf16 outputs."""
+    scale = 4096 ** -0.25
+    for Z, M, N, K, out_dtype in (((12,), 512, 512, 4096, torch.float32), ((12,), 512, 4096, 512, torch.bfloat16),
+                                  ((3,), 200, 136, 4096 + 64, torch.float32)):
+        if dtype == torch.float32 and out_dtype == torch.bfloat16:
+            continue
+        dev = cuda_device
+        a = _rand((*Z, M, K), dtype, dev, 21, scale)
+        b = _rand((*Z, N, K), dtype, dev, 22, scale)
+        c = torch.empty((*Z, M, N), dtype=out_dtype, device=dev)
+        ops.gemm(a, b, c.reshape(1, 1, *Z, 1, M, 1, N))
+        ref = torch.einsum("zmk,znk->zmn", a.double(), b.double())
+        torch.cuda.synchronize()
+        e = rel_l2(c, ref)
+        assert e < (tol(torch.bfloat16) if out_dtype == torch.bfloat16 else 2e-5), f"{(Z, M, N, K)}: rel-l2 {e}"
+
+
 @pytest.mark.parametrize("shape", [(40000, 768, 384), (33000, 1536, 288), (2 * 17000, 384, 384)])
 def test_gemm_large_m_bf16_out(cuda_device, shape):
     """Large-M, short-K projections with bf16 output take the TMA-store epilogue path
@@ -338,7 +358,7 @@ def test_favor_attention(cuda_device, dtype, kind, cfg):
     REF.favor_attention(q, k, v, ref, proj, kind, H)
     torch.cuda.synchronize()
     e = rel_l2(out, ref)
-    assert e < (1e-4 if dtype == torch.float32 else 1.5e-2), f"rel-l2 {e}"
+    assert e < (1e-4 if dtype == torch.float32 else 1e-2), f"rel-l2 {e}"
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])

@@ -2,8 +2,8 @@
 against the golden vectors of the unmodified reference and against the oracle restatement.
 
 Tolerances are the north star's: relative L2 <= 1e-4 in the fp32 validation mode and <= 1e-2 in
-the bf16 tensor-core mode (per trunk stage, each stage fed the reference's inputs; the free-running
-chain is checked against 2e-2 for the whole block because rounding compounds over the stages)."""
+the bf16 tensor-core mode, per trunk stage with each stage fed the reference's inputs AND for the free-running
+chain of the whole block. The BASELINE.json shapes are in tests/test_gpu_baseline_configs.py."""
 import pytest
 import torch
 
@@ -47,10 +47,10 @@ def test_bf16_mode_matches_golden(cuda_device, name):
     print("bf16 chain", name, e_chain)
     for k in STAGES:
         assert e_forced[k] < 1e-2, e_forced
-        assert e_chain[k] < 2e-2, e_chain
+        assert e_chain[k] < 1e-2, e_chain
 
 
-@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
 def test_block_vs_restatement_mid_size(cuda_device, mode, tol):
     """Default widths, tile-crossing sizes (L=136 > one 128-row tile, N=40), 2 layers: whole block
     vs the CPU restatement."""

@@ -7,10 +7,10 @@ import torch
 from oracle import reference_loader as rl
 from oracle import trunk_ref
 from oracle.weights import checksum, push_to_reference, synth_inputs, synth_state_dict
-from tests.helpers import STAGES, build_block, load_golden, rel_l2
+from tests.helpers import STAGES, build_block, load_golden, rel_l2, subset_stages
 
 
-@pytest.mark.parametrize("name", ["two_track_small", "two_track_default"])
+@pytest.mark.parametrize("name", ["two_track_small", "two_track_default", "two_track_tile_crossing"])
 def test_restatement_matches_golden(name):
     gold = load_golden(name)
     cfg = gold["config"]
@@ -20,6 +20,7 @@ def test_restatement_matches_golden(name):
     stages = {}
     with torch.no_grad():
         trunk_ref.two_track_block(msa, pair, sd, cfg["n_layers"], stages=stages)
+    stages = subset_stages(stages, cfg)
     for k in STAGES:
         assert rel_l2(stages[k], gold[k]) < 2e-5, k
 
