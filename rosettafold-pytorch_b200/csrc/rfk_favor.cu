@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(256, 1) favor_simt_kernel(const FavorDev p) {
   }
 }
 
-int favor_tc_launch(const rfk_favor_desc* d, cudaStream_t stream);  // rfk_favor_tc.cu
+int favor_tc_launch(const rfk_favor_desc* d, cudaStream_t stream);  // rfk_favor_tc.cu (round-1 kernel: features via shared memory)
+int favor_tm_launch(const rfk_favor_desc* d, cudaStream_t stream);  // rfk_favor_tm.cu (features kept in tensor memory)
 
 }  // namespace rfk
 
@@ -207,7 +208,8 @@ extern "C" int rfk_favor_attention(const rfk_favor_desc* d, rfk_stream_t stream_
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   static const bool force_simt = getenv("RFK_FAVOR_FORCE_SIMT") != nullptr;  // A/B debugging aid
   if (d->io_dtype == RFK_BF16 && !force_simt) {
-    int rc = favor_tc_launch(d, stream);
+    static const bool old_kernel = getenv("RFK_FAVOR_SMEM_FEATURES") != nullptr;  // A/B: the round-1 kernel
+    int rc = old_kernel ? favor_tc_launch(d, stream) : favor_tm_launch(d, stream);
     if (rc != RFK_ERR_UNSUPPORTED) return rc;
     // shapes the tensor-core kernel does not cover run on the SIMT kernel (same arithmetic)
   }

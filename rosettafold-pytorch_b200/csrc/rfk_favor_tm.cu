@@ -1,0 +1,860 @@
+// rfk_favor_tm.cu — fused Performer FAVOR+ attention with the random FEATURES KEPT IN TENSOR MEMORY
+// (tcgen05.st + A-operand-from-TMEM MMAs), bf16 operands, fp32 accumulation. Replaces
+// performer_pytorch FastAttention (softmax_kernel / generalized_kernel + linear_attention) as called at
+// rosettafold_pytorch.py:313-318 (MSA columns, softmax kernel) and :505-518 (pair axes, ReLU kernel).
+//
+// One persistent CTA per SM walks a stream of 128 x 128 JOBS; nothing of size tokens x m ever leaves the
+// SM and — unlike the round-1 kernel (rfk_favor_tc.cu) — the features never touch shared memory either:
+// the feature warps read the projection accumulator U out of TMEM, apply the feature map in registers and
+// write the packed bf16 features back IN PLACE over the accumulator (tcgen05.st); the consuming MMA takes
+// them as its A operand straight from TMEM. Per job that removes 32 KB of shared-memory stores, 32 KB of
+// shared-memory operand reads and a fence.proxy.async from the round-1 formulation, whose measured limit
+// was shared-memory bandwidth (profiles/r01_favor_pipeline_notes.md).
+//
+// A-from-TMEM fixes the orientation of every product (A rows sit on TMEM lanes, A is K-major):
+//   key side    U^T[m, tok] = Omega_c (A, smem) . K_tile^T (B, smem)    features ON THE LANES
+//               k'^T = phi(U^T) -> TMEM (in place)
+//               ctx^T_c[m, d|1] (+)= k'^T (A, TMEM, K = tokens) . [V | 1] (B, smem, MN-major)
+//   query side  U[tok, m]   = Q_tile (A, smem) . Omega_c^T (B, smem)    tokens on the lanes
+//               q' = phi(U) -> TMEM (in place)
+//               out|den[tok, d|1] (+)= q' (A, TMEM, K = features) . ctx_c (B, smem, K-major)
+// The 272 (padded) features are split into chunks c of 128 | 128 | 16. Job types per item (group, head):
+//   relu kernel  K(t,c)*, read-out of ctx, Q(t,c)*;
+//   softmax      KMAX(t,c)*, K(t,c)*, read-out, then per tile QMAX(t,c)*, Q(t,c)*   (stabiliser passes).
+//
+// Roles (19 warps):
+//   warp 0 lane 0  TMA producer: K/V/Q tiles into a 5-slot ring + an L2 prefetch cursor 6 tiles ahead
+//   warp 1         U issuer: the projection MMAs of every job, as far ahead as the two U slots allow
+//   warp 2         consumer issuer: context / output MMAs (A from TMEM); for the stabiliser jobs it only
+//                  hands the U slot back
+//   warps 3..18    16 feature warps, all on every job: warp (lane group lg = warp % 4, column quarter cq) owns
+//                  32 lanes x 32 accumulator columns: tcgen05.ld x32 -> feature map -> 16 packed words ->
+//                  tcgen05.st x16 over the first half of its own columns (no warp ever writes columns another
+//                  warp still has to read). MMA k-step s (16 features / tokens) therefore reads A at column
+//                  32 (s / 2) + 8 (s % 2) of the slot.
+// TMEM (512 columns): ctx^T blocks b = 0..2 (lanes = m - 128 b; 80 columns = d | 1) at [0,240);
+//   U slots 2 x 128 columns at [256,512); out|den accumulators D3[s] alias ctx blocks 0 / 1 (dead in the
+//   query phase; reuse ordered through the d3free barriers).
+// Shared memory (1024-byte aligned tiles, 128-byte swizzle):
+//   omega' [384][64] bf16 K-major (rows >= m zero) | tile ring 5 x [128 tok][64 d] | cslab [128 tok][64],
+//   column 0 = 1 (second MN chunk of "[V | 1]") | ctx 5 x [80][64 m] K-major B of the output MMA.
+#include <cstdio>
+#include <cstdlib>
+#include <type_traits>
+
+#include "rfk_common.cuh"
+
+namespace rfk {
+
+namespace {
+
+constexpr int kFeatWarps = 16;
+constexpr int kFeatThreads = 32 * kFeatWarps;
+constexpr int kThreads = 32 * (3 + kFeatWarps);  // TMA producer, two MMA issuers, feature warps
+constexpr int kMP = 272;     // padded feature count
+constexpr int kMRows = 384;  // omega rows in shared memory (3 chunks x 128 lanes)
+constexpr int kTile = 128;   // tokens per tile
+constexpr int kRing = 5;
+constexpr uint32_t kSlabBytes = kTile * 128;    // 16384
+constexpr uint32_t kOmegaBytes = kMRows * 128;  // 49152
+constexpr uint32_t kCtxSlabBytes = 80 * 128;    // 10240
+constexpr uint32_t kOffOmega = 0;
+constexpr uint32_t kOffRing = kOffOmega + kOmegaBytes;
+constexpr uint32_t kOffCslab = kOffRing + kRing * kSlabBytes;  // after the ring: LBO of [V | 1] > 0
+constexpr uint32_t kOffCtx = kOffCslab + kSlabBytes;
+constexpr uint32_t kOffBar = kOffCtx + 5 * kCtxSlabBytes;
+constexpr uint32_t kOffScratch = kOffBar + 256;
+constexpr uint32_t kScratchFloats = 4 * 128 + 4 * 128 + 128 + 32;  // diag partials, row maxima, per-token sub, warp maxima
+constexpr uint32_t kSmemBytes = kOffScratch + kScratchFloats * 4 + 1024;
+static_assert(kOffRing % 1024 == 0 && kOffCslab % 1024 == 0 && kOffCtx % 1024 == 0, "align");
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+
+constexpr uint32_t kColCtx = 0, kColU = 256;
+
+struct FavorTmParams {
+  const float* proj;
+  void* out;
+  int m, heads;
+  int tokens;
+  int64_t G0, G1, items;
+  int64_t ogs0, ogs1, ots;
+};
+
+// MN-major SW128 descriptor: rows are K indices (128 B each, 8-row groups SBO=1024 apart),
+// 64-element MN chunks are `lbo_bytes` apart.
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t idesc_bf16_major(int M, int N, int a_mn, int b_mn) {
+  return umma_idesc_bf16(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
+}
+// D[tmem] (+)= A[tmem, K-major: lane = row, two bf16 per 32-bit column] * B[smem]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_shared_b16(uint32_t addr, float f) {
+  const unsigned short h = __bfloat16_as_ushort(__float2bfloat16_rn(f));
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(h) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// one lane of the (fully active) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tmem_ld_32x32p(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16p(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// {bf16(max(lo,0)), bf16(max(hi,0))} in one instruction
+__device__ __forceinline__ uint32_t cvt_relu_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+
+template <int KIND>  // 0: softmax kernel (exp features, stabilisers), 1: generalized ReLU kernel
+__global__ void __launch_bounds__(kThreads, 1)
+favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const FavorTmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t s_omega = base + kOffOmega, s_ring = base + kOffRing, s_cslab = base + kOffCslab, s_ctx = base + kOffCtx;
+  const uint32_t bars = base + kOffBar;
+  auto bar_tfull = [&](uint32_t s) { return bars + 8u * s; };            // [kRing]
+  auto bar_tempty = [&](uint32_t s) { return bars + 40u + 8u * s; };     // [kRing]
+  auto bar_ufull = [&](uint32_t s) { return bars + 80u + 8u * s; };      // U accumulator of the slot complete
+  auto bar_ufree = [&](uint32_t s) { return bars + 96u + 8u * s; };      // slot may be overwritten by the next U
+  auto bar_fready = [&](uint32_t s) { return bars + 112u + 8u * s; };    // features of the slot stored (or max taken)
+  auto bar_d3full = [&](uint32_t s) { return bars + 128u + 8u * s; };
+  auto bar_d3free = [&](uint32_t s) { return bars + 144u + 8u * s; };
+  const uint32_t bar_ctxfull = bars + 160u, bar_ctxready = bars + 168u;
+  const uint32_t tmem_slot = bars + 176u;
+  float* scratch = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + kOffScratch);
+  float* part = scratch;          // [4][128] partial |x|^2 of the four channel quarters
+  float* rmaxs = scratch + 512;   // [4][128] partial row maxima
+  float* ssub = scratch + 1024;   // [128] per-token exponent offset of the key tile
+  float* red = scratch + 1152;    // [16] per-warp maxima
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = (p.tokens + kTile - 1) / kTile;
+  const int64_t istride = gridDim.x;
+
+  // ---- one-time setup ----
+  if (warp == 0 && lane == 0) {
+    for (uint32_t s = 0; s < kRing; ++s) {
+      mbar_init(bar_tfull(s), 1);
+      mbar_init(bar_tempty(s), 1);
+    }
+    for (uint32_t s = 0; s < 2; ++s) {
+      mbar_init(bar_ufull(s), 1);
+      mbar_init(bar_ufree(s), 1);
+      mbar_init(bar_fready(s), kFeatWarps);
+      mbar_init(bar_d3full(s), 1);
+      mbar_init(bar_d3free(s), kFeatWarps);
+    }
+    mbar_init(bar_ctxfull, 1);
+    mbar_init(bar_ctxready, kFeatWarps);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  {
+    // omega' = dn * proj (rows >= m zero), K-major swizzled; constant slab: column 0 = 1
+    const float dn = 0.35355339059327373f;  // 64^-1/4
+    for (int i = threadIdx.x; i < kMRows * 8; i += kThreads) {
+      const int r = i >> 3, c = (i & 7) * 8;
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = r < p.m ? __ldg(p.proj + (int64_t)r * 64 + c + j) * dn : 0.f;
+      uint4 v;
+      v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+      v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+      st_shared_v4(s_omega + sw128_offset(r, c), v);
+    }
+    for (int i = threadIdx.x; i < kTile * 8; i += kThreads) {
+      const int r = i >> 3, c = (i & 7) * 8;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (c == 0) v.x = 0x00003F80u;  // bf16(1.0) in element 0
+      st_shared_v4(s_cslab + sw128_offset(r, c), v);
+    }
+    // ctx rows 65..79 (never written by the read-out) feed never-read accumulator columns: zero once
+    for (int i = threadIdx.x; i < (int)(5 * kCtxSlabBytes / 16); i += kThreads)
+      st_shared_v4(s_ctx + i * 16, make_uint4(0, 0, 0, 0));
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+
+  constexpr int kPassM = 0, kPassK = 1, kPassX = 2, kPassQ = 3;  // key max, keys, query max, queries
+  const int P = KIND == 0 ? 4 * nt : 2 * nt;
+  auto decode = [&](int ps, int& t) -> int {
+    if (KIND == 1) {
+      if (ps < nt) { t = ps; return kPassK; }
+      t = ps - nt;
+      return kPassQ;
+    }
+    if (ps < nt) { t = ps; return kPassM; }
+    if (ps < 2 * nt) { t = ps - nt; return kPassK; }
+    const int r = ps - 2 * nt;
+    t = r >> 1;
+    return (r & 1) ? kPassQ : kPassX;
+  };
+  using C0 = std::integral_constant<int, 0>;
+  using C1 = std::integral_constant<int, 1>;
+  using C2 = std::integral_constant<int, 2>;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // =================== TMA producer ===================
+      struct Cursor {
+        int64_t item;
+        int ph, i;  // phase: 0 = key-max pass (softmax kernel), 1 = K/V pairs, 2 = Q
+      };
+      auto cur_init = [&](Cursor& c) { c.item = blockIdx.x; c.ph = KIND == 0 ? 0 : 1; c.i = 0; };
+      auto cur_get = [&](const Cursor& c, const CUtensorMap*& tm, int& t) {
+        if (c.ph == 1) { tm = (c.i & 1) ? &tm_v : &tm_k; t = c.i >> 1; }
+        else { tm = c.ph == 0 ? &tm_k : &tm_q; t = c.i; }
+      };
+      auto cur_next = [&](Cursor& c) {
+        const int n = c.ph == 1 ? 2 * nt : nt;
+        if (++c.i < n) return;
+        c.i = 0;
+        if (++c.ph == 3) { c.ph = KIND == 0 ? 0 : 1; c.item += istride; }
+      };
+      auto coords = [&](int64_t item, int& h, int& g0, int& g1) {
+        h = (int)(item % p.heads);
+        const int64_t g = item / p.heads;
+        g0 = (int)(g % p.G0);
+        g1 = (int)(g / p.G0);
+      };
+      constexpr int kPrefetch = 8;
+      Cursor pf, ld;
+      cur_init(pf);
+      cur_init(ld);
+      auto prefetch_one = [&]() {
+        if (pf.item >= p.items) return;
+        const CUtensorMap* tm; int t, h, g0, g1;
+        cur_get(pf, tm, t);
+        coords(pf.item, h, g0, g1);
+        tma_prefetch_4d(tm, h * 64, t * kTile, g0, g1);
+        cur_next(pf);
+      };
+      for (int i = 0; i < kPrefetch; ++i) prefetch_one();
+      uint32_t slot = 0, par = 0;
+      while (ld.item < p.items) {
+        prefetch_one();
+        const CUtensorMap* tm; int t, h, g0, g1;
+        cur_get(ld, tm, t);
+        coords(ld.item, h, g0, g1);
+        mbar_wait(bar_tempty(slot), par ^ 1u);
+        mbar_arrive_expect_tx(bar_tfull(slot), kSlabBytes);
+        tma_load_4d(tm, bar_tfull(slot), s_ring + slot * kSlabBytes, h * 64, t * kTile, g0, g1);
+        if (++slot == kRing) { slot = 0; par ^= 1u; }
+        cur_next(ld);
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    // =================== MMA issuers ===================
+    // All 32 lanes run the warp-uniform control flow and one elected lane issues the tcgen05 instructions.
+    // Both walk the same nest (item, pass = (kind, tile), chunk) and mirror the producer's ring allocation.
+    struct Tile { uint32_t slot, par; };
+    uint32_t r_slot = 0, r_par = 0;  // ring position of the next tile to allocate
+    auto alloc = [&]() {
+      Tile x{r_slot, r_par};
+      if (++r_slot == kRing) { r_slot = 0; r_par ^= 1u; }
+      return x;
+    };
+    if (warp == 1) {
+      const uint64_t d_omega = umma_desc_sw128(s_omega);  // + c * 1024 + 2 k
+      const uint64_t d_ring = umma_desc_sw128(s_ring);    // + slot * 1024 + 2 k
+      uint32_t nJ = 0;  // U jobs issued (job parity = U slot)
+      // key side: U^T = Omega_c . X^T (features on the lanes); query side: U = X . Omega_c^T
+      auto issue_u = [&](const Tile& a, auto cc, bool key_side, bool release) {
+        constexpr int C = decltype(cc)::value;
+        const uint32_t us = nJ & 1u;
+        mbar_wait(bar_ufree(us), ((nJ >> 1) & 1u) ^ 1u);
+        if (C == 0) mbar_wait(bar_tfull(a.slot), a.par);
+        tc_fence_after();
+        const uint64_t dx = d_ring + (uint64_t)(a.slot * 1024u);
+        const uint64_t dw = d_omega + (uint64_t)(C * 1024);
+        const uint64_t da = key_side ? dw : dx;
+        const uint64_t db = key_side ? dx : dw;
+        const uint32_t idesc = (!key_side && C == 2) ? umma_idesc_bf16(128, 16) : umma_idesc_bf16(128, 128);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem + kColU + us * 128u, da + 2 * k, db + 2 * k, idesc, k > 0);
+          umma_commit(bar_ufull(us));
+          if (C == 2 && release) umma_commit(bar_tempty(a.slot));
+        }
+        __syncwarp();
+        ++nJ;
+      };
+      Tile a{0, 0};
+      for (int64_t item = blockIdx.x; item < p.items; item += istride) {
+        for (int ps = 0; ps < P; ++ps) {
+          int t;
+          const int kind = decode(ps, t);
+          if (!(KIND == 0 && kind == kPassQ)) a = alloc();  // a softmax Q pass reuses its QMAX tile
+          if (kind == kPassK) (void)alloc();                 // the V tile
+          const bool key_side = kind == kPassM || kind == kPassK;
+          issue_u(a, C0{}, key_side, false);
+          issue_u(a, C1{}, key_side, false);
+          issue_u(a, C2{}, key_side, kind != kPassX);
+        }
+      }
+    } else {
+      const uint64_t d_ctx = umma_desc_sw128(s_ctx);  // + slab * 640 + 2 k
+      uint32_t nC = 0;                                // jobs consumed (parity = U slot)
+      uint32_t nD3 = 0, d3u0 = 0, d3u1 = 0;           // output tiles started / fills per D3 slot
+      uint32_t nItems = 0;
+      auto wait_d3_region = [&](uint32_t s) {
+        const uint32_t uses = s ? d3u1 : d3u0;
+        if (uses > 0) mbar_wait(bar_d3free(s), (uses - 1u) & 1u);
+      };
+      // A operand of k-step k inside U slot fs: the feature warp of column quarter k / 2 wrote its 16 packed
+      // columns at the start of its own 32-column range
+      auto a_col = [&](uint32_t fs, int k) { return tmem + kColU + fs * 128u + 32u * (uint32_t)(k >> 1) + 8u * (uint32_t)(k & 1); };
+      // ctx^T_c[128 m x 80] (+)= k'^T_c (A, TMEM, K = tokens) . [V | 1] (B, MN-major)
+      auto consume_k = [&](const Tile& v, int t, auto cc) {
+        constexpr int C = decltype(cc)::value;
+        const uint32_t fs = nC & 1u;
+        const uint32_t par = (nC >> 1) & 1u;
+        ++nC;
+        if (t == 0 && C < 2) wait_d3_region((uint32_t)C);  // ctx block c aliases D3[c]
+        if (C == 0) mbar_wait(bar_tfull(v.slot), v.par);
+        mbar_wait(bar_fready(fs), par);
+        tc_fence_after();
+        const uint64_t db = desc_mn_sw128(s_ring + v.slot * kSlabBytes, s_cslab - s_ring - v.slot * kSlabBytes);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16_ts(tmem + kColCtx + 80u * C, a_col(fs, k), db + 128 * k, idesc_bf16_major(128, 80, 0, 1), (t > 0 || k > 0));
+          umma_commit(bar_ufree(fs));
+          if (C == 2) {
+            umma_commit(bar_tempty(v.slot));
+            if (t == nt - 1) umma_commit(bar_ctxfull);
+          }
+        }
+        __syncwarp();
+      };
+      // out|den [128 tok x 80] (+)= q'_c (A, TMEM, K = features) . ctx_c (B, K-major over m)
+      auto consume_q = [&](int t, auto cc) {
+        constexpr int C = decltype(cc)::value;
+        const uint32_t fs = nC & 1u;
+        const uint32_t par = (nC >> 1) & 1u;
+        ++nC;
+        const uint32_t ds = nD3 & 1u;
+        if (C == 0) {
+          if (t == 0) {
+            mbar_wait(bar_ctxready, nItems & 1u);
+            ++nItems;
+          }
+          wait_d3_region(ds);
+        }
+        mbar_wait(bar_fready(fs), par);
+        tc_fence_after();
+        const uint64_t db = d_ctx + (uint64_t)(2 * C * 640);
+        if (elect_one()) {
+          constexpr int NK = C == 2 ? 1 : 8;
+#pragma unroll
+          for (int k = 0; k < NK; ++k)
+            umma_bf16_ts(tmem + kColCtx + 80u * ds, a_col(fs, k), db + (k >> 2) * 640 + 2 * (k & 3), umma_idesc_bf16(128, 80),
+                         (C > 0 || k > 0));
+          umma_commit(bar_ufree(fs));
+          if (C == 2) umma_commit(bar_d3full(ds));
+        }
+        __syncwarp();
+        if (C == 2) {
+          if (ds) ++d3u1; else ++d3u0;
+          ++nD3;
+        }
+      };
+      // stabiliser job: the feature warps have taken their maxima, hand the U slot back
+      auto consume_max = [&]() {
+        const uint32_t fs = nC & 1u;
+        const uint32_t par = (nC >> 1) & 1u;
+        ++nC;
+        mbar_wait(bar_fready(fs), par);
+        if (elect_one()) mbar_arrive(bar_ufree(fs));
+        __syncwarp();
+      };
+      Tile v{0, 0};
+      for (int64_t item = blockIdx.x; item < p.items; item += istride) {
+        for (int ps = 0; ps < P; ++ps) {
+          int t;
+          const int kind = decode(ps, t);
+          if (!(KIND == 0 && kind == kPassQ)) (void)alloc();
+          if (kind == kPassK) {
+            v = alloc();
+            consume_k(v, t, C0{});
+            consume_k(v, t, C1{});
+            consume_k(v, t, C2{});
+          } else if (kind == kPassQ) {
+            consume_q(t, C0{});
+            consume_q(t, C1{});
+            consume_q(t, C2{});
+          } else {
+            consume_max();
+            consume_max();
+            consume_max();
+          }
+        }
+      }
+    }
+  } else {
+    // =================== feature / epilogue warps ===================
+    const int fw = warp - 3;         // 0..15
+    const int lg = warp & 3;         // TMEM lane group this warp may touch
+    const int cq = fw >> 2;          // column quarter of the U slot owned by this warp
+    const int row = lg * 32 + lane;  // TMEM lane: token row (query side) / feature row of the chunk (key side)
+    const uint32_t t_lane = ((uint32_t)(lg * 32) << 16);
+    constexpr float kLog2e = 1.4426950408889634f;
+    constexpr float kEps = KIND == 0 ? 1e-4f : 1e-3f;
+    const uint32_t eps2 = pack_bf16x2(kEps, kEps);
+    const uint32_t ubase = tmem + t_lane + kColU + 32u * (uint32_t)cq;  // + us * 128
+
+    uint32_t nJ = 0;  // jobs processed (job parity = U slot)
+    uint32_t nItems = 0, nD3 = 0, tile_seq = 0;
+    float gmax = 0.f, sub = 0.f;
+    const int64_t last_item = blockIdx.x + ((p.items - 1 - blockIdx.x) / istride) * istride;
+
+    uint32_t raw[32];
+    // wait for the accumulator of job nJ and issue its TMEM loads. Q2: the job is a query-side chunk 2
+    // (16 feature columns, read by the cq == 0 warps only)
+    auto prefetch = [&](bool q2) {
+      const uint32_t us = nJ & 1u;
+      mbar_wait(bar_ufull(us), (nJ >> 1) & 1u);
+      tc_fence_after();
+      if (!q2) {
+        tmem_ld_32x32p(ubase + us * 128u, raw);
+      } else if (cq == 0) {
+        tmem_ld_32x16p(ubase + us * 128u, raw);
+      }
+    };
+    // publish: features of job nJ are in TMEM (or its maxima taken) -> the consumer issuer may proceed
+    auto publish = [&](bool stored) {
+      if (stored) tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_fready(nJ & 1u));
+      ++nJ;
+    };
+    // two accumulator values -> one packed bf16x2 feature pair; s0 / s1: exponent offsets (softmax kernel)
+    auto feat2 = [&](uint32_t r0, uint32_t r1, float s0, float s1) -> uint32_t {
+      const float x0 = __uint_as_float(r0), x1 = __uint_as_float(r1);
+      if (KIND == 0)
+        return add_bf16x2(pack_bf16x2(ex2_approx(fmaf(x0, kLog2e, -s0)), ex2_approx(fmaf(x1, kLog2e, -s1))), eps2);
+      return add_bf16x2(cvt_relu_bf16x2(x0, x1), eps2);
+    };
+
+    // ---- key-side job: this thread holds feature row (128 C + row) x tokens [32 cq, 32 cq + 32) of the tile ----
+    // ntok: valid tokens of the tile; next_q2: shape of the following job
+    auto key_feat_job = [&](int C, int ntok, bool has_next, bool next_q2) {
+      const uint32_t us = nJ & 1u;
+      tmem_ld_wait();
+      const bool row_ok = 128 * C + row < p.m;
+      const int lim = ntok - 32 * cq;  // token columns >= lim are padding (only in a ragged last tile)
+      uint32_t pk[16];
+      if (KIND == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 s4 = *reinterpret_cast<const float4*>(ssub + 32 * cq + 4 * q);
+          pk[2 * q] = feat2(raw[4 * q], raw[4 * q + 1], s4.x, s4.y);
+          pk[2 * q + 1] = feat2(raw[4 * q + 2], raw[4 * q + 3], s4.z, s4.w);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = feat2(raw[2 * i], raw[2 * i + 1], 0.f, 0.f);
+      }
+      if (!row_ok) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = 0u;
+      } else if (lim < 32) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (2 * i >= lim) pk[i] = 0u;
+          else if (2 * i + 1 >= lim) pk[i] &= 0x0000ffffu;
+        }
+      }
+      tmem_st_32x16(ubase + us * 128u, pk);
+      publish(true);
+      if (has_next) prefetch(next_q2);
+    };
+    // ---- key-side stabiliser job (softmax kernel): max of the raw projections over valid rows / tokens ----
+    auto key_max_job = [&](int C, int ntok, float& acc) {
+      tmem_ld_wait();
+      const bool row_ok = 128 * C + row < p.m;
+      const int lim = ntok - 32 * cq;
+      float mx = -INFINITY;
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < lim) mx = fmaxf(mx, __uint_as_float(raw[i]));
+      }
+      acc = fmaxf(acc, mx);
+      publish(false);
+      prefetch(false);  // a key-side job always follows
+    };
+    // ---- query-side job: this thread holds token row `row` x features [128 C + 32 cq, + 32) ----
+    auto query_feat_job = [&](auto cc, bool has_next, bool next_q2) {
+      constexpr int C = decltype(cc)::value;
+      const uint32_t us = nJ & 1u;
+      if (C < 2) {
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = feat2(raw[2 * i], raw[2 * i + 1], sub, sub);
+        tmem_st_32x16(ubase + us * 128u, pk);
+        publish(true);
+      } else if (cq == 0) {
+        tmem_ld_wait();
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = feat2(raw[2 * i], raw[2 * i + 1], sub, sub);
+        tmem_st_32x8(ubase + us * 128u, pk);
+        publish(true);
+      } else {
+        publish(false);
+      }
+      if (has_next) prefetch(next_q2);
+    };
+    // ---- query-side stabiliser job (softmax kernel): per-row max over the valid feature columns ----
+    auto query_max_job = [&](auto cc, float& acc) {
+      constexpr int C = decltype(cc)::value;
+      constexpr int NC = C < 2 ? 32 : 16;
+      if (C < 2 || cq == 0) {
+        tmem_ld_wait();
+        const int lim = p.m - (128 * C + 32 * cq);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+          if (i < lim) mx = fmaxf(mx, __uint_as_float(raw[i]));
+        acc = fmaxf(acc, mx);
+      }
+      publish(false);
+      prefetch(C == 1);  // QMAX chunk 2 follows chunk 1; the query chunk 0 follows QMAX chunk 2
+    };
+
+    // 0.5 * dn^2 * |x|^2 of token `row` of ring tile a_seq (softmax kernel): the four warps of a lane group sum
+    // 16 channels each, the partials meet in shared memory
+    auto row_diag = [&](uint32_t a_seq) {
+      mbar_wait(bar_tfull(a_seq % kRing), (a_seq / kRing) & 1u);  // TMA bytes visible to this thread
+      const uint32_t tile = s_ring + (a_seq % kRing) * kSlabBytes;
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint4 v = ld_shared_v4(tile + sw128_offset(row, cq * 16 + j * 8));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float a = bf16lo(w[i]), b = bf16hi(w[i]);
+          s = fmaf(a, a, s);
+          s = fmaf(b, b, s);
+        }
+      }
+      part[cq * 128 + row] = s;
+      named_bar_sync(1, kFeatThreads);
+      return (part[row] + part[128 + row] + part[256 + row] + part[384 + row]) * (0.5f * 0.125f);
+    };
+
+    // out/den epilogue of one query tile: warp (lg, cq) stores channels [16 cq, 16 cq + 16) of its 32 tokens
+    auto epilogue = [&](int64_t item, int t) {
+      const uint32_t ds = nD3 & 1u;
+      mbar_wait(bar_d3full(ds), (nD3 >> 1) & 1u);
+      tc_fence_after();
+      uint32_t rd[16], r0[16];
+      tmem_ld_32x16p(tmem + t_lane + kColCtx + 80u * ds + 64, rd);  // column 64 = normaliser
+      tmem_ld_32x16p(tmem + t_lane + kColCtx + 80u * ds + 16u * (uint32_t)cq, r0);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_d3free(ds));
+      ++nD3;
+      if (t * kTile + row < p.tokens) {
+        const int h = (int)(item % p.heads);
+        const int64_t g = item / p.heads;
+        const int64_t g0 = g % p.G0, g1 = g / p.G0;
+        const float inv = 1.f / __uint_as_float(rd[0]);
+        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + g1 * p.ogs1 + g0 * p.ogs0 +
+                                             (int64_t)(t * kTile + row) * p.ots + h * 64 + 16 * cq);
+        uint4 w;
+        w.x = pack_bf16x2(__uint_as_float(r0[0]) * inv, __uint_as_float(r0[1]) * inv);
+        w.y = pack_bf16x2(__uint_as_float(r0[2]) * inv, __uint_as_float(r0[3]) * inv);
+        w.z = pack_bf16x2(__uint_as_float(r0[4]) * inv, __uint_as_float(r0[5]) * inv);
+        w.w = pack_bf16x2(__uint_as_float(r0[6]) * inv, __uint_as_float(r0[7]) * inv);
+        op[0] = w;
+        w.x = pack_bf16x2(__uint_as_float(r0[8]) * inv, __uint_as_float(r0[9]) * inv);
+        w.y = pack_bf16x2(__uint_as_float(r0[10]) * inv, __uint_as_float(r0[11]) * inv);
+        w.z = pack_bf16x2(__uint_as_float(r0[12]) * inv, __uint_as_float(r0[13]) * inv);
+        w.w = pack_bf16x2(__uint_as_float(r0[14]) * inv, __uint_as_float(r0[15]) * inv);
+        op[1] = w;
+      }
+    };
+
+    if ((int64_t)blockIdx.x < p.items) prefetch(false);
+    for (int64_t item = blockIdx.x; item < p.items; item += istride) {
+      if (KIND == 0) {
+        // ---- key stabiliser: global max of Omega'.K^T over the valid features / tokens ----
+        float kmx = -INFINITY;
+        for (int t = 0; t < nt; ++t) {
+          ++tile_seq;
+          const int ntok = min(kTile, p.tokens - t * kTile);
+          key_max_job(0, ntok, kmx);
+          key_max_job(1, ntok, kmx);
+          key_max_job(2, ntok, kmx);
+        }
+        kmx = warp_max(kmx);
+        if (lane == 0) red[fw] = kmx;
+        named_bar_sync(1, kFeatThreads);
+        gmax = red[0];
+#pragma unroll
+        for (int i = 1; i < kFeatWarps; ++i) gmax = fmaxf(gmax, red[i]);
+      }
+      // ---- keys: k'^T chunks feed the context MMAs ----
+      for (int t = 0; t < nt; ++t) {
+        if (KIND == 0) {
+          const float dg = row_diag(tile_seq);
+          if (cq == 0) ssub[row] = (dg + gmax) * kLog2e;
+          named_bar_sync(1, kFeatThreads);
+        }
+        tile_seq += 2;
+        const int ntok = min(kTile, p.tokens - t * kTile);
+        key_feat_job(0, ntok, true, false);
+        key_feat_job(1, ntok, true, false);
+        key_feat_job(2, ntok, true, false);
+      }
+      // ---- context read-out: TMEM ctx^T blocks -> bf16 K-major smem. Warp (lg, cq) converts columns
+      //      [16 cq, 16 cq + 16) of blocks 0 and 1 for its 32 feature rows; the normaliser column 64 and the
+      //      16-row block 2 are spread over the column quarters ----
+      {
+        mbar_wait(bar_ctxfull, nItems & 1u);
+        ++nItems;
+        tc_fence_after();
+        tmem_ld_wait();  // the prefetch of the first query job is in flight: one wait covers all loads
+        auto put = [&](int m, uint32_t n, float v) {
+          const uint32_t mc = (uint32_t)m & 63u;
+          st_shared_b16(s_ctx + (uint32_t)(m >> 6) * kCtxSlabBytes + (n >> 3) * 1024u + (n & 7u) * 128u +
+                            ((((mc >> 3) ^ n) & 7u) << 4) + (mc & 7u) * 2u,
+                        v);
+        };
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          uint32_t r[16];
+          tmem_ld_32x16p(tmem + t_lane + kColCtx + 80u * b + 16u * (uint32_t)cq, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) put(128 * b + row, 16u * cq + i, __uint_as_float(r[i]));
+        }
+        if (cq < 2) {  // normaliser column of block cq
+          uint32_t r[16];
+          tmem_ld_32x16p(tmem + t_lane + kColCtx + 80u * (uint32_t)cq + 64u, r);
+          tmem_ld_wait();
+          put(128 * cq + row, 64u, __uint_as_float(r[0]));
+        }
+        if (lg == 0) {  // block 2: features 256..271 live in lanes 0..15
+          uint32_t r[16], r2[16];
+          tmem_ld_32x16p(tmem + kColCtx + 160u + 16u * (uint32_t)cq, r);
+          tmem_ld_32x16p(tmem + kColCtx + 160u + 64u, r2);
+          tmem_ld_wait();
+          if (lane < 16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) put(256 + lane, 16u * cq + i, __uint_as_float(r[i]));
+            if (cq == 3) put(256 + lane, 64u, __uint_as_float(r2[0]));
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_ctxready);
+      }
+      // ---- queries: q' chunks feed the output MMAs; the out/den epilogue of tile t runs behind
+      //      the first job of tile t+1 ----
+      bool pending = false;
+      for (int t = 0; t < nt; ++t) {
+        const bool more = t + 1 < nt || item != last_item;  // another job follows this tile
+        if (KIND == 0) {
+          const float diag = row_diag(tile_seq);
+          float rmx = -INFINITY;
+          query_max_job(C0{}, rmx);
+          if (pending) { epilogue(item, t - 1); pending = false; }
+          query_max_job(C1{}, rmx);
+          query_max_job(C2{}, rmx);
+          rmaxs[cq * 128 + row] = rmx;
+          named_bar_sync(1, kFeatThreads);
+          sub = (diag + fmaxf(fmaxf(rmaxs[row], rmaxs[128 + row]), fmaxf(rmaxs[256 + row], rmaxs[384 + row]))) * kLog2e;
+        }
+        ++tile_seq;
+        query_feat_job(C0{}, true, false);
+        if (pending) { epilogue(item, t - 1); pending = false; }
+        query_feat_job(C1{}, true, true);
+        query_feat_job(C2{}, more, false);
+        pending = true;
+      }
+      epilogue(item, nt - 1);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_head_tmap(CUtensorMap* map, const void* ptr, const rfk_favor_desc* d) {
+  static EncodeTiledFn enc = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  if (!enc) return RFK_ERR_TMA_ENCODE;
+  // dims: (column within the heads*64 slice, token, g0, g1)
+  cuuint64_t dims[4] = {(cuuint64_t)d->heads * 64, (cuuint64_t)d->tokens, (cuuint64_t)d->G[0], (cuuint64_t)d->G[1]};
+  cuuint64_t strides[3] = {(cuuint64_t)d->ts * 2, (cuuint64_t)d->gs[0] * 2, (cuuint64_t)d->gs[1] * 2};
+  if (d->G[0] == 1) strides[1] = strides[0] * (cuuint64_t)d->tokens;
+  if (d->G[1] == 1) strides[2] = strides[1] * (cuuint64_t)d->G[0];
+  cuuint32_t box[4] = {64, (cuuint32_t)kTile, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? RFK_OK : RFK_ERR_TMA_ENCODE;
+}
+
+template <int KIND>
+int launch_kind(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const FavorTmParams& p,
+                cudaStream_t stream) {
+  static PerDeviceOnce once;
+  const int cfg_rc = per_device_once(once, []() {
+    return cuda_status(cudaFuncSetAttribute(favor_tm_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  });
+  if (cfg_rc != RFK_OK) return cfg_rc;
+  int grid = num_sms();
+  if (p.items < grid) grid = (int)p.items;
+  favor_tm_kernel<KIND><<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, p);
+  return post_launch();
+}
+
+}  // namespace
+
+int favor_tm_launch(const rfk_favor_desc* d, cudaStream_t stream) {
+  // shapes the tensor-core kernel covers; anything else runs on the SIMT kernel
+  if (d->m_features > kMP || d->m_features < 16) return RFK_ERR_UNSUPPORTED;
+  if (d->tokens > (1 << 24)) return RFK_ERR_UNSUPPORTED;
+  if (!aligned16(d->q) || !aligned16(d->k) || !aligned16(d->v) || !aligned16(d->out)) return RFK_ERR_UNSUPPORTED;
+  if (d->ts % 8 || d->gs[0] % 8 || d->gs[1] % 8 || d->out_ts % 8 || d->out_gs[0] % 8 || d->out_gs[1] % 8)
+    return RFK_ERR_UNSUPPORTED;
+  int rc = check_arch();
+  if (rc != RFK_OK) return rc;
+  CUtensorMap tq, tk, tv;
+  if ((rc = make_head_tmap(&tq, d->q, d)) != RFK_OK) return rc;
+  if ((rc = make_head_tmap(&tk, d->k, d)) != RFK_OK) return rc;
+  if ((rc = make_head_tmap(&tv, d->v, d)) != RFK_OK) return rc;
+  FavorTmParams p{};
+  p.proj = d->proj; p.out = d->out; p.m = d->m_features; p.heads = d->heads;
+  p.tokens = (int)d->tokens; p.G0 = d->G[0]; p.G1 = d->G[1];
+  p.items = d->G[0] * d->G[1] * d->heads;
+  p.ogs0 = d->out_gs[0]; p.ogs1 = d->out_gs[1]; p.ots = d->out_ts;
+  return d->kind == 0 ? launch_kind<0>(tq, tk, tv, p, stream) : launch_kind<1>(tq, tk, tv, p, stream);
+}
+
+}  // namespace rfk
