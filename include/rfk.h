@@ -256,6 +256,11 @@ int rfk_conv3x3_nhwc(const void* x, const void* w_packed, void* y, int y_dtype, 
 int rfk_conv3x3_nhwc_hw(const void* x, const void* w_packed, void* y, int y_dtype, int B, int H, int L,
                         int C, int Cout, rfk_stream_t stream);
 
+/* fp32 validation-mode form of the same convolution (SIMT, fp32 FMA, fixed summation order):
+ *   x: f32 [B][H][L][C];  w_packed: f32 [9][C][Cout], w_packed[3*di+dj][c][o] = W[o][c][di][dj];  y: f32 [B][H][L][Cout]. */
+int rfk_conv3x3_nhwc_f32(const float* x, const float* w_packed, float* y, int B, int H, int L, int C, int Cout,
+                         rfk_stream_t stream);
+
 /* Cast / copy rows between dtypes with row strides (host-side plumbing for column slices). */
 int rfk_convert_rows(const void* x, int x_dtype, int64_t x_row_stride, void* y, int y_dtype,
                      int64_t y_row_stride, int64_t rows, int cols, rfk_stream_t stream);

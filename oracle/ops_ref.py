@@ -186,5 +186,11 @@ class RefBackend:
         y = torch.nn.functional.conv2d(x.to(self.acc).permute(0, 3, 1, 2), w, padding=1)
         out.copy_(y.permute(0, 2, 3, 1).to(out.dtype))
 
+    def conv3x3_f32(self, x, w_packed, out):
+        _, Cin, Cout = w_packed.shape
+        w = w_packed.to(self.acc).reshape(3, 3, Cin, Cout).permute(3, 2, 0, 1)
+        y = torch.nn.functional.conv2d(x.to(self.acc).permute(0, 3, 1, 2), w, padding=1)
+        out.copy_(y.permute(0, 2, 3, 1).to(out.dtype))
+
     def convert_rows(self, x, out):
         out.copy_(x.to(out.dtype))

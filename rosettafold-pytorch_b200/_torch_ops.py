@@ -34,6 +34,7 @@ SCHEMAS = {
                       "Tensor(a!) out) -> ()",
     "favor_attention": "(Tensor q, Tensor k, Tensor v, Tensor(a!) out, Tensor proj, int kind, int heads) -> ()",
     "conv3x3": "(Tensor x, Tensor w_packed, Tensor(a!) out) -> ()",
+    "conv3x3_f32": "(Tensor x, Tensor w_packed, Tensor(a!) out) -> ()",
     "convert_rows": "(Tensor x, Tensor(a!) out) -> ()",
 }
 

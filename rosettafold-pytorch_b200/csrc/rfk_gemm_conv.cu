@@ -86,3 +86,78 @@ extern "C" int rfk_conv3x3_nhwc(const void* x, const void* w_packed, void* y, in
                                 int C, int Cout, rfk_stream_t stream_) {
   return rfk_conv3x3_nhwc_hw(x, w_packed, y, y_dtype, B, L, L, C, Cout, stream_);
 }
+
+// ----------------------------------------------------------------------------------------------
+// fp32 validation mode: direct 3x3 convolution on CUDA cores (reference :452, :456 in fp32).
+// Block = 32 consecutive positions of one image row x 64 output channels; the input window
+// (3 rows x 34 columns x 32 channels) and one tap's weights (32 x 64) are staged in shared memory;
+// thread (pg, cg) accumulates positions {2 pg, 2 pg + 1} x channels [4 cg, 4 cg + 4). Fixed summation
+// order (channel chunks, taps, channels): run-to-run reproducible.
+// ----------------------------------------------------------------------------------------------
+namespace rfk {
+namespace {
+constexpr int kCvW = 32, kCvCo = 64, kCvCk = 32;
+
+__global__ void __launch_bounds__(256) conv3x3_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          float* __restrict__ y, int B, int H, int W, int Cin, int Cout,
+                                                          int co_blocks) {
+  __shared__ float xs[3][kCvW + 2][kCvCk];
+  __shared__ __align__(16) float ws[kCvCk][kCvCo];
+  const int j0 = blockIdx.x * kCvW, i = blockIdx.y;
+  const int b = blockIdx.z / co_blocks, co0 = (blockIdx.z % co_blocks) * kCvCo;
+  const int tid = threadIdx.x, pg = tid >> 4, cg = tid & 15;
+  float acc[2][4] = {};
+  for (int c0 = 0; c0 < Cin; c0 += kCvCk) {
+    for (int e = tid; e < 3 * (kCvW + 2) * kCvCk; e += 256) {
+      const int ck = e % kCvCk, col = (e / kCvCk) % (kCvW + 2), r = e / (kCvCk * (kCvW + 2));
+      const int ii = i + r - 1, jj = j0 + col - 1, c = c0 + ck;
+      float v = 0.f;
+      if (ii >= 0 && ii < H && jj >= 0 && jj < W && c < Cin) v = x[(((int64_t)b * H + ii) * W + jj) * Cin + c];
+      xs[r][col][ck] = v;
+    }
+    for (int tap = 0; tap < 9; ++tap) {
+      __syncthreads();  // xs complete (first tap) / previous tap's ws consumed
+      for (int e = tid; e < kCvCk * kCvCo; e += 256) {
+        const int co = e % kCvCo, ck = e / kCvCo;
+        const int c = c0 + ck, o = co0 + co;
+        ws[ck][co] = (c < Cin && o < Cout) ? w[((int64_t)tap * Cin + c) * Cout + o] : 0.f;
+      }
+      __syncthreads();
+      const int di = tap / 3, dj = tap % 3;
+#pragma unroll 8
+      for (int ck = 0; ck < kCvCk; ++ck) {
+        const float x0 = xs[di][2 * pg + dj][ck], x1 = xs[di][2 * pg + 1 + dj][ck];
+        const float4 w4 = *reinterpret_cast<const float4*>(&ws[ck][4 * cg]);
+        acc[0][0] = fmaf(x0, w4.x, acc[0][0]); acc[0][1] = fmaf(x0, w4.y, acc[0][1]);
+        acc[0][2] = fmaf(x0, w4.z, acc[0][2]); acc[0][3] = fmaf(x0, w4.w, acc[0][3]);
+        acc[1][0] = fmaf(x1, w4.x, acc[1][0]); acc[1][1] = fmaf(x1, w4.y, acc[1][1]);
+        acc[1][2] = fmaf(x1, w4.z, acc[1][2]); acc[1][3] = fmaf(x1, w4.w, acc[1][3]);
+      }
+    }
+    __syncthreads();  // before the next channel chunk overwrites xs
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int j = j0 + 2 * pg + q;
+    if (j >= W) continue;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int o = co0 + 4 * cg + r;
+      if (o < Cout) y[(((int64_t)b * H + i) * W + j) * Cout + o] = acc[q][r];
+    }
+  }
+}
+}  // namespace
+}  // namespace rfk
+
+extern "C" int rfk_conv3x3_nhwc_f32(const float* x, const float* w_packed, float* y, int B, int H, int L, int C, int Cout,
+                                    rfk_stream_t stream_) {
+  if (!x || !w_packed || !y) return RFK_ERR_NULL_POINTER;
+  if (B <= 0 || H <= 0 || L <= 0 || C <= 0 || Cout <= 0 || H > 65535) return RFK_ERR_BAD_DIMS;
+  const int co_blocks = (Cout + rfk::kCvCo - 1) / rfk::kCvCo;
+  if ((int64_t)B * co_blocks > 65535) return RFK_ERR_BAD_DIMS;
+  if (rfk::check_arch() != RFK_OK) return RFK_ERR_UNSUPPORTED_ARCH;
+  dim3 grid((unsigned)((L + rfk::kCvW - 1) / rfk::kCvW), (unsigned)H, (unsigned)(B * co_blocks));
+  rfk::conv3x3_f32_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(x, w_packed, y, B, H, L, C, Cout, co_blocks);
+  return rfk::post_launch();
+}

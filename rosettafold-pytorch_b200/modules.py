@@ -5,7 +5,7 @@ Same class names, constructor signatures, forward signatures/returns and paramet
 one-to-one. The forwards are inference (eval-mode) computations built ONLY from librfk kernels
 (`ops`): dropout is the identity and autograd is not recorded. torch is used for allocation and
 views. The 3x3 Conv2d pair of PairUpdateWithMsa (:451-457) runs on the tcgen05 implicit-GEMM kernel
-in bf16 mode; only the fp32 validation mode still calls the library convolution for it.
+in bf16 mode and on a SIMT fp32 kernel in the fp32 validation mode: no library kernel is on the path.
 
 Residual streams (msa, pair) are float32. `set_mode("bf16")` (default) feeds bf16 operands to the
 tcgen05 kernels with fp32 accumulation; `set_mode("fp32")` is the fp32 validation mode.
@@ -19,7 +19,6 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import ops
 from .ops import ACT_RELU, EPI_BLOCKLN32, cview
@@ -568,20 +567,18 @@ class PairUpdateWithMsa(nn.Module):
                 Wr=W[:, c0:c1].detach().float().contiguous(), Wc=W[:, c1:c2].detach().float().contiguous(),
                 # bf16 mode: tap-major packed weights of the implicit-GEMM conv kernel; fp32
                 # validation mode: plain fp32 weights for the library convolution
-                conv1=ops.pack_conv3x3_weight(fn[1].weight) if _MODE == 0 else fn[1].weight.detach().float().contiguous(memory_format=torch.channels_last),
-                conv2=ops.pack_conv3x3_weight(fn[5].weight) if _MODE == 0 else fn[5].weight.detach().float().contiguous(memory_format=torch.channels_last),
+                conv1=ops.pack_conv3x3_weight(fn[1].weight) if _MODE == 0 else ops.pack_conv3x3_weight_f32(fn[1].weight),
+                conv2=ops.pack_conv3x3_weight(fn[5].weight) if _MODE == 0 else ops.pack_conv3x3_weight_f32(fn[5].weight),
                 g1=_f(fn[2].weight), b1=_f(fn[2].bias), g2=_f(fn[6].weight), b2=_f(fn[6].bias))
         return _packed(self, build)
 
     def _conv(self, x_bhwc, w):
         """3x3 'same' convolution on a channels-last [B,H,W,C] map: rfk_conv3x3_nhwc (tcgen05
-        implicit GEMM) in bf16 mode; the fp32 validation mode uses the library convolution."""
+        implicit GEMM) in bf16 mode, rfk_conv3x3_nhwc_f32 (SIMT fp32) in the fp32 validation mode."""
+        B, H, Wd, _ = x_bhwc.shape
         if _MODE == 0:
-            B, H, Wd, _ = x_bhwc.shape
             return ops.conv3x3(x_bhwc, w, _empty((B, H, Wd, w.shape[0]), torch.bfloat16, x_bhwc))
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            y = F.conv2d(x_bhwc.permute(0, 3, 1, 2), w, padding=1)
-        return y.permute(0, 2, 3, 1).contiguous()
+        return ops.conv3x3_f32(x_bhwc, w, _empty((B, H, Wd, w.shape[2]), torch.float32, x_bhwc))
 
     def _conv_rows(self, x_rows, w, halo):
         """Convolution of a row shard [B, Li, L, C]: `halo(x)` returns the shard with one neighbour row

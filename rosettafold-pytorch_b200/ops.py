@@ -24,7 +24,7 @@ __all__ = [
     "ACT_NONE", "ACT_RELU", "ACT_ELU", "EPI_STD", "EPI_BLOCKLN32",
     "gemm", "layernorm", "softmax_rows", "tied_att_symmetrize", "poswise_weight", "opm_prep",
     "pair2att_logits", "channel_stats", "instnorm_apply", "favor_attention", "convert_rows", "dist_mask_logits",
-    "conv3x3", "pack_conv3x3_weight",
+    "conv3x3", "pack_conv3x3_weight", "conv3x3_f32", "pack_conv3x3_weight_f32",
 ]
 
 
@@ -190,6 +190,11 @@ class _CudaBackend:
         B, H, L, Cin = x.shape
         _lib.check(self.lib.rfk_conv3x3_nhwc_hw(_ptr(x), _ptr(w_packed), _ptr(out), _dt(out), B, H, L, Cin,
                                                 out.shape[3], self._stream(x)), "rfk_conv3x3_nhwc_hw")
+
+    def conv3x3_f32(self, x, w_packed, out):
+        B, H, L, Cin = x.shape
+        _lib.check(self.lib.rfk_conv3x3_nhwc_f32(_ptr(x), _ptr(w_packed), _ptr(out), B, H, L, Cin, out.shape[3],
+                                                 self._stream(x)), "rfk_conv3x3_nhwc_f32")
 
     def convert_rows(self, x, out):
         _lib.check(self.lib.rfk_convert_rows(_ptr(x), _dt(x), x.stride(0), _ptr(out), _dt(out),
@@ -525,6 +530,26 @@ def conv3x3(x, w_packed, out):
         raise ValueError("conv3x3: bad output shape")
     with _Timed("conv3x3", 2.0 * x.shape[0] * x.shape[1] * x.shape[2] * 9 * x.shape[3] * Cout):
         _call("conv3x3", x, w_packed, out)
+    return out
+
+
+def pack_conv3x3_weight_f32(w: torch.Tensor) -> torch.Tensor:
+    """nn.Conv2d weight [Cout, Cin, 3, 3] -> f32 [9, Cin, Cout] (tap-major) for the fp32 validation-mode kernel."""
+    Cout, Cin = w.shape[:2]
+    return w.detach().float().permute(2, 3, 1, 0).reshape(9, Cin, Cout).contiguous()
+
+
+def conv3x3_f32(x, w_packed, out):
+    """fp32 validation-mode 3x3 'same' convolution: x f32 [B,H,W,Cin], w_packed from pack_conv3x3_weight_f32,
+    out f32 [B,H,W,Cout], all contiguous."""
+    if x.dim() != 4 or not x.is_contiguous() or x.dtype != torch.float32:
+        raise ValueError("conv3x3_f32: x must be contiguous f32 [B,H,W,C]")
+    if w_packed.dim() != 3 or w_packed.shape[0] != 9 or w_packed.shape[1] != x.shape[3] or w_packed.dtype != torch.float32 \
+            or not w_packed.is_contiguous():
+        raise ValueError("conv3x3_f32: w_packed must come from pack_conv3x3_weight_f32 for this channel count")
+    if tuple(out.shape) != (*x.shape[:3], w_packed.shape[2]) or not out.is_contiguous() or out.dtype != torch.float32:
+        raise ValueError("conv3x3_f32: bad output")
+    _call("conv3x3_f32", x, w_packed, out)
     return out
 
 
