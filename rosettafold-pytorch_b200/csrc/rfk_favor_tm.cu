@@ -22,12 +22,11 @@
 //   relu kernel  K(t,c)*, read-out of ctx, Q(t,c)*;
 //   softmax      KMAX(t,c)*, K(t,c)*, read-out, then per tile QMAX(t,c)*, Q(t,c)*   (stabiliser passes).
 //
-// Roles (19 warps):
-//   warp 0 lane 0  TMA producer: K/V/Q tiles into a 5-slot ring + an L2 prefetch cursor 6 tiles ahead
-//   warp 1         U issuer: the projection MMAs of every job, as far ahead as the two U slots allow
-//   warp 2         consumer issuer: context / output MMAs (A from TMEM); for the stabiliser jobs it only
-//                  hands the U slot back
-//   warps 3..18    16 feature warps, all on every job: warp (lane group lg = warp % 4, column quarter cq) owns
+// Roles (18 warps):
+//   warp 0 lane 0  TMA producer: K/V/Q tiles into a 5-slot ring + an L2 prefetch cursor 8 tiles ahead
+//   warp 1         MMA issuer: per job one burst = the context / output MMAs of job j (A from TMEM) followed by
+//                  the projection of job j + 2 into the same U slot (same-thread issue order hands the slot on)
+//   warps 2..17    16 feature warps, all on every job: warp (lane group lg = warp % 4, column quarter cq) owns
 //                  32 lanes x 32 accumulator columns: tcgen05.ld x32 -> feature map -> 16 packed words ->
 //                  tcgen05.st x16 over the first half of its own columns (no warp ever writes columns another
 //                  warp still has to read). MMA k-step s (16 features / tokens) therefore reads A at column
@@ -49,10 +48,8 @@ namespace rfk {
 namespace {
 
 constexpr int kFeatWarps = 16;
-constexpr int kGroupWarps = 4;  // warps per feature group (one per TMEM lane group)
-constexpr int kSlots = 4;       // U slots of 64 columns = feature groups
 constexpr int kFeatThreads = 32 * kFeatWarps;
-constexpr int kThreads = 32 * (3 + kFeatWarps);  // TMA producer, two MMA issuers, feature warps
+constexpr int kThreads = 32 * (2 + kFeatWarps);  // TMA producer, MMA issuer, feature warps
 constexpr int kMP = 272;     // padded feature count
 constexpr int kMRows = 384;  // omega rows in shared memory (3 chunks x 128 lanes)
 constexpr int kTile = 128;   // tokens per tile
@@ -197,9 +194,8 @@ __device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
   return d;
 }
 
-// Walks the PASSES of one CTA in issue order: item -> pass (kind, tile t). A key-side pass (key max / keys) has 6
-// half-jobs (chunk c = sub / 2, token half h = sub % 2), a query-side pass (query max / queries) has 5 (64-feature
-// group f = sub; f = 4 holds the last 16 features). The iterator also mirrors the producer's ring allocation (the
+// Walks the PASSES of one CTA in issue order: item -> pass (kind, tile t); every pass has three jobs (feature
+// chunks c = 0, 1, 2 of 128 | 128 | 16 features). The iterator also mirrors the producer's ring allocation (the
 // producer loads tiles in exactly this order), so the pass knows the ring slots of its tiles.
 constexpr int kPassM = 0, kPassK = 1, kPassX = 2, kPassQ = 3;  // key max, keys, query max, queries
 struct PassInfo {
@@ -207,7 +203,7 @@ struct PassInfo {
   bool valid;
   uint32_t a_slot, a_par;  // the pass's K (key side) or Q (query side) tile
   uint32_t v_slot, v_par;  // the pass's V tile (kPassK)
-  uint32_t j0;             // running index of the pass's first half-job (slot = j % 4)
+  uint32_t j0;             // running index of the pass's first job (U slot = j % 2)
   __device__ bool key_side() const { return kind == kPassM || kind == kPassK; }
 };
 template <int KIND>
@@ -238,7 +234,7 @@ struct PassIter {
     if (!(KIND == 0 && x.kind == kPassQ)) take(x.a_slot, x.a_par);  // a softmax Q pass reuses its QMAX tile
     if (x.kind == kPassK) take(x.v_slot, x.v_par);
     x.j0 = j;
-    j += x.key_side() ? 6u : 5u;
+    j += 3u;
     if (++ps == P) { ps = 0; item += istride; }
     last = x;
     return x;
@@ -255,13 +251,13 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t bars = base + kOffBar;
   auto bar_tfull = [&](uint32_t s) { return bars + 8u * s; };            // [kRing]
   auto bar_tempty = [&](uint32_t s) { return bars + 40u + 8u * s; };     // [kRing]
-  auto bar_ufull = [&](uint32_t s) { return bars + 80u + 8u * s; };      // [4] projection accumulator of the slot complete
-  auto bar_fready = [&](uint32_t s) { return bars + 112u + 8u * s; };    // [4] features of the slot stored (or maxima taken)
-  auto bar_d3full = [&](uint32_t s) { return bars + 144u + 8u * s; };
-  auto bar_d3free = [&](uint32_t s) { return bars + 160u + 8u * s; };
-  const uint32_t bar_ctxfull = bars + 176u, bar_ctxready = bars + 184u;
-  auto bar_issued = [&](uint32_t s) { return bars + 192u + 8u * s; };    // [4] consumer MMAs of the slot's job have been issued
-  const uint32_t tmem_slot = bars + 224u;
+  auto bar_ufull = [&](uint32_t s) { return bars + 80u + 8u * s; };      // U accumulator of the slot complete
+  auto bar_ufree = [&](uint32_t s) { return bars + 96u + 8u * s; };      // slot may be overwritten by the next U
+  auto bar_fready = [&](uint32_t s) { return bars + 112u + 8u * s; };    // features of the slot stored (or max taken)
+  auto bar_d3full = [&](uint32_t s) { return bars + 128u + 8u * s; };
+  auto bar_d3free = [&](uint32_t s) { return bars + 144u + 8u * s; };
+  const uint32_t bar_ctxfull = bars + 160u, bar_ctxready = bars + 168u;
+  const uint32_t tmem_slot = bars + 176u;
   float* scratch = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + kOffScratch);
   float* part = scratch;          // [4][128] partial |x|^2 of the four channel quarters
   float* rmaxs = scratch + 512;   // [4][128] partial row maxima
@@ -278,12 +274,10 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_init(bar_tfull(s), 1);
       mbar_init(bar_tempty(s), 1);
     }
-    for (uint32_t s = 0; s < kSlots; ++s) {
-      mbar_init(bar_ufull(s), 1);
-      mbar_init(bar_fready(s), kGroupWarps);
-      mbar_init(bar_issued(s), 1);
-    }
     for (uint32_t s = 0; s < 2; ++s) {
+      mbar_init(bar_ufull(s), 1);
+      mbar_init(bar_ufree(s), 1);
+      mbar_init(bar_fready(s), kFeatWarps);
       mbar_init(bar_d3full(s), 1);
       mbar_init(bar_d3free(s), kFeatWarps);
     }
@@ -325,14 +319,12 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  {
-    // all 512 columns are allocated, so the allocation can only start at column 0: the TMEM addresses below are
-    // compile-time constants (keeps them in uniform registers for the issuers). Trap if that ever fails to hold.
-    uint32_t tmem_base;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-    if (tmem_base != 0u) __trap();
-  }
-  constexpr uint32_t tmem = 0u;
+  uint32_t tmem;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+
+  using C0 = std::integral_constant<int, 0>;
+  using C1 = std::integral_constant<int, 1>;
+  using C2 = std::integral_constant<int, 2>;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -384,163 +376,154 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         cur_next(ld);
       }
     }
-  } else if (warp == 1 || warp == 2) {
-    // =================== MMA issuers ===================
-    // An issuer is a scalar program on the critical path of the whole CTA (~5 cycles per SASS instruction, ~45
-    // instructions per group of four MMAs), so the work of a half-job is split over two warps and the job nest is
-    // unrolled per pass with compile-time sub-job indices:
-    //   warp 1  consumer issuer: context / output MMAs of job j (A = the features in U slot j % 4), in job order
-    //   warp 2  projection issuer: U of job j + 4 into the same slot
-    // Slot hand-over without a completion round trip: the tensor pipe executes MMAs in issue order, so the
-    // projection may be ISSUED as soon as the consumer MMAs of the slot's previous job have been issued (they read
-    // their A operand out of the slot before the projection's write can start). Warp 1 therefore signals "issued"
-    // with a plain mbarrier arrive right behind its MMAs instead of a tcgen05.commit. All 32 lanes run the
-    // warp-uniform control flow, one elected lane issues.
-    using S0 = std::integral_constant<int, 0>;
-    using S1 = std::integral_constant<int, 1>;
-    using S2 = std::integral_constant<int, 2>;
-    using S3 = std::integral_constant<int, 3>;
-    using S4 = std::integral_constant<int, 4>;
-    using S5 = std::integral_constant<int, 5>;
+  } else if (warp == 1) {
+    // =================== MMA issuer ===================
+    // ONE warp issues every MMA, in BURSTS of up to 12: the consumer MMAs of job j (A = the features in U slot
+    // j % 2) followed by the projection of job j + 2 into the same slot. tcgen05.mma instructions of one thread
+    // execute in issue order, so the projection cannot overwrite the slot before the consumer MMAs issued ahead of
+    // it have read their A operand out of it: the slot is handed on without a commit / mbarrier round trip (across
+    // issuing threads that order is NOT guaranteed: versions with separate consumer / projection issuer warps were
+    // faster but produced NaNs once the bursts got longer; profiles/r02_favor_notes.md). Measured issue cost
+    // (tools/micro/umma_bench.cu): ~300 cycles per burst (mbarrier try_wait, elect / reconvergence) + 50-70 cycles
+    // per MMA in real code (operand descriptors into uniform registers), against 30-70 cycles of execution per
+    // 128 x (64..128) x 16 MMA: long bursts keep the fixed part small.
+    // The job nest is unrolled per pass (three jobs); all 32 lanes run the warp-uniform control flow, one elected
+    // lane issues.
+    const uint64_t d_omega = umma_desc_sw128(s_omega);  // + c * 1024 + 2 k
+    const uint64_t d_ring = umma_desc_sw128(s_ring);    // + slot * 1024 + 2 k
+    const uint64_t d_ctx = umma_desc_sw128(s_ctx);      // + slab * 640 + 2 k
+    uint32_t nD3 = 0, d3u0 = 0, d3u1 = 0;               // output tiles started / fills per D3 slot
+    uint32_t nItems = 0;
+    auto wait_d3_region = [&](uint32_t s) {
+      const uint32_t uses = s ? d3u1 : d3u0;
+      if (uses > 0) mbar_wait(bar_d3free(s), (uses - 1u) & 1u);
+    };
+    // projection of job CU of pass `u` (elected lane): key side U^T[m, tok] = Omega_c . X^T (features on the lanes);
+    // query side U[tok, m] = X . Omega_c^T (16 columns for chunk 2)
+    auto issue_u = [&](const PassInfo& u, auto cu_c) {
+      constexpr int CU = decltype(cu_c)::value;
+      const uint32_t us = (u.j0 + CU) & 1u;
+      const bool key = u.key_side();
+      const uint64_t dx = d_ring + (uint64_t)(u.a_slot * 1024u);
+      const uint64_t dw = d_omega + (uint64_t)(CU * 1024);
+      const uint64_t da = key ? dw : dx;
+      const uint64_t db = key ? dx : dw;
+      const uint32_t idesc = (!key && CU == 2) ? umma_idesc_bf16(128, 16) : umma_idesc_bf16(128, 128);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem + kColU + us * 128u, da + 2 * k, db + 2 * k, idesc, k > 0);
+      umma_commit(bar_ufull(us));
+      // the tile's last projection: hand the ring slot back (a softmax QMAX pass keeps its tile for the Q pass)
+      if (CU == 2 && u.kind != kPassX) umma_commit(bar_tempty(u.a_slot));
+    };
+    // burst C of pass `c`: consumer MMAs of its job C, then the projection of the job two ahead (pass `u`, job CU)
+    auto burst = [&](const PassInfo& c, const PassInfo& u, auto c_c, auto cu_c) {
+      constexpr int C = decltype(c_c)::value;
+      constexpr int CU = decltype(cu_c)::value;
+      const uint32_t jc = c.j0 + C;
+      const uint32_t fs = jc & 1u;
+      const uint32_t par = (jc >> 1) & 1u;
+      const uint32_t ds = nD3 & 1u;
+      // A operand of k-step k inside the U slot: the feature warp of column quarter k / 2 wrote its 16 packed
+      // columns at the start of its own 32-column range
+      const uint32_t a0 = tmem + kColU + fs * 128u;
+      if (c.kind == kPassK) {
+        if (c.t == 0 && C < 2) wait_d3_region((uint32_t)C);  // ctx block c aliases D3[c]
+        if (C == 0) mbar_wait(bar_tfull(c.v_slot), c.v_par);
+      } else if (c.kind == kPassQ && C == 0) {
+        if (c.t == 0) mbar_wait(bar_ctxready, nItems & 1u);
+        wait_d3_region(ds);
+      }
+      if (u.valid && CU == 0 && !(KIND == 0 && u.kind == kPassQ)) mbar_wait(bar_tfull(u.a_slot), u.a_par);
+      mbar_wait(bar_fready(fs), par);
+      tc_fence_after();
+      if (elect_one()) {
+        if (c.kind == kPassK) {
+          // ctx^T_c[128 m x 80] (+)= k'^T (A, TMEM, K = tokens) . [V | 1] (B, MN-major; second MN chunk = cslab)
+          const uint64_t dbv = desc_mn_sw128(s_ring + c.v_slot * kSlabBytes, s_cslab - s_ring - c.v_slot * kSlabBytes);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16_ts(tmem + kColCtx + 80u * C, a0 + 32u * (k >> 1) + 8u * (k & 1), dbv + 128 * k, idesc_bf16_major(128, 80, 0, 1),
+                         (c.t > 0 || k > 0));
+          if (C == 2) {
+            umma_commit(bar_tempty(c.v_slot));
+            if (c.t == nt - 1) umma_commit(bar_ctxfull);
+          }
+        } else if (c.kind == kPassQ) {
+          // out|den [128 tok x 80] (+)= q'_c (A, TMEM, K = features) . ctx_c (B, K-major over m)
+          const uint64_t db = d_ctx + (uint64_t)(2 * C * 640);
+          constexpr int NK = C == 2 ? 1 : 8;
+#pragma unroll
+          for (int k = 0; k < NK; ++k)
+            umma_bf16_ts(tmem + kColCtx + 80u * ds, a0 + 32u * (k >> 1) + 8u * (k & 1), db + (k >> 2) * 640 + 2 * (k & 3),
+                         umma_idesc_bf16(128, 80), (C > 0 || k > 0));
+          if (C == 2) umma_commit(bar_d3full(ds));
+        }
+        // (stabiliser passes: the feature warps have taken their maxima, nothing to consume)
+        if (u.valid) issue_u(u, cu_c);
+      }
+      __syncwarp();
+    };
     PassIter<KIND> it;
     it.init(blockIdx.x, p.items, istride, nt);
-    if (warp == 2) {
-      const uint64_t d_omega = umma_desc_sw128(s_omega);  // + (row / 8) * 64 [+ 2 k]
-      const uint64_t d_ring = umma_desc_sw128(s_ring);    // + slot * 1024 [+ (row / 8) * 64] [+ 2 k]
-      // projection of half-job SUB of pass `u`: key side U^T[m, tok] = Omega_c . X^T; query side U[tok, m] = X . Omega_f^T
-      auto issue_u = [&](const PassInfo& u, auto sub_c) {
-        constexpr int SUB = decltype(sub_c)::value;
-        const bool key = u.key_side();
-        const uint32_t ju = u.j0 + SUB;
-        const uint32_t us = ju & (kSlots - 1);
-        if (ju >= kSlots) mbar_wait(bar_issued(us), ((ju >> 2) - 1u) & 1u);  // previous job of the slot has been issued
-        if (SUB == 0 && !(KIND == 0 && u.kind == kPassQ)) mbar_wait(bar_tfull(u.a_slot), u.a_par);
-        tc_fence_after();
-        const uint64_t dx = d_ring + (uint64_t)(u.a_slot * 1024u);
-        const uint64_t da = key ? d_omega + (uint64_t)((SUB >> 1) * 1024) : dx;
-        const uint64_t db = key ? dx + (uint64_t)((SUB & 1) * 512) : d_omega + (uint64_t)(SUB * 512);
-        const uint32_t idesc = (!key && SUB == 4) ? umma_idesc_bf16(128, 16) : umma_idesc_bf16(128, 64);
-        const bool release = key ? SUB == 5 : (SUB == 4 && u.kind == kPassQ);
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(kColU + us * 64u, da + 2 * k, db + 2 * k, idesc, k > 0);
-          umma_commit(bar_ufull(us));
-          if (release) umma_commit(bar_tempty(u.a_slot));
-        }
-        __syncwarp();
-      };
-      for (PassInfo u = it.next(); u.valid; u = it.next()) {
-        issue_u(u, S0{}); issue_u(u, S1{}); issue_u(u, S2{}); issue_u(u, S3{}); issue_u(u, S4{});
-        if (u.key_side()) issue_u(u, S5{});
+    PassInfo cur = it.next(), nxt = it.next();
+    if (cur.valid) {  // prologue: the first two projections
+      mbar_wait(bar_tfull(cur.a_slot), cur.a_par);
+      tc_fence_after();
+      if (elect_one()) {
+        issue_u(cur, C0{});
+        issue_u(cur, C1{});
       }
-    } else {
-      const uint64_t d_ctx = umma_desc_sw128(s_ctx);  // + slab * 640 [+ 2 k]
-      uint32_t nD3 = 0, d3u0 = 0, d3u1 = 0;           // output tiles started / fills per D3 slot
-      uint32_t nItems = 0;
-      auto wait_d3_region = [&](uint32_t s) {
-        const uint32_t uses = s ? d3u1 : d3u0;
-        if (uses > 0) mbar_wait(bar_d3free(s), (uses - 1u) & 1u);
-      };
-      // consumer MMAs of half-job SUB of pass `c`: A = packed features at the start of its U slot (k-step k at column 8 k)
-      auto consume = [&](const PassInfo& c, auto sub_c) {
-        constexpr int SUB = decltype(sub_c)::value;
-        const uint32_t jc = c.j0 + SUB;
-        const uint32_t fs = jc & (kSlots - 1);
-        const uint32_t par = (jc >> 2) & 1u;
-        const uint32_t a0 = kColU + fs * 64u;
-        if (c.kind == kPassK) {
-          // ctx^T_c[128 m x 80] (+)= k'^T (A, TMEM, K = 64 tokens of half h) . [V | 1] (B, MN-major)
-          constexpr int C = SUB >> 1, h = SUB & 1;
-          if (c.t == 0 && h == 0 && C < 2) wait_d3_region((uint32_t)C);  // ctx block c aliases D3[c]
-          if (SUB == 0) mbar_wait(bar_tfull(c.v_slot), c.v_par);
-          mbar_wait(bar_fready(fs), par);
-          tc_fence_after();
-          const uint64_t db = desc_mn_sw128(s_ring + c.v_slot * kSlabBytes, s_cslab - s_ring - c.v_slot * kSlabBytes) + (uint64_t)(h * 512);
-          const bool first = c.t == 0 && h == 0;
-          if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_ts(kColCtx + 80u * C, a0 + 8u * k, db + 128 * k, idesc_bf16_major(128, 80, 0, 1), (!first || k > 0));
-            mbar_arrive(bar_issued(fs));
-            if (SUB == 5) {
-              umma_commit(bar_tempty(c.v_slot));
-              if (c.t == nt - 1) umma_commit(bar_ctxfull);
-            }
-          }
-          __syncwarp();
-        } else if (c.kind == kPassQ) {
-          // out|den [128 tok x 80] (+)= q' (A, TMEM, K = 64 features of group f) . ctx slab f (B, K-major over m)
-          const uint32_t ds = nD3 & 1u;
-          if (SUB == 0) {
-            if (c.t == 0) {
-              mbar_wait(bar_ctxready, nItems & 1u);
-              ++nItems;
-            }
-            wait_d3_region(ds);
-          }
-          mbar_wait(bar_fready(fs), par);
-          tc_fence_after();
-          const uint64_t db = d_ctx + (uint64_t)(SUB * 640);
-          if (elect_one()) {
-            if (SUB < 4) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16_ts(kColCtx + 80u * ds, a0 + 8u * k, db + 2 * k, umma_idesc_bf16(128, 80), (SUB > 0 || k > 0));
-              mbar_arrive(bar_issued(fs));
-            } else {
-              umma_bf16_ts(kColCtx + 80u * ds, a0, db, umma_idesc_bf16(128, 80), 1u);
-              mbar_arrive(bar_issued(fs));
-              umma_commit(bar_d3full(ds));
-            }
-          }
-          __syncwarp();
-          if (SUB == 4) {
-            if (ds) ++d3u1; else ++d3u0;
-            ++nD3;
-          }
-        } else {
-          // stabiliser job: the feature group has taken its maxima, the slot is free again
-          mbar_wait(bar_fready(fs), par);
-          if (elect_one()) mbar_arrive(bar_issued(fs));
-          __syncwarp();
-        }
-      };
-      for (PassInfo c = it.next(); c.valid; c = it.next()) {
-        consume(c, S0{}); consume(c, S1{}); consume(c, S2{}); consume(c, S3{}); consume(c, S4{});
-        if (c.key_side()) consume(c, S5{});
+      __syncwarp();
+    }
+    while (cur.valid) {
+      burst(cur, cur, C0{}, C2{});
+      burst(cur, nxt, C1{}, C0{});
+      burst(cur, nxt, C2{}, C1{});
+      if (cur.kind == kPassQ) {
+        if (cur.t == 0) ++nItems;
+        if (nD3 & 1u) ++d3u1; else ++d3u0;
+        ++nD3;
       }
+      cur = nxt;
+      nxt = it.next();
     }
   } else {
     // =================== feature / epilogue warps ===================
-    // Four groups of four warps; group g owns U slot g, i.e. the jobs j = g (mod 4); warp (g, lg) owns TMEM lanes
-    // [32 lg, 32 lg + 32) of that slot: 64 accumulator columns in two 32-column steps, packed in place to columns
-    // [0, 32). Shared work (tile norms, context read-out, out/den epilogue) is split over all 16 warps with g as the
-    // channel / column quarter.
-    const int fw = warp - 3;         // 0..15
+    const int fw = warp - 2;         // 0..15
     const int lg = warp & 3;         // TMEM lane group this warp may touch
-    const int g = fw >> 2;           // feature group = U slot
+    const int cq = fw >> 2;          // column quarter of the U slot owned by this warp
     const int row = lg * 32 + lane;  // TMEM lane: token row (query side) / feature row of the chunk (key side)
     const uint32_t t_lane = ((uint32_t)(lg * 32) << 16);
     constexpr float kLog2e = 1.4426950408889634f;
     constexpr float kEps = KIND == 0 ? 1e-4f : 1e-3f;
     const uint32_t eps2 = pack_bf16x2(kEps, kEps);
-    const uint32_t ubase = tmem + t_lane + kColU + 64u * (uint32_t)g;
+    const uint32_t ubase = tmem + t_lane + kColU + 32u * (uint32_t)cq;  // + us * 128
 
-    uint32_t nMine = 0;  // jobs of this group done (parity of its slot's barriers)
+    uint32_t nJ = 0;  // jobs processed (job parity = U slot)
     uint32_t nItems = 0, nD3 = 0, tile_seq = 0;
-    uint32_t j = 0;      // running job index of the CTA
     float gmax = 0.f, sub = 0.f;
+    const int64_t last_item = blockIdx.x + ((p.items - 1 - blockIdx.x) / istride) * istride;
 
-    auto wait_u = [&]() {
-      mbar_wait(bar_ufull((uint32_t)g), nMine & 1u);
+    uint32_t raw[32];
+    // wait for the accumulator of job nJ and issue its TMEM loads. Q2: the job is a query-side chunk 2
+    // (16 feature columns, read by the cq == 0 warps only)
+    auto prefetch = [&](bool q2) {
+      const uint32_t us = nJ & 1u;
+      mbar_wait(bar_ufull(us), (nJ >> 1) & 1u);
       tc_fence_after();
+      if (!q2) {
+        tmem_ld_32x32p(ubase + us * 128u, raw);
+      } else if (cq == 0) {
+        tmem_ld_32x16p(ubase + us * 128u, raw);
+      }
     };
+    // publish: features of job nJ are in TMEM (or its maxima taken) -> the consumer issuer may proceed
     auto publish = [&](bool stored) {
       if (stored) tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_fready((uint32_t)g));
-      ++nMine;
+      if (lane == 0) mbar_arrive(bar_fready(nJ & 1u));
+      ++nJ;
     };
     // two accumulator values -> one packed bf16x2 feature pair; s0 / s1: exponent offsets (softmax kernel)
     auto feat2 = [&](uint32_t r0, uint32_t r1, float s0, float s1) -> uint32_t {
@@ -550,121 +533,103 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       return add_bf16x2(cvt_relu_bf16x2(x0, x1), eps2);
     };
 
-    // ---- key-side job (chunk C, token half h): this thread holds feature row 128 C + row x 64 tokens ----
-    auto key_feat_job = [&](int C, int h, int ntok) {
-      wait_u();
+    // ---- key-side job: this thread holds feature row (128 C + row) x tokens [32 cq, 32 cq + 32) of the tile ----
+    // ntok: valid tokens of the tile; next_q2: shape of the following job
+    auto key_feat_job = [&](int C, int ntok, bool has_next, bool next_q2) {
+      const uint32_t us = nJ & 1u;
+      tmem_ld_wait();
       const bool row_ok = 128 * C + row < p.m;
-      uint32_t raw[32], pk[16];
-      tmem_ld_32x32p(ubase, raw);
+      const int lim = ntok - 32 * cq;  // token columns >= lim are padding (only in a ragged last tile)
+      uint32_t pk[16];
+      if (KIND == 0) {
 #pragma unroll
-      for (int s2 = 0; s2 < 2; ++s2) {
-        tmem_ld_wait();
-        const int lim = ntok - 64 * h - 32 * s2;  // token columns >= lim are padding (ragged last tile)
-        if (KIND == 0) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 s4 = *reinterpret_cast<const float4*>(ssub + 64 * h + 32 * s2 + 4 * q);
-            pk[2 * q] = feat2(raw[4 * q], raw[4 * q + 1], s4.x, s4.y);
-            pk[2 * q + 1] = feat2(raw[4 * q + 2], raw[4 * q + 3], s4.z, s4.w);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = feat2(raw[2 * i], raw[2 * i + 1], 0.f, 0.f);
+        for (int q = 0; q < 8; ++q) {
+          const float4 s4 = *reinterpret_cast<const float4*>(ssub + 32 * cq + 4 * q);
+          pk[2 * q] = feat2(raw[4 * q], raw[4 * q + 1], s4.x, s4.y);
+          pk[2 * q + 1] = feat2(raw[4 * q + 2], raw[4 * q + 3], s4.z, s4.w);
         }
-        if (!row_ok) {
+      } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = 0u;
-        } else if (lim < 32) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (2 * i >= lim) pk[i] = 0u;
-            else if (2 * i + 1 >= lim) pk[i] &= 0x0000ffffu;
-          }
-        }
-        if (s2 == 0) tmem_ld_32x32p(ubase + 32u, raw);  // next 32 columns on their way while this half is stored
-        tmem_st_32x16(ubase + 16u * s2, pk);
+        for (int i = 0; i < 16; ++i) pk[i] = feat2(raw[2 * i], raw[2 * i + 1], 0.f, 0.f);
       }
+      if (!row_ok) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = 0u;
+      } else if (lim < 32) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (2 * i >= lim) pk[i] = 0u;
+          else if (2 * i + 1 >= lim) pk[i] &= 0x0000ffffu;
+        }
+      }
+      tmem_st_32x16(ubase + us * 128u, pk);
       publish(true);
+      if (has_next) prefetch(next_q2);
     };
     // ---- key-side stabiliser job (softmax kernel): max of the raw projections over valid rows / tokens ----
-    auto key_max_job = [&](int C, int h, int ntok, float& acc) {
-      wait_u();
+    auto key_max_job = [&](int C, int ntok, float& acc) {
+      tmem_ld_wait();
       const bool row_ok = 128 * C + row < p.m;
-      uint32_t raw[32];
+      const int lim = ntok - 32 * cq;
       float mx = -INFINITY;
-#pragma unroll
-      for (int s2 = 0; s2 < 2; ++s2) {
-        tmem_ld_32x32p(ubase + 32u * s2, raw);
-        tmem_ld_wait();
-        const int lim = ntok - 64 * h - 32 * s2;
+      if (row_ok) {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           if (i < lim) mx = fmaxf(mx, __uint_as_float(raw[i]));
       }
-      if (row_ok) acc = fmaxf(acc, mx);
-      publish(false);
-    };
-    // ---- query-side job (feature group f): this thread holds token row `row` x features [64 f, 64 f + 64) ----
-    auto query_feat_job = [&](int f) {
-      wait_u();
-      if (f < 4) {
-        uint32_t raw[32], pk[16];
-        tmem_ld_32x32p(ubase, raw);
-#pragma unroll
-        for (int s2 = 0; s2 < 2; ++s2) {
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = feat2(raw[2 * i], raw[2 * i + 1], sub, sub);
-          if (s2 == 0) tmem_ld_32x32p(ubase + 32u, raw);
-          tmem_st_32x16(ubase + 16u * s2, pk);
-        }
-      } else {
-        uint32_t raw[16], pk[8];
-        tmem_ld_32x16p(ubase, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) pk[i] = feat2(raw[2 * i], raw[2 * i + 1], sub, sub);
-        tmem_st_32x8(ubase, pk);
-      }
-      publish(true);
-    };
-    // ---- query-side stabiliser job (softmax kernel): per-row max over the valid feature columns ----
-    auto query_max_job = [&](int f, float& acc) {
-      wait_u();
-      float mx = -INFINITY;
-      if (f < 4) {
-        uint32_t raw[32];
-#pragma unroll
-        for (int s2 = 0; s2 < 2; ++s2) {
-          tmem_ld_32x32p(ubase + 32u * s2, raw);
-          tmem_ld_wait();
-          const int lim = p.m - (64 * f + 32 * s2);
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i < lim) mx = fmaxf(mx, __uint_as_float(raw[i]));
-        }
-      } else {
-        uint32_t raw[16];
-        tmem_ld_32x16p(ubase, raw);
-        tmem_ld_wait();
-        const int lim = p.m - 256;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (i < lim) mx = fmaxf(mx, __uint_as_float(raw[i]));
-      }
       acc = fmaxf(acc, mx);
       publish(false);
+      prefetch(false);  // a key-side job always follows
+    };
+    // ---- query-side job: this thread holds token row `row` x features [128 C + 32 cq, + 32) ----
+    auto query_feat_job = [&](auto cc, bool has_next, bool next_q2) {
+      constexpr int C = decltype(cc)::value;
+      const uint32_t us = nJ & 1u;
+      if (C < 2) {
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = feat2(raw[2 * i], raw[2 * i + 1], sub, sub);
+        tmem_st_32x16(ubase + us * 128u, pk);
+        publish(true);
+      } else if (cq == 0) {
+        tmem_ld_wait();
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = feat2(raw[2 * i], raw[2 * i + 1], sub, sub);
+        tmem_st_32x8(ubase + us * 128u, pk);
+        publish(true);
+      } else {
+        publish(false);
+      }
+      if (has_next) prefetch(next_q2);
+    };
+    // ---- query-side stabiliser job (softmax kernel): per-row max over the valid feature columns ----
+    auto query_max_job = [&](auto cc, float& acc) {
+      constexpr int C = decltype(cc)::value;
+      constexpr int NC = C < 2 ? 32 : 16;
+      if (C < 2 || cq == 0) {
+        tmem_ld_wait();
+        const int lim = p.m - (128 * C + 32 * cq);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+          if (i < lim) mx = fmaxf(mx, __uint_as_float(raw[i]));
+        acc = fmaxf(acc, mx);
+      }
+      publish(false);
+      prefetch(C == 1);  // QMAX chunk 2 follows chunk 1; the query chunk 0 follows QMAX chunk 2
     };
 
-    // 0.5 * dn^2 * |x|^2 of token `row` of ring tile a_seq (softmax kernel): the four groups sum 16 channels each,
-    // the partials meet in shared memory
+    // 0.5 * dn^2 * |x|^2 of token `row` of ring tile a_seq (softmax kernel): the four warps of a lane group sum
+    // 16 channels each, the partials meet in shared memory
     auto row_diag = [&](uint32_t a_seq) {
       mbar_wait(bar_tfull(a_seq % kRing), (a_seq / kRing) & 1u);  // TMA bytes visible to this thread
       const uint32_t tile = s_ring + (a_seq % kRing) * kSlabBytes;
       float s = 0.f;
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const uint4 v = ld_shared_v4(tile + sw128_offset(row, g * 16 + q * 8));
+      for (int j = 0; j < 2; ++j) {
+        const uint4 v = ld_shared_v4(tile + sw128_offset(row, cq * 16 + j * 8));
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -673,19 +638,19 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           s = fmaf(b, b, s);
         }
       }
-      part[g * 128 + row] = s;
+      part[cq * 128 + row] = s;
       named_bar_sync(1, kFeatThreads);
       return (part[row] + part[128 + row] + part[256 + row] + part[384 + row]) * (0.5f * 0.125f);
     };
 
-    // out/den epilogue of one query tile: warp (g, lg) stores channels [16 g, 16 g + 16) of its 32 tokens
+    // out/den epilogue of one query tile: warp (lg, cq) stores channels [16 cq, 16 cq + 16) of its 32 tokens
     auto epilogue = [&](int64_t item, int t) {
       const uint32_t ds = nD3 & 1u;
       mbar_wait(bar_d3full(ds), (nD3 >> 1) & 1u);
       tc_fence_after();
       uint32_t rd[16], r0[16];
       tmem_ld_32x16p(tmem + t_lane + kColCtx + 80u * ds + 64, rd);  // column 64 = normaliser
-      tmem_ld_32x16p(tmem + t_lane + kColCtx + 80u * ds + 16u * (uint32_t)g, r0);
+      tmem_ld_32x16p(tmem + t_lane + kColCtx + 80u * ds + 16u * (uint32_t)cq, r0);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -693,11 +658,11 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       ++nD3;
       if (t * kTile + row < p.tokens) {
         const int h = (int)(item % p.heads);
-        const int64_t gi = item / p.heads;
-        const int64_t g0 = gi % p.G0, g1 = gi / p.G0;
+        const int64_t g = item / p.heads;
+        const int64_t g0 = g % p.G0, g1 = g / p.G0;
         const float inv = 1.f / __uint_as_float(rd[0]);
         uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + g1 * p.ogs1 + g0 * p.ogs0 +
-                                             (int64_t)(t * kTile + row) * p.ots + h * 64 + 16 * g);
+                                             (int64_t)(t * kTile + row) * p.ots + h * 64 + 16 * cq);
         uint4 w;
         w.x = pack_bf16x2(__uint_as_float(r0[0]) * inv, __uint_as_float(r0[1]) * inv);
         w.y = pack_bf16x2(__uint_as_float(r0[2]) * inv, __uint_as_float(r0[3]) * inv);
@@ -712,7 +677,7 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     };
 
-    auto mine = [&]() { return (int)(j & (kSlots - 1)) == g; };
+    if ((int64_t)blockIdx.x < p.items) prefetch(false);
     for (int64_t item = blockIdx.x; item < p.items; item += istride) {
       if (KIND == 0) {
         // ---- key stabiliser: global max of Omega'.K^T over the valid features / tokens ----
@@ -720,8 +685,9 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int t = 0; t < nt; ++t) {
           ++tile_seq;
           const int ntok = min(kTile, p.tokens - t * kTile);
-          for (int s = 0; s < 6; ++s, ++j)
-            if (mine()) key_max_job(s >> 1, s & 1, ntok, kmx);
+          key_max_job(0, ntok, kmx);
+          key_max_job(1, ntok, kmx);
+          key_max_job(2, ntok, kmx);
         }
         kmx = warp_max(kmx);
         if (lane == 0) red[fw] = kmx;
@@ -730,25 +696,27 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
         for (int i = 1; i < kFeatWarps; ++i) gmax = fmaxf(gmax, red[i]);
       }
-      // ---- keys: k'^T half-jobs feed the context MMAs ----
+      // ---- keys: k'^T chunks feed the context MMAs ----
       for (int t = 0; t < nt; ++t) {
         if (KIND == 0) {
           const float dg = row_diag(tile_seq);
-          if (g == 0) ssub[row] = (dg + gmax) * kLog2e;
+          if (cq == 0) ssub[row] = (dg + gmax) * kLog2e;
           named_bar_sync(1, kFeatThreads);
         }
         tile_seq += 2;
         const int ntok = min(kTile, p.tokens - t * kTile);
-        for (int s = 0; s < 6; ++s, ++j)
-          if (mine()) key_feat_job(s >> 1, s & 1, ntok);
+        key_feat_job(0, ntok, true, false);
+        key_feat_job(1, ntok, true, false);
+        key_feat_job(2, ntok, true, false);
       }
-      // ---- context read-out: TMEM ctx^T blocks -> bf16 K-major smem. Warp (g, lg) converts columns
-      //      [16 g, 16 g + 16) of blocks 0 and 1 for its 32 feature rows; the normaliser column 64 and the
-      //      16-row block 2 are spread over the groups ----
+      // ---- context read-out: TMEM ctx^T blocks -> bf16 K-major smem. Warp (lg, cq) converts columns
+      //      [16 cq, 16 cq + 16) of blocks 0 and 1 for its 32 feature rows; the normaliser column 64 and the
+      //      16-row block 2 are spread over the column quarters ----
       {
         mbar_wait(bar_ctxfull, nItems & 1u);
         ++nItems;
         tc_fence_after();
+        tmem_ld_wait();  // the prefetch of the first query job is in flight: one wait covers all loads
         auto put = [&](int m, uint32_t n, float v) {
           const uint32_t mc = (uint32_t)m & 63u;
           st_shared_b16(s_ctx + (uint32_t)(m >> 6) * kCtxSlabBytes + (n >> 3) * 1024u + (n & 7u) * 128u +
@@ -758,26 +726,26 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
           uint32_t r[16];
-          tmem_ld_32x16p(tmem + t_lane + kColCtx + 80u * b + 16u * (uint32_t)g, r);
+          tmem_ld_32x16p(tmem + t_lane + kColCtx + 80u * b + 16u * (uint32_t)cq, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) put(128 * b + row, 16u * g + i, __uint_as_float(r[i]));
+          for (int i = 0; i < 16; ++i) put(128 * b + row, 16u * cq + i, __uint_as_float(r[i]));
         }
-        if (g < 2) {  // normaliser column of block g
+        if (cq < 2) {  // normaliser column of block cq
           uint32_t r[16];
-          tmem_ld_32x16p(tmem + t_lane + kColCtx + 80u * (uint32_t)g + 64u, r);
+          tmem_ld_32x16p(tmem + t_lane + kColCtx + 80u * (uint32_t)cq + 64u, r);
           tmem_ld_wait();
-          put(128 * g + row, 64u, __uint_as_float(r[0]));
+          put(128 * cq + row, 64u, __uint_as_float(r[0]));
         }
         if (lg == 0) {  // block 2: features 256..271 live in lanes 0..15
           uint32_t r[16], r2[16];
-          tmem_ld_32x16p(tmem + kColCtx + 160u + 16u * (uint32_t)g, r);
+          tmem_ld_32x16p(tmem + kColCtx + 160u + 16u * (uint32_t)cq, r);
           tmem_ld_32x16p(tmem + kColCtx + 160u + 64u, r2);
           tmem_ld_wait();
           if (lane < 16) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) put(256 + lane, 16u * g + i, __uint_as_float(r[i]));
-            if (g == 3) put(256 + lane, 64u, __uint_as_float(r2[0]));
+            for (int i = 0; i < 16; ++i) put(256 + lane, 16u * cq + i, __uint_as_float(r[i]));
+            if (cq == 3) put(256 + lane, 64u, __uint_as_float(r2[0]));
           }
         }
         fence_proxy_async_smem();
@@ -785,28 +753,27 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_ctxready);
       }
-      // ---- queries: q' jobs feed the output MMAs; the out/den epilogue of tile t runs behind this group's
-      //      first job of tile t+1 (no loss: its next projection cannot be issued before that tile is consumed) ----
+      // ---- queries: q' chunks feed the output MMAs; the out/den epilogue of tile t runs behind
+      //      the first job of tile t+1 ----
       bool pending = false;
       for (int t = 0; t < nt; ++t) {
+        const bool more = t + 1 < nt || item != last_item;  // another job follows this tile
         if (KIND == 0) {
           const float diag = row_diag(tile_seq);
           float rmx = -INFINITY;
-          for (int f = 0; f < 5; ++f, ++j)
-            if (mine()) query_max_job(f, rmx);
+          query_max_job(C0{}, rmx);
           if (pending) { epilogue(item, t - 1); pending = false; }
-          rmaxs[g * 128 + row] = rmx;
+          query_max_job(C1{}, rmx);
+          query_max_job(C2{}, rmx);
+          rmaxs[cq * 128 + row] = rmx;
           named_bar_sync(1, kFeatThreads);
           sub = (diag + fmaxf(fmaxf(rmaxs[row], rmaxs[128 + row]), fmaxf(rmaxs[256 + row], rmaxs[384 + row]))) * kLog2e;
         }
         ++tile_seq;
-        for (int f = 0; f < 5; ++f, ++j) {
-          if (mine()) {
-            query_feat_job(f);
-            if (pending) { epilogue(item, t - 1); pending = false; }
-          }
-        }
-        if (pending) { epilogue(item, t - 1); pending = false; }  // (a group without a job in this tile)
+        query_feat_job(C0{}, true, false);
+        if (pending) { epilogue(item, t - 1); pending = false; }
+        query_feat_job(C1{}, true, true);
+        query_feat_job(C2{}, more, false);
         pending = true;
       }
       epilogue(item, nt - 1);
