@@ -8,7 +8,8 @@
  *    (a cudaStream_t passed as void*), never synchronises, never allocates persistent memory and
  *    keeps no pointer after it returns; the caller owns all buffers including workspaces;
  *  - returns 0 (RFK_OK) or an error code; never throws, never exits; rfk_strerror() names a code;
- *  - dtypes are RFK_F32 / RFK_BF16; "mode 0" callers hand bf16 operands to the tcgen05 kernels,
+ *  - dtypes are RFK_F32 / RFK_BF16 / RFK_F16 (IEEE half: same tensor-core rate as bf16, 11 instead of 8 significand
+ *    bits; used for the range-bounded operands of the MSA track); "mode 0" callers hand 16-bit operands to the tcgen05 kernels,
  *    "mode 1" (fp32 validation) callers hand fp32 operands to the SIMT fp32 kernels;
  *  - all index arithmetic is in ELEMENTS (not bytes).
  *
@@ -26,7 +27,7 @@ extern "C" {
 
 typedef void* rfk_stream_t; /* cudaStream_t */
 
-enum { RFK_F32 = 0, RFK_BF16 = 1 };
+enum { RFK_F32 = 0, RFK_BF16 = 1, RFK_F16 = 2 };
 
 enum {
   RFK_OK = 0,
@@ -75,7 +76,7 @@ enum { RFK_EPI_STD = 0, RFK_EPI_BLOCKLN32 = 1 };
  * Replaces: nn.Linear (:195-202, :235-238, :274-277, :436, :448, :566, :574, performer
  * to_q/to_k/to_v/to_out), the einsums at :212, :254, :257, :424, :592 and the Residual adds
  * at :26-28, :346, :595.
- * ab_dtype RFK_BF16 -> tcgen05/TMEM/TMA kernel (fp32 accumulate); RFK_F32 -> SIMT fp32 kernel.
+ * ab_dtype RFK_BF16 / RFK_F16 -> tcgen05/TMEM/TMA kernel (fp32 accumulate); RFK_F32 -> SIMT fp32 kernel.
  * bf16 operands need: 16-byte aligned base pointers, lda/ldb/z-strides multiples of 8 elements.
  */
 typedef struct {

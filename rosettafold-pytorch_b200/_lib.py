@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librfk.so")
 
-RFK_F32, RFK_BF16 = 0, 1
+RFK_F32, RFK_BF16, RFK_F16 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
 EPI_STD, EPI_BLOCKLN32 = 0, 1
 

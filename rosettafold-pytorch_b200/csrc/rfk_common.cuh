@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -57,20 +58,35 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-__device__ __forceinline__ float load_as_float(const void* p, int dtype, int64_t i) {
-  return dtype == RFK_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i])
-                           : reinterpret_cast<const float*>(p)[i];
-}
-__device__ __forceinline__ void store_from_float(void* p, int dtype, int64_t i, float v) {
-  if (dtype == RFK_BF16)
-    reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
-  else
-    reinterpret_cast<float*>(p)[i] = v;
-}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+// ---- the two 16-bit operand formats (dtype = RFK_BF16 or RFK_F16; the branch is warp-uniform) ----
+__device__ __forceinline__ float h16_to_float(uint16_t bits, int dtype) {
+  return dtype == RFK_F16 ? __half2float(__ushort_as_half(bits)) : __uint_as_float((uint32_t)bits << 16);
+}
+__device__ __forceinline__ uint16_t cvt_h16(float v, int dtype) {
+  return dtype == RFK_F16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ uint32_t pack_h16x2(float lo, float hi, int dtype) {
+  if (dtype == RFK_F16) {
+    __half2 t = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+  }
+  return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float load_as_float(const void* p, int dtype, int64_t i) {
+  return dtype == RFK_F32 ? reinterpret_cast<const float*>(p)[i]
+                          : h16_to_float(reinterpret_cast<const uint16_t*>(p)[i], dtype);
+}
+__device__ __forceinline__ void store_from_float(void* p, int dtype, int64_t i, float v) {
+  if (dtype == RFK_F32)
+    reinterpret_cast<float*>(p)[i] = v;
+  else
+    reinterpret_cast<uint16_t*>(p)[i] = cvt_h16(v, dtype);
+}
+inline bool is_h16(int dtype) { return dtype == RFK_BF16 || dtype == RFK_F16; }
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == RFK_ACT_RELU) return fmaxf(x, 0.f);
   if (act == RFK_ACT_ELU) return x > 0.f ? x : expm1f(x);
@@ -224,6 +240,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }
+// A / B format fields of the instruction descriptor: 1 = bf16, 0 = f16. XOR this into a bf16 descriptor to get the f16 one.
+constexpr uint32_t kIdescBf16Bits = (1u << 7) | (1u << 10);
 // Byte offset of element (row, k) inside a [rows][64] bf16 tile with the 128-byte swizzle.
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t k) {
   return (row >> 3) * 1024u + (row & 7u) * 128u + ((((k >> 3) ^ row) & 7u) << 4) + (k & 7u) * 2u;

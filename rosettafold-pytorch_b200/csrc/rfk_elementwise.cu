@@ -23,8 +23,22 @@ __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, flo
   const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
   o[0] = __low2float(a); o[1] = __high2float(a); o[2] = __low2float(b); o[3] = __high2float(b);
 }
+template <>
+__device__ __forceinline__ void load4<__half>(const __half* p, float (&o)[4]) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
 template <typename T>
 __device__ __forceinline__ void store4(T* p, const float (&v)[4]);
+template <>
+__device__ __forceinline__ void store4<__half>(__half* p, const float (&v)[4]) {
+  uint2 t;
+  t.x = pack_h16x2(v[0], v[1], RFK_F16);
+  t.y = pack_h16x2(v[2], v[3], RFK_F16);
+  *reinterpret_cast<uint2*>(p) = t;
+}
 template <>
 __device__ __forceinline__ void store4<float>(float* p, const float (&v)[4]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
@@ -247,33 +261,43 @@ poswise_kernel(const void* __restrict__ pq, int64_t pqs, const void* __restrict_
 // reads whole 128-byte lines of pk / q and writes whole lines of qt. Phase 1: logits[n][h] into
 // shared memory (the dh/8 threads of a head meet by shuffle); phase 2: softmax over n per head;
 // phase 3: qt[b,h,l,n,:] = q[b,n,l,h,:] * w[n,h] * q_scale.
-__device__ __forceinline__ void ld8_bf16(const __nv_bfloat16* p, float (&v)[8]) {
+// F16: the 16-bit operands are IEEE half instead of bf16
+template <bool F16>
+__device__ __forceinline__ void ld8_h16(const uint16_t* p, float (&v)[8]) {
   const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    v[2 * i] = __uint_as_float(w[i] << 16);
-    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    if (F16) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    } else {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
   }
 }
+template <bool F16>
 __global__ void __launch_bounds__(256)
-poswise_vec_kernel(const __nv_bfloat16* __restrict__ pq, int64_t pqs, const __nv_bfloat16* __restrict__ pk,
-                   int64_t pks, float scale, float* __restrict__ w_out, const __nv_bfloat16* __restrict__ q,
-                   int64_t qs, float q_scale, __nv_bfloat16* __restrict__ qt, int N, int L, int H, int dh,
+poswise_vec_kernel(const uint16_t* __restrict__ pq, int64_t pqs, const uint16_t* __restrict__ pk,
+                   int64_t pks, float scale, float* __restrict__ w_out, const uint16_t* __restrict__ q,
+                   int64_t qs, float q_scale, uint16_t* __restrict__ qt, int N, int L, int H, int dh,
                    int rows, float* __restrict__ stats) {
+  constexpr int kDt = F16 ? RFK_F16 : RFK_BF16;
   extern __shared__ float lg[];  // [N][H]
   const int CH = (H * dh) >> 3, gsz = dh >> 3;
   const int c = threadIdx.x % CH, r = threadIdx.x / CH;
   const int h = c / gsz;
   const int l = blockIdx.x % L, b = blockIdx.x / L;
   float pqv[8];
-  ld8_bf16(pq + ((int64_t)b * L + l) * pqs + c * 8, pqv);
+  ld8_h16<F16>(pq + ((int64_t)b * L + l) * pqs + c * 8, pqv);
   for (int n0 = 0; n0 < N; n0 += rows) {
     const int n = n0 + r;
     float acc = 0.f;
     if (n < N) {
       float kv[8];
-      ld8_bf16(pk + (((int64_t)b * N + n) * L + l) * pks + c * 8, kv);
+      ld8_h16<F16>(pk + (((int64_t)b * N + n) * L + l) * pks + c * 8, kv);
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc = fmaf(pqv[i], kv[i], acc);
     }
@@ -311,11 +335,11 @@ poswise_vec_kernel(const __nv_bfloat16* __restrict__ pq, int64_t pqs, const __nv
   const int64_t out_base = (((int64_t)b * H + h) * L + l) * ((int64_t)N * dh) + (c % gsz) * 8;
   for (int n = r; n < N; n += rows) {
     float qv[8];
-    ld8_bf16(q + (((int64_t)b * N + n) * L + l) * qs + c * 8, qv);
+    ld8_h16<F16>(q + (((int64_t)b * N + n) * L + l) * qs + c * 8, qv);
     const float wn = lg[n * H + h] * q_scale;
     uint4 u;
-    u.x = pack_bf16x2(qv[0] * wn, qv[1] * wn); u.y = pack_bf16x2(qv[2] * wn, qv[3] * wn);
-    u.z = pack_bf16x2(qv[4] * wn, qv[5] * wn); u.w = pack_bf16x2(qv[6] * wn, qv[7] * wn);
+    u.x = pack_h16x2(qv[0] * wn, qv[1] * wn, kDt); u.y = pack_h16x2(qv[2] * wn, qv[3] * wn, kDt);
+    u.z = pack_h16x2(qv[4] * wn, qv[5] * wn, kDt); u.w = pack_h16x2(qv[6] * wn, qv[7] * wn, kDt);
     *reinterpret_cast<uint4*>(qt + out_base + (int64_t)n * dh) = u;
   }
 }
@@ -656,8 +680,26 @@ __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float
     v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
   }
 }
+template <>
+__device__ __forceinline__ void ld8<__half>(const __half* p, float (&v)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
 template <typename T>
 __device__ __forceinline__ void st8(T* p, const float (&v)[8]);
+template <>
+__device__ __forceinline__ void st8<__half>(__half* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_h16x2(v[0], v[1], RFK_F16); u.y = pack_h16x2(v[2], v[3], RFK_F16);
+  u.z = pack_h16x2(v[4], v[5], RFK_F16); u.w = pack_h16x2(v[6], v[7], RFK_F16);
+  *reinterpret_cast<uint4*>(p) = u;
+}
 template <>
 __device__ __forceinline__ void st8<float>(float* p, const float (&v)[8]) {
   reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -821,7 +863,7 @@ channel_stats_vec_kernel(const TX* __restrict__ x, double* __restrict__ stats, i
 
 using namespace rfk;
 
-static inline bool dtype_ok(int d) { return d == RFK_F32 || d == RFK_BF16; }
+static inline bool dtype_ok(int d) { return d == RFK_F32 || d == RFK_BF16 || d == RFK_F16; }
 
 static int layernorm_impl(const void* x, int xdt, int64_t xs, const float* gamma, const float* beta,
                           float eps, const float* res, int64_t rs, void* y, int ydt, int64_t ys,
@@ -839,11 +881,13 @@ static int layernorm_impl(const void* x, int xdt, int64_t xs, const float* gamma
                       (ys * ye) % ya == 0 &&
                       (!gamma || (aligned16(gamma) && aligned16(beta))) &&
                       (!res || (aligned16(res) && rs % 4 == 0));
-  if (vec_ok) {
+  if (vec_ok && !(xdt == RFK_F16 || (ydt == RFK_F16 && xdt != RFK_F32))) {  // (f16 inputs take the generic kernel)
     if (xdt == RFK_F32 && ydt == RFK_F32)
       return launch_ln_vec<float, float>(x, xs, gamma, beta, eps, y, ys, rows, D, st, res, rs);
     if (xdt == RFK_F32 && ydt == RFK_BF16)
       return launch_ln_vec<float, __nv_bfloat16>(x, xs, gamma, beta, eps, y, ys, rows, D, st, res, rs);
+    if (xdt == RFK_F32 && ydt == RFK_F16)
+      return launch_ln_vec<float, __half>(x, xs, gamma, beta, eps, y, ys, rows, D, st, res, rs);
     if (xdt == RFK_BF16 && ydt == RFK_BF16)
       return launch_ln_vec<__nv_bfloat16, __nv_bfloat16>(x, xs, gamma, beta, eps, y, ys, rows, D, st, res, rs);
     return launch_ln_vec<__nv_bfloat16, float>(x, xs, gamma, beta, eps, y, ys, rows, D, st, res, rs);
@@ -939,17 +983,16 @@ extern "C" int rfk_poswise_weight_stats(const void* pq, int64_t pqs, const void*
     const int D = H * dh, gsz = dh / 8, CH = D / 8;
     auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
     const bool pow2 = gsz > 0 && (gsz & (gsz - 1)) == 0 && gsz <= 32;
-    if (dt == RFK_BF16 && (!qt || qtdt == RFK_BF16) && dh % 8 == 0 && pow2 && CH <= 256 && pqs % 8 == 0 &&
+    if (is_h16(dt) && (!qt || qtdt == dt) && dh % 8 == 0 && pow2 && CH <= 256 && pqs % 8 == 0 &&
         pks % 8 == 0 && (!qt || qs % 8 == 0) && al16(pq) && al16(pk) && (!qt || (al16(q) && al16(qt))) &&
         (size_t)N * H * sizeof(float) <= 48 * 1024) {
       int rows = 256 / CH;
       while (rows > 1 && (rows * CH) % 32 != 0) --rows;
       if ((rows * CH) % 32 == 0) {
-        poswise_vec_kernel<<<(unsigned)(B * L), rows * CH, (size_t)N * H * sizeof(float),
-                             reinterpret_cast<cudaStream_t>(stream)>>>(
-            reinterpret_cast<const __nv_bfloat16*>(pq), pqs, reinterpret_cast<const __nv_bfloat16*>(pk), pks, scale,
-            w_out, reinterpret_cast<const __nv_bfloat16*>(q), qs, q_scale, reinterpret_cast<__nv_bfloat16*>(qt), N, L,
-            H, dh, rows, stats);
+        auto* k = dt == RFK_F16 ? poswise_vec_kernel<true> : poswise_vec_kernel<false>;
+        k<<<(unsigned)(B * L), rows * CH, (size_t)N * H * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const uint16_t*>(pq), pqs, reinterpret_cast<const uint16_t*>(pk), pks, scale, w_out,
+            reinterpret_cast<const uint16_t*>(q), qs, q_scale, reinterpret_cast<uint16_t*>(qt), N, L, H, dh, rows, stats);
         return post_launch();
       }
     }
@@ -1028,7 +1071,7 @@ extern "C" int rfk_channel_stats(const void* x, int xdt, double* stats, int B, i
   if (!x || !stats) return RFK_ERR_NULL_POINTER;
   if (B <= 0 || positions <= 0 || C <= 0) return RFK_ERR_BAD_DIMS;
   if (!dtype_ok(xdt)) return RFK_ERR_BAD_DTYPE;
-  if (C % 8 == 0 && C <= 2048 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+  if (xdt != RFK_F16 && C % 8 == 0 && C <= 2048 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
     const int groups = C / 8;
     const int threads = groups >= 256 ? 256 : (256 / groups) * groups;
     const int rows_per_iter = threads / groups;
@@ -1063,7 +1106,8 @@ extern "C" int rfk_instnorm_apply(const void* x, int xdt, const double* stats, c
   if (!dtype_ok(xdt) || !dtype_ok(ydt) || (res && !dtype_ok(rdt))) return RFK_ERR_BAD_DTYPE;
   const int64_t total = (int64_t)B * positions * C;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  if (C % 8 == 0 && C <= 2048 && al16(x) && al16(y) && (!res || al16(res)) && (!res || rdt == RFK_F32)) {
+  if (xdt != RFK_F16 && ydt != RFK_F16 && C % 8 == 0 && C <= 2048 && al16(x) && al16(y) && (!res || al16(res)) &&
+      (!res || rdt == RFK_F32)) {
     const int chunk = 256;
     const int groups = C / 8;
     const int threads = groups >= 256 ? 256 : (256 / groups) * groups;
@@ -1101,11 +1145,17 @@ extern "C" int rfk_convert_rows(const void* x, int xdt, int64_t xs, void* y, int
     auto ok = [](const void* q, int64_t stride, int es) {
       return (reinterpret_cast<uintptr_t>(q) & 15) == 0 && (stride * es) % 16 == 0;
     };
-    if (cols % 8 == 0 && ok(x, xs, xe) && ok(y, ys, ye) && xdt != ydt) {
+    if (cols % 8 == 0 && ok(x, xs, xe) && ok(y, ys, ye) && xdt != ydt && (xdt == RFK_F32 || ydt == RFK_F32)) {
       const int groups = cols / 8;
       const int64_t work = rows * groups;
       cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-      if (xdt == RFK_F32)
+      if (xdt == RFK_F32 && ydt == RFK_F16)
+        convert_rows_vec_kernel<float, __half><<<(unsigned)((work + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const float*>(x), xs, reinterpret_cast<__half*>(y), ys, rows, groups);
+      else if (xdt == RFK_F16)
+        convert_rows_vec_kernel<__half, float><<<(unsigned)((work + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const __half*>(x), xs, reinterpret_cast<float*>(y), ys, rows, groups);
+      else if (xdt == RFK_F32)
         convert_rows_vec_kernel<float, __nv_bfloat16><<<(unsigned)((work + 255) / 256), 256, 0, st>>>(
             reinterpret_cast<const float*>(x), xs, reinterpret_cast<__nv_bfloat16*>(y), ys, rows, groups);
       else

@@ -204,12 +204,12 @@ extern "C" int rfk_favor_attention(const rfk_favor_desc* d, rfk_stream_t stream_
   if (d->tokens <= 0 || d->G[0] <= 0 || d->G[1] <= 0 || d->heads <= 0) return RFK_ERR_BAD_DIMS;
   if (d->m_features <= 0 || d->m_features > kFavorMaxM) return RFK_ERR_BAD_DIMS;
   if (d->kind != 0 && d->kind != 1) return RFK_ERR_UNSUPPORTED;
-  if (d->io_dtype != RFK_F32 && d->io_dtype != RFK_BF16) return RFK_ERR_BAD_DTYPE;
+  if (d->io_dtype != RFK_F32 && !is_h16(d->io_dtype)) return RFK_ERR_BAD_DTYPE;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   static const bool force_simt = getenv("RFK_FAVOR_FORCE_SIMT") != nullptr;  // A/B debugging aid
-  if (d->io_dtype == RFK_BF16 && !force_simt) {
+  if (is_h16(d->io_dtype) && !force_simt) {
     static const bool old_kernel = getenv("RFK_FAVOR_SMEM_FEATURES") != nullptr;  // A/B: the round-1 kernel
-    int rc = old_kernel ? favor_tc_launch(d, stream) : favor_tm_launch(d, stream);
+    int rc = (old_kernel && d->io_dtype == RFK_BF16) ? favor_tc_launch(d, stream) : favor_tm_launch(d, stream);
     if (rc != RFK_ERR_UNSUPPORTED) return rc;
     // shapes the tensor-core kernel does not cover run on the SIMT kernel (same arithmetic)
   }

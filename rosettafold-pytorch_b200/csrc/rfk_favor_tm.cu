@@ -123,8 +123,9 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ void st_shared_b16(uint32_t addr, float f) {
-  const unsigned short h = __bfloat16_as_ushort(__float2bfloat16_rn(f));
+template <bool F16>
+__device__ __forceinline__ void st_shared_h16(uint32_t addr, float f) {
+  const unsigned short h = cvt_h16(f, F16 ? RFK_F16 : RFK_BF16);
   asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(h) : "memory");
 }
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
@@ -183,14 +184,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 // {bf16(max(lo,0)), bf16(max(hi,0))} in one instruction
-__device__ __forceinline__ uint32_t cvt_relu_bf16x2(float lo, float hi) {
+template <bool F16>
+__device__ __forceinline__ uint32_t cvt_relu_h16x2(float lo, float hi) {
   uint32_t d;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  if (F16) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
-__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+template <bool F16>
+__device__ __forceinline__ uint32_t add_h16x2(uint32_t a, uint32_t b) {
   uint32_t d;
-  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  if (F16) asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  else asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
   return d;
 }
 
@@ -241,10 +246,16 @@ struct PassIter {
   }
 };
 
-template <int KIND>  // 0: softmax kernel (exp features, stabilisers), 1: generalized ReLU kernel
+// KIND 0: softmax kernel (exp features, stabilisers), 1: generalized ReLU kernel. F16: q, k, v, out, the projection
+// matrix, the features and the context are IEEE half instead of bf16 (same tensor-core rate, 11 instead of 8 significand
+// bits; meant for the softmax kernel, whose features are bounded by 1 + eps: the ReLU features and their context sums
+// over up to thousands of tokens are unbounded and stay in bf16)
+template <int KIND, bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
 favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const FavorTmParams p) {
+  constexpr int kDt = F16 ? RFK_F16 : RFK_BF16;
+  constexpr uint32_t kFmt = F16 ? kIdescBf16Bits : 0u;  // instruction-descriptor A / B format bits
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_omega = base + kOffOmega, s_ring = base + kOffRing, s_cslab = base + kOffCslab, s_ctx = base + kOffCtx;
@@ -301,14 +312,14 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = r < p.m ? __ldg(p.proj + (int64_t)r * 64 + c + j) * dn : 0.f;
       uint4 v;
-      v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
-      v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+      v.x = pack_h16x2(f[0], f[1], kDt); v.y = pack_h16x2(f[2], f[3], kDt);
+      v.z = pack_h16x2(f[4], f[5], kDt); v.w = pack_h16x2(f[6], f[7], kDt);
       st_shared_v4(s_omega + sw128_offset(r, c), v);
     }
     for (int i = threadIdx.x; i < kTile * 8; i += kThreads) {
       const int r = i >> 3, c = (i & 7) * 8;
       uint4 v = make_uint4(0, 0, 0, 0);
-      if (c == 0) v.x = 0x00003F80u;  // bf16(1.0) in element 0
+      if (c == 0) v.x = F16 ? 0x00003C00u : 0x00003F80u;  // 1.0 in element 0
       st_shared_v4(s_cslab + sw128_offset(r, c), v);
     }
     // ctx rows 65..79 (never written by the read-out) feed never-read accumulator columns: zero once
@@ -408,7 +419,7 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const uint64_t dw = d_omega + (uint64_t)(CU * 1024);
       const uint64_t da = key ? dw : dx;
       const uint64_t db = key ? dx : dw;
-      const uint32_t idesc = (!key && CU == 2) ? umma_idesc_bf16(128, 16) : umma_idesc_bf16(128, 128);
+      const uint32_t idesc = ((!key && CU == 2) ? umma_idesc_bf16(128, 16) : umma_idesc_bf16(128, 128)) ^ kFmt;
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma_bf16(tmem + kColU + us * 128u, da + 2 * k, db + 2 * k, idesc, k > 0);
       umma_commit(bar_ufull(us));
@@ -442,7 +453,7 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           const uint64_t dbv = desc_mn_sw128(s_ring + c.v_slot * kSlabBytes, s_cslab - s_ring - c.v_slot * kSlabBytes);
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma_bf16_ts(tmem + kColCtx + 80u * C, a0 + 32u * (k >> 1) + 8u * (k & 1), dbv + 128 * k, idesc_bf16_major(128, 80, 0, 1),
+            umma_bf16_ts(tmem + kColCtx + 80u * C, a0 + 32u * (k >> 1) + 8u * (k & 1), dbv + 128 * k, idesc_bf16_major(128, 80, 0, 1) ^ kFmt,
                          (c.t > 0 || k > 0));
           if (C == 2) {
             umma_commit(bar_tempty(c.v_slot));
@@ -455,7 +466,7 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < NK; ++k)
             umma_bf16_ts(tmem + kColCtx + 80u * ds, a0 + 32u * (k >> 1) + 8u * (k & 1), db + (k >> 2) * 640 + 2 * (k & 3),
-                         umma_idesc_bf16(128, 80), (C > 0 || k > 0));
+                         umma_idesc_bf16(128, 80) ^ kFmt, (C > 0 || k > 0));
           if (C == 2) umma_commit(bar_d3full(ds));
         }
         // (stabiliser passes: the feature warps have taken their maxima, nothing to consume)
@@ -496,7 +507,7 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t t_lane = ((uint32_t)(lg * 32) << 16);
     constexpr float kLog2e = 1.4426950408889634f;
     constexpr float kEps = KIND == 0 ? 1e-4f : 1e-3f;
-    const uint32_t eps2 = pack_bf16x2(kEps, kEps);
+    const uint32_t eps2 = pack_h16x2(kEps, kEps, kDt);
     const uint32_t ubase = tmem + t_lane + kColU + 32u * (uint32_t)cq;  // + us * 128
 
     uint32_t nJ = 0;  // jobs processed (job parity = U slot)
@@ -529,8 +540,8 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     auto feat2 = [&](uint32_t r0, uint32_t r1, float s0, float s1) -> uint32_t {
       const float x0 = __uint_as_float(r0), x1 = __uint_as_float(r1);
       if (KIND == 0)
-        return add_bf16x2(pack_bf16x2(ex2_approx(fmaf(x0, kLog2e, -s0)), ex2_approx(fmaf(x1, kLog2e, -s1))), eps2);
-      return add_bf16x2(cvt_relu_bf16x2(x0, x1), eps2);
+        return add_h16x2<F16>(pack_h16x2(ex2_approx(fmaf(x0, kLog2e, -s0)), ex2_approx(fmaf(x1, kLog2e, -s1)), kDt), eps2);
+      return add_h16x2<F16>(cvt_relu_h16x2<F16>(x0, x1), eps2);
     };
 
     // ---- key-side job: this thread holds feature row (128 C + row) x tokens [32 cq, 32 cq + 32) of the tile ----
@@ -633,7 +644,7 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float a = bf16lo(w[i]), b = bf16hi(w[i]);
+          const float a = h16_to_float((uint16_t)(w[i] & 0xffffu), kDt), b = h16_to_float((uint16_t)(w[i] >> 16), kDt);
           s = fmaf(a, a, s);
           s = fmaf(b, b, s);
         }
@@ -664,15 +675,15 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + g1 * p.ogs1 + g0 * p.ogs0 +
                                              (int64_t)(t * kTile + row) * p.ots + h * 64 + 16 * cq);
         uint4 w;
-        w.x = pack_bf16x2(__uint_as_float(r0[0]) * inv, __uint_as_float(r0[1]) * inv);
-        w.y = pack_bf16x2(__uint_as_float(r0[2]) * inv, __uint_as_float(r0[3]) * inv);
-        w.z = pack_bf16x2(__uint_as_float(r0[4]) * inv, __uint_as_float(r0[5]) * inv);
-        w.w = pack_bf16x2(__uint_as_float(r0[6]) * inv, __uint_as_float(r0[7]) * inv);
+        w.x = pack_h16x2(__uint_as_float(r0[0]) * inv, __uint_as_float(r0[1]) * inv, kDt);
+        w.y = pack_h16x2(__uint_as_float(r0[2]) * inv, __uint_as_float(r0[3]) * inv, kDt);
+        w.z = pack_h16x2(__uint_as_float(r0[4]) * inv, __uint_as_float(r0[5]) * inv, kDt);
+        w.w = pack_h16x2(__uint_as_float(r0[6]) * inv, __uint_as_float(r0[7]) * inv, kDt);
         op[0] = w;
-        w.x = pack_bf16x2(__uint_as_float(r0[8]) * inv, __uint_as_float(r0[9]) * inv);
-        w.y = pack_bf16x2(__uint_as_float(r0[10]) * inv, __uint_as_float(r0[11]) * inv);
-        w.z = pack_bf16x2(__uint_as_float(r0[12]) * inv, __uint_as_float(r0[13]) * inv);
-        w.w = pack_bf16x2(__uint_as_float(r0[14]) * inv, __uint_as_float(r0[15]) * inv);
+        w.x = pack_h16x2(__uint_as_float(r0[8]) * inv, __uint_as_float(r0[9]) * inv, kDt);
+        w.y = pack_h16x2(__uint_as_float(r0[10]) * inv, __uint_as_float(r0[11]) * inv, kDt);
+        w.z = pack_h16x2(__uint_as_float(r0[12]) * inv, __uint_as_float(r0[13]) * inv, kDt);
+        w.w = pack_h16x2(__uint_as_float(r0[14]) * inv, __uint_as_float(r0[15]) * inv, kDt);
         op[1] = w;
       }
     };
@@ -719,7 +730,7 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tmem_ld_wait();  // the prefetch of the first query job is in flight: one wait covers all loads
         auto put = [&](int m, uint32_t n, float v) {
           const uint32_t mc = (uint32_t)m & 63u;
-          st_shared_b16(s_ctx + (uint32_t)(m >> 6) * kCtxSlabBytes + (n >> 3) * 1024u + (n & 7u) * 128u +
+          st_shared_h16<F16>(s_ctx + (uint32_t)(m >> 6) * kCtxSlabBytes + (n >> 3) * 1024u + (n & 7u) * 128u +
                             ((((mc >> 3) ^ n) & 7u) << 4) + (mc & 7u) * 2u,
                         v);
         };
@@ -815,17 +826,17 @@ int make_head_tmap(CUtensorMap* map, const void* ptr, const rfk_favor_desc* d) {
   return r == CUDA_SUCCESS ? RFK_OK : RFK_ERR_TMA_ENCODE;
 }
 
-template <int KIND>
+template <int KIND, bool F16>
 int launch_kind(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const FavorTmParams& p,
                 cudaStream_t stream) {
   static PerDeviceOnce once;
   const int cfg_rc = per_device_once(once, []() {
-    return cuda_status(cudaFuncSetAttribute(favor_tm_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    return cuda_status(cudaFuncSetAttribute(favor_tm_kernel<KIND, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   });
   if (cfg_rc != RFK_OK) return cfg_rc;
   int grid = num_sms();
   if (p.items < grid) grid = (int)p.items;
-  favor_tm_kernel<KIND><<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, p);
+  favor_tm_kernel<KIND, F16><<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, p);
   return post_launch();
 }
 
@@ -849,7 +860,9 @@ int favor_tm_launch(const rfk_favor_desc* d, cudaStream_t stream) {
   p.tokens = (int)d->tokens; p.G0 = d->G[0]; p.G1 = d->G[1];
   p.items = d->G[0] * d->G[1] * d->heads;
   p.ogs0 = d->out_gs[0]; p.ogs1 = d->out_gs[1]; p.ots = d->out_ts;
-  return d->kind == 0 ? launch_kind<0>(tq, tk, tv, p, stream) : launch_kind<1>(tq, tk, tv, p, stream);
+  if (d->io_dtype == RFK_F16)
+    return d->kind == 0 ? launch_kind<0, true>(tq, tk, tv, p, stream) : launch_kind<1, true>(tq, tk, tv, p, stream);
+  return d->kind == 0 ? launch_kind<0, false>(tq, tk, tv, p, stream) : launch_kind<1, false>(tq, tk, tv, p, stream);
 }
 
 }  // namespace rfk

@@ -139,7 +139,7 @@ static int make_tmap_raw(CUtensorMap* map, const void* ptr, int rank, const uint
 // Returns RFK_ERR_UNSUPPORTED when the view needs more than 5 dims or breaks a TMA rule.
 int make_epi_tmap(CUtensorMap* map, int cmap[5], const void* ptr, int dtype, const rfk_addr& a,
                   const int64_t ext[7]) {
-  const int es = dtype == RFK_BF16 ? 2 : 4;
+  const int es = dtype == RFK_F32 ? 4 : 2;
   if (!aligned16(ptr) || a.ns[0] != 1) return RFK_ERR_UNSUPPORTED;
   const int64_t strides[7] = {a.ns[0], a.ns[1], a.ms[0], a.ms[1], a.zs[0], a.zs[1], a.zs[2]};
   uint64_t dims[5] = {1, 1, 1, 1, 1}, sb[4] = {16, 16, 16, 16};
@@ -161,8 +161,8 @@ int make_epi_tmap(CUtensorMap* map, int cmap[5], const void* ptr, int dtype, con
   }
   for (int d = nd; d < 5; ++d) cmap[d] = -1;
   return make_tmap_raw(map, ptr, 5, dims, sb, box,
-                       dtype == RFK_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
-                       dtype == RFK_BF16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+                       dtype == RFK_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,  // (f16: same 2-byte moves)
+                       dtype == RFK_F32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 int make_tmap_bf16_raw(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims,
@@ -241,7 +241,8 @@ extern "C" int rfk_gemm(const rfk_gemm_desc* d, rfk_stream_t stream_) {
     gemm_f32_kernel<<<(unsigned)tiles, 256, 0, stream>>>(p);
     return post_launch();
   }
-  if (d->ab_dtype != RFK_BF16) return RFK_ERR_BAD_DTYPE;
+  if (!is_h16(d->ab_dtype)) return RFK_ERR_BAD_DTYPE;
+  p.ab_f16 = d->ab_dtype == RFK_F16;
   int rc = check_arch();
   if (rc != RFK_OK) return rc;
 
@@ -276,7 +277,7 @@ extern "C" int rfk_gemm(const rfk_gemm_desc* d, rfk_stream_t stream_) {
               (!d->bias || aligned16(d->bias)) && d->ln_gamma == nullptr;
   for (int i = 0; i < 3; ++i) lean = lean && (d->bias_zs[i] % 4 == 0);
   int epi = 0;
-  if (lean && d->c_dtype == RFK_BF16 && !d->r0 && !d->r1 && addr_aligned(d->c, d->c_addr, 2)) epi = 1;
+  if (lean && is_h16(d->c_dtype) && !d->r0 && !d->r1 && addr_aligned(d->c, d->c_addr, 2)) epi = 1;
   if (lean && d->c_dtype == RFK_F32 && d->epi == RFK_EPI_STD && addr_aligned(d->c, d->c_addr, 4) &&
       (!d->r0 || (d->r0_dtype == RFK_F32 && addr_aligned(d->r0, d->r0_addr, 4))) &&
       (!d->r1 || (d->r1_dtype == RFK_F32 && addr_aligned(d->r1, d->r1_addr, 4))))

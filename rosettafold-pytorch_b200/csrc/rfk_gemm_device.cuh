@@ -23,6 +23,7 @@ struct GemmDev {
   const float* ln_beta;
   // tcgen05 path only
   int bmask[3];  // 0 -> broadcast B over that z level
+  int ab_f16;    // A / B are IEEE half instead of bf16 (instruction-descriptor format bits)
   // implicit-GEMM 3x3 convolution mode (CONV kernels): A is the NHWC image [B][L][L][C]; a tile is
   // 128 consecutive columns j of one image row; K runs over 9 taps x conv_cblocks 64-channel blocks
   int conv_L, conv_H, conv_Lp, conv_cblocks, conv_last_k16, conv_cpad;  // conv_L = image width, conv_H = rows
@@ -89,9 +90,9 @@ __device__ __forceinline__ void epilogue_row_chunk(const GemmDev& p, int64_t z0,
           for (int i = 0; i < CH; ++i) v[i] += __ldg(rp + i);
         }
       } else {
-        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(r) + off;
+        const uint16_t* rp = reinterpret_cast<const uint16_t*>(r) + off;
 #pragma unroll
-        for (int i = 0; i < CH; ++i) v[i] += __bfloat162float(rp[i]);
+        for (int i = 0; i < CH; ++i) v[i] += h16_to_float(rp[i], rdt);
       }
     } else {
 #pragma unroll
@@ -114,20 +115,20 @@ __device__ __forceinline__ void epilogue_row_chunk(const GemmDev& p, int64_t z0,
         for (int i = 0; i < CH; ++i) cp[i] = v[i];
       }
     } else {
-      __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.c) + off;
+      uint16_t* cp = reinterpret_cast<uint16_t*>(p.c) + off;
       if (CH % 8 == 0 && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
 #pragma unroll
         for (int i = 0; i + 7 < CH; i += 8) {
           uint4 t;
-          t.x = pack_bf16x2(v[i], v[i + 1]);
-          t.y = pack_bf16x2(v[i + 2], v[i + 3]);
-          t.z = pack_bf16x2(v[i + 4], v[i + 5]);
-          t.w = pack_bf16x2(v[i + 6], v[i + 7]);
+          t.x = pack_h16x2(v[i], v[i + 1], p.c_dtype);
+          t.y = pack_h16x2(v[i + 2], v[i + 3], p.c_dtype);
+          t.z = pack_h16x2(v[i + 4], v[i + 5], p.c_dtype);
+          t.w = pack_h16x2(v[i + 6], v[i + 7], p.c_dtype);
           *reinterpret_cast<uint4*>(cp + i) = t;
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < CH; ++i) cp[i] = __float2bfloat16_rn(v[i]);
+        for (int i = 0; i < CH; ++i) cp[i] = cvt_h16(v[i], p.c_dtype);
       }
     }
   } else {
@@ -181,9 +182,9 @@ __device__ __forceinline__ void load4_any(const void* r, int rdt, int64_t off, f
       for (int j = 0; j < 4; ++j) o[j] = __ldg(rp + j);
     }
   } else {
-    const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(r) + off;
+    const uint16_t* rp = reinterpret_cast<const uint16_t*>(r) + off;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = __bfloat162float(rp[j]);
+    for (int j = 0; j < 4; ++j) o[j] = h16_to_float(rp[j], rdt);
   }
 }
 
@@ -295,15 +296,15 @@ __device__ __forceinline__ void epilogue_warp_chunk(const GemmDev& p, float* st,
             load4_any(p.r1, p.r1_dtype, o1 + r1col + col + 4, t);
             x[4] += t[0]; x[5] += t[1]; x[6] += t[2]; x[7] += t[3];
           }
-          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.c) + oc + ccol + col;
+          uint16_t* cp = reinterpret_cast<uint16_t*>(p.c) + oc + ccol + col;
           if ((reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
             uint4 t;
-            t.x = pack_bf16x2(x[0], x[1]); t.y = pack_bf16x2(x[2], x[3]);
-            t.z = pack_bf16x2(x[4], x[5]); t.w = pack_bf16x2(x[6], x[7]);
+            t.x = pack_h16x2(x[0], x[1], p.c_dtype); t.y = pack_h16x2(x[2], x[3], p.c_dtype);
+            t.z = pack_h16x2(x[4], x[5], p.c_dtype); t.w = pack_h16x2(x[6], x[7], p.c_dtype);
             *reinterpret_cast<uint4*>(cp) = t;
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) cp[j] = __float2bfloat16_rn(x[j]);
+            for (int j = 0; j < 8; ++j) cp[j] = cvt_h16(x[j], p.c_dtype);
           }
         }
       }
@@ -316,7 +317,7 @@ __device__ __forceinline__ void epilogue_warp_chunk(const GemmDev& p, float* st,
     const int64_t coff_mine = lane < CW ? addr_n(p.c_addr, n0 + lane, p.NR) : 0;
     const float bias_mine = (bias && lane < CW) ? __ldg(bias + n0 + lane) : 0.f;
     const int64_t rowbase = __shfl_sync(0xffffffffu, c_row, 0);
-    if (p.c_dtype == RFK_BF16) {
+    if (p.c_dtype != RFK_F32) {
       const int csub = lane >> 2, r8 = (lane & 3) * 8;
 #pragma unroll
       for (int it = 0; it < CW / 8; ++it) {
@@ -326,15 +327,15 @@ __device__ __forceinline__ void epilogue_warp_chunk(const GemmDev& p, float* st,
         float x[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[j] = apply_act(st[(r8 + j) * LD + col] * p.alpha + b, p.act);
-        __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.c) + rowbase + r8 + coff;
+        uint16_t* cp = reinterpret_cast<uint16_t*>(p.c) + rowbase + r8 + coff;
         if ((reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
           uint4 t;
-          t.x = pack_bf16x2(x[0], x[1]); t.y = pack_bf16x2(x[2], x[3]);
-          t.z = pack_bf16x2(x[4], x[5]); t.w = pack_bf16x2(x[6], x[7]);
+          t.x = pack_h16x2(x[0], x[1], p.c_dtype); t.y = pack_h16x2(x[2], x[3], p.c_dtype);
+          t.z = pack_h16x2(x[4], x[5], p.c_dtype); t.w = pack_h16x2(x[6], x[7], p.c_dtype);
           *reinterpret_cast<uint4*>(cp) = t;
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) cp[j] = __float2bfloat16_rn(x[j]);
+          for (int j = 0; j < 8; ++j) cp[j] = cvt_h16(x[j], p.c_dtype);
         }
       }
     } else {
@@ -410,7 +411,7 @@ __device__ __forceinline__ void epilogue_fast_chunk(const GemmDev& p, float4* st
       b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + col + 4));
     }
     const bool relu = p.act == RFK_ACT_RELU;
-    __nv_bfloat16* cbase = reinterpret_cast<__nv_bfloat16*>(p.c) + c_base + ccol + col;
+    uint16_t* cbase = reinterpret_cast<uint16_t*>(p.c) + c_base + ccol + col;
     const int64_t ms0 = p.c_addr.ms[0];
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
@@ -425,8 +426,8 @@ __device__ __forceinline__ void epilogue_fast_chunk(const GemmDev& p, float4* st
         b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
       }
       uint4 t;
-      t.x = pack_bf16x2(a.x, a.y); t.y = pack_bf16x2(a.z, a.w);
-      t.z = pack_bf16x2(b.x, b.y); t.w = pack_bf16x2(b.z, b.w);
+      t.x = pack_h16x2(a.x, a.y, p.c_dtype); t.y = pack_h16x2(a.z, a.w, p.c_dtype);
+      t.z = pack_h16x2(b.x, b.y, p.c_dtype); t.w = pack_h16x2(b.z, b.w, p.c_dtype);
       if (row < rows_valid) *reinterpret_cast<uint4*>(cbase + row * ms0) = t;
     }
   } else {
@@ -640,7 +641,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
+    const uint32_t fmt = p.ab_f16 ? kIdescBf16Bits : 0u;  // operands are f16 instead of bf16
+    const uint32_t idesc = umma_idesc_bf16(kBlockM, BN) ^ fmt;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -648,7 +650,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // the last column block may be narrower than BN: its MMAs only cover the real columns (rounded up to the
     // instruction granularity of 16), so a wide BN costs no tensor time on the ragged edge
     const uint32_t n_tail = (uint32_t)p.N - (n_blocks - 1) * (uint32_t)BN;
-    const uint32_t idesc_tail = umma_idesc_bf16(kBlockM, (int)((n_tail + 15u) & ~15u));
+    const uint32_t idesc_tail = umma_idesc_bf16(kBlockM, (int)((n_tail + 15u) & ~15u)) ^ fmt;
     for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
       const uint32_t idesc_t = (t % n_blocks == n_blocks - 1) ? idesc_tail : idesc;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -837,9 +839,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const uint32_t rowb = buf + myrow * 64u, sw = (myrow >> 1) & 3u;
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              st_shared_v4u(rowb + ((((uint32_t)q) ^ sw) << 4), pack_bf16x2(v[8 * q], v[8 * q + 1]),
-                            pack_bf16x2(v[8 * q + 2], v[8 * q + 3]), pack_bf16x2(v[8 * q + 4], v[8 * q + 5]),
-                            pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+              st_shared_v4u(rowb + ((((uint32_t)q) ^ sw) << 4), pack_h16x2(v[8 * q], v[8 * q + 1], p.c_dtype),
+                            pack_h16x2(v[8 * q + 2], v[8 * q + 3], p.c_dtype), pack_h16x2(v[8 * q + 4], v[8 * q + 5], p.c_dtype),
+                            pack_h16x2(v[8 * q + 6], v[8 * q + 7], p.c_dtype));
           } else {
             const uint32_t rowb = buf + myrow * 128u, sw = myrow & 7u;
             if (use_res) {

@@ -23,7 +23,17 @@ import torch.nn as nn
 from . import ops
 from .ops import ACT_RELU, EPI_BLOCKLN32, cview
 
-_MODE = 0  # 0 = bf16 tensor-core mode, 1 = fp32 validation mode
+_MODE = 0  # 0 = 16-bit tensor-core mode ("bf16"), 1 = fp32 validation mode
+# 16-bit format of the RANGE-BOUNDED operands in the tensor-core mode: the whole MSA track (LayerNorm outputs, the
+# projections q / k / v / FeedForward hidden of those, softmax probabilities, the softmax-kernel FAVOR features) and the
+# LayerNorm-ed operands in front of the convolution block of PairUpdateWithMsa. IEEE half runs at the bf16 tensor-core
+# rate with 11 instead of 8 significand bits: it cuts the rounding error of those stages ~8x, which is what keeps a
+# 13-block trunk inside the 1e-2 budget (profiles/r02_parity.md). Every such value is bounded by
+# sqrt(d) * max|gamma| * max row-norm of the weights, far below half's 65504 for any sane weights;
+# set_bounded_operand_dtype("bf16") restores bf16 everywhere. The unbounded pair-track operands (ReLU-kernel FAVOR
+# features and contexts, which sum over up to thousands of tokens, pair FeedForward hidden, convolution
+# activations) always stay bf16.
+_BOUNDED_DT = torch.float16
 
 
 def set_mode(mode: str):
@@ -37,8 +47,22 @@ def get_mode() -> str:
     return "bf16" if _MODE == 0 else "fp32"
 
 
+def set_bounded_operand_dtype(name: str):
+    """"f16" (default) or "bf16": the 16-bit format of the range-bounded operands in the tensor-core mode."""
+    global _BOUNDED_DT
+    if name not in ("f16", "bf16"):
+        raise ValueError("bounded operand dtype must be 'f16' or 'bf16'")
+    _BOUNDED_DT = torch.float16 if name == "f16" else torch.bfloat16
+
+
 def _adt():
+    """Operand dtype of the unbounded pair-track tensors."""
     return torch.bfloat16 if _MODE == 0 else torch.float32
+
+
+def _bdt():
+    """Operand dtype of the range-bounded tensors (see _BOUNDED_DT)."""
+    return _BOUNDED_DT if _MODE == 0 else torch.float32
 
 
 def _up8(n: int) -> int:
@@ -51,7 +75,7 @@ def _up8(n: int) -> int:
 # ---------------------------------------------------------------------------------------------
 def _packed(module: nn.Module, builder):
     params = list(module.parameters()) + list(module.buffers())
-    sig = (_MODE, tuple((p.data_ptr(), p._version, p.device) for p in params))
+    sig = (_MODE, _BOUNDED_DT, tuple((p.data_ptr(), p._version, p.device) for p in params))
     cache = module.__dict__.get("_rfk_pack")
     if cache is None or cache[0] != sig:
         with torch.no_grad():
@@ -60,9 +84,8 @@ def _packed(module: nn.Module, builder):
     return cache[1]
 
 
-def _w(t: torch.Tensor, dtype=None) -> torch.Tensor:
-    """Weight matrix [N, K] in the operand dtype with K padded to a multiple of 8 elements."""
-    dtype = dtype or _adt()
+def _w(t: torch.Tensor, dtype) -> torch.Tensor:
+    """Weight matrix [N, K] in the operand dtype `dtype` with K padded to a multiple of 8 elements."""
     N, K = t.shape
     buf = torch.zeros((N, _up8(K)), dtype=dtype, device=t.device)
     buf[:, :K] = t.detach().to(dtype)
@@ -140,17 +163,23 @@ class FeedForward(nn.Module):
                                  nn.Linear(d_ff, d_emb))
 
     def _pack(self):
-        return _packed(self, lambda: dict(W1=_w(self.net[0].weight), b1=_f(self.net[0].bias),
-                                          W2=_w(self.net[3].weight), b2=_f(self.net[3].bias)))
+        def build():
+            d = dict(b1=_f(self.net[0].bias), b2=_f(self.net[3].bias))
+            for dt in {_adt(), _bdt()}:  # pair-track and MSA-track callers
+                d[dt] = (_w(self.net[0].weight, dt), _w(self.net[3].weight, dt))
+            return d
+        return _packed(self, build)
 
     def _run(self, xn2, res2=None, out_dtype=torch.float32):
-        """xn2: [T, d_emb] operand dtype; returns W2 relu(W1 xn + b1) + b2 (+ res2)."""
+        """xn2: [T, d_emb] in an operand dtype (it selects the format of the weights and of the hidden tensor);
+        returns W2 relu(W1 xn + b1) + b2 (+ res2)."""
         pk = self._pack()
+        W1, W2 = pk[xn2.dtype]
         T = xn2.shape[0]
-        hid = _empty((T, pk["W1"].shape[0]), _adt(), xn2)
-        ops.gemm(xn2, pk["W1"], cview(hid), bias=pk["b1"], act=ACT_RELU)
-        out = _empty((T, pk["W2"].shape[0]), out_dtype, xn2)
-        ops.gemm(hid, pk["W2"], cview(out), bias=pk["b2"],
+        hid = _empty((T, W1.shape[0]), xn2.dtype, xn2)
+        ops.gemm(xn2, W1, cview(hid), bias=pk["b1"], act=ACT_RELU)
+        out = _empty((T, W2.shape[0]), out_dtype, xn2)
+        ops.gemm(hid, W2, cview(out), bias=pk["b2"],
                  r0=None if res2 is None else cview(res2))
         return out
 
@@ -161,9 +190,9 @@ class FeedForward(nn.Module):
         return self._run(xin).reshape(x.shape)
 
 
-def _ff_block(ln: nn.LayerNorm, ff: FeedForward, x2: torch.Tensor) -> torch.Tensor:
-    """x + FF(LN(x)) on a [T, D] float32 residual stream (:326-332, :352)."""
-    xn = _ln_into(x2, ln, _empty(x2.shape, _adt(), x2))
+def _ff_block(ln: nn.LayerNorm, ff: FeedForward, x2: torch.Tensor, dt) -> torch.Tensor:
+    """x + FF(LN(x)) on a [T, D] float32 residual stream (:326-332, :352); dt: operand dtype of the track."""
+    xn = _ln_into(x2, ln, _empty(x2.shape, dt, x2))
     return ff._run(xn, res2=x2)
 
 
@@ -184,14 +213,15 @@ class PositionWiseWeightFactor(nn.Module):
         self.dropout = nn.Dropout(p_dropout)
 
     def _pack(self):
-        return _packed(self, lambda: dict(Wq=_w(self.to_q[0].weight), bq=_f(self.to_q[0].bias),
-                                          Wk=_w(self.to_k[0].weight), bk=_f(self.to_k[0].bias)))
+        dt = _bdt()  # every caller hands LayerNorm outputs: range-bounded operands
+        return _packed(self, lambda: dict(Wq=_w(self.to_q[0].weight, dt), bq=_f(self.to_q[0].bias),
+                                          Wk=_w(self.to_k[0].weight, dt), bk=_f(self.to_k[0].bias)))
 
     def _project_query(self, x4):
         """x4: [B,N,L,D] operand dtype -> pq [B,L,D] = to_q(x[:, 0]) (:207-209, unscaled)."""
         pk = self._pack()
         B, N, L, D = x4.shape
-        pq = _empty((B, L, D), _adt(), x4)
+        pq = _empty((B, L, D), x4.dtype, x4)
         ops.gemm(x4[:, 0], pk["Wq"], pq.view(1, 1, B, 1, L, 1, D), bias=pk["bq"])
         return pq
 
@@ -200,7 +230,7 @@ class PositionWiseWeightFactor(nn.Module):
         pk = self._pack()
         B, N, L, D = x4.shape
         pq = self._project_query(x4)
-        pkk = _empty((B, N, L, D), _adt(), x4)
+        pkk = _empty((B, N, L, D), x4.dtype, x4)
         ops.gemm(x4.reshape(-1, D), pk["Wk"], cview(pkk.view(-1, D)), bias=pk["bk"])
         w = _empty((B, N, L, self.n_heads), torch.float32, x4)
         ops.poswise_weight(pq, pkk, self.scale, w_out=w, heads=self.n_heads, d_head=self.d_head)
@@ -211,7 +241,7 @@ class PositionWiseWeightFactor(nn.Module):
         """msa : (B, N, L, d_msa) -> (B, N, h, L, 1)"""
         x = _as_f32(msa_emb).contiguous()
         xin = x if _MODE == 1 else ops.convert_rows(x.view(-1, x.shape[-1]),
-                                                    _empty((x.numel() // x.shape[-1], x.shape[-1]), _adt(), x)).view(x.shape)
+                                                    _empty((x.numel() // x.shape[-1], x.shape[-1]), _bdt(), x)).view(x.shape)
         w = self._weights(xin)
         return w.permute(0, 1, 3, 2).unsqueeze(-1)
 
@@ -238,14 +268,14 @@ class SoftTiedAttentionOverResidues(nn.Module):
 
     def _pack(self):
         def build():
-            pw = self.poswise_weight
+            pw, dt = self.poswise_weight, _bdt()
             return dict(
                 # fused [q | poswise-k] projection: both stay in the (b n l) row layout
-                Wqp=_w(torch.cat([self.to_q.weight, pw.to_k[0].weight], 0)),
+                Wqp=_w(torch.cat([self.to_q.weight, pw.to_k[0].weight], 0), dt),
                 bqp=_f(torch.cat([self.to_q.bias, pw.to_k[0].bias], 0)),
-                Wk=_w(self.to_k.weight), bk=_f(self.to_k.bias),
-                Wv=_w(self.to_v.weight), bv=_f(self.to_v.bias),
-                Wo=_w(self.to_out.weight), bo=_f(self.to_out.bias))
+                Wk=_w(self.to_k.weight, dt), bk=_f(self.to_k.bias),
+                Wv=_w(self.to_v.weight, dt), bv=_f(self.to_v.bias),
+                Wo=_w(self.to_out.weight, dt), bo=_f(self.to_out.bias))
         return _packed(self, build)
 
     def _attend(self, xn4, res2, want_att, shard=None):
@@ -261,7 +291,7 @@ class SoftTiedAttentionOverResidues(nn.Module):
         B, N, L, D = xn4.shape
         H, dh = self.n_heads, self.d_head
         T = B * N * L
-        adt = _adt()
+        adt = xn4.dtype
         xn2 = xn4.view(T, D)
         xb = xn4.view(B, N * L, D)
         # q and the poswise keys (plain rows); K and V go straight to their contraction layouts
@@ -305,7 +335,7 @@ class SoftTiedAttentionOverResidues(nn.Module):
         """x : (B, N, L, d_msa)"""
         x = _as_f32(x).contiguous()
         D = x.shape[-1]
-        xin = x if _MODE == 1 else ops.convert_rows(x.view(-1, D), _empty((x.numel() // D, D), _adt(), x)).view(x.shape)
+        xin = x if _MODE == 1 else ops.convert_rows(x.view(-1, D), _empty((x.numel() // D, D), _bdt(), x)).view(x.shape)
         out, att = self._attend(xin, None, self.return_att)
         out = out.view(x.shape)
         return (out, att) if self.return_att else out
@@ -347,10 +377,15 @@ class PerformerSelfAttention(nn.Module):
         self.to_out = nn.Linear(inner, dim, bias=True)
         self.dropout = nn.Dropout(dropout)
 
+    def _dt(self):
+        """Operand dtype: the softmax kernel (MSA columns) works on bounded features, the ReLU kernel (pair axes) does not."""
+        return _adt() if self.fast_attention.generalized_attention else _bdt()
+
     def _pack(self):
+        dt = self._dt()
         return _packed(self, lambda: dict(
-            Wqkv=_w(torch.cat([self.to_q.weight, self.to_k.weight, self.to_v.weight], 0)),
-            Wo=_w(self.to_out.weight), bo=_f(self.to_out.bias),
+            Wqkv=_w(torch.cat([self.to_q.weight, self.to_k.weight, self.to_v.weight], 0), dt),
+            Wo=_w(self.to_out.weight, dt), bo=_f(self.to_out.bias),
             proj=_f(self.fast_attention.projection_matrix)))
 
     def _run(self, xn4, token_dim, res2, out_dtype=torch.float32):
@@ -360,7 +395,7 @@ class PerformerSelfAttention(nn.Module):
         A0, A1, A2, D = xn4.shape
         T = A0 * A1 * A2
         inner = self.heads * self.DIM_HEAD
-        adt = _adt()
+        adt = xn4.dtype
         qkv = _empty((T, 3 * inner), adt, xn4)
         ops.gemm(xn4.view(T, D), pk["Wqkv"], cview(qkv))
         ao = _empty((T, inner), adt, xn4)
@@ -379,7 +414,7 @@ class PerformerSelfAttention(nn.Module):
     def _attend(self, x4, token_dim):
         x4 = _as_f32(x4).contiguous()
         D = x4.shape[-1]
-        xin = x4 if _MODE == 1 else ops.convert_rows(x4.view(-1, D), _empty((x4.numel() // D, D), _adt(), x4)).view(x4.shape)
+        xin = x4 if _MODE == 1 else ops.convert_rows(x4.view(-1, D), _empty((x4.numel() // D, D), self._dt(), x4)).view(x4.shape)
         return self._run(xin, token_dim, None).view(x4.shape)
 
     @torch.no_grad()
@@ -392,7 +427,7 @@ def _performer_block(ln: nn.LayerNorm, attn: PerformerSelfAttention, x4, token_d
     """x + attn(LN(x)) on a float32 [A0,A1,A2,D] stream, attention over `token_dim`."""
     D = x4.shape[-1]
     x2 = x4.view(-1, D)
-    xn = _ln_into(x2, ln, _empty(x2.shape, _adt(), x2))
+    xn = _ln_into(x2, ln, _empty(x2.shape, attn._dt(), x2))
     return attn._run(xn.view(x4.shape), token_dim, x2).view(x4.shape)
 
 
@@ -429,12 +464,12 @@ class EncoderLayer(nn.Module):
         x2 = x4.view(-1, D)
         att = None
         if self.tied:
-            xn = _ln_into(x2, self.ln, _empty(x2.shape, _adt(), x2))
+            xn = _ln_into(x2, self.ln, _empty(x2.shape, _bdt(), x2))
             want = self.return_att if want_att is None else want_att
             x1, att = self.attn._attend(xn.view(x4.shape), x2, want, shard)
         else:
             x1 = _performer_block(self.ln, self.attn, x4, token_dim).view(-1, D)
-        out = _ff_block(self.ff.fn[0], self.ff.fn[1], x1).view(x4.shape)
+        out = _ff_block(self.ff.fn[0], self.ff.fn[1], x1, _bdt()).view(x4.shape)
         return out, att
 
     @torch.no_grad()
@@ -487,8 +522,9 @@ class OuterProductMean(nn.Module):
             Wl, bl = lin.weight.detach().float(), lin.bias.detach().float()
             # bf16 mode: the LayerNorm(1024) affine is folded into the Linear (exact algebra), so the
             # GEMM epilogue only normalises: Linear(g*xhat + b) = (W*g) xhat + (W b + bias)
-            return dict(g=g.contiguous(), b=b.contiguous(), W=_w(lin.weight), bias=_f(lin.bias),
-                        Wfold=_w(Wl * g[None, :]), bfold=(bl + Wl @ b).contiguous())
+            dt = _bdt()  # the operands are LayerNorm outputs (proj_msa, the in-epilogue LayerNorm(1024))
+            return dict(g=g.contiguous(), b=b.contiguous(), W=_w(lin.weight, dt), bias=_f(lin.bias),
+                        Wfold=_w(Wl * g[None, :], dt), bfold=(bl + Wl @ b).contiguous())
         return _packed(self, build)
 
     def _run(self, xt, yt, B, L):
@@ -496,7 +532,7 @@ class OuterProductMean(nn.Module):
         Returns Linear(LN(outer-product sum)) f32 [B*Li*L, out]."""
         pk = self._pack()
         P = self.in_features
-        adt = _adt()
+        adt = xt.dtype
         ln = self.to_out[0]
         Li = xt.shape[1] // P
         o = _empty((B, Li, L, P * P), adt, xt)
@@ -518,7 +554,7 @@ class OuterProductMean(nn.Module):
         y = x if y is None else y
         B, N, L, P = x.shape
         Np = _up8(N)
-        adt = _adt()
+        adt = _bdt()
         xt = torch.zeros((B, L * P, Np), dtype=adt, device=x.device)
         yt = torch.zeros((B, L * P, Np), dtype=adt, device=x.device)
         # standalone API path only: relayout with torch (the fused path uses rfk_opm_prep)
@@ -558,11 +594,11 @@ class PairUpdateWithMsa(nn.Module):
             W = self.resnet[0].weight  # [d_pair, P | 2Q | 2Q | P | H]  (:487-496)
             c0, c1, c2, c3 = P, P + 2 * Q, P + 4 * Q, 2 * P + 4 * Q
             fn = self.resnet[1].fn
-            adt = _adt()
+            bdt = _bdt()  # LayerNorm outputs and attention probabilities in front of the convolution block
             return dict(
-                Wproj=_w(self.proj_msa[1].weight), bproj=_f(self.proj_msa[1].bias),
+                Wproj=_w(self.proj_msa[1].weight, bdt), bproj=_f(self.proj_msa[1].bias),
                 # dense part of the 716-wide Linear: [coevol | ln_pair | att]
-                Wf=_w(torch.cat([W[:, :c0], W[:, c2:c3], W[:, c3:]], 1)), bf=_f(self.resnet[0].bias),
+                Wf=_w(torch.cat([W[:, :c0], W[:, c2:c3], W[:, c3:]], 1), bdt), bf=_f(self.resnet[0].bias),
                 # rank-1 parts: row-tiled and column-tiled msa_1d (fp32 SIMT GEMMs, K = 2Q)
                 Wr=W[:, c0:c1].detach().float().contiguous(), Wc=W[:, c1:c2].detach().float().contiguous(),
                 # bf16 mode: tap-major packed weights of the implicit-GEMM conv kernel; fp32
@@ -603,7 +639,7 @@ class PairUpdateWithMsa(nn.Module):
         msa = _as_f32(msa).contiguous()
         pk = self._pack()
         T, D = msa.numel() // msa.shape[-1], msa.shape[-1]
-        xn = _ln_into(msa.view(T, D), self.proj_msa[0], _empty((T, D), _adt(), msa))
+        xn = _ln_into(msa.view(T, D), self.proj_msa[0], _empty((T, D), _bdt(), msa))
         mraw = _empty((T, self.d_proj), torch.float32, msa)
         ops.gemm(xn, pk["Wproj"], cview(mraw), bias=pk["bproj"])
         return mraw.view(*msa.shape[:-1], self.d_proj)
@@ -623,21 +659,21 @@ class PairUpdateWithMsa(nn.Module):
         Li = hi - lo
         P, H = self.d_pair, self.n_heads
         T, TP = B * N * L, B * Li * L
-        adt = _adt()
+        adt, bdt = _adt(), _bdt()
         # third step of proj_msa (LN, :438); m kept in float32 (tiny), operand copy for GEMMs
         m32 = _ln_into(mraw, self.proj_msa[2], _empty((T, Q), torch.float32, msa))
-        m_op = m32 if _MODE == 1 else _ln_into(mraw, self.proj_msa[2], _empty((T, Q), adt, msa))
+        m_op = m32 if _MODE == 1 else _ln_into(mraw, self.proj_msa[2], _empty((T, Q), bdt, msa))
         w = self.poswise_weight._weights(m_op.view(B, N, L, Q))  # [B,N,L,1] (:469-470)
         # outer-product sum operands + msa_1d (:472-482)
         Np = _up8(N)
-        xt = _empty((B, L * Q, Np), adt, msa)
-        yt = _empty((B, L * Q, Np), adt, msa)
+        xt = _empty((B, L * Q, Np), bdt, msa)
+        yt = _empty((B, L * Q, Np), bdt, msa)
         msa1d = _empty((B, L, 2 * Q), torch.float32, msa)
         ops.opm_prep(m32.view(B, N, L, Q), w.view(B, N, L), xt[..., :N], yt[..., :N], msa1d)
         coevol = self.outer_product_mean._run(xt[:, lo * Q:hi * Q, :N], yt[..., :N], B, L)  # f32 [TP, P]
         # feature buffer [coevol_ln | ln_pair | att] — the 716-wide concat is never built (:487-496)
         KF = 2 * P + H
-        feat = _empty((TP, _up8(KF)), adt, msa)
+        feat = _empty((TP, _up8(KF)), bdt, msa)
         _ln_into(coevol, self.ln_coevol_feat, feat[:, :P])
         _ln_into(pair.view(TP, P), self.ln_pair, feat[:, P:2 * P])
         ops.convert_rows(att.view(TP, H), feat[:, 2 * P:KF])
@@ -693,7 +729,7 @@ class PairUpdateWithAxialAttentionLayer(nn.Module):
         x4 = _performer_block(self.layer[0].fn[0], self.row_attn, x4, token_dim=1)
         x4 = _performer_block(self.layer[1].fn[0], self.col_attn, x4, token_dim=2)
         D = x4.shape[-1]
-        return _ff_block(self.layer[2].fn[0], self.ff, x4.view(-1, D)).view(x4.shape)
+        return _ff_block(self.layer[2].fn[0], self.ff, x4.view(-1, D), _adt()).view(x4.shape)
 
     @torch.no_grad()
     def forward(self, x):
@@ -744,7 +780,7 @@ class MsaUpdateWithPairLayer(nn.Module):
             ln, lin = self.pair2att[1], self.pair2att[2]
             Wf = (lin.weight * ln.weight[None, :]).detach().float().contiguous()
             bf = (lin.weight @ ln.bias + lin.bias).detach().float().contiguous()
-            return dict(Wf=Wf, bf=bf, Wv=_w(self.msa2value[1].weight), bv=_f(self.msa2value[1].bias))
+            return dict(Wf=Wf, bf=bf, Wv=_w(self.msa2value[1].weight, _bdt()), bv=_f(self.msa2value[1].bias))
         return _packed(self, build)
 
     def _run(self, msa, att_p):
@@ -754,7 +790,7 @@ class MsaUpdateWithPairLayer(nn.Module):
         H = self.n_heads
         dh = D // H
         T = B * N * L
-        adt = _adt()
+        adt = _bdt()
         Lp = att_p.shape[-1]
         xn = _ln_into(msa.view(T, D), self.msa2value[0], _empty((T, D), adt, msa))
         vt = _empty((B, H, N * dh, Lp), adt, msa)  # b h (n d) j
@@ -766,7 +802,7 @@ class MsaUpdateWithPairLayer(nn.Module):
             return t.view(B, N, L, H, dh).permute(0, 3, 2, 1, 4).unsqueeze(2)[None]
 
         ops.gemm(att_p[..., :L], vt[..., :L], as_out(y), r0=as_out(msa))  # msa + updated (:592-595)
-        return _ff_block(self.ff.fn[0], self.ff.fn[1], y.view(T, D)).view(B, N, L, D)
+        return _ff_block(self.ff.fn[0], self.ff.fn[1], y.view(T, D), _bdt()).view(B, N, L, D)
 
     @torch.no_grad()
     def forward(self, msa, pair):
@@ -786,7 +822,7 @@ def _pair2att(layers, pair):
     logits = _empty((B, Cn, L, L), torch.float32, pair)
     ops.pair2att_logits(pair, Wf, bf, eps, logits)
     Lp = _up8(L)
-    att_p = _empty((B, Cn, L, Lp), _adt(), pair)
+    att_p = _empty((B, Cn, L, Lp), _bdt(), pair)
     ops.softmax_rows(logits.view(B * Cn * L, L), att_p.view(B * Cn * L, Lp)[:, :L])
     return att_p
 
@@ -803,7 +839,7 @@ def _pair2att_rows(layers, rows, cols_t, gather_rows):
     ops.pair2att_logits_rows(rows, cols_t, Wf, bf, layers[0].pair2att[1].eps, part)
     logits = gather_rows(part)
     Lp = _up8(L)
-    att_p = _empty((B, Cn, L, Lp), _adt(), rows)
+    att_p = _empty((B, Cn, L, Lp), _bdt(), rows)
     ops.softmax_rows(logits.view(B * Cn * L, L), att_p.view(B * Cn * L, Lp)[:, :L])
     return att_p
 
@@ -857,9 +893,9 @@ class MsaUpdateWithPairAndCoord(nn.Module):
 
     def _pack(self):
         return _packed(self, lambda: dict(
-            Wqk=_w(torch.cat([self.to_q.weight, self.to_k.weight], 0)),
+            Wqk=_w(torch.cat([self.to_q.weight, self.to_k.weight], 0), _bdt()),
             bqk=_f(torch.cat([self.to_q.bias, self.to_k.bias], 0)),
-            Wv=_w(self.to_v.weight), bv=_f(self.to_v.bias),
+            Wv=_w(self.to_v.weight, _bdt()), bv=_f(self.to_v.bias),
             bins=torch.tensor([float(b) for b in self.distance_bins], dtype=torch.float32,
                               device=self.to_v.weight.device)))
 
@@ -873,7 +909,7 @@ class MsaUpdateWithPairAndCoord(nn.Module):
         H, di = self.n_heads, self.d_inner
         dh = D // H
         T = B * N * L
-        adt = _adt()
+        adt = _bdt()
         Lp = _up8(L)
         # distance-masked attention map from the state track (:892-913)
         sn = _ln_into(state.view(B * L, -1), self.ln_state, _empty((B * L, state.shape[-1]), adt, msa))
@@ -897,7 +933,7 @@ class MsaUpdateWithPairAndCoord(nn.Module):
         ops.gemm(att[..., :L], vt[..., :L], out.view(B, N, L, H, dh).permute(0, 3, 2, 1, 4).unsqueeze(2)[None])
         y = _empty((T, D), torch.float32, msa)
         ops.layernorm(out.view(T, D), _f(self.ln_out.weight), _f(self.ln_out.bias), self.ln_out.eps, y, res=mn32)
-        return _ff_block(self.to_out.fn[0], self.to_out.fn[1], y).view(B, N, L, D)
+        return _ff_block(self.to_out.fn[0], self.to_out.fn[1], y, _bdt()).view(B, N, L, D)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -17,7 +17,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (ACT_ELU, ACT_NONE, ACT_RELU, EPI_BLOCKLN32, EPI_STD, RFK_BF16, RFK_F32,
+from ._lib import (ACT_ELU, ACT_NONE, ACT_RELU, EPI_BLOCKLN32, EPI_STD, RFK_BF16, RFK_F16, RFK_F32,
                    RfkAddr, RfkFavorDesc, RfkGemmDesc)
 
 __all__ = [
@@ -33,7 +33,9 @@ def _dt(t: torch.Tensor) -> int:
         return RFK_F32
     if t.dtype == torch.bfloat16:
         return RFK_BF16
-    raise TypeError(f"rfk ops take float32 or bfloat16 tensors, got {t.dtype}")
+    if t.dtype == torch.float16:
+        return RFK_F16
+    raise TypeError(f"rfk ops take float32, bfloat16 or float16 tensors, got {t.dtype}")
 
 
 def _ptr(t):
@@ -338,7 +340,7 @@ def gemm(a, b, c_view, *, bias=None, act=ACT_NONE, alpha=1.0, r0=None, r1=None, 
             raise ValueError("gemm: residual views must share c_view's (M1,MR,N1,NR) split")
     if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
         raise ValueError("gemm: bias must be contiguous float32 of length N")
-    name = "gemm_bf16" if a.dtype == torch.bfloat16 else "gemm_f32"
+    name = "gemm_f32" if a.dtype == torch.float32 else "gemm_bf16"  # (bucket of the 16-bit tensor-core GEMMs)
     with _Timed(name, 2.0 * Zs[0] * Zs[1] * Zs[2] * M * N * ash[4]):  # algorithmic FLOPs
         _call("gemm", a, b, c_view, bias, act, float(alpha), r0, r1, epi, ln_gamma, ln_beta, float(ln_eps))
     return c_view

@@ -94,7 +94,7 @@ class SequenceShard:
 
     def first_sequence(self, xn4: torch.Tensor) -> torch.Tensor:
         """[B, N/P, L, D] -> [B, 1, L, D]: sequence 0 of the whole MSA (rank 0's first row)."""
-        row = xn4[:, :1].contiguous()
+        row = xn4[:, :1].clone()  # (a size-1 slice is "contiguous": .contiguous() would alias xn4 and the broadcast overwrite it)
         dist.broadcast(row, src=self.root, group=self.group)
         return row
 
@@ -165,7 +165,7 @@ class ShardedPairAxialAttention(nn.Module):
             x.view(Li, world, L // world, D).add_(back.permute(1, 0, 2, 3))
             # ---- column attention and feed-forward are local to the row shard ----
             x = M._performer_block(layer.layer[1].fn[0], layer.col_attn, x, token_dim=2)
-            x = M._ff_block(layer.layer[2].fn[0], layer.ff, x.view(-1, D)).view(1, Li, L, D)
+            x = M._ff_block(layer.layer[2].fn[0], layer.ff, x.view(-1, D), adt).view(1, Li, L, D)
         return x
 
 
