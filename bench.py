@@ -304,7 +304,7 @@ def run_b200(args):
         dom, work, e = max(buckets, key=lambda t: t[2]["ms"])
         avg_ms = e["ms"] / e["calls"]
         ach = work / (avg_ms * 1e-3) / 1e12
-        kernel = {"gemm_bf16": "rfk::gemm_tc_kernel (tcgen05)", "favor_attention": "rfk::favor_tc_kernel (tcgen05 FAVOR+)",
+        kernel = {"gemm_bf16": "rfk::gemm_tc_kernel (tcgen05)", "favor_attention": "rfk::favor_tm_kernel (tcgen05 FAVOR+, features in TMEM)",
                   "gemm_f32": "rfk::gemm_f32_kernel", "conv3x3": "rfk::gemm_tc_kernel<CONV> (implicit GEMM)"}[dom]
         # DRAM bytes per launch of that kernel from the round's `ncu --set full` capture (profiles/)
         traffic = None

@@ -103,6 +103,28 @@ def test_cuda_graph_replay_matches_eager(cuda_device):
         gblk(msa.cpu(), pair.cpu())
 
 
+def test_cuda_graph_follows_mode_and_weight_changes(cuda_device):
+    """A captured graph has the numerics mode and the packed weights baked in: GraphedModule must re-capture when
+    either changes instead of replaying the stale graph."""
+    cfg = dict(d_msa=96, d_pair=72, n_layers=1, B=1, N=9, L=40, seed=12)
+    blk, _, msa, pair = build_block(cfg, cuda_device)
+    gblk = rf.GraphedModule(blk)
+    m16, p16 = (t.clone() for t in gblk(msa, pair))
+    rf.set_mode("fp32")
+    m_ref, p_ref = blk(msa, pair)
+    m32, p32 = gblk(msa, pair)
+    torch.cuda.synchronize()
+    assert rel_l2(m32, m_ref) < 1e-6 and rel_l2(p32, p_ref) < 1e-6
+    assert rel_l2(m32, m16) > 1e-6  # (the two modes do differ: the check above is not vacuous)
+    rf.set_mode("bf16")
+    with torch.no_grad():
+        blk.msa_update_with_pair.encoder_layers[0].ff.fn[1].net[3].bias.add_(0.5)
+    m_ref, p_ref = blk(msa, pair)
+    m, p = gblk(msa, pair)
+    torch.cuda.synchronize()
+    assert rel_l2(m, m_ref) < 1e-6 and rel_l2(m, m16) > 1e-3
+
+
 @pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
 def test_msa_update_with_pair_and_coord_vs_golden(cuda_device, mode, tol):
     """MsaUpdateWithPairAndCoord (:865-920) through librfk vs the unmodified reference's output."""
