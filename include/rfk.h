@@ -262,6 +262,26 @@ int rfk_conv3x3_nhwc_hw(const void* x, const void* w_packed, void* y, int y_dtyp
 int rfk_conv3x3_nhwc_f32(const float* x, const float* w_packed, float* y, int B, int H, int L, int C, int Cout,
                          rfk_stream_t stream);
 
+/*
+ * Embeddings that feed the trunk (reference :57-181), fused gathers on the device
+ * (the reference gathers CPU-resident tables in Python loops over the batch, :73, :98, :115-116).
+ *   rfk_msa_embed:  MsaEmbedding.forward :114-120.  tokens i64 [B][N][L] in [0, V), aa_idx i64 [B][L] in [0, max_len);
+ *     emb f32 [V][D], pos_enc f32 [max_len][D] (SinusoidalPositionalEncoding table :63-68), query_enc f32 [2][D];
+ *     out f32 [B][N][L][D] = emb[tok] + pos_enc[aa] + query_enc[n == 0 ? 0 : 1].   D % 4 == 0.
+ *   rfk_pair_embed: PairEmbedding.forward :147-175 without template. seq, aa_idx i64 [B][L];
+ *     table_left / table_right f32 [V][D] = embed_seq.weight @ proj.weight[:, :D/2]^T / [:, D/2:D]^T (the Linear of :173
+ *     applied to the two gathered halves of the concatenation), w_sep f32 [D] = proj.weight[:, D], bias f32 [D],
+ *     pos_enc_half f32 [max_len][D/2] (SinusoidalPositionalEncoding2D table :86-91);
+ *     out f32 [B][L][L][D] = table_left[seq_j] + table_right[seq_i] + w_sep log(|aa_i - aa_j| + 1) + bias
+ *                            + [pos_enc_half[aa_i] | pos_enc_half[aa_j]].   D % 8 == 0.
+ * Index ranges are the caller's contract (the Python modules check them like nn.Embedding does).
+ */
+int rfk_msa_embed(const int64_t* tokens, const int64_t* aa_idx, const float* emb, const float* pos_enc,
+                  const float* query_enc, float* out, int B, int N, int L, int D, rfk_stream_t stream);
+int rfk_pair_embed(const int64_t* seq, const int64_t* aa_idx, const float* table_left, const float* table_right,
+                   const float* w_sep, const float* bias, const float* pos_enc_half, float* out, int B, int L, int D,
+                   rfk_stream_t stream);
+
 /* Cast / copy rows between dtypes with row strides (host-side plumbing for column slices). */
 int rfk_convert_rows(const void* x, int x_dtype, int64_t x_row_stride, void* y, int y_dtype,
                      int64_t y_row_stride, int64_t rows, int cols, rfk_stream_t stream);

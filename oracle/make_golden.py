@@ -43,6 +43,49 @@ def subset(stages, c):
                 msa_d=stages["msa_d"][:, mr].clone())
 
 
+# MsaEmbedding / PairEmbedding (:106-181): reduced widths with a template, default widths without; residue indices
+# with a chain break (a gap in aa_idx) so the sequence-separation feature and the positional tables see non-trivial input
+EMBED_CONFIGS = {
+    "small_template": dict(d_input=21, d_msa=96, d_pair=72, max_len=64, d_template=16, use_template=True, B=2, N=5, L=20, seed=70),
+    "default": dict(d_input=21, d_msa=384, d_pair=288, max_len=300, d_template=64, use_template=False, B=1, N=3, L=12, seed=71),
+}
+
+
+def synth_embed_inputs(c):
+    g = torch.Generator().manual_seed(c["seed"] + 100)
+    B, N, L = c["B"], c["N"], c["L"]
+    tokens = torch.randint(0, c["d_input"], (B, N, L), generator=g)
+    seq = torch.randint(0, c["d_input"], (B, L), generator=g)
+    aa_idx = torch.arange(L).repeat(B, 1)
+    aa_idx[:, L // 2:] += 17  # chain break
+    template = torch.randn((B, L, L, c["d_template"]), generator=g) if c["use_template"] else None
+    return tokens, seq, aa_idx, template
+
+
+def make_embeddings(ref, rf):
+    out = {}
+    for name, c in EMBED_CONFIGS.items():
+        mine_m = rf.MsaEmbedding(c["d_input"], c["d_msa"], c["max_len"])
+        mine_p = rf.PairEmbedding(c["d_input"], c["d_pair"], c["max_len"], use_template=c["use_template"], d_template=c["d_template"])
+        sd_m = synth_state_dict(mine_m.state_dict(), seed=c["seed"])
+        sd_p = synth_state_dict(mine_p.state_dict(), seed=c["seed"] + 1)
+        rm = ref.MsaEmbedding(c["d_input"], c["d_msa"], c["max_len"])
+        rp = ref.PairEmbedding(c["d_input"], c["d_pair"], c["max_len"], use_template=c["use_template"], d_template=c["d_template"])
+        rm.load_state_dict(sd_m, strict=True)
+        rp.load_state_dict(sd_p, strict=True)
+        rm.eval(), rp.eval()
+        tokens, seq, aa_idx, template = synth_embed_inputs(c)
+        with torch.no_grad():
+            msa = rm(tokens, aa_idx)
+            pair = rp(seq, aa_idx, template) if c["use_template"] else rp(seq, aa_idx)
+        out[name] = dict(config=c, weight_checksums=(checksum(sd_m), checksum(sd_p)), msa=msa, pair=pair)
+        print("embeddings", name, tuple(msa.shape), tuple(pair.shape))
+    path = os.path.join(ROOT, "tests", "golden", "embeddings.pt")
+    out["generator"] = "oracle/make_golden.py --embeddings-only on the unmodified reference (CPU fp32, eval)"
+    torch.save(out, path)
+    print(os.path.getsize(path))
+
+
 COORD_CONFIGS = {
     # MsaUpdateWithPairAndCoord (:865-920) as built by the three-track blocks (:1028-1035), ragged N / L
     "msa_pair_coord": dict(d_msa=96, d_state=32, d_inner=32, d_ff=192, B=2, N=5, L=20, seed=6),
@@ -145,7 +188,10 @@ def main():
             return make_model_trace(ref, rf)
         finally:
             os.chdir(cwd)
+    if "--embeddings-only" in sys.argv:
+        return make_embeddings(ref, rf)
     if "--subset-only" not in sys.argv:
+        make_embeddings(ref, rf)
         make_coord(ref, rf)
     if "--coord-only" in sys.argv:
         return

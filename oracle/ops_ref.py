@@ -192,5 +192,19 @@ class RefBackend:
         y = torch.nn.functional.conv2d(x.to(self.acc).permute(0, 3, 1, 2), w, padding=1)
         out.copy_(y.permute(0, 2, 3, 1).to(out.dtype))
 
+    # MsaEmbedding.forward (:114-120) / PairEmbedding.forward (:147-175) at the C-ABI boundary
+    def msa_embed(self, tokens, aa_idx, emb, pos_enc, query_enc, out):
+        B, N, L = tokens.shape
+        q = torch.ones(N, dtype=torch.long)
+        q[0] = 0
+        out.copy_((emb[tokens] + pos_enc[aa_idx][:, None]) + query_enc[q][None, :, None, :])
+
+    def pair_embed(self, seq, aa_idx, table_left, table_right, w_sep, bias, pos_enc_half, out):
+        sep = torch.log((aa_idx[:, :, None] - aa_idx[:, None, :]).abs().float() + 1.0)[..., None]
+        x = table_left[seq][:, None, :, :] + table_right[seq][:, :, None, :] + w_sep * sep + bias
+        pe = pos_enc_half[aa_idx]
+        L = seq.shape[1]
+        out.copy_(x + torch.cat([pe[:, :, None, :].expand(-1, -1, L, -1), pe[:, None, :, :].expand(-1, L, -1, -1)], -1))
+
     def convert_rows(self, x, out):
         out.copy_(x.to(out.dtype))

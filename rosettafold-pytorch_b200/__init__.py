@@ -13,6 +13,8 @@ from .modules import (ColWise, EncoderLayer, FeedForward, MsaUpdateUsingSelfAtte
                       PairUpdateWithMsa, PerformerSelfAttention, PositionWiseWeightFactor, Residual,
                       RowWise, SoftTiedAttentionOverResidues, Symmetrization, TrunkBlocks,
                       TwoTrackBlock, get_mode, load_reference_weights, set_bounded_operand_dtype, set_mode)
+from .embeddings import (MsaEmbedding, PairEmbedding, SinusoidalPositionalEncoding,  # noqa: E402,F401
+                         SinusoidalPositionalEncoding2D)
 from . import replicas  # noqa: E402,F401
 from .integration import accelerate, accelerate_block  # noqa: E402,F401
 from .graphs import GraphedModule  # noqa: E402,F401

@@ -36,6 +36,9 @@ SCHEMAS = {
     "conv3x3": "(Tensor x, Tensor w_packed, Tensor(a!) out) -> ()",
     "conv3x3_f32": "(Tensor x, Tensor w_packed, Tensor(a!) out) -> ()",
     "convert_rows": "(Tensor x, Tensor(a!) out) -> ()",
+    "msa_embed": "(Tensor tokens, Tensor aa_idx, Tensor emb, Tensor pos_enc, Tensor query_enc, Tensor(a!) out) -> ()",
+    "pair_embed": "(Tensor seq, Tensor aa_idx, Tensor table_left, Tensor table_right, Tensor w_sep, Tensor bias, "
+                  "Tensor pos_enc_half, Tensor(a!) out) -> ()",
 }
 
 _library = None

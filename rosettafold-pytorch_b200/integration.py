@@ -89,8 +89,23 @@ def accelerate_block(block: nn.Module, device=None, hop: bool = False) -> nn.Mod
     return block
 
 
-def accelerate(model: nn.Module, device=None, hop: bool = False) -> nn.Module:
-    """Replace the trunk of every block of a reference RoseTTAFold (rosettafold_pytorch.py:1220-1267).
+def _make_embedding(name: str, ref: nn.Module) -> nn.Module:
+    from . import embeddings as E
+
+    if name == "msa_emb":  # MsaEmbedding (:106-120)
+        return E.MsaEmbedding(d_input=ref.to_embedding.num_embeddings, d_msa=ref.to_embedding.embedding_dim,
+                              max_len=ref.pos_enc.max_len)
+    use_template = bool(ref.use_template)  # PairEmbedding (:123-181)
+    d_pair = ref.proj.out_features
+    return E.PairEmbedding(d_input=ref.embed_seq.num_embeddings, d_pair=d_pair, max_len=ref.pos_enc.max_len,
+                           use_template=use_template,
+                           d_template=ref.proj.in_features - d_pair - 1 if use_template else 64)
+
+
+def accelerate(model: nn.Module, device=None, hop: bool = False, embeddings: bool = True) -> nn.Module:
+    """Replace the trunk of every block of a reference RoseTTAFold (rosettafold_pytorch.py:1220-1267) and, with
+    `embeddings` (default), the two embeddings that feed it (`msa_emb`, `pair_emb`, :1205-1219): the reference's
+    own embeddings cannot run on a GPU at all (CPU-resident tables gathered by Python loops).
 
     `hop=True` is for the UNMODIFIED reference model, which only runs on the CPU (its embeddings index CPU tables
     with Python loops and its list-held layers ignore `.to()`): the swapped trunk
@@ -107,6 +122,13 @@ def accelerate(model: nn.Module, device=None, hop: bool = False) -> nn.Module:
         blocks = [model]
     for blk in blocks:
         accelerate_block(blk, device, hop)
+    if embeddings and whole_model:
+        for name in ("msa_emb", "pair_emb"):
+            old = getattr(model, name, None)
+            if old is not None and not type(old).__module__.startswith("rosettafold_pytorch_b200"):
+                new = _make_embedding(name, old)
+                new.load_state_dict(old.state_dict(), strict=True)
+                setattr(model, name, new.eval().to(device) if device is not None else new.eval())
     if hop and whole_model:
         # the model's own direct children (embeddings, initial coordinates, prediction head); the block containers
         # are skipped, their blocks were handled above

@@ -24,7 +24,7 @@ __all__ = [
     "ACT_NONE", "ACT_RELU", "ACT_ELU", "EPI_STD", "EPI_BLOCKLN32",
     "gemm", "layernorm", "softmax_rows", "tied_att_symmetrize", "poswise_weight", "opm_prep",
     "pair2att_logits", "channel_stats", "instnorm_apply", "favor_attention", "convert_rows", "dist_mask_logits",
-    "conv3x3", "pack_conv3x3_weight", "conv3x3_f32", "pack_conv3x3_weight_f32",
+    "conv3x3", "pack_conv3x3_weight", "conv3x3_f32", "pack_conv3x3_weight_f32", "msa_embed", "pair_embed",
 ]
 
 
@@ -197,6 +197,17 @@ class _CudaBackend:
         B, H, L, Cin = x.shape
         _lib.check(self.lib.rfk_conv3x3_nhwc_f32(_ptr(x), _ptr(w_packed), _ptr(out), B, H, L, Cin, out.shape[3],
                                                  self._stream(x)), "rfk_conv3x3_nhwc_f32")
+
+    def msa_embed(self, tokens, aa_idx, emb, pos_enc, query_enc, out):
+        B, N, L = tokens.shape
+        _lib.check(self.lib.rfk_msa_embed(_ptr(tokens), _ptr(aa_idx), _ptr(emb), _ptr(pos_enc), _ptr(query_enc), _ptr(out),
+                                          B, N, L, emb.shape[1], self._stream(out)), "rfk_msa_embed")
+
+    def pair_embed(self, seq, aa_idx, table_left, table_right, w_sep, bias, pos_enc_half, out):
+        B, L = seq.shape
+        _lib.check(self.lib.rfk_pair_embed(_ptr(seq), _ptr(aa_idx), _ptr(table_left), _ptr(table_right), _ptr(w_sep),
+                                           _ptr(bias), _ptr(pos_enc_half), _ptr(out), B, L, table_left.shape[1],
+                                           self._stream(out)), "rfk_pair_embed")
 
     def convert_rows(self, x, out):
         _lib.check(self.lib.rfk_convert_rows(_ptr(x), _dt(x), x.stride(0), _ptr(out), _dt(out),
@@ -552,6 +563,51 @@ def conv3x3_f32(x, w_packed, out):
     if tuple(out.shape) != (*x.shape[:3], w_packed.shape[2]) or not out.is_contiguous() or out.dtype != torch.float32:
         raise ValueError("conv3x3_f32: bad output")
     _call("conv3x3_f32", x, w_packed, out)
+    return out
+
+
+def _check_index(name, idx, shape, limit):
+    """Integer gather indices: contiguous int64 of the given shape with values in [0, limit) (checked like nn.Embedding
+    does; the check reads the tensor back, once per forward of an embedding)."""
+    if idx.dtype != torch.int64 or tuple(idx.shape) != tuple(shape) or not idx.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous int64 tensor of shape {tuple(shape)}")
+    if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= limit):
+        raise IndexError(f"{name}: index out of range [0, {limit})")
+
+
+def _f32c(name, t, shape):
+    if t.dtype != torch.float32 or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous float32 tensor of shape {tuple(shape)}")
+
+
+def msa_embed(tokens, aa_idx, emb, pos_enc, query_enc, out):
+    """MsaEmbedding.forward (reference :114-120): out[b,n,l] = emb[tokens[b,n,l]] + pos_enc[aa_idx[b,l]] + query_enc[n>0]."""
+    B, N, L = tokens.shape
+    V, D = emb.shape
+    _check_index("tokens", tokens, (B, N, L), V)
+    _check_index("aa_idx", aa_idx, (B, L), pos_enc.shape[0])
+    _f32c("pos_enc", pos_enc, (pos_enc.shape[0], D))
+    _f32c("query_enc", query_enc, (2, D))
+    _f32c("emb", emb, (V, D))
+    _f32c("out", out, (B, N, L, D))
+    _call("msa_embed", tokens, aa_idx, emb, pos_enc, query_enc, out)
+    return out
+
+
+def pair_embed(seq, aa_idx, table_left, table_right, w_sep, bias, pos_enc_half, out):
+    """PairEmbedding.forward without template (reference :147-175) from the per-vocabulary tables of the split Linear
+    (include/rfk.h): out[b,i,j] = table_left[seq[b,j]] + table_right[seq[b,i]] + w_sep log(|aa_i - aa_j| + 1) + bias + PE."""
+    B, L = seq.shape
+    V, D = table_left.shape
+    _check_index("seq", seq, (B, L), V)
+    _check_index("aa_idx", aa_idx, (B, L), pos_enc_half.shape[0])
+    _f32c("table_left", table_left, (V, D))
+    _f32c("table_right", table_right, (V, D))
+    _f32c("w_sep", w_sep, (D,))
+    _f32c("bias", bias, (D,))
+    _f32c("pos_enc_half", pos_enc_half, (pos_enc_half.shape[0], D // 2))
+    _f32c("out", out, (B, L, L, D))
+    _call("pair_embed", seq, aa_idx, table_left, table_right, w_sep, bias, pos_enc_half, out)
     return out
 
 

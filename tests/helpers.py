@@ -104,3 +104,18 @@ def run_trace_block(blk, coord, rec):
         errs["msa_coord"] = rel_l2(coord(rec["xyz"], rec["state"], rec["msa_coord_in"]), rec["msa_coord_out"])
         errs["msa_coord_chain"] = rel_l2(coord(rec["xyz"], rec["state"], msa), rec["msa_coord_out"])
     return errs
+
+
+def build_embeddings(c, device="cpu"):
+    """The b200 MsaEmbedding / PairEmbedding with a fixture's synthetic weights (oracle/make_golden.py EMBED_CONFIGS),
+    and the fixture's inputs."""
+    import rosettafold_pytorch_b200 as rf
+    from oracle.make_golden import synth_embed_inputs
+
+    m = rf.MsaEmbedding(c["d_input"], c["d_msa"], c["max_len"]).eval()
+    p = rf.PairEmbedding(c["d_input"], c["d_pair"], c["max_len"], use_template=c["use_template"], d_template=c["d_template"]).eval()
+    sd_m = synth_state_dict(m.state_dict(), seed=c["seed"])
+    sd_p = synth_state_dict(p.state_dict(), seed=c["seed"] + 1)
+    m.load_state_dict(sd_m, strict=True)
+    p.load_state_dict(sd_p, strict=True)
+    return m.to(device), p.to(device), sd_m, sd_p, synth_embed_inputs(c)

@@ -206,6 +206,49 @@ def test_accelerate_whole_reference_model(emulated_ops, tmp_path, monkeypatch):
     assert rel_l2(xyz2, xyz) < 1e-4 and rel_l2(plddt2, plddt) < 1e-4
 
 
+@pytest.mark.skipif(not __import__("oracle.reference_loader", fromlist=["x"]).available(),
+                    reason="reference source only exists in the build container")
+def test_whole_model_drift_with_16bit_operands(emulated_ops, tmp_path, monkeypatch, capsys):
+    """Row (g) of the scope table, bounded on the CPU: the whole unmodified reference model (README widths: d_msa 384,
+    d_pair 288; 2 two-track + 2 three-track blocks + final block, kNN graphs with n_neighbors < L so that a trunk
+    perturbation CAN flip a neighbour) with its trunk swapped for the b200 modules in the TENSOR-CORE mode, the ops
+    emulated by oracle/ops_ref.py on tensors stored in the kernels' operand formats (bf16 / IEEE half).
+
+    Asserted: what the trunk hands to the final block stays inside the 1e-2 budget. Measured and printed (DESIGN.md
+    section 4 quotes them): the four logits, xyz and pLDDT of the whole model. Those sit DOWNSTREAM of reference code
+    that amplifies any perturbation with random-init weights (InstanceNorm ResNet heads: x2.5; the SE(3) track behind
+    a top-k kNN graph: x10 and more, SURVEY.md section 7 "hard parts"), so for them only a sanity bound is asserted;
+    the fp32 validation mode reproduces all of them to 1e-4 (test_accelerate_whole_reference_model)."""
+    from oracle import reference_loader as rl
+
+    monkeypatch.chdir(tmp_path)
+    ref = rl.load()
+    torch.manual_seed(0)
+    model = rl.fix_eval(ref.RoseTTAFold(d_input=21, d_msa=384, d_pair=288, d_node=32, d_edge=32, d_state=32,
+                                        n_two_track_blocks=2, n_three_track_blocks=3, n_encoder_layers=2,
+                                        n_neighbors=[12, 12], p_dropout=0.1, max_len=64))
+    g = torch.Generator().manual_seed(1234)
+    B, N, L = 1, 6, 24
+    msa, seq = torch.randint(0, 21, (B, N, L), generator=g), torch.randint(0, 21, (B, L), generator=g)
+    aa_idx = torch.arange(L).repeat(B, 1)
+    seen = []
+    model.final_block.register_forward_pre_hook(lambda m, a: seen.append((a[0].clone(), a[1].clone())))
+    with torch.no_grad():
+        logits, xyz, plddt = model(msa, seq, aa_idx)
+    rf.set_mode("bf16")
+    rf.accelerate(model)
+    with torch.no_grad():
+        logits2, xyz2, plddt2 = model(msa, seq, aa_idx)
+    trunk = dict(msa=rel_l2(seen[1][0], seen[0][0]), pair=rel_l2(seen[1][1], seen[0][1]))
+    errs = {k: rel_l2(logits2[k], logits[k]) for k in logits}
+    errs.update(xyz=rel_l2(xyz2, xyz), plddt=rel_l2(plddt2, plddt))
+    with capsys.disabled():
+        print("\nwhole model, 16-bit operand emulation vs reference: trunk into the final block",
+              {k: f"{v:.2e}" for k, v in trunk.items()}, "model outputs", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(trunk.values()) < 1e-2, trunk
+    assert max(errs[k] for k in logits) < 5e-2 and errs["xyz"] < 0.5 and errs["plddt"] < 0.5, errs
+
+
 @pytest.mark.parametrize("name", ["two_track_blocks.0", "three_track_blocks.0", "final_block"])
 def test_blocks_in_situ_match_model_trace(emulated_ops, name):
     """Host logic on the activations / coordinates of a whole reference-model forward (tests/golden/model_trace.pt)."""
@@ -284,3 +327,22 @@ def test_accelerate_with_device_hops_keeps_structure_and_results(emulated_ops, t
     for k in logits:
         assert rel_l2(logits2[k], logits[k]) < 1e-4
     assert rel_l2(xyz2, xyz) < 1e-4 and rel_l2(plddt2, plddt) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["small_template", "default"])
+def test_embeddings_match_golden(emulated_ops, name):
+    """Host logic of the embedding modules (table packing of the split Linear, template path, index handling)
+    against the unmodified reference's outputs; the kernels themselves are checked by `-m gpu`."""
+    from tests.helpers import build_embeddings
+
+    gold = load_golden("embeddings")[name]
+    m, p, _, _, (tokens, seq, aa_idx, template) = build_embeddings(gold["config"])
+    rf.set_mode("fp32")
+    assert rel_l2(m(tokens, aa_idx), gold["msa"]) < 1e-6
+    out = p(seq, aa_idx, template) if template is not None else p(seq, aa_idx)
+    assert rel_l2(out, gold["pair"]) < 1e-6
+    with pytest.raises(IndexError):
+        m(tokens + 100, aa_idx)
+    if template is None:
+        with pytest.raises(ValueError):
+            p(seq, aa_idx, torch.zeros(1))

@@ -101,3 +101,20 @@ def test_performer_restatement_is_an_unbiased_softmax_attention_estimator():
     proj = P.gaussian_orthogonal_random_matrix(4096, d, generator=torch.Generator().manual_seed(3)).double()
     gen = P.favor_attention(q, k, v, proj, True)
     assert float((gen - exact).norm() / exact.norm()) > 0.05
+
+
+@pytest.mark.parametrize("name", ["small_template", "default"])
+def test_embedding_restatement_matches_golden(name):
+    """oracle/embed_ref.py against the outputs of the unmodified reference's MsaEmbedding / PairEmbedding."""
+    from oracle import embed_ref
+    from tests.helpers import build_embeddings
+
+    gold = load_golden("embeddings")[name]
+    c = gold["config"]
+    _, _, sd_m, sd_p, (tokens, seq, aa_idx, template) = build_embeddings(c)
+    assert abs(checksum(sd_m) - gold["weight_checksums"][0]) < 1e-6 * gold["weight_checksums"][0]
+    assert abs(checksum(sd_p) - gold["weight_checksums"][1]) < 1e-6 * gold["weight_checksums"][1]
+    msa = embed_ref.msa_embedding(tokens, aa_idx, sd_m, c["max_len"])
+    pair = embed_ref.pair_embedding(seq, aa_idx, sd_p, c["max_len"], template=template)
+    assert torch.equal(msa, gold["msa"])          # integer gathers and two fp32 adds in the reference's order: exact
+    assert rel_l2(pair, gold["pair"]) < 1e-6

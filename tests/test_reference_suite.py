@@ -21,12 +21,14 @@ REF_TESTS = "/root/reference/tests/test_module.py"
 pytestmark = pytest.mark.skipif(not (rl.available() and os.path.exists(REF_TESTS)),
                                 reason="reference source only exists in the build container")
 
-PATH_CLASSES = ["PositionWiseWeightFactor", "SoftTiedAttentionOverResidues", "EncoderLayer",
+PATH_CLASSES = ["SinusoidalPositionalEncoding", "SinusoidalPositionalEncoding2D", "MsaEmbedding", "PairEmbedding",
+                "PositionWiseWeightFactor", "SoftTiedAttentionOverResidues", "EncoderLayer",
                 "MsaUpdateUsingSelfAttention", "OuterProductMean", "PairUpdateWithMsa", "PairUpdateWithAxialAttention",
                 "Symmetrization", "MsaUpdateWithPair", "MsaUpdateWithPairAndCoord", "TwoTrackBlock"]
 ACCELERATED = ["ThreeTrackBlock", "FinalBlock", "RoseTTAFold"]
-# reference tests that exercise the path (the others test embeddings / the SE(3) track, which stay on the reference)
-SELECTED = ["PositionWiseWeightFactor", "SoftTiedAttentionOverResidues", "EncoderLayer", "MsaUpdateUsingSelfAttention",
+# reference tests that exercise the path and its callers on the input side (the others test the SE(3) track, which
+# stays on the reference)
+SELECTED = ["sinusoidal_positional_encoding", "PairEmbedding_raises", "MsaEmbedding", "PairEmbedding", "PositionWiseWeightFactor", "SoftTiedAttentionOverResidues", "EncoderLayer", "MsaUpdateUsingSelfAttention",
             "OuterProductMean", "PairUpdateWithMsa", "PairUpdateWithAxialAttention", "Symmetrization",
             "MSAUpdateWithPair", "MsaUpdateWithPairAndCoord", "TwoTrackBlock", "ThreeTrackBlock", "FinalBlock",
             "RoseTTAFold"]
