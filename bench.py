@@ -38,6 +38,10 @@ def parse():
     ap.add_argument("--batch", type=int, default=1, help="samples per GPU per step")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-long-protein", action="store_true", help="skip the config-4 record of multi-GPU runs")
+    ap.add_argument("--long-L", type=int, default=1024)
+    ap.add_argument("--long-N", type=int, default=256)
+    ap.add_argument("--long-blocks", type=int, default=2)
     return ap.parse_args()
 
 
@@ -352,10 +356,62 @@ def run_b200(args):
         line["cpu_baseline"] = {"value": B / (args.blocks * block_s), "unit": "samples/s", "cores": threads, "kind": "port",
                                 "sample": sample_desc(args) + " (one timed block here; `--impl reference` averages K)",
                                 "block_s": round(block_s, 2)}
+    if world > 1 and not args.no_long_protein:
+        # outside the timed regions above; appended to the same JSON line so that the driver's scaling run carries it
+        try:
+            line["long_protein"] = long_protein_record(args, torch, dist, rf, dev, rank, world)
+        except Exception as e:  # the headline (replicas) number must survive a failure of the extra record
+            line["long_protein"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def long_protein_record(args, torch, dist, rf, dev, rank, world):
+    """BASELINE.json config 4 under the driver's multi-GPU runs: ONE long protein (1, 256, 1024) through a trunk of
+    `long_blocks` blocks sharded over the ranks (rosettafold_pytorch_b200/sharded.py: MSA sequence- / residue-sharded,
+    pair map row-sharded, NCCL all-to-all / all-reduce / all-gather between the stages), against the same trunk on one
+    GPU of the same box: ms per block (CUDA events, max over ranks), speed-up, and rel-L2 of the sharded result."""
+    L, N, nb = args.long_L, args.long_N, args.long_blocks
+    if N % world or L % world:
+        return {"skipped": f"Nseq {N} / L {L} not divisible by {world} ranks"}
+    torch.manual_seed(4321)  # identical weights (and FAVOR projections) on every rank
+    trunk = rf.TrunkBlocks(D_MSA, D_PAIR, n_blocks=nb, n_encoder_layers=N_LAYERS).eval().to(dev)
+    g = torch.Generator().manual_seed(77)
+    msa = torch.randn((1, N, L, D_MSA), generator=g).to(dev)
+    pair = torch.randn((1, L, L, D_PAIR), generator=g).to(dev)
+    sharded = rf.ShardedTrunkBlocks(trunk)
+
+    def timed(fn, steps=3):
+        for _ in range(2):
+            out = fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            out = fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b) / steps], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / nb, out
+
+    ms_sharded, (m_s, p_s) = timed(lambda: sharded(msa, pair))
+    ms_single, (m_1, p_1) = timed(lambda: trunk(msa, pair))  # every rank runs the whole protein on its own GPU
+
+    def rel(a, b):
+        return float((a.double() - b.double()).norm() / b.double().norm())
+
+    rec = {"config": f"one protein (1,{N},{L}), {nb} blocks x {N_LAYERS} encoder layers, sharded over {world} GPUs "
+                     "(MSA by sequence / residue, pair map by row; NCCL all-to-all, all-reduce, all-gather)",
+           "n_gpus": world, "ms_per_block_sharded": ms_sharded, "ms_per_block_one_gpu": ms_single,
+           "speedup": ms_single / ms_sharded, "scaling": "strong",
+           "rel_l2_vs_one_gpu": {"msa": rel(m_s, m_1), "pair": rel(p_s, p_1)}}
+    del trunk, sharded, msa, pair, m_s, p_s, m_1, p_1
+    torch.cuda.empty_cache()
+    return rec
 
 
 def main():
