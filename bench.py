@@ -381,7 +381,8 @@ def long_protein_record(args, torch, dist, rf, dev, rank, world):
     g = torch.Generator().manual_seed(77)
     msa = torch.randn((1, N, L, D_MSA), generator=g).to(dev)
     pair = torch.randn((1, L, L, D_PAIR), generator=g).to(dev)
-    sharded = rf.ShardedTrunkBlocks(trunk)
+    eager = rf.ShardedTrunkBlocks(trunk)
+    sharded = rf.sharded.SegmentedGraph(eager)  # CUDA graphs of the compute segments, collectives eager in between
 
     def timed(fn, steps=3):
         for _ in range(2):
@@ -399,6 +400,7 @@ def long_protein_record(args, torch, dist, rf, dev, rank, world):
         return float(ms.item()) / nb, out
 
     ms_sharded, (m_s, p_s) = timed(lambda: sharded(msa, pair))
+    ms_eager, _ = timed(lambda: eager(msa, pair))
     ms_single, (m_1, p_1) = timed(lambda: trunk(msa, pair))  # every rank runs the whole protein on its own GPU
 
     def rel(a, b):
@@ -406,10 +408,13 @@ def long_protein_record(args, torch, dist, rf, dev, rank, world):
 
     rec = {"config": f"one protein (1,{N},{L}), {nb} blocks x {N_LAYERS} encoder layers, sharded over {world} GPUs "
                      "(MSA by sequence / residue, pair map by row; NCCL all-to-all, all-reduce, all-gather)",
-           "n_gpus": world, "ms_per_block_sharded": ms_sharded, "ms_per_block_one_gpu": ms_single,
+           "execution": "rf.sharded.SegmentedGraph: one CUDA graph per compute segment, NCCL collectives issued eagerly in between",
+           "segments": sharded.segments(),
+           "n_gpus": world, "ms_per_block_sharded": ms_sharded, "ms_per_block_sharded_eager_launches": ms_eager,
+           "ms_per_block_one_gpu": ms_single,
            "speedup": ms_single / ms_sharded, "scaling": "strong",
            "rel_l2_vs_one_gpu": {"msa": rel(m_s, m_1), "pair": rel(p_s, p_1)}}
-    del trunk, sharded, msa, pair, m_s, p_s, m_1, p_1
+    del trunk, sharded, eager, msa, pair, m_s, p_s, m_1, p_1
     torch.cuda.empty_cache()
     return rec
 

@@ -46,6 +46,106 @@ from . import modules as M
 
 _STAGE_TIMING = bool(os.environ.get("RFK_SHARD_TIMING"))  # developer aid: per-stage device times of every block
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Collectives go through `_collective`, which is what lets `SegmentedGraph` run a sharded module as CUDA graphs of the
+# compute segments with the NCCL calls issued eagerly in between (NCCL itself is never captured).
+# ---------------------------------------------------------------------------------------------------------------------
+_recorder = None
+
+
+def _collective(fn):
+    """Run one collective (`fn()` = a torch.distributed call on tensors that already exist). Under a SegmentedGraph
+    recording the current capture is cut here and `fn` is kept for the replays."""
+    if _recorder is None:
+        fn()
+    else:
+        _recorder.cut(fn)
+
+
+class SegmentedGraph(nn.Module):
+    """CUDA-graph execution of a module whose forward mixes librfk kernels with torch.distributed collectives.
+
+    A sharded block issues ~200 kernel launches and ~40 collectives; at 8 ranks each GPU has ~10 ms of work per
+    block while the host needs ~14 ms to enqueue it through Python: the sharded path is host-bound exactly where it is
+    supposed to scale. The first call with a given input shape runs the module once under a recorder: everything
+    between two collectives is captured into its own CUDA graph (all graphs share one memory pool, so the tensors that
+    cross a cut keep their addresses), every collective is executed eagerly and its closure kept. Later calls copy
+    the inputs into the static input buffers and replay graph, collective, graph, ... in the recorded order: one
+    graph launch per segment instead of one Python round trip per kernel. Every rank records and replays the same
+    sequence (the control flow of the sharded modules depends on shapes only). The outputs are views of graph-owned
+    buffers, overwritten by the next call."""
+
+    def __init__(self, module: nn.Module, warmup: int = 2):
+        super().__init__()
+        self.module = module
+        self.warmup = warmup
+        self._plans = {}
+
+    def _record(self, inputs):
+        global _recorder
+        static_in = [t.clone() for t in inputs]
+        with torch.no_grad():
+            for _ in range(self.warmup):  # communicators, kernel attributes, weight packing: all outside the capture
+                self.module(*static_in)
+        torch.cuda.synchronize()
+        plan = self
+        graphs, colls = [], []
+
+        class Rec:
+            def __init__(self):
+                self.pool = torch.cuda.graph_pool_handle()
+                self.cur = None
+
+            def begin(self):
+                self.cur = torch.cuda.CUDAGraph()
+                self.cur.capture_begin(pool=self.pool)
+
+            def cut(self, fn):
+                self.cur.capture_end()
+                graphs.append(self.cur)
+                fn()  # (moves whatever the buffers hold: the captured kernels have not run; only the order matters)
+                colls.append(fn)
+                self.begin()
+
+            def end(self):
+                self.cur.capture_end()
+                graphs.append(self.cur)
+
+        side = torch.cuda.Stream(device=static_in[0].device)
+        side.wait_stream(torch.cuda.current_stream())
+        rec = Rec()
+        with torch.cuda.stream(side), torch.no_grad():
+            _recorder = rec
+            try:
+                rec.begin()
+                out = self.module(*static_in)
+                rec.end()
+            finally:
+                _recorder = None
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        del plan
+        return static_in, out, graphs, colls
+
+    @torch.no_grad()
+    def forward(self, *inputs):
+        key = tuple((tuple(t.shape), t.dtype, t.device) for t in inputs) + (M.get_mode(), M._BOUNDED_DT)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._plans[key] = self._record(inputs)
+        static_in, out, graphs, colls = plan
+        for s_, t in zip(static_in, inputs):
+            s_.copy_(t, non_blocking=True)
+        for i, g in enumerate(graphs):
+            g.replay()
+            if i < len(colls):
+                colls[i]()
+        return out
+
+    def segments(self):
+        """(number of graphs, number of collectives) of the recorded plans (diagnostics)."""
+        return [(len(p[2]), len(p[3])) for p in self._plans.values()]
+
 
 def _as_like(t):
     return t if t.dtype == torch.float32 else t.float()
@@ -66,7 +166,7 @@ def all_to_all_rows_to_cols(x_rows: torch.Tensor, group=None) -> torch.Tensor:
     # chunk p = my rows x the columns of rank p
     send = x_rows.view(Li, world, Lj, D).permute(1, 0, 2, 3).contiguous()
     recv = torch.empty_like(send)  # chunk p = rows of rank p x my columns: [P, Li, Lj, D] == [L, Lj, D]
-    dist.all_to_all_single(recv, send, group=group)
+    _collective(lambda: dist.all_to_all_single(recv, send, group=group))
     return recv.view(world * Li, Lj, D)
 
 
@@ -78,7 +178,7 @@ def all_to_all_cols_to_rows(x_cols: torch.Tensor, group=None) -> torch.Tensor:
     Li = L // world
     send = x_cols.contiguous().view(world, Li, Lj, D)  # chunk p = rows of rank p
     recv = torch.empty_like(send)
-    dist.all_to_all_single(recv, send, group=group)
+    _collective(lambda: dist.all_to_all_single(recv, send, group=group))
     return recv
 
 
@@ -95,20 +195,21 @@ class SequenceShard:
     def first_sequence(self, xn4: torch.Tensor) -> torch.Tensor:
         """[B, N/P, L, D] -> [B, 1, L, D]: sequence 0 of the whole MSA (rank 0's first row)."""
         row = xn4[:, :1].clone()  # (a size-1 slice is "contiguous": .contiguous() would alias xn4 and the broadcast overwrite it)
-        dist.broadcast(row, src=self.root, group=self.group)
+        _collective(lambda: dist.broadcast(row, src=self.root, group=self.group))
         return row
 
     def softmax_correction(self, stats: torch.Tensor) -> torch.Tensor:
         """stats [B, L, H, 2] = (max, sum of exp) of this rank's position-wise logits -> the factor [B, L, H]
         that turns weights normalised over this rank's sequences into weights normalised over all of them."""
         allst = torch.empty((self.world,) + tuple(stats.shape), dtype=stats.dtype, device=stats.device)
-        dist.all_gather_into_tensor(allst.view(-1), stats.reshape(-1), group=self.group)
+        dst, src = allst.view(-1), stats.reshape(-1)
+        _collective(lambda: dist.all_gather_into_tensor(dst, src, group=self.group))
         gmax = allst[..., 0].max(dim=0).values
         gsum = (allst[..., 1] * torch.exp(allst[..., 0] - gmax)).sum(dim=0)
         return stats[..., 1] * torch.exp(stats[..., 0] - gmax) / gsum
 
     def allreduce(self, t: torch.Tensor) -> None:
-        dist.all_reduce(t, group=self.group)
+        _collective(lambda: dist.all_reduce(t, group=self.group))
 
 
 def all_to_all_seqs_to_residues(x_seqs: torch.Tensor, group=None) -> torch.Tensor:
@@ -118,7 +219,7 @@ def all_to_all_seqs_to_residues(x_seqs: torch.Tensor, group=None) -> torch.Tenso
     Ll = L // world
     send = x_seqs.view(Nl, world, Ll, D).permute(1, 0, 2, 3).contiguous()  # chunk p = my sequences x residues of p
     recv = torch.empty_like(send)                                           # chunk q = sequences of q x my residues
-    dist.all_to_all_single(recv, send, group=group)
+    _collective(lambda: dist.all_to_all_single(recv, send, group=group))
     return recv.view(1, world * Nl, Ll, D)
 
 
@@ -129,7 +230,7 @@ def all_to_all_residues_to_seqs(x_res: torch.Tensor, group=None) -> torch.Tensor
     Nl = N // world
     send = x_res.contiguous().view(world, Nl, Ll, D)       # chunk p = sequences of rank p x my residues
     recv = torch.empty_like(send)                          # chunk q = my sequences x residues of rank q
-    dist.all_to_all_single(recv, send, group=group)
+    _collective(lambda: dist.all_to_all_single(recv, send, group=group))
     return recv.permute(1, 0, 2, 3).reshape(1, Nl, world * Ll, D)
 
 
@@ -206,20 +307,22 @@ class ShardedTwoTrackBlock(nn.Module):
         mod = self.block.pair_update_with_msa
         part = mod._project(msa_res)                                             # [1, N, L/P, Q]
         allm = torch.empty((world,) + tuple(part.shape), dtype=part.dtype, device=part.device)
-        dist.all_gather_into_tensor(allm.view(-1), part.reshape(-1), group=group)
+        dst, src = allm.view(-1), part.reshape(-1)
+        _collective(lambda: dist.all_gather_into_tensor(dst, src, group=group))
         mraw = allm.permute(1, 2, 0, 3, 4).reshape(part.shape[0], part.shape[1], -1, part.shape[3])  # [1, N, L, Q]
 
         def halo(x):  # [1, Li, L, C] -> [1, Li + 2, L, C]
             edges = torch.stack([x[:, 0], x[:, -1]], 0).contiguous()            # my first / last row
             allv = torch.empty((world,) + tuple(edges.shape), dtype=x.dtype, device=x.device)
-            dist.all_gather_into_tensor(allv.view(-1), edges.view(-1), group=group)
+            dst, src = allv.view(-1), edges.view(-1)
+            _collective(lambda: dist.all_gather_into_tensor(dst, src, group=group))
             zero = torch.zeros_like(x[:, :1])
             top = allv[rank - 1, 1].unsqueeze(1) if rank > 0 else zero          # last row of the rank above
             bottom = allv[rank + 1, 0].unsqueeze(1) if rank + 1 < world else zero
             return torch.cat([top, x, bottom], 1)
 
         def allreduce(st):
-            dist.all_reduce(st, group=group)
+            _collective(lambda: dist.all_reduce(st, group=group))
 
         return mod._forward_rows(None, rows, att[:, lo:hi], lo, hi, halo, allreduce, mraw=mraw)
 
@@ -237,7 +340,8 @@ class ShardedTwoTrackBlock(nn.Module):
 
         def gather_rows(part):  # [1, C, Li, L] -> [1, C, L, L]
             allp = torch.empty((world,) + tuple(part.shape), dtype=part.dtype, device=part.device)
-            dist.all_gather_into_tensor(allp.view(-1), part.reshape(-1), group=group)
+            dst, src = allp.view(-1), part.reshape(-1)
+            _collective(lambda: dist.all_gather_into_tensor(dst, src, group=group))
             return allp.permute(1, 2, 0, 3, 4).reshape(part.shape[0], part.shape[1], -1, part.shape[3])
 
         mod = self.block.msa_update_with_pair
@@ -297,7 +401,8 @@ def gather_shards(x: torch.Tensor, group=None) -> torch.Tensor:
     """[1, X/P, ...] shards of axis 1 on every rank -> the whole [1, X, ...] tensor on every rank."""
     world = dist.get_world_size(group)
     full = torch.empty((x.shape[0], x.shape[1] * world) + tuple(x.shape[2:]), dtype=x.dtype, device=x.device)
-    dist.all_gather_into_tensor(full.view(-1), x.reshape(-1), group=group)
+    dst, src = full.view(-1), x.reshape(-1)
+    _collective(lambda: dist.all_gather_into_tensor(dst, src, group=group))
     return full
 
 

@@ -28,13 +28,22 @@ N, L = 24, 136   # ragged against the 128-row tiles, divisible by the 2 ranks
 msa = torch.randn((1, N, L, 384), generator=g).to(dev)
 pair = torch.randn((1, L, L, 288), generator=g).to(dev)
 out = {}
+rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
 for mode in ("fp32", "bf16"):
     rf.set_mode(mode)
-    m_s, p_s = rf.ShardedTrunkBlocks(trunk)(msa, pair)
+    sharded = rf.ShardedTrunkBlocks(trunk)
+    m_s, p_s = sharded(msa, pair)
     m_1, p_1 = trunk(msa, pair)
     torch.cuda.synchronize()
-    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
     out[mode] = [rel(m_s, m_1), rel(p_s, p_1)]
+    # the same through CUDA graphs of the compute segments (collectives eager in between): record, then replay twice
+    seg = rf.sharded.SegmentedGraph(sharded)
+    for scale in (1.0, 0.5):
+        m_g, p_g = seg(msa * scale, pair * scale)
+        m_e, p_e = sharded(msa * scale, pair * scale)
+        torch.cuda.synchronize()
+        out[mode + "_graph_vs_eager_%g" % scale] = [rel(m_g, m_e), rel(p_g, p_e)]
+    out[mode + "_segments"] = seg.segments()
 if rank == 0:
     print("RESULT " + json.dumps(out), flush=True)
 dist.barrier()
@@ -57,3 +66,6 @@ def test_sharded_trunk_matches_single_gpu_over_nccl(cuda_device, tmp_path):
     print(res)
     assert max(res["fp32"]) < 1e-4, res   # same arithmetic, different summation order of the sharded reductions
     assert max(res["bf16"]) < 1e-2, res
+    for k, v in res.items():
+        if "graph_vs_eager" in k:
+            assert max(v) < 1e-5, (k, res)  # same kernels, same order (atomics of the InstanceNorm statistics aside)
