@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--long-L", type=int, default=1024)
     ap.add_argument("--long-N", type=int, default=256)
     ap.add_argument("--long-blocks", type=int, default=2)
+    ap.add_argument("--long-timeout", type=float, default=300.0, help="seconds before the config-4 record is abandoned")
     return ap.parse_args()
 
 
@@ -357,11 +358,24 @@ def run_b200(args):
                                 "sample": sample_desc(args) + " (one timed block here; `--impl reference` averages K)",
                                 "block_s": round(block_s, 2)}
     if world > 1 and not args.no_long_protein:
-        # outside the timed regions above; appended to the same JSON line so that the driver's scaling run carries it
+        # outside the timed regions above; appended to the same JSON line so that the driver's scaling run carries it.
+        # The headline (replicas) number must survive any failure of this extra record: exceptions are caught, and a
+        # watchdog on every rank prints the line without the record and leaves if the section does not finish in time
+        # (a collective that never completes cannot be caught any other way).
+        def bail():
+            line["long_protein"] = {"error": f"did not finish within {args.long_timeout} s"}
+            if rank == 0:
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+
+        dog = threading.Timer(args.long_timeout, bail)
+        dog.daemon = True
+        dog.start()
         try:
             line["long_protein"] = long_protein_record(args, torch, dist, rf, dev, rank, world)
-        except Exception as e:  # the headline (replicas) number must survive a failure of the extra record
+        except Exception as e:
             line["long_protein"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        dog.cancel()
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
