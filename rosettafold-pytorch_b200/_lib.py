@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librfk.so")
+# RFK_LIB_PATH: developer override used by tools/ to time experimental builds of the same library
+LIB_PATH = os.environ.get("RFK_LIB_PATH") or os.path.join(_HERE, "librfk.so")
 
 RFK_F32, RFK_BF16, RFK_F16 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2

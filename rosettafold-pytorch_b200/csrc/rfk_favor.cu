@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(256, 1) favor_simt_kernel(const FavorDev p) {
 
 int favor_tc_launch(const rfk_favor_desc* d, cudaStream_t stream);  // rfk_favor_tc.cu (round-1 kernel: features via shared memory)
 int favor_tm_launch(const rfk_favor_desc* d, cudaStream_t stream);  // rfk_favor_tm.cu (features kept in tensor memory)
+int favor_col_launch(const rfk_favor_desc* d, cudaStream_t stream);  // rfk_favor_col.cu (softmax kernel, tokens <= 128)
 
 }  // namespace rfk
 
@@ -209,7 +210,14 @@ extern "C" int rfk_favor_attention(const rfk_favor_desc* d, rfk_stream_t stream_
   static const bool force_simt = getenv("RFK_FAVOR_FORCE_SIMT") != nullptr;  // A/B debugging aid
   if (is_h16(d->io_dtype) && !force_simt) {
     static const bool old_kernel = getenv("RFK_FAVOR_SMEM_FEATURES") != nullptr;  // A/B: the round-1 kernel
-    int rc = (old_kernel && d->io_dtype == RFK_BF16) ? favor_tc_launch(d, stream) : favor_tm_launch(d, stream);
+    static const bool no_col = getenv("RFK_FAVOR_NO_COL") != nullptr;  // A/B: short token axes on the general kernel
+    int rc = RFK_ERR_UNSUPPORTED;
+    if (old_kernel && d->io_dtype == RFK_BF16) {
+      rc = favor_tc_launch(d, stream);
+    } else {
+      if (!no_col) rc = favor_col_launch(d, stream);  // one-tile items of the softmax kernel (MSA columns)
+      if (rc == RFK_ERR_UNSUPPORTED) rc = favor_tm_launch(d, stream);
+    }
     if (rc != RFK_ERR_UNSUPPORTED) return rc;
     // shapes the tensor-core kernel does not cover run on the SIMT kernel (same arithmetic)
   }

@@ -37,11 +37,7 @@
 // Shared memory (1024-byte aligned tiles, 128-byte swizzle):
 //   omega' [384][64] bf16 K-major (rows >= m zero) | tile ring 5 x [128 tok][64 d] | cslab [128 tok][64],
 //   column 0 = 1 (second MN chunk of "[V | 1]") | ctx 5 x [80][64 m] K-major B of the output MMA.
-#include <cstdio>
-#include <cstdlib>
-#include <type_traits>
-
-#include "rfk_common.cuh"
+#include "rfk_favor_device.cuh"
 
 namespace rfk {
 
@@ -52,7 +48,6 @@ constexpr int kFeatThreads = 32 * kFeatWarps;
 constexpr int kThreads = 32 * (2 + kFeatWarps);  // TMA producer, MMA issuer, feature warps
 constexpr int kMP = 272;     // padded feature count
 constexpr int kMRows = 384;  // omega rows in shared memory (3 chunks x 128 lanes)
-constexpr int kTile = 128;   // tokens per tile
 constexpr int kRing = 5;
 constexpr uint32_t kSlabBytes = kTile * 128;    // 16384
 constexpr uint32_t kOmegaBytes = kMRows * 128;  // 49152
@@ -69,135 +64,6 @@ static_assert(kOffRing % 1024 == 0 && kOffCslab % 1024 == 0 && kOffCtx % 1024 ==
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 constexpr uint32_t kColCtx = 0, kColU = 256;
-
-struct FavorTmParams {
-  const float* proj;
-  void* out;
-  int m, heads;
-  int tokens;
-  int64_t G0, G1, items;
-  int64_t ogs0, ogs1, ots;
-};
-
-// MN-major SW128 descriptor: rows are K indices (128 B each, 8-row groups SBO=1024 apart),
-// 64-element MN chunks are `lbo_bytes` apart.
-__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-__host__ __device__ constexpr uint32_t idesc_bf16_major(int M, int N, int a_mn, int b_mn) {
-  return umma_idesc_bf16(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
-}
-// D[tmem] (+)= A[tmem, K-major: lane = row, two bf16 per 32-bit column] * B[smem]
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t* r) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
-               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-template <bool F16>
-__device__ __forceinline__ void st_shared_h16(uint32_t addr, float f) {
-  const unsigned short h = cvt_h16(f, F16 ? RFK_F16 : RFK_BF16);
-  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(h) : "memory");
-}
-__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)),
-               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-// one lane of the (fully active) warp
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t"
-      "}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tmem_ld_32x32p(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x16p(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int n) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
-}
-__device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// {bf16(max(lo,0)), bf16(max(hi,0))} in one instruction
-template <bool F16>
-__device__ __forceinline__ uint32_t cvt_relu_h16x2(float lo, float hi) {
-  uint32_t d;
-  if (F16) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
-}
-template <bool F16>
-__device__ __forceinline__ uint32_t add_h16x2(uint32_t a, uint32_t b) {
-  uint32_t d;
-  if (F16) asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  else asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  return d;
-}
 
 // Walks the PASSES of one CTA in issue order: item -> pass (kind, tile t); every pass has three jobs (feature
 // chunks c = 0, 1, 2 of 128 | 128 | 16 features). The iterator also mirrors the producer's ring allocation (the
@@ -263,7 +129,6 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   auto bar_tfull = [&](uint32_t s) { return bars + 8u * s; };            // [kRing]
   auto bar_tempty = [&](uint32_t s) { return bars + 40u + 8u * s; };     // [kRing]
   auto bar_ufull = [&](uint32_t s) { return bars + 80u + 8u * s; };      // U accumulator of the slot complete
-  auto bar_ufree = [&](uint32_t s) { return bars + 96u + 8u * s; };      // slot may be overwritten by the next U
   auto bar_fready = [&](uint32_t s) { return bars + 112u + 8u * s; };    // features of the slot stored (or max taken)
   auto bar_d3full = [&](uint32_t s) { return bars + 128u + 8u * s; };
   auto bar_d3free = [&](uint32_t s) { return bars + 144u + 8u * s; };
@@ -287,7 +152,6 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     for (uint32_t s = 0; s < 2; ++s) {
       mbar_init(bar_ufull(s), 1);
-      mbar_init(bar_ufree(s), 1);
       mbar_init(bar_fready(s), kFeatWarps);
       mbar_init(bar_d3full(s), 1);
       mbar_init(bar_d3free(s), kFeatWarps);
@@ -796,34 +660,6 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int make_head_tmap(CUtensorMap* map, const void* ptr, const rfk_favor_desc* d) {
-  static EncodeTiledFn enc = []() -> EncodeTiledFn {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    return reinterpret_cast<EncodeTiledFn>(f);
-  }();
-  if (!enc) return RFK_ERR_TMA_ENCODE;
-  // dims: (column within the heads*64 slice, token, g0, g1)
-  cuuint64_t dims[4] = {(cuuint64_t)d->heads * 64, (cuuint64_t)d->tokens, (cuuint64_t)d->G[0], (cuuint64_t)d->G[1]};
-  cuuint64_t strides[3] = {(cuuint64_t)d->ts * 2, (cuuint64_t)d->gs[0] * 2, (cuuint64_t)d->gs[1] * 2};
-  if (d->G[0] == 1) strides[1] = strides[0] * (cuuint64_t)d->tokens;
-  if (d->G[1] == 1) strides[2] = strides[1] * (cuuint64_t)d->G[0];
-  cuuint32_t box[4] = {64, (cuuint32_t)kTile, 1, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? RFK_OK : RFK_ERR_TMA_ENCODE;
 }
 
 template <int KIND, bool F16>
