@@ -12,15 +12,18 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 for rep in sys.argv[1:]:
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[2]
-    d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
-    print(f"## {d.get('Kernel Name', ('?',''))[0][:90]}  (`{rep}`)\n\n| metric | value | unit |\n|---|---:|---|")
-    for k in KEYS:
-        if k in d:
-            print(f"| `{k}` | {d[k][0]} | {d[k][1]} |")
-    try:
-        tr = float(d["dram__bytes_read.sum"][0].replace(",", "")) + float(d["dram__bytes_write.sum"][0].replace(",", ""))
-        print(f"| **traffic = dram read + write** | {tr:.1f} | {d['dram__bytes_read.sum'][1]} |")
-    except Exception:
-        pass
-    print()
+    hdr, units = rows[0], rows[1]
+    for vals in rows[2:]:  # one row per captured launch
+        if len(vals) < len(hdr):
+            continue
+        d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+        print(f"## {d.get('Kernel Name', ('?',''))[0][:90]}  (`{rep}`)\n\n| metric | value | unit |\n|---|---:|---|")
+        for k in KEYS:
+            if k in d:
+                print(f"| `{k}` | {d[k][0]} | {d[k][1]} |")
+        try:
+            tr = float(d["dram__bytes_read.sum"][0].replace(",", "")) + float(d["dram__bytes_write.sum"][0].replace(",", ""))
+            print(f"| **traffic = dram read + write** | {tr:.1f} | {d['dram__bytes_read.sum'][1]} |")
+        except Exception:
+            pass
+        print()
