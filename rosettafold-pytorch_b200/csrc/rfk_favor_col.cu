@@ -161,11 +161,11 @@ favor_col_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (warp == 0) {
     if (lane == 0) {
       // =================== TMA producer ===================
-      auto coords = [&](int64_t item, int& h, int& g0, int& g1) {
-        h = (int)(item % p.heads);
-        const int64_t g = item / p.heads;
-        g0 = (int)(g % p.G0);
-        g1 = (int)(g / p.G0);
+      auto coords = [&](int64_t item, int& h, int& g0, int& g1) {  // (the launcher checks that items fit 32 bits)
+        const uint32_t it32 = (uint32_t)item, g = it32 / (uint32_t)p.heads;
+        h = (int)(it32 - g * (uint32_t)p.heads);
+        g1 = (int)(g / (uint32_t)p.G0);
+        g0 = (int)(g - (uint32_t)g1 * (uint32_t)p.G0);
       };
       // L2 prefetch two items ahead of the loads
       auto prefetch_item = [&](int64_t item) {
@@ -372,7 +372,12 @@ favor_col_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                          v);
     };
     // out/den epilogue: warp (lg, cq) stores channels [16 cq, 16 cq + 16) of its 32 tokens
-    auto epilogue = [&](int64_t item, uint32_t n) {
+    auto item_out_ptr = [&](int64_t item) {  // 32-bit arithmetic (the launcher checks that items fit), once per item
+      const uint32_t it32 = (uint32_t)item, g = it32 / (uint32_t)p.heads, h = it32 - g * (uint32_t)p.heads;
+      const uint32_t g1 = g / (uint32_t)p.G0, g0 = g - g1 * (uint32_t)p.G0;
+      return reinterpret_cast<uint16_t*>(p.out) + (int64_t)g1 * p.ogs1 + (int64_t)g0 * p.ogs0 + (int64_t)row * p.ots + h * 64 + 16 * cq;
+    };
+    auto epilogue = [&](uint16_t* out_ptr, uint32_t n) {
       mbar_wait(bar_outfull, n & 1u);
       tc_fence_after();
       uint32_t rd[16], r0[16];
@@ -381,12 +386,8 @@ favor_col_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       tmem_ld_wait();
       tc_fence_before();
       if (row < ntok) {
-        const int h = (int)(item % p.heads);
-        const int64_t g = item / p.heads;
-        const int64_t g0 = g % p.G0, g1 = g / p.G0;
-        const float inv = 1.f / __uint_as_float(rd[0]);
-        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + g1 * p.ogs1 + g0 * p.ogs0 +
-                                             (int64_t)row * p.ots + h * 64 + 16 * cq);
+        const float inv = __fdividef(1.f, __uint_as_float(rd[0]));
+        uint4* op = reinterpret_cast<uint4*>(out_ptr);
         uint4 w;
         w.x = pack_h16x2(__uint_as_float(r0[0]) * inv, __uint_as_float(r0[1]) * inv, kDt);
         w.y = pack_h16x2(__uint_as_float(r0[2]) * inv, __uint_as_float(r0[3]) * inv, kDt);
@@ -405,11 +406,12 @@ favor_col_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #ifdef RFK_COL_TIMELINE
     long long tlf[24] = {};
 #endif
-    int64_t prev_item = -1;
+    uint16_t* prev_out = nullptr;  // output rows of the item whose out | den is still in block C
     uint32_t raw[32];
     for (int64_t item = blockIdx.x; item < p.items; item += istride, ++n) {
       const uint32_t par = n & 1u, tpar = (n >> 1) & 1u;
       RFK_TL(tlf, 0);
+      uint16_t* const cur_out = item_out_ptr(item);
       // ---- per-token |k|^2 term of the exponent: needs the K tile only, so it runs while the previous item's
       //      output MMAs are still in flight ----
       diag_partial(partk, slot_of(n, 0), tpar);
@@ -438,8 +440,8 @@ favor_col_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           }
         }
         if (cc == 0) {
-          if (prev_item >= 0) epilogue(prev_item, n - 1u);
-          prev_item = item;
+          if (prev_out) epilogue(prev_out, n - 1u);
+          prev_out = cur_out;
           RFK_TL(tlf, 1);
         }
       }
@@ -593,7 +595,7 @@ favor_col_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       printf("feat base %lld\n", tlf[0]);
     }
 #endif
-    if (prev_item >= 0) epilogue(prev_item, n - 1u);
+    if (prev_out) epilogue(prev_out, n - 1u);
   }
   tc_fence_before();
   __syncthreads();
@@ -636,6 +638,7 @@ int favor_col_launch(const rfk_favor_desc* d, cudaStream_t stream) {
   p.proj = d->proj; p.out = d->out; p.m = d->m_features; p.heads = d->heads;
   p.tokens = (int)d->tokens; p.G0 = d->G[0]; p.G1 = d->G[1];
   p.items = d->G[0] * d->G[1] * d->heads;
+  if (p.items > 0x7fffffffLL || d->G[0] > 0x7fffffffLL) return RFK_ERR_UNSUPPORTED;  // 32-bit item decode in the kernel
   p.ogs0 = d->out_gs[0]; p.ogs1 = d->out_gs[1]; p.ots = d->out_ts;
   return d->io_dtype == RFK_F16 ? launch_col<true>(tq, tk, tv, p, stream) : launch_col<false>(tq, tk, tv, p, stream);
 }

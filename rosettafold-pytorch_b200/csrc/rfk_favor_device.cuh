@@ -66,6 +66,9 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t h) {
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(h) : "memory");
+}
 template <bool F16>
 __device__ __forceinline__ void st_shared_h16(uint32_t addr, float f) {
   const unsigned short h = cvt_h16(f, F16 ? RFK_F16 : RFK_BF16);

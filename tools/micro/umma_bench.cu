@@ -13,7 +13,7 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint3
 }
 
 // mode 0: SS (A, B from smem), mode 1: TS (A from TMEM). group: MMAs per commit. reps: groups.
-template <int MODE>
+template <int MODE, int ELECT_ONCE>
 __global__ void __launch_bounds__(128, 1) bench(int N, int group, int reps, int wait_each, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -31,6 +31,39 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int group, int reps, int 
     const uint32_t idesc = umma_idesc_bf16(128, N);
     uint32_t par = 0;
     const long long t0 = clock64();
+    if (ELECT_ONCE) {
+      // CUTLASS style: ONE election, the elected thread runs the whole loop (waits included)
+      uint32_t el;
+      asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(el));
+      if (el) {
+        for (int r = 0; r < reps; ++r) {
+          if (group == 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (MODE == 0) umma_bf16(0, da + 2 * k, db + 2 * k, idesc, 1);
+              else mma_ts(0, 256 + 8 * k, db + 2 * k, idesc, 1);
+            }
+          } else if (group == 16) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              if (MODE == 0) umma_bf16(0, da + 2 * (k & 3), db + 2 * (k & 3), idesc, 1);
+              else mma_ts(0, 256 + 8 * (k & 3), db + 2 * (k & 3), idesc, 1);
+            }
+          } else {
+            for (int k = 0; k < group; ++k) {
+              if (MODE == 0) umma_bf16(0, da + 2 * (k & 3), db + 2 * (k & 3), idesc, 1);
+              else mma_ts(0, 256 + 8 * (k & 3), db + 2 * (k & 3), idesc, 1);
+            }
+          }
+          if (wait_each || r == reps - 1) {
+            umma_commit(bar);
+            mbar_wait(bar, par);
+            par ^= 1;
+          }
+        }
+      }
+      __syncwarp();
+    } else {
     for (int r = 0; r < reps; ++r) {
       uint32_t el;
       asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(el));
@@ -61,6 +94,7 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int group, int reps, int 
         par ^= 1;
       }
     }
+    }
     const long long t1 = clock64();
     if (lane == 0) out[0] = t1 - t0;
   }
@@ -73,23 +107,31 @@ int main() {
   long long* d;
   cudaMalloc(&d, 8);
   const int smem = 65536 + 1024 + 1024;
-  cudaFuncSetAttribute(bench<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(bench<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  const int Ns[] = {16, 64, 128, 256};
+  cudaFuncSetAttribute(bench<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(bench<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(bench<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(bench<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int Ns[] = {16, 80, 128};
+  for (int once = 0; once < 2; ++once)
   for (int mode = 0; mode < 2; ++mode)
     for (int N : Ns)
       for (int wait_each = 0; wait_each < 2; ++wait_each) {
         for (int group : {4, 16, 5}) {
         const int reps = 2000;
         for (int it = 0; it < 2; ++it) {
-          if (mode == 0) bench<0><<<1, 128, smem>>>(N, group, reps, wait_each, d);
-          else bench<1><<<1, 128, smem>>>(N, group, reps, wait_each, d);
+          if (once == 0) {
+            if (mode == 0) bench<0, 0><<<1, 128, smem>>>(N, group, reps, wait_each, d);
+            else bench<1, 0><<<1, 128, smem>>>(N, group, reps, wait_each, d);
+          } else {
+            if (mode == 0) bench<0, 1><<<1, 128, smem>>>(N, group, reps, wait_each, d);
+            else bench<1, 1><<<1, 128, smem>>>(N, group, reps, wait_each, d);
+          }
           cudaError_t e = cudaDeviceSynchronize();
           if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
         }
         long long c;
         cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
-        printf("%s M=128 N=%3d K=16  group=%d %s: %.1f cycles / MMA (math floor %d)\n", mode ? "TS" : "SS", N, group,
+        printf("%s %s M=128 N=%3d K=16  group=%d %s: %.1f cycles / MMA (math floor %d)\n", once ? "elect-once    " : "elect-per-group", mode ? "TS" : "SS", N, group,
                wait_each ? "commit+wait per group" : "back-to-back          ", (double)c / (group * reps), 128 * N / 256);
         }
       }

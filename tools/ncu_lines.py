@@ -25,7 +25,9 @@ tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, capture_output=True)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 dis = subprocess.run(["nvdisasm", "--print-line-info-inline", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
-lines, cur, infn, src_file = [], None, False, None
+# RFK_LINES_INNER=1: attribute to the INNERMOST frame that lies in a .cu file (lambda bodies) instead of the outermost
+inner = os.environ.get("RFK_LINES_INNER") is not None
+lines, cur, infn, block = [], None, False, []
 for ln in dis.splitlines():
     if ln.startswith(".text."):
         infn = kname in ln
@@ -34,10 +36,17 @@ for ln in dis.splitlines():
         continue
     m = re.match(r'\s*//## File "([^"]+)", line (\d+)(.*)', ln)
     if m:
-        if "inlined at" not in m.group(3):
-            cur = (m.group(1), int(m.group(2)))
+        block.append((m.group(1), int(m.group(2)), "inlined at" in m.group(3)))
         continue
     if re.match(r"\s*/\*[0-9a-f]{4,}\*/", ln):
+        if block:
+            if inner:
+                cu = [b for b in block if b[0].endswith(".cu")]
+                cur = (cu[0][0], cu[0][1]) if cu else (block[-1][0], block[-1][1])
+            else:
+                outer = [b for b in block if not b[2]]
+                cur = (outer[-1][0], outer[-1][1]) if outer else (block[-1][0], block[-1][1])
+            block = []
         lines.append(cur)
 if len(lines) != len(sass):
     print(f"warning: {len(lines)} instructions in the object vs {len(sass)} in the report")
