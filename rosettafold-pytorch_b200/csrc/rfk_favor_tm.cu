@@ -18,17 +18,9 @@
 //   query side  U[tok, m]   = Q_tile (A, smem) . Omega_c^T (B, smem)    tokens on the lanes
 //               q' = phi(U) -> TMEM (in place)
 //               out|den[tok, d|1] (+)= q' (A, TMEM, K = features) . ctx_c (B, smem, K-major)
-// The 272 (padded) features are split into chunks of 128 | 128 | 16, and every (pass, tile) into TWO jobs: J0 = chunk 0,
-// J1 = chunks 1 and 2 together. The 16-feature chunk rides along with chunk 1 in the same accumulator slot (144
-// columns) and in the same issuer <-> feature-warp round trip; on BOTH sides it is projected with the tokens on the
-// lanes (U_2 = X . Omega_2^T, 16 columns). On the key side its features therefore cannot feed an A-from-TMEM MMA (that
-// would need them on the lanes): they go through a 4 KB shared-memory tile instead and the context block is
-// accumulated transposed,  ctx_2[d|1, m] (+)= [V | 1]^T (A, smem, MN-major) . k'_2 (B, smem, K-major over tokens),
-// which costs 16 accumulator columns instead of the 128 + 80 a features-on-lanes third chunk took (that third job was
-// a sixth of all round trips of a tile for 6 % of the features).
-// Passes per item (group, head):
-//   relu kernel  K(t)*, read-out of ctx, Q(t)*;
-//   softmax      KMAX(t)*, K(t)*, read-out, then per tile QMAX(t), Q(t)   (stabiliser passes).
+// The 272 (padded) features are split into chunks c of 128 | 128 | 16. Job types per item (group, head):
+//   relu kernel  K(t,c)*, read-out of ctx, Q(t,c)*;
+//   softmax      KMAX(t,c)*, K(t,c)*, read-out, then per tile QMAX(t,c)*, Q(t,c)*   (stabiliser passes).
 //
 // Roles (18 warps):
 //   warp 0 lane 0  TMA producer: K/V/Q tiles into a 5-slot ring + an L2 prefetch cursor 8 tiles ahead
@@ -38,14 +30,13 @@
 //                  32 lanes x 32 accumulator columns: tcgen05.ld x32 -> feature map -> 16 packed words ->
 //                  tcgen05.st x16 over the first half of its own columns (no warp ever writes columns another
 //                  warp still has to read). MMA k-step s (16 features / tokens) therefore reads A at column
-//                  32 (s / 2) + 8 (s % 2) of the slot. The cq == 0 warps also own the 16 columns of chunk 2.
-// TMEM (512 columns): ctx^T_0 [0,80) | ctx^T_1 [80,160) (lanes = feature, columns = d | 1) | ctx_2 [160,176)
-//   (lanes = d | 1, columns = feature) | U slots 2 x 144 columns at [176,464); out|den accumulators D3[s] alias
-//   ctx blocks 0 / 1 (dead in the query phase; reuse ordered through the d3free barriers).
+//                  32 (s / 2) + 8 (s % 2) of the slot.
+// TMEM (512 columns): ctx^T blocks b = 0..2 (lanes = m - 128 b; 80 columns = d | 1) at [0,240);
+//   U slots 2 x 128 columns at [256,512); out|den accumulators D3[s] alias ctx blocks 0 / 1 (dead in the
+//   query phase; reuse ordered through the d3free barriers).
 // Shared memory (1024-byte aligned tiles, 128-byte swizzle):
-//   omega' [384][64] K-major (rows >= m zero) | tile ring 5 x [128 tok][64 d] | cslab [128 tok][64],
-//   column 0 = 1 (second MN chunk of "[V | 1]") | ctx 5 x [80][64 m] K-major B of the output MMA |
-//   k'_2 tiles 2 x [16 m][128 tok] K-major (one per U slot).
+//   omega' [384][64] bf16 K-major (rows >= m zero) | tile ring 5 x [128 tok][64 d] | cslab [128 tok][64],
+//   column 0 = 1 (second MN chunk of "[V | 1]") | ctx 5 x [80][64 m] K-major B of the output MMA.
 #include "rfk_favor_device.cuh"
 
 namespace rfk {
@@ -65,26 +56,17 @@ constexpr uint32_t kOffOmega = 0;
 constexpr uint32_t kOffRing = kOffOmega + kOmegaBytes;
 constexpr uint32_t kOffCslab = kOffRing + kRing * kSlabBytes;  // after the ring: LBO of [V | 1] > 0
 constexpr uint32_t kOffCtx = kOffCslab + kSlabBytes;
-constexpr uint32_t kOffK2 = kOffCtx + 5 * kCtxSlabBytes;  // k'_2 tiles: 2 x (2 chunks of 64 tokens x [16][64])
-constexpr uint32_t kK2Bytes = 4096;
-constexpr uint32_t kOffBar = kOffK2 + 2 * kK2Bytes;
+constexpr uint32_t kOffBar = kOffCtx + 5 * kCtxSlabBytes;
 constexpr uint32_t kOffScratch = kOffBar + 256;
 constexpr uint32_t kScratchFloats = 4 * 128 + 4 * 128 + 128 + 32;  // diag partials, row maxima, per-token sub, warp maxima
 constexpr uint32_t kSmemBytes = kOffScratch + kScratchFloats * 4 + 1024;
-static_assert(kOffRing % 1024 == 0 && kOffCslab % 1024 == 0 && kOffCtx % 1024 == 0 && kOffK2 % 1024 == 0, "align");
+static_assert(kOffRing % 1024 == 0 && kOffCslab % 1024 == 0 && kOffCtx % 1024 == 0, "align");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
-// developer timeline (-DRFK_TM_TIMELINE): clock64 stamps of CTA 0's issuer and first feature warp for 16 jobs
-#ifdef RFK_TM_TIMELINE
-#define RFK_TMTL(arr, job, k) do { if (blockIdx.x == 0 && lane == 0 && (job) >= 200u && (job) < 216u) arr[((job) - 200u) * 8 + (k)] = clock64(); } while (0)
-#else
-#define RFK_TMTL(arr, job, k) do { } while (0)
-#endif
+constexpr uint32_t kColCtx = 0, kColU = 256;
 
-constexpr uint32_t kColCtx = 0, kColCtx2 = 160, kColU = 176, kSlotCols = 144;
-
-// Walks the PASSES of one CTA in issue order: item -> pass (kind, tile t); every pass has two jobs (feature
-// chunk 0 | chunks 1 + 2). The iterator also mirrors the producer's ring allocation (the
+// Walks the PASSES of one CTA in issue order: item -> pass (kind, tile t); every pass has three jobs (feature
+// chunks c = 0, 1, 2 of 128 | 128 | 16 features). The iterator also mirrors the producer's ring allocation (the
 // producer loads tiles in exactly this order), so the pass knows the ring slots of its tiles.
 constexpr int kPassM = 0, kPassK = 1, kPassX = 2, kPassQ = 3;  // key max, keys, query max, queries
 struct PassInfo {
@@ -123,7 +105,7 @@ struct PassIter {
     if (!(KIND == 0 && x.kind == kPassQ)) take(x.a_slot, x.a_par);  // a softmax Q pass reuses its QMAX tile
     if (x.kind == kPassK) take(x.v_slot, x.v_par);
     x.j0 = j;
-    j += 2u;
+    j += 3u;
     if (++ps == P) { ps = 0; item += istride; }
     last = x;
     return x;
@@ -143,7 +125,6 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_omega = base + kOffOmega, s_ring = base + kOffRing, s_cslab = base + kOffCslab, s_ctx = base + kOffCtx;
-  const uint32_t s_k2 = base + kOffK2;
   const uint32_t bars = base + kOffBar;
   auto bar_tfull = [&](uint32_t s) { return bars + 8u * s; };            // [kRing]
   auto bar_tempty = [&](uint32_t s) { return bars + 40u + 8u * s; };     // [kRing]
@@ -218,6 +199,7 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   using C0 = std::integral_constant<int, 0>;
   using C1 = std::integral_constant<int, 1>;
+  using C2 = std::integral_constant<int, 2>;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -271,8 +253,8 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
   } else if (warp == 1) {
     // =================== MMA issuer ===================
-    // ONE warp issues every MMA, in BURSTS: the consumer MMAs of job j (A = the features in U slot j % 2) followed by
-    // the projection of job j + 2 into the same slot. tcgen05.mma instructions of one thread
+    // ONE warp issues every MMA, in BURSTS of up to 12: the consumer MMAs of job j (A = the features in U slot
+    // j % 2) followed by the projection of job j + 2 into the same slot. tcgen05.mma instructions of one thread
     // execute in issue order, so the projection cannot overwrite the slot before the consumer MMAs issued ahead of
     // it have read their A operand out of it: the slot is handed on without a commit / mbarrier round trip (across
     // issuing threads that order is NOT guaranteed: versions with separate consumer / projection issuer warps were
@@ -280,105 +262,81 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // (tools/micro/umma_bench.cu): ~300 cycles per burst (mbarrier try_wait, elect / reconvergence) + 50-70 cycles
     // per MMA in real code (operand descriptors into uniform registers), against 30-70 cycles of execution per
     // 128 x (64..128) x 16 MMA: long bursts keep the fixed part small.
-    // The job nest is unrolled per pass (two jobs); all 32 lanes run the warp-uniform control flow, one elected
+    // The job nest is unrolled per pass (three jobs); all 32 lanes run the warp-uniform control flow, one elected
     // lane issues.
     const uint64_t d_omega = umma_desc_sw128(s_omega);  // + c * 1024 + 2 k
     const uint64_t d_ring = umma_desc_sw128(s_ring);    // + slot * 1024 + 2 k
     const uint64_t d_ctx = umma_desc_sw128(s_ctx);      // + slab * 640 + 2 k
-    const uint64_t d_k2 = umma_desc_sw128(s_k2);        // + slot * 256 + chunk * 128 + 2 k
-    constexpr uint32_t kIdU = umma_idesc_bf16(128, 128) ^ kFmt;
-    constexpr uint32_t kIdU16 = umma_idesc_bf16(128, 16) ^ kFmt;
-    constexpr uint32_t kIdCtx = idesc_bf16_major(128, 80, 0, 1) ^ kFmt;   // B = [V | 1], MN-major
-    constexpr uint32_t kIdCtx2 = idesc_bf16_major(128, 16, 1, 0) ^ kFmt;  // A = [V | 1]^T, MN-major
-    constexpr uint32_t kIdOut = umma_idesc_bf16(128, 80) ^ kFmt;
     uint32_t nD3 = 0, d3u0 = 0, d3u1 = 0;               // output tiles started / fills per D3 slot
     uint32_t nItems = 0;
-#ifdef RFK_TM_TIMELINE
-    long long tli[128] = {};
-#endif
     auto wait_d3_region = [&](uint32_t s) {
       const uint32_t uses = s ? d3u1 : d3u0;
       if (uses > 0) mbar_wait(bar_d3free(s), (uses - 1u) & 1u);
     };
     // projection of job CU of pass `u` (elected lane): key side U^T[m, tok] = Omega_c . X^T (features on the lanes);
-    // query side U[tok, m] = X . Omega_c^T; job 1 adds the 16-feature chunk, tokens on the lanes on both sides
+    // query side U[tok, m] = X . Omega_c^T (16 columns for chunk 2)
     auto issue_u = [&](const PassInfo& u, auto cu_c) {
       constexpr int CU = decltype(cu_c)::value;
       const uint32_t us = (u.j0 + CU) & 1u;
-      const uint32_t ub = tmem + kColU + us * kSlotCols;
       const bool key = u.key_side();
       const uint64_t dx = d_ring + (uint64_t)(u.a_slot * 1024u);
       const uint64_t dw = d_omega + (uint64_t)(CU * 1024);
       const uint64_t da = key ? dw : dx;
       const uint64_t db = key ? dx : dw;
+      const uint32_t idesc = ((!key && CU == 2) ? umma_idesc_bf16(128, 16) : umma_idesc_bf16(128, 128)) ^ kFmt;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(ub, da + 2 * k, db + 2 * k, kIdU, k > 0);
-      if (CU == 1) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(ub + 128u, dx + 2 * k, d_omega + 2048 + 2 * k, kIdU16, k > 0);
-      }
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem + kColU + us * 128u, da + 2 * k, db + 2 * k, idesc, k > 0);
       umma_commit(bar_ufull(us));
-      // the tile's last projection: hand the ring slot back. A softmax QMAX pass keeps its tile for the Q pass; a
-      // softmax K pass keeps it until the feature warps have taken |k|^2 from it (released in its own first burst:
-      // projections run a whole pass ahead of the feature warps)
-      if (CU == 1 && u.kind != kPassX && !(KIND == 0 && u.kind == kPassK)) umma_commit(bar_tempty(u.a_slot));
+      // the tile's last projection: hand the ring slot back (a softmax QMAX pass keeps its tile for the Q pass)
+      if (CU == 2 && u.kind != kPassX) umma_commit(bar_tempty(u.a_slot));
     };
-    // burst C of pass `c`: consumer MMAs of its job C, then the projection of the job two ahead = job C of pass `u`
-    auto burst = [&](const PassInfo& c, const PassInfo& u, auto c_c) {
+    // burst C of pass `c`: consumer MMAs of its job C, then the projection of the job two ahead (pass `u`, job CU)
+    auto burst = [&](const PassInfo& c, const PassInfo& u, auto c_c, auto cu_c) {
       constexpr int C = decltype(c_c)::value;
+      constexpr int CU = decltype(cu_c)::value;
       const uint32_t jc = c.j0 + C;
       const uint32_t fs = jc & 1u;
       const uint32_t par = (jc >> 1) & 1u;
       const uint32_t ds = nD3 & 1u;
       // A operand of k-step k inside the U slot: the feature warp of column quarter k / 2 wrote its 16 packed
       // columns at the start of its own 32-column range
-      const uint32_t a0 = tmem + kColU + fs * kSlotCols;
-      RFK_TMTL(tli, jc, 0);
+      const uint32_t a0 = tmem + kColU + fs * 128u;
       if (c.kind == kPassK) {
-        if (c.t == 0) wait_d3_region((uint32_t)C);  // ctx block C aliases D3[C]
+        if (c.t == 0 && C < 2) wait_d3_region((uint32_t)C);  // ctx block c aliases D3[c]
         if (C == 0) mbar_wait(bar_tfull(c.v_slot), c.v_par);
       } else if (c.kind == kPassQ && C == 0) {
         if (c.t == 0) mbar_wait(bar_ctxready, nItems & 1u);
         wait_d3_region(ds);
       }
-      if (u.valid && C == 0 && !(KIND == 0 && u.kind == kPassQ)) mbar_wait(bar_tfull(u.a_slot), u.a_par);
+      if (u.valid && CU == 0 && !(KIND == 0 && u.kind == kPassQ)) mbar_wait(bar_tfull(u.a_slot), u.a_par);
       mbar_wait(bar_fready(fs), par);
-      RFK_TMTL(tli, jc, 1);
       tc_fence_after();
       if (elect_one()) {
         if (c.kind == kPassK) {
-          // ctx^T_C[128 m x 80] (+)= k'^T (A, TMEM, K = tokens) . [V | 1] (B, MN-major; second MN chunk = cslab)
+          // ctx^T_c[128 m x 80] (+)= k'^T (A, TMEM, K = tokens) . [V | 1] (B, MN-major; second MN chunk = cslab)
           const uint64_t dbv = desc_mn_sw128(s_ring + c.v_slot * kSlabBytes, s_cslab - s_ring - c.v_slot * kSlabBytes);
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma_bf16_ts(tmem + kColCtx + 80u * C, a0 + 32u * (k >> 1) + 8u * (k & 1), dbv + 128 * k, kIdCtx, (c.t > 0 || k > 0));
-          if (KIND == 0 && C == 0) umma_commit(bar_tempty(c.a_slot));  // row_diag of this pass precedes its first fready
-          if (C == 1) {
-            // ctx_2[128 (d | 1) x 16 m] (+)= [V | 1]^T (A, smem, MN-major) . k'_2 (B, smem, K-major over tokens)
-            const uint64_t dk2 = d_k2 + (uint64_t)(fs * (kK2Bytes >> 4));
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              umma_bf16(tmem + kColCtx2, dbv + 128 * k, dk2 + (k >> 2) * 128 + 2 * (k & 3), kIdCtx2, (c.t > 0 || k > 0));
+            umma_bf16_ts(tmem + kColCtx + 80u * C, a0 + 32u * (k >> 1) + 8u * (k & 1), dbv + 128 * k, idesc_bf16_major(128, 80, 0, 1) ^ kFmt,
+                         (c.t > 0 || k > 0));
+          if (C == 2) {
             umma_commit(bar_tempty(c.v_slot));
             if (c.t == nt - 1) umma_commit(bar_ctxfull);
           }
         } else if (c.kind == kPassQ) {
           // out|den [128 tok x 80] (+)= q'_c (A, TMEM, K = features) . ctx_c (B, K-major over m)
           const uint64_t db = d_ctx + (uint64_t)(2 * C * 640);
+          constexpr int NK = C == 2 ? 1 : 8;
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_bf16_ts(tmem + kColCtx + 80u * ds, a0 + 32u * (k >> 1) + 8u * (k & 1), db + (k >> 2) * 640 + 2 * (k & 3), kIdOut,
-                         (C > 0 || k > 0));
-          if (C == 1) {
-            umma_bf16_ts(tmem + kColCtx + 80u * ds, a0 + 128u, d_ctx + (uint64_t)(4 * 640), kIdOut, 1u);
-            umma_commit(bar_d3full(ds));
-          }
+          for (int k = 0; k < NK; ++k)
+            umma_bf16_ts(tmem + kColCtx + 80u * ds, a0 + 32u * (k >> 1) + 8u * (k & 1), db + (k >> 2) * 640 + 2 * (k & 3),
+                         umma_idesc_bf16(128, 80) ^ kFmt, (C > 0 || k > 0));
+          if (C == 2) umma_commit(bar_d3full(ds));
         }
         // (stabiliser passes: the feature warps have taken their maxima, nothing to consume)
-        if (u.valid) issue_u(u, c_c);
+        if (u.valid) issue_u(u, cu_c);
       }
       __syncwarp();
-      RFK_TMTL(tli, jc, 2);
     };
     PassIter<KIND> it;
     it.init(blockIdx.x, p.items, istride, nt);
@@ -393,8 +351,9 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       __syncwarp();
     }
     while (cur.valid) {
-      burst(cur, nxt, C0{});
-      burst(cur, nxt, C1{});
+      burst(cur, cur, C0{}, C2{});
+      burst(cur, nxt, C1{}, C0{});
+      burst(cur, nxt, C2{}, C1{});
       if (cur.kind == kPassQ) {
         if (cur.t == 0) ++nItems;
         if (nD3 & 1u) ++d3u1; else ++d3u0;
@@ -403,55 +362,45 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       cur = nxt;
       nxt = it.next();
     }
-#ifdef RFK_TM_TIMELINE
-    if (blockIdx.x == 0 && lane == 0)
-      for (int i = 0; i < 16; ++i)
-        printf("I job %d: enter %lld fready %lld issued %lld\n", 200 + i, tli[8 * i] - tli[0], tli[8 * i + 1] - tli[0], tli[8 * i + 2] - tli[0]);
-    if (blockIdx.x == 0 && lane == 0) printf("I base %lld\n", tli[0]);
-#endif
   } else {
     // =================== feature / epilogue warps ===================
     const int fw = warp - 2;         // 0..15
     const int lg = warp & 3;         // TMEM lane group this warp may touch
     const int cq = fw >> 2;          // column quarter of the U slot owned by this warp
-    const int row = lg * 32 + lane;  // TMEM lane: token row (query side, chunk 2) / feature row of the chunk (key side)
+    const int row = lg * 32 + lane;  // TMEM lane: token row (query side) / feature row of the chunk (key side)
     const uint32_t t_lane = ((uint32_t)(lg * 32) << 16);
     constexpr float kLog2e = 1.4426950408889634f;
     constexpr float kEps = KIND == 0 ? 1e-4f : 1e-3f;
     const uint32_t eps2 = pack_h16x2(kEps, kEps, kDt);
-    const uint32_t ubase = tmem + t_lane + kColU + 32u * (uint32_t)cq;  // + us * kSlotCols: this warp's 32 x 32 block
-    const uint32_t u2base = tmem + t_lane + kColU + 128u;               // + us * kSlotCols: chunk 2 (cq == 0 warps)
+    const uint32_t ubase = tmem + t_lane + kColU + 32u * (uint32_t)cq;  // + us * 128
 
     uint32_t nJ = 0;  // jobs processed (job parity = U slot)
     uint32_t nItems = 0, nD3 = 0, tile_seq = 0;
     float gmax = 0.f, sub = 0.f;
     const int64_t last_item = blockIdx.x + ((p.items - 1 - blockIdx.x) / istride) * istride;
 
-    uint32_t raw[32], raw2[16];
-#ifdef RFK_TM_TIMELINE
-    long long tlf[128] = {};
-#endif
-    // wait for the accumulator of job nJ and issue its TMEM loads. j1: the job carries chunk 2 as well
-    // (16 feature columns, tokens on the lanes, read by the cq == 0 warps)
-    auto prefetch = [&](bool j1) {
+    uint32_t raw[32];
+    // wait for the accumulator of job nJ and issue its TMEM loads. Q2: the job is a query-side chunk 2
+    // (16 feature columns, read by the cq == 0 warps only)
+    auto prefetch = [&](bool q2) {
       const uint32_t us = nJ & 1u;
-      RFK_TMTL(tlf, nJ, 0);
       mbar_wait(bar_ufull(us), (nJ >> 1) & 1u);
-      RFK_TMTL(tlf, nJ, 1);
       tc_fence_after();
-      tmem_ld_32x32p(ubase + us * kSlotCols, raw);
-      if (j1 && cq == 0) tmem_ld_32x16p(u2base + us * kSlotCols, raw2);
+      if (!q2) {
+        tmem_ld_32x32p(ubase + us * 128u, raw);
+      } else if (cq == 0) {
+        tmem_ld_32x16p(ubase + us * 128u, raw);
+      }
     };
-    // publish: features of job nJ are in place (or its maxima taken) -> the consumer issuer may proceed
+    // publish: features of job nJ are in TMEM (or its maxima taken) -> the consumer issuer may proceed
     auto publish = [&](bool stored) {
       if (stored) tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_fready(nJ & 1u));
-      RFK_TMTL(tlf, nJ, 3);
       ++nJ;
     };
-    // two accumulator values -> one packed 16-bit feature pair; s0 / s1: exponent offsets (softmax kernel)
+    // two accumulator values -> one packed bf16x2 feature pair; s0 / s1: exponent offsets (softmax kernel)
     auto feat2 = [&](uint32_t r0, uint32_t r1, float s0, float s1) -> uint32_t {
       const float x0 = __uint_as_float(r0), x1 = __uint_as_float(r1);
       if (KIND == 0)
@@ -459,13 +408,11 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       return add_h16x2<F16>(cvt_relu_h16x2<F16>(x0, x1), eps2);
     };
 
-    // ---- key-side job C: this thread holds feature row (128 C + row) x tokens [32 cq, 32 cq + 32) of the tile; in
-    //      job 1 the cq == 0 warps also hold token `row` x features 256..271 ----
-    // ntok: valid tokens of the tile
-    auto key_feat_job = [&](int C, int ntok, bool has_next) {
+    // ---- key-side job: this thread holds feature row (128 C + row) x tokens [32 cq, 32 cq + 32) of the tile ----
+    // ntok: valid tokens of the tile; next_q2: shape of the following job
+    auto key_feat_job = [&](int C, int ntok, bool has_next, bool next_q2) {
       const uint32_t us = nJ & 1u;
       tmem_ld_wait();
-      RFK_TMTL(tlf, nJ, 2);
       const bool row_ok = 128 * C + row < p.m;
       const int lim = ntok - 32 * cq;  // token columns >= lim are padding (only in a ragged last tile)
       uint32_t pk[16];
@@ -490,26 +437,9 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           else if (2 * i + 1 >= lim) pk[i] &= 0x0000ffffu;
         }
       }
-      tmem_st_32x16(ubase + us * kSlotCols, pk);
-      if (C == 1 && cq == 0) {
-        // chunk 2: k'_2[m, tok] into the K-major (over tokens) shared-memory tile of this slot
-        const float s = KIND == 0 ? ssub[row] : 0.f;
-        const bool tok_ok = row < ntok;
-        const uint32_t dst = s_k2 + us * kK2Bytes + (uint32_t)(row >> 6) * 2048u;
-        const uint32_t tk = (uint32_t)row & 63u;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          uint32_t w = feat2(raw2[2 * i], raw2[2 * i + 1], s, s);
-          if (!tok_ok) w = 0u;
-          if (256 + 2 * i >= p.m) w = 0u;
-          else if (256 + 2 * i + 1 >= p.m) w &= 0x0000ffffu;
-          st_shared_u16(dst + sw128_offset(2 * i, tk), (uint16_t)(w & 0xffffu));
-          st_shared_u16(dst + sw128_offset(2 * i + 1, tk), (uint16_t)(w >> 16));
-        }
-        fence_proxy_async_smem();
-      }
+      tmem_st_32x16(ubase + us * 128u, pk);
       publish(true);
-      if (has_next) prefetch(C == 0);
+      if (has_next) prefetch(next_q2);
     };
     // ---- key-side stabiliser job (softmax kernel): max of the raw projections over valid rows / tokens ----
     auto key_max_job = [&](int C, int ntok, float& acc) {
@@ -522,51 +452,48 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int i = 0; i < 32; ++i)
           if (i < lim) mx = fmaxf(mx, __uint_as_float(raw[i]));
       }
-      if (C == 1 && cq == 0 && row < ntok) {
-        const int lim2 = p.m - 256;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (i < lim2) mx = fmaxf(mx, __uint_as_float(raw2[i]));
-      }
       acc = fmaxf(acc, mx);
       publish(false);
-      prefetch(C == 0);  // a key-side job always follows
+      prefetch(false);  // a key-side job always follows
     };
-    // ---- query-side job C: this thread holds token row `row` x features [128 C + 32 cq, + 32) (+ 256..271) ----
-    auto query_feat_job = [&](int C, bool has_next) {
+    // ---- query-side job: this thread holds token row `row` x features [128 C + 32 cq, + 32) ----
+    auto query_feat_job = [&](auto cc, bool has_next, bool next_q2) {
+      constexpr int C = decltype(cc)::value;
       const uint32_t us = nJ & 1u;
-      tmem_ld_wait();
-      RFK_TMTL(tlf, nJ, 2);
-      uint32_t pk[16];
+      if (C < 2) {
+        tmem_ld_wait();
+        uint32_t pk[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) pk[i] = feat2(raw[2 * i], raw[2 * i + 1], sub, sub);
-      tmem_st_32x16(ubase + us * kSlotCols, pk);
-      if (C == 1 && cq == 0) {
-        uint32_t pk2[8];
+        for (int i = 0; i < 16; ++i) pk[i] = feat2(raw[2 * i], raw[2 * i + 1], sub, sub);
+        tmem_st_32x16(ubase + us * 128u, pk);
+        publish(true);
+      } else if (cq == 0) {
+        tmem_ld_wait();
+        uint32_t pk[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) pk2[i] = feat2(raw2[2 * i], raw2[2 * i + 1], sub, sub);
-        tmem_st_32x8(u2base + us * kSlotCols, pk2);
+        for (int i = 0; i < 8; ++i) pk[i] = feat2(raw[2 * i], raw[2 * i + 1], sub, sub);
+        tmem_st_32x8(ubase + us * 128u, pk);
+        publish(true);
+      } else {
+        publish(false);
       }
-      publish(true);
-      if (has_next) prefetch(C == 0);
+      if (has_next) prefetch(next_q2);
     };
     // ---- query-side stabiliser job (softmax kernel): per-row max over the valid feature columns ----
-    auto query_max_job = [&](int C, float& acc) {
-      tmem_ld_wait();
-      const int lim = p.m - (128 * C + 32 * cq);
-      float mx = -INFINITY;
+    auto query_max_job = [&](auto cc, float& acc) {
+      constexpr int C = decltype(cc)::value;
+      constexpr int NC = C < 2 ? 32 : 16;
+      if (C < 2 || cq == 0) {
+        tmem_ld_wait();
+        const int lim = p.m - (128 * C + 32 * cq);
+        float mx = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < lim) mx = fmaxf(mx, __uint_as_float(raw[i]));
-      if (C == 1 && cq == 0) {
-        const int lim2 = p.m - 256;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (i < lim2) mx = fmaxf(mx, __uint_as_float(raw2[i]));
+        for (int i = 0; i < NC; ++i)
+          if (i < lim) mx = fmaxf(mx, __uint_as_float(raw[i]));
+        acc = fmaxf(acc, mx);
       }
-      acc = fmaxf(acc, mx);
       publish(false);
-      prefetch(C == 0);  // the query jobs of the tile follow
+      prefetch(C == 1);  // QMAX chunk 2 follows chunk 1; the query chunk 0 follows QMAX chunk 2
     };
 
     // 0.5 * dn^2 * |x|^2 of token `row` of ring tile a_seq (softmax kernel): the four warps of a lane group sum
@@ -592,8 +519,8 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     };
 
     // out/den epilogue of one query tile: warp (lg, cq) stores channels [16 cq, 16 cq + 16) of its 32 tokens
-    // (the item's output row pointer is resolved once per item, in 32-bit arithmetic, off the critical path: four
-    // 64-bit divisions per tile in front of the stores used to keep every feature warp busy for ~1500 cycles)
+    // (the item's output row pointer is resolved once per item, in 32-bit arithmetic: four 64-bit divisions per tile
+    // in front of the stores sat on the feature warps' critical path)
     const uint16_t* out_item = nullptr;
     auto item_out_ptr = [&](int64_t item) {
       const uint32_t it32 = (uint32_t)item, g = it32 / (uint32_t)p.heads, h = it32 - g * (uint32_t)p.heads;
@@ -602,9 +529,7 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     };
     auto epilogue = [&](int t) {
       const uint32_t ds = nD3 & 1u;
-      RFK_TMTL(tlf, nJ, 4);
       mbar_wait(bar_d3full(ds), (nD3 >> 1) & 1u);
-      RFK_TMTL(tlf, nJ, 5);
       tc_fence_after();
       uint32_t rd[16], r0[16];
       tmem_ld_32x16p(tmem + t_lane + kColCtx + 80u * ds + 64, rd);  // column 64 = normaliser
@@ -613,7 +538,6 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_d3free(ds));
-      RFK_TMTL(tlf, nJ, 6);
       ++nD3;
       if (t * kTile + row < p.tokens) {
         const float inv = __fdividef(1.f, __uint_as_float(rd[0]));
@@ -630,7 +554,6 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         w.w = pack_h16x2(__uint_as_float(r0[14]) * inv, __uint_as_float(r0[15]) * inv, kDt);
         op[1] = w;
       }
-      RFK_TMTL(tlf, nJ, 7);
     };
 
     if ((int64_t)blockIdx.x < p.items) prefetch(false);
@@ -644,6 +567,7 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           const int ntok = min(kTile, p.tokens - t * kTile);
           key_max_job(0, ntok, kmx);
           key_max_job(1, ntok, kmx);
+          key_max_job(2, ntok, kmx);
         }
         kmx = warp_max(kmx);
         if (lane == 0) red[fw] = kmx;
@@ -652,7 +576,7 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
         for (int i = 1; i < kFeatWarps; ++i) gmax = fmaxf(gmax, red[i]);
       }
-      // ---- keys: k' chunks feed the context MMAs ----
+      // ---- keys: k'^T chunks feed the context MMAs ----
       for (int t = 0; t < nt; ++t) {
         if (KIND == 0) {
           const float dg = row_diag(tile_seq);
@@ -661,12 +585,13 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         tile_seq += 2;
         const int ntok = min(kTile, p.tokens - t * kTile);
-        key_feat_job(0, ntok, true);
-        key_feat_job(1, ntok, true);
+        key_feat_job(0, ntok, true, false);
+        key_feat_job(1, ntok, true, false);
+        key_feat_job(2, ntok, true, false);
       }
-      // ---- context read-out: TMEM -> 16-bit K-major smem. Warp (lg, cq) converts columns [16 cq, 16 cq + 16) of
-      //      ctx^T blocks 0 and 1 for its 32 feature rows; the normaliser column 64 goes to the cq < 2 warps, the
-      //      transposed block 2 (lanes = d | 1, 16 feature columns) to the cq == 2 warps ----
+      // ---- context read-out: TMEM ctx^T blocks -> bf16 K-major smem. Warp (lg, cq) converts columns
+      //      [16 cq, 16 cq + 16) of blocks 0 and 1 for its 32 feature rows; the normaliser column 64 and the
+      //      16-row block 2 are spread over the column quarters ----
       {
         mbar_wait(bar_ctxfull, nItems & 1u);
         ++nItems;
@@ -692,24 +617,15 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tmem_ld_wait();
           put(128 * cq + row, 64u, __uint_as_float(r[0]));
         }
-        if (cq == 2 && lg < 3) {  // block 2: this lane = row n of ctx (d | 1), columns = features 256..271
-          uint32_t r[16];
-          tmem_ld_32x16p(tmem + t_lane + kColCtx2, r);
+        if (lg == 0) {  // block 2: features 256..271 live in lanes 0..15
+          uint32_t r[16], r2[16];
+          tmem_ld_32x16p(tmem + kColCtx + 160u + 16u * (uint32_t)cq, r);
+          tmem_ld_32x16p(tmem + kColCtx + 160u + 64u, r2);
           tmem_ld_wait();
-          if (row <= 64) {
-            const uint32_t n = (uint32_t)row;
-            const uint32_t rb = s_ctx + 4u * kCtxSlabBytes + (n >> 3) * 1024u + (n & 7u) * 128u;
-            uint4 w;
-            w.x = pack_h16x2(__uint_as_float(r[0]), __uint_as_float(r[1]), kDt);
-            w.y = pack_h16x2(__uint_as_float(r[2]), __uint_as_float(r[3]), kDt);
-            w.z = pack_h16x2(__uint_as_float(r[4]), __uint_as_float(r[5]), kDt);
-            w.w = pack_h16x2(__uint_as_float(r[6]), __uint_as_float(r[7]), kDt);
-            st_shared_v4(rb + (((0u ^ n) & 7u) << 4), w);
-            w.x = pack_h16x2(__uint_as_float(r[8]), __uint_as_float(r[9]), kDt);
-            w.y = pack_h16x2(__uint_as_float(r[10]), __uint_as_float(r[11]), kDt);
-            w.z = pack_h16x2(__uint_as_float(r[12]), __uint_as_float(r[13]), kDt);
-            w.w = pack_h16x2(__uint_as_float(r[14]), __uint_as_float(r[15]), kDt);
-            st_shared_v4(rb + (((1u ^ n) & 7u) << 4), w);
+          if (lane < 16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) put(256 + lane, 16u * cq + i, __uint_as_float(r[i]));
+            if (cq == 3) put(256 + lane, 64u, __uint_as_float(r2[0]));
           }
         }
         fence_proxy_async_smem();
@@ -725,30 +641,23 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (KIND == 0) {
           const float diag = row_diag(tile_seq);
           float rmx = -INFINITY;
-          query_max_job(0, rmx);
+          query_max_job(C0{}, rmx);
           if (pending) { epilogue(t - 1); pending = false; }
-          query_max_job(1, rmx);
+          query_max_job(C1{}, rmx);
+          query_max_job(C2{}, rmx);
           rmaxs[cq * 128 + row] = rmx;
           named_bar_sync(1, kFeatThreads);
           sub = (diag + fmaxf(fmaxf(rmaxs[row], rmaxs[128 + row]), fmaxf(rmaxs[256 + row], rmaxs[384 + row]))) * kLog2e;
         }
         ++tile_seq;
-        query_feat_job(0, true);
+        query_feat_job(C0{}, true, false);
         if (pending) { epilogue(t - 1); pending = false; }
-        query_feat_job(1, more);
+        query_feat_job(C1{}, true, true);
+        query_feat_job(C2{}, more, false);
         pending = true;
       }
       epilogue(nt - 1);
     }
-#ifdef RFK_TM_TIMELINE
-    if (blockIdx.x == 0 && warp == 2 && lane == 0) {
-      for (int i = 0; i < 16; ++i)
-        printf("F job %d: wait %lld ufull %lld loaded %lld published %lld | epi: enter %lld d3full %lld ld %lld done %lld\n", 200 + i,
-               tlf[8 * i] - tlf[0], tlf[8 * i + 1] - tlf[0], tlf[8 * i + 2] - tlf[0], tlf[8 * i + 3] - tlf[0], tlf[8 * i + 4] - tlf[0],
-               tlf[8 * i + 5] - tlf[0], tlf[8 * i + 6] - tlf[0], tlf[8 * i + 7] - tlf[0]);
-      printf("F base %lld\n", tlf[0]);
-    }
-#endif
   }
   tc_fence_before();
   __syncthreads();
