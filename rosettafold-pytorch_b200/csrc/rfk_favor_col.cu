@@ -98,7 +98,7 @@ favor_col_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   float* partq = scratch + 1184;  // [4][128] partial |q|^2
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t istride = gridDim.x;
+  const uint32_t istride = gridDim.x, items = (uint32_t)p.items;  // (the launcher checks that items fit 32 bits)
 
   // ---- one-time setup ----
   if (warp == 0 && lane == 0) {
@@ -161,15 +161,15 @@ favor_col_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (warp == 0) {
     if (lane == 0) {
       // =================== TMA producer ===================
-      auto coords = [&](int64_t item, int& h, int& g0, int& g1) {  // (the launcher checks that items fit 32 bits)
-        const uint32_t it32 = (uint32_t)item, g = it32 / (uint32_t)p.heads;
+      auto coords = [&](uint32_t it32, int& h, int& g0, int& g1) {
+        const uint32_t g = it32 / (uint32_t)p.heads;
         h = (int)(it32 - g * (uint32_t)p.heads);
         g1 = (int)(g / (uint32_t)p.G0);
         g0 = (int)(g - (uint32_t)g1 * (uint32_t)p.G0);
       };
       // L2 prefetch two items ahead of the loads
-      auto prefetch_item = [&](int64_t item) {
-        if (item >= p.items) return;
+      auto prefetch_item = [&](uint32_t item) {
+        if (item >= items) return;
         int h, g0, g1;
         coords(item, h, g0, g1);
         tma_prefetch_4d(&tm_k, h * 64, 0, g0, g1);
@@ -179,7 +179,7 @@ favor_col_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       prefetch_item(blockIdx.x);
       prefetch_item(blockIdx.x + istride);
       uint32_t n = 0;
-      for (int64_t item = blockIdx.x; item < p.items; item += istride, ++n) {
+      for (uint32_t item = blockIdx.x; item < items; item += istride, ++n) {
         prefetch_item(item + 2 * istride);
         int h, g0, g1;
         coords(item, h, g0, g1);
@@ -226,11 +226,11 @@ favor_col_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #ifdef RFK_COL_TIMELINE
     long long tli[24] = {};
 #endif
-    if ((int64_t)blockIdx.x < p.items) {
+    if (blockIdx.x < items) {
       proj_keys(0, true);
       proj_keys(0, false);
     }
-    for (int64_t item = blockIdx.x; item < p.items; item += istride, ++n) {
+    for (uint32_t item = blockIdx.x; item < items; item += istride, ++n) {
       const uint32_t par = n & 1u, tpar = (n >> 1) & 1u;
       const uint32_t ks = slot_of(n, 0), vs = slot_of(n, 1), qs = slot_of(n, 2);
       // ---- context: ctx^T_c[128 m x 80] = k'^T_c (A, TMEM, K = tokens) . [V | 1] (B, MN-major; second chunk = cslab)
@@ -286,7 +286,7 @@ favor_col_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       RFK_TL(tli, 5);
       mbar_wait(bar_ctxready, par);
       RFK_TL(tli, 6);
-      const bool has_next = item + istride < p.items;
+      const bool has_next = item + istride < items;
       if (has_next) proj_keys(n + 1, true);  // U1 is free: ctx^T_2 has been read out of it
 #pragma unroll
       for (int cc = 0; cc < 3; ++cc) {
@@ -372,16 +372,16 @@ favor_col_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                          v);
     };
     // out/den epilogue: warp (lg, cq) stores channels [16 cq, 16 cq + 16) of its 32 tokens
-    auto item_out_ptr = [&](int64_t item) {  // 32-bit arithmetic (the launcher checks that items fit), once per item
-      const uint32_t it32 = (uint32_t)item, g = it32 / (uint32_t)p.heads, h = it32 - g * (uint32_t)p.heads;
+    auto item_out_ptr = [&](uint32_t it32) {  // once per item
+      const uint32_t g = it32 / (uint32_t)p.heads, h = it32 - g * (uint32_t)p.heads;
       const uint32_t g1 = g / (uint32_t)p.G0, g0 = g - g1 * (uint32_t)p.G0;
       return reinterpret_cast<uint16_t*>(p.out) + (int64_t)g1 * p.ogs1 + (int64_t)g0 * p.ogs0 + (int64_t)row * p.ots + h * 64 + 16 * cq;
     };
     auto epilogue = [&](uint16_t* out_ptr, uint32_t n) {
       mbar_wait(bar_outfull, n & 1u);
       tc_fence_after();
-      uint32_t rd[16], r0[16];
-      tmem_ld_32x16p(tl + kColC + 64, rd);  // column 64 = normaliser
+      uint32_t rd[1], r0[16];
+      tmem_ld_32x1p(tl + kColC + 64, rd);  // column 64 = normaliser
       tmem_ld_32x16p(tl + kColC + 16u * (uint32_t)cq, r0);
       tmem_ld_wait();
       tc_fence_before();
@@ -408,7 +408,7 @@ favor_col_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #endif
     uint16_t* prev_out = nullptr;  // output rows of the item whose out | den is still in block C
     uint32_t raw[32];
-    for (int64_t item = blockIdx.x; item < p.items; item += istride, ++n) {
+    for (uint32_t item = blockIdx.x; item < items; item += istride, ++n) {
       const uint32_t par = n & 1u, tpar = (n >> 1) & 1u;
       RFK_TL(tlf, 0);
       uint16_t* const cur_out = item_out_ptr(item);
@@ -485,13 +485,13 @@ favor_col_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       //      columns [16 cq, 16 cq + 16) of blocks 0 and 1 for its 32 feature rows; the normaliser column 64 and the
       //      16-row block 2 are spread over the column quarters ----
       {
-        uint32_t r[16], r2[16];
+        uint32_t r[16], r2[1];
         RFK_TL(tlf, 4);
         mbar_wait(bar_ctxfull(0), par);
         RFK_TL(tlf, 5);
         tc_fence_after();
         tmem_ld_32x16p(tl + kColC + 16u * (uint32_t)cq, r);
-        if (cq == 0) tmem_ld_32x16p(tl + kColC + 64u, r2);
+        if (cq == 0) tmem_ld_32x1p(tl + kColC + 64u, r2);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) put(row, 16u * cq + i, __uint_as_float(r[i]));
@@ -499,7 +499,7 @@ favor_col_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         mbar_wait(bar_ctxfull(1), par);
         tc_fence_after();
         tmem_ld_32x16p(tl + kColU0 + 16u * (uint32_t)cq, r);
-        if (cq == 1) tmem_ld_32x16p(tl + kColU0 + 64u, r2);
+        if (cq == 1) tmem_ld_32x1p(tl + kColU0 + 64u, r2);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -512,7 +512,7 @@ favor_col_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         tc_fence_after();
         if (lg == 0) {  // block 2: features 256..271 live in lanes 0..15
           tmem_ld_32x16p(tmem + kColU1 + 16u * (uint32_t)cq, r);
-          tmem_ld_32x16p(tmem + kColU1 + 64u, r2);
+          tmem_ld_32x1p(tmem + kColU1 + 64u, r2);
           tmem_ld_wait();
           if (lane < 16) {
 #pragma unroll

@@ -79,7 +79,7 @@ struct PassInfo {
 };
 template <int KIND>
 struct PassIter {
-  int64_t item, items, istride;
+  uint32_t item, items, istride;  // (the launcher checks that items fit 32 bits)
   int nt, P, ps;
   uint32_t r_slot, r_par, j;
   PassInfo last;
@@ -87,7 +87,7 @@ struct PassIter {
     slot = r_slot; par = r_par;
     if (++r_slot == kRing) { r_slot = 0; r_par ^= 1u; }
   }
-  __device__ void init(int64_t first, int64_t n_items, int64_t stride, int n_tiles) {
+  __device__ void init(uint32_t first, uint32_t n_items, uint32_t stride, int n_tiles) {
     item = first; items = n_items; istride = stride; nt = n_tiles;
     P = KIND == 0 ? 4 * nt : 2 * nt;
     ps = 0; r_slot = 0; r_par = 0; j = 0;
@@ -142,7 +142,7 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = (p.tokens + kTile - 1) / kTile;
-  const int64_t istride = gridDim.x;
+  const uint32_t istride = gridDim.x, items = (uint32_t)p.items;  // (the launcher checks that items fit 32 bits)
 
   // ---- one-time setup ----
   if (warp == 0 && lane == 0) {
@@ -205,7 +205,7 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (lane == 0) {
       // =================== TMA producer ===================
       struct Cursor {
-        int64_t item;
+        uint32_t item;
         int ph, i;  // phase: 0 = key-max pass (softmax kernel), 1 = K/V pairs, 2 = Q
       };
       auto cur_init = [&](Cursor& c) { c.item = blockIdx.x; c.ph = KIND == 0 ? 0 : 1; c.i = 0; };
@@ -219,8 +219,8 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         c.i = 0;
         if (++c.ph == 3) { c.ph = KIND == 0 ? 0 : 1; c.item += istride; }
       };
-      auto coords = [&](int64_t item, int& h, int& g0, int& g1) {  // (the launcher checks that items fit 32 bits)
-        const uint32_t it32 = (uint32_t)item, g = it32 / (uint32_t)p.heads;
+      auto coords = [&](uint32_t it32, int& h, int& g0, int& g1) {
+        const uint32_t g = it32 / (uint32_t)p.heads;
         h = (int)(it32 - g * (uint32_t)p.heads);
         g1 = (int)(g / (uint32_t)p.G0);
         g0 = (int)(g - (uint32_t)g1 * (uint32_t)p.G0);
@@ -230,7 +230,7 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       cur_init(pf);
       cur_init(ld);
       auto prefetch_one = [&]() {
-        if (pf.item >= p.items) return;
+        if (pf.item >= items) return;
         const CUtensorMap* tm; int t, h, g0, g1;
         cur_get(pf, tm, t);
         coords(pf.item, h, g0, g1);
@@ -239,7 +239,7 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       };
       for (int i = 0; i < kPrefetch; ++i) prefetch_one();
       uint32_t slot = 0, par = 0;
-      while (ld.item < p.items) {
+      while (ld.item < items) {
         prefetch_one();
         const CUtensorMap* tm; int t, h, g0, g1;
         cur_get(ld, tm, t);
@@ -339,7 +339,7 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       __syncwarp();
     };
     PassIter<KIND> it;
-    it.init(blockIdx.x, p.items, istride, nt);
+    it.init(blockIdx.x, items, istride, nt);
     PassInfo cur = it.next(), nxt = it.next();
     if (cur.valid) {  // prologue: the first two projections
       mbar_wait(bar_tfull(cur.a_slot), cur.a_par);
@@ -377,7 +377,7 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     uint32_t nJ = 0;  // jobs processed (job parity = U slot)
     uint32_t nItems = 0, nD3 = 0, tile_seq = 0;
     float gmax = 0.f, sub = 0.f;
-    const int64_t last_item = blockIdx.x + ((p.items - 1 - blockIdx.x) / istride) * istride;
+    const uint32_t last_item = blockIdx.x + ((items - 1u - blockIdx.x) / istride) * istride;
 
     uint32_t raw[32];
     // wait for the accumulator of job nJ and issue its TMEM loads. Q2: the job is a query-side chunk 2
@@ -522,8 +522,8 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // (the item's output row pointer is resolved once per item, in 32-bit arithmetic: four 64-bit divisions per tile
     // in front of the stores sat on the feature warps' critical path)
     const uint16_t* out_item = nullptr;
-    auto item_out_ptr = [&](int64_t item) {
-      const uint32_t it32 = (uint32_t)item, g = it32 / (uint32_t)p.heads, h = it32 - g * (uint32_t)p.heads;
+    auto item_out_ptr = [&](uint32_t it32) {
+      const uint32_t g = it32 / (uint32_t)p.heads, h = it32 - g * (uint32_t)p.heads;
       const uint32_t g1 = g / (uint32_t)p.G0, g0 = g - g1 * (uint32_t)p.G0;
       return reinterpret_cast<const uint16_t*>(p.out) + (int64_t)g1 * p.ogs1 + (int64_t)g0 * p.ogs0 + (int64_t)row * p.ots + h * 64 + 16 * cq;
     };
@@ -531,8 +531,8 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const uint32_t ds = nD3 & 1u;
       mbar_wait(bar_d3full(ds), (nD3 >> 1) & 1u);
       tc_fence_after();
-      uint32_t rd[16], r0[16];
-      tmem_ld_32x16p(tmem + t_lane + kColCtx + 80u * ds + 64, rd);  // column 64 = normaliser
+      uint32_t rd[1], r0[16];
+      tmem_ld_32x1p(tmem + t_lane + kColCtx + 80u * ds + 64, rd);  // column 64 = normaliser
       tmem_ld_32x16p(tmem + t_lane + kColCtx + 80u * ds + 16u * (uint32_t)cq, r0);
       tmem_ld_wait();
       tc_fence_before();
@@ -556,8 +556,8 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     };
 
-    if ((int64_t)blockIdx.x < p.items) prefetch(false);
-    for (int64_t item = blockIdx.x; item < p.items; item += istride) {
+    if (blockIdx.x < items) prefetch(false);
+    for (uint32_t item = blockIdx.x; item < items; item += istride) {
       out_item = item_out_ptr(item);
       if (KIND == 0) {
         // ---- key stabiliser: global max of Omega'.K^T over the valid features / tokens ----
@@ -612,15 +612,15 @@ favor_tm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           for (int i = 0; i < 16; ++i) put(128 * b + row, 16u * cq + i, __uint_as_float(r[i]));
         }
         if (cq < 2) {  // normaliser column of block cq
-          uint32_t r[16];
-          tmem_ld_32x16p(tmem + t_lane + kColCtx + 80u * (uint32_t)cq + 64u, r);
+          uint32_t r[1];
+          tmem_ld_32x1p(tmem + t_lane + kColCtx + 80u * (uint32_t)cq + 64u, r);
           tmem_ld_wait();
           put(128 * cq + row, 64u, __uint_as_float(r[0]));
         }
         if (lg == 0) {  // block 2: features 256..271 live in lanes 0..15
-          uint32_t r[16], r2[16];
+          uint32_t r[16], r2[1];
           tmem_ld_32x16p(tmem + kColCtx + 160u + 16u * (uint32_t)cq, r);
-          tmem_ld_32x16p(tmem + kColCtx + 160u + 64u, r2);
+          tmem_ld_32x1p(tmem + kColCtx + 160u + 64u, r2);
           tmem_ld_wait();
           if (lane < 16) {
 #pragma unroll
