@@ -103,6 +103,27 @@ def test_performer_restatement_is_an_unbiased_softmax_attention_estimator():
     assert float((gen - exact).norm() / exact.norm()) > 0.05
 
 
+@pytest.mark.parametrize("generalized", [False, True])
+def test_performer_restatement_matches_the_package_when_importable(generalized):
+    """The pin the oracle lacks: wherever the real `performer_pytorch` can be imported (not in this image: the test
+    skips, and the oracle header keeps saying "parity unpinned"), its SelfAttention with the restatement's weights and
+    projection matrix must give the restatement's output. The state_dict keys are the package's own (the reference's
+    checkpoints carry them), so loading is strict."""
+    pp = pytest.importorskip("performer_pytorch")
+    from oracle import performer_ref as P
+
+    torch.manual_seed(5)
+    dim, heads = 96, 3
+    mine = P.SelfAttention(dim, heads=heads, generalized_attention=generalized).eval()
+    kw = dict(generalized_attention=True, kernel_fn=torch.nn.ReLU()) if generalized else {}
+    theirs = pp.SelfAttention(dim=dim, heads=heads, dropout=0.0, **kw).eval()
+    assert theirs.fast_attention.nb_features == mine.fast_attention.nb_features == 266
+    theirs.load_state_dict(mine.state_dict(), strict=True)
+    x = torch.randn(2, 50, dim)
+    with torch.no_grad():
+        assert rel_l2(mine(x), theirs(x)) < 1e-5
+
+
 @pytest.mark.parametrize("name", ["small_template", "default"])
 def test_embedding_restatement_matches_golden(name):
     """oracle/embed_ref.py against the outputs of the unmodified reference's MsaEmbedding / PairEmbedding."""
