@@ -262,6 +262,23 @@ int rfk_conv3x3_nhwc_hw(const void* x, const void* w_packed, void* y, int y_dtyp
 int rfk_conv3x3_nhwc_f32(const float* x, const float* w_packed, float* y, int B, int H, int L, int C, int Cout,
                          rfk_stream_t stream);
 
+/* Dilated forms (ResBlock2D of the prediction heads, resnet.py:14-44: nn.Conv2d(C, C, 3, dilation=d, padding="same",
+ * bias=False)): tap (di, dj) reads the image at (i + (di - 1) d, j + (dj - 1) d), zeros outside. dilation 1 = the calls above.
+ * tcgen05 form: 1 <= dilation <= 64, image and packed weights of `x_dtype` = RFK_BF16 or RFK_F16 (the heads' convolution
+ * inputs follow an InstanceNorm + ELU: range-bounded, so IEEE half), y of RFK_BF16 / RFK_F16 / RFK_F32;
+ * fp32 SIMT form: 1 <= dilation <= 8. */
+int rfk_conv3x3_nhwc_dil(const void* x, int x_dtype, const void* w_packed, void* y, int y_dtype, int B, int H, int L,
+                         int C, int Cout, int dilation, rfk_stream_t stream);
+int rfk_conv3x3_nhwc_f32_dil(const float* x, const float* w_packed, float* y, int B, int H, int L, int C, int Cout,
+                             int dilation, rfk_stream_t stream);
+
+/*
+ * Prediction heads (reference :1130-1172): symmetrisation of the projected pair map in
+ * front of the distance / omega heads (:1166), channels-last:  y[b][i][j][:] = 0.5 (x[b][i][j][:] + x[b][j][i][:]).
+ *   x, y: [B][L][L][C] of `dtype` (RFK_F32: C % 4 == 0; 16-bit: C % 8 == 0), contiguous, 16-byte aligned, x != y.
+ */
+int rfk_pair_symmetrize(const void* x, void* y, int dtype, int B, int L, int C, rfk_stream_t stream);
+
 /*
  * Embeddings that feed the trunk (reference :57-181), fused gathers on the device
  * (the reference gathers CPU-resident tables in Python loops over the batch, :73, :98, :115-116).

@@ -86,6 +86,37 @@ def make_embeddings(ref, rf):
     print(os.path.getsize(path))
 
 
+HEAD_CONFIGS = {
+    # PredictionHead (:1130-1172): all four dilations (1, 2, 4, 8) in every ResNet; L ragged (not a multiple of 8)
+    "small": dict(in_channels=64, n_res_blocks=4, B=2, L=21, seed=90),
+    # default width (d_pair 288), the README depth of 4 residual blocks, L past the largest dilation
+    "default": dict(in_channels=288, n_res_blocks=4, B=1, L=28, seed=91),
+}
+
+
+def synth_head_input(c):
+    g = torch.Generator().manual_seed(c["seed"] + 100)
+    return torch.randn((c["B"], c["L"], c["L"], c["in_channels"]), generator=g)
+
+
+def make_heads(ref, rf):
+    out = {}
+    for name, c in HEAD_CONFIGS.items():
+        mine = rf.PredictionHead(c["in_channels"], c["n_res_blocks"], 0.1)
+        sd = synth_state_dict(mine.state_dict(), seed=c["seed"])
+        rh = ref.PredictionHead(c["in_channels"], c["n_res_blocks"], 0.1)
+        rh.load_state_dict(sd, strict=True)
+        rh.eval()
+        with torch.no_grad():
+            logits = rh(synth_head_input(c))
+        out[name] = dict(config=c, weight_checksum=checksum(sd), **{k: v.contiguous() for k, v in logits.items()})
+        print("heads", name, {k: tuple(v.shape) for k, v in logits.items()})
+    path = os.path.join(ROOT, "tests", "golden", "prediction_head.pt")
+    out["generator"] = "oracle/make_golden.py --heads-only on the unmodified reference (CPU fp32, eval)"
+    torch.save(out, path)
+    print(os.path.getsize(path))
+
+
 COORD_CONFIGS = {
     # MsaUpdateWithPairAndCoord (:865-920) as built by the three-track blocks (:1028-1035), ragged N / L
     "msa_pair_coord": dict(d_msa=96, d_state=32, d_inner=32, d_ff=192, B=2, N=5, L=20, seed=6),
@@ -190,8 +221,11 @@ def main():
             os.chdir(cwd)
     if "--embeddings-only" in sys.argv:
         return make_embeddings(ref, rf)
+    if "--heads-only" in sys.argv:
+        return make_heads(ref, rf)
     if "--subset-only" not in sys.argv:
         make_embeddings(ref, rf)
+        make_heads(ref, rf)
         make_coord(ref, rf)
     if "--coord-only" in sys.argv:
         return

@@ -179,18 +179,23 @@ class RefBackend:
         out.copy_(o.permute(0, 1, 3, 2, 4).reshape(G1, G0, T, heads * 64).to(out.dtype))
 
     # nn.Conv2d(C, C, 3, padding="same", bias=False) on b l1 l2 d (:451-457)
-    def conv3x3(self, x, w_packed, out):
+    def conv3x3(self, x, w_packed, out, dilation=1):
         Cout, _, cpad = w_packed.shape
         Cin = x.shape[3]
         w = w_packed.to(self.acc)[:, :, :Cin].reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
-        y = torch.nn.functional.conv2d(x.to(self.acc).permute(0, 3, 1, 2), w, padding=1)
+        y = torch.nn.functional.conv2d(x.to(self.acc).permute(0, 3, 1, 2), w, padding=dilation, dilation=dilation)
         out.copy_(y.permute(0, 2, 3, 1).to(out.dtype))
 
-    def conv3x3_f32(self, x, w_packed, out):
+    def conv3x3_f32(self, x, w_packed, out, dilation=1):
         _, Cin, Cout = w_packed.shape
         w = w_packed.to(self.acc).reshape(3, 3, Cin, Cout).permute(3, 2, 0, 1)
-        y = torch.nn.functional.conv2d(x.to(self.acc).permute(0, 3, 1, 2), w, padding=1)
+        y = torch.nn.functional.conv2d(x.to(self.acc).permute(0, 3, 1, 2), w, padding=dilation, dilation=dilation)
         out.copy_(y.permute(0, 2, 3, 1).to(out.dtype))
+
+    # PredictionHead :1166 on a channels-last map
+    def pair_symmetrize(self, x, out):
+        xa = x.to(self.acc)
+        out.copy_((0.5 * (xa + xa.transpose(1, 2))).to(out.dtype))
 
     # MsaEmbedding.forward (:114-120) / PairEmbedding.forward (:147-175) at the C-ABI boundary
     def msa_embed(self, tokens, aa_idx, emb, pos_enc, query_enc, out):

@@ -33,8 +33,9 @@ SCHEMAS = {
     "instnorm_apply": "(Tensor x, Tensor stats, Tensor gamma, Tensor beta, float eps, Tensor? res, bool elu, "
                       "Tensor(a!) out) -> ()",
     "favor_attention": "(Tensor q, Tensor k, Tensor v, Tensor(a!) out, Tensor proj, int kind, int heads) -> ()",
-    "conv3x3": "(Tensor x, Tensor w_packed, Tensor(a!) out) -> ()",
-    "conv3x3_f32": "(Tensor x, Tensor w_packed, Tensor(a!) out) -> ()",
+    "conv3x3": "(Tensor x, Tensor w_packed, Tensor(a!) out, int dilation) -> ()",
+    "conv3x3_f32": "(Tensor x, Tensor w_packed, Tensor(a!) out, int dilation) -> ()",
+    "pair_symmetrize": "(Tensor x, Tensor(a!) out) -> ()",
     "convert_rows": "(Tensor x, Tensor(a!) out) -> ()",
     "msa_embed": "(Tensor tokens, Tensor aa_idx, Tensor emb, Tensor pos_enc, Tensor query_enc, Tensor(a!) out) -> ()",
     "pair_embed": "(Tensor seq, Tensor aa_idx, Tensor table_left, Tensor table_right, Tensor w_sep, Tensor bias, "

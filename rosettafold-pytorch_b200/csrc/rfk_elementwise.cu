@@ -1106,7 +1106,8 @@ extern "C" int rfk_instnorm_apply(const void* x, int xdt, const double* stats, c
   if (!dtype_ok(xdt) || !dtype_ok(ydt) || (res && !dtype_ok(rdt))) return RFK_ERR_BAD_DTYPE;
   const int64_t total = (int64_t)B * positions * C;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  if (xdt != RFK_F16 && ydt != RFK_F16 && C % 8 == 0 && C <= 2048 && al16(x) && al16(y) && (!res || al16(res)) &&
+  const bool f16_out = xdt == RFK_F32 && ydt == RFK_F16;  // (the heads: fp32 convolution output -> IEEE-half operand)
+  if (xdt != RFK_F16 && (ydt != RFK_F16 || f16_out) && C % 8 == 0 && C <= 2048 && al16(x) && al16(y) && (!res || al16(res)) &&
       (!res || rdt == RFK_F32)) {
     const int chunk = 256;
     const int groups = C / 8;
@@ -1119,7 +1120,8 @@ extern "C" int rfk_instnorm_apply(const void* x, int xdt, const double* stats, c
   instnorm_apply_vec_kernel<TX, float, TY><<<grid, threads, 0, st>>>(                                \
       reinterpret_cast<const TX*>(x), stats, gamma, beta, eps, rf, elu, reinterpret_cast<TY*>(y), \
       positions, C, chunk)
-      if (xdt == RFK_BF16 && ydt == RFK_BF16) RFK_IN_LAUNCH(__nv_bfloat16, __nv_bfloat16);
+      if (f16_out) RFK_IN_LAUNCH(float, __half);
+      else if (xdt == RFK_BF16 && ydt == RFK_BF16) RFK_IN_LAUNCH(__nv_bfloat16, __nv_bfloat16);
       else if (xdt == RFK_BF16) RFK_IN_LAUNCH(__nv_bfloat16, float);
       else if (ydt == RFK_BF16) RFK_IN_LAUNCH(float, __nv_bfloat16);
       else RFK_IN_LAUNCH(float, float);

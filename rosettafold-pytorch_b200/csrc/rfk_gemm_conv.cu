@@ -30,12 +30,13 @@ int launch_tc_conv(int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb
 
 using namespace rfk;
 
-extern "C" int rfk_conv3x3_nhwc_hw(const void* x, const void* w_packed, void* y, int y_dtype, int B, int H,
-                                   int L, int C, int Cout, rfk_stream_t stream_) {
+extern "C" int rfk_conv3x3_nhwc_dil(const void* x, int x_dtype, const void* w_packed, void* y, int y_dtype, int B, int H,
+                                    int L, int C, int Cout, int dilation, rfk_stream_t stream_) {
   if (!x || !w_packed || !y) return RFK_ERR_NULL_POINTER;
-  if (B <= 0 || H <= 0 || L <= 0 || C <= 0 || Cout <= 0) return RFK_ERR_BAD_DIMS;
+  if (B <= 0 || H <= 0 || L <= 0 || C <= 0 || Cout <= 0 || dilation < 1 || dilation > 64) return RFK_ERR_BAD_DIMS;
+  if (!is_h16(x_dtype)) return RFK_ERR_BAD_DTYPE;
   if (C % 8) return RFK_ERR_BAD_DIMS;  // TMA stride rule (16-byte rows)
-  if (y_dtype != RFK_BF16 && y_dtype != RFK_F32) return RFK_ERR_BAD_DTYPE;
+  if (!is_h16(y_dtype) && y_dtype != RFK_F32) return RFK_ERR_BAD_DTYPE;
   if (!aligned16(x) || !aligned16(w_packed) || !aligned16(y)) return RFK_ERR_MISALIGNED;
   int rc = check_arch();
   if (rc != RFK_OK) return rc;
@@ -46,7 +47,7 @@ extern "C" int rfk_conv3x3_nhwc_hw(const void* x, const void* w_packed, void* y,
     if (Cout % cand == 0) { bn = cand; break; }
   static const char* force_bn = getenv("RFK_CONV_BN");  // A/B debugging aid: 256 / 128 / 96 / 64 / 32
   if (force_bn && atoi(force_bn) >= 32 && Cout % 32 == 0) bn = atoi(force_bn);
-  const bool lean = Cout % 32 == 0 && (y_dtype == RFK_BF16 ? Cout % 8 == 0 : Cout % 4 == 0);
+  const bool lean = Cout % 32 == 0 && (is_h16(y_dtype) ? Cout % 8 == 0 : Cout % 4 == 0);
 
   GemmDev p{};
   p.M = (int64_t)B * H * Lp;  // padded so that every tile lies inside one image row
@@ -60,6 +61,8 @@ extern "C" int rfk_conv3x3_nhwc_hw(const void* x, const void* w_packed, void* y,
   p.c_addr.ms[1] = (int64_t)L * Cout;    // (b, i)
   p.c_addr.ns[0] = 1; p.c_addr.ns[1] = 0;
   p.conv_L = L; p.conv_H = H; p.conv_Lp = Lp; p.conv_cblocks = cblocks; p.conv_cpad = cpad;
+  p.conv_dil = dilation;
+  p.ab_f16 = x_dtype == RFK_F16;  // image and packed weights are IEEE half instead of bf16
   p.conv_last_k16 = (C - (cblocks - 1) * 64 + 15) / 16;
 
   CUtensorMap ta, tb;
@@ -78,8 +81,13 @@ extern "C" int rfk_conv3x3_nhwc_hw(const void* x, const void* w_packed, void* y,
     if ((rc = make_tmap_bf16_raw(&tb, w_packed, 5, dims, strides, box)) != RFK_OK) return rc;
   }
   const int64_t tiles = (p.M / kBlockM) * ((Cout + bn - 1) / bn);
-  return launch_tc_conv(bn, !lean ? 0 : (y_dtype == RFK_BF16 ? 1 : 2), ta, tb, p, tiles,
+  return launch_tc_conv(bn, !lean ? 0 : (is_h16(y_dtype) ? 1 : 2), ta, tb, p, tiles,
                         reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int rfk_conv3x3_nhwc_hw(const void* x, const void* w_packed, void* y, int y_dtype, int B, int H,
+                                   int L, int C, int Cout, rfk_stream_t stream_) {
+  return rfk_conv3x3_nhwc_dil(x, RFK_BF16, w_packed, y, y_dtype, B, H, L, C, Cout, 1, stream_);
 }
 
 extern "C" int rfk_conv3x3_nhwc(const void* x, const void* w_packed, void* y, int y_dtype, int B, int L,
@@ -96,21 +104,22 @@ extern "C" int rfk_conv3x3_nhwc(const void* x, const void* w_packed, void* y, in
 // ----------------------------------------------------------------------------------------------
 namespace rfk {
 namespace {
-constexpr int kCvW = 32, kCvCo = 64, kCvCk = 32;
+constexpr int kCvW = 32, kCvCo = 64, kCvCk = 32, kCvMaxDil = 8;
 
 __global__ void __launch_bounds__(256) conv3x3_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                           float* __restrict__ y, int B, int H, int W, int Cin, int Cout,
-                                                          int co_blocks) {
-  __shared__ float xs[3][kCvW + 2][kCvCk];
+                                                          int co_blocks, int dil) {
+  __shared__ float xs[3][kCvW + 2 * kCvMaxDil][kCvCk];  // window columns j0 - dil .. j0 + 31 + dil
   __shared__ __align__(16) float ws[kCvCk][kCvCo];
   const int j0 = blockIdx.x * kCvW, i = blockIdx.y;
   const int b = blockIdx.z / co_blocks, co0 = (blockIdx.z % co_blocks) * kCvCo;
   const int tid = threadIdx.x, pg = tid >> 4, cg = tid & 15;
   float acc[2][4] = {};
   for (int c0 = 0; c0 < Cin; c0 += kCvCk) {
-    for (int e = tid; e < 3 * (kCvW + 2) * kCvCk; e += 256) {
-      const int ck = e % kCvCk, col = (e / kCvCk) % (kCvW + 2), r = e / (kCvCk * (kCvW + 2));
-      const int ii = i + r - 1, jj = j0 + col - 1, c = c0 + ck;
+    const int wcols = kCvW + 2 * dil;
+    for (int e = tid; e < 3 * wcols * kCvCk; e += 256) {
+      const int ck = e % kCvCk, col = (e / kCvCk) % wcols, r = e / (kCvCk * wcols);
+      const int ii = i + (r - 1) * dil, jj = j0 + col - dil, c = c0 + ck;
       float v = 0.f;
       if (ii >= 0 && ii < H && jj >= 0 && jj < W && c < Cin) v = x[(((int64_t)b * H + ii) * W + jj) * Cin + c];
       xs[r][col][ck] = v;
@@ -126,7 +135,7 @@ __global__ void __launch_bounds__(256) conv3x3_f32_kernel(const float* __restric
       const int di = tap / 3, dj = tap % 3;
 #pragma unroll 8
       for (int ck = 0; ck < kCvCk; ++ck) {
-        const float x0 = xs[di][2 * pg + dj][ck], x1 = xs[di][2 * pg + 1 + dj][ck];
+        const float x0 = xs[di][2 * pg + dj * dil][ck], x1 = xs[di][2 * pg + 1 + dj * dil][ck];
         const float4 w4 = *reinterpret_cast<const float4*>(&ws[ck][4 * cg]);
         acc[0][0] = fmaf(x0, w4.x, acc[0][0]); acc[0][1] = fmaf(x0, w4.y, acc[0][1]);
         acc[0][2] = fmaf(x0, w4.z, acc[0][2]); acc[0][3] = fmaf(x0, w4.w, acc[0][3]);
@@ -150,14 +159,21 @@ __global__ void __launch_bounds__(256) conv3x3_f32_kernel(const float* __restric
 }  // namespace
 }  // namespace rfk
 
-extern "C" int rfk_conv3x3_nhwc_f32(const float* x, const float* w_packed, float* y, int B, int H, int L, int C, int Cout,
-                                    rfk_stream_t stream_) {
+extern "C" int rfk_conv3x3_nhwc_f32_dil(const float* x, const float* w_packed, float* y, int B, int H, int L, int C,
+                                        int Cout, int dilation, rfk_stream_t stream_) {
   if (!x || !w_packed || !y) return RFK_ERR_NULL_POINTER;
   if (B <= 0 || H <= 0 || L <= 0 || C <= 0 || Cout <= 0 || H > 65535) return RFK_ERR_BAD_DIMS;
+  if (dilation < 1 || dilation > rfk::kCvMaxDil) return RFK_ERR_BAD_DIMS;
   const int co_blocks = (Cout + rfk::kCvCo - 1) / rfk::kCvCo;
   if ((int64_t)B * co_blocks > 65535) return RFK_ERR_BAD_DIMS;
   if (rfk::check_arch() != RFK_OK) return RFK_ERR_UNSUPPORTED_ARCH;
   dim3 grid((unsigned)((L + rfk::kCvW - 1) / rfk::kCvW), (unsigned)H, (unsigned)(B * co_blocks));
-  rfk::conv3x3_f32_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(x, w_packed, y, B, H, L, C, Cout, co_blocks);
+  rfk::conv3x3_f32_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(x, w_packed, y, B, H, L, C, Cout, co_blocks,
+                                                                                     dilation);
   return rfk::post_launch();
+}
+
+extern "C" int rfk_conv3x3_nhwc_f32(const float* x, const float* w_packed, float* y, int B, int H, int L, int C, int Cout,
+                                    rfk_stream_t stream_) {
+  return rfk_conv3x3_nhwc_f32_dil(x, w_packed, y, B, H, L, C, Cout, 1, stream_);
 }

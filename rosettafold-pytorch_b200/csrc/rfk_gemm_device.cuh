@@ -27,6 +27,7 @@ struct GemmDev {
   // implicit-GEMM 3x3 convolution mode (CONV kernels): A is the NHWC image [B][L][L][C]; a tile is
   // 128 consecutive columns j of one image row; K runs over 9 taps x conv_cblocks 64-channel blocks
   int conv_L, conv_H, conv_Lp, conv_cblocks, conv_last_k16, conv_cpad;  // conv_L = image width, conv_H = rows
+  int conv_dil;  // dilation: tap (di, dj) reads the image at (i + di * dil, j + dj * dil)
   // TMA-store epilogues (EPI 3/4): tensor-map dimension d takes logical coordinate cmap[d] of
   // {0: n % NR, 1: n / NR, 2: m % MR, 3: m / MR, 4: z0, 5: z1, 6: z2}; -1 -> 0
   int cmap[5];
@@ -623,7 +624,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (gemm_elect_one()) {
               mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-              tma_load_5d(&tma_a, full_bar(stage), smem_a(stage), cb * kBlockK, j0 + dj, ii + di, bi, 0);
+              tma_load_5d(&tma_a, full_bar(stage), smem_a(stage), cb * kBlockK, j0 + dj * p.conv_dil, ii + di * p.conv_dil, bi, 0);
               tma_load_5d(&tma_b, full_bar(stage), smem_b(stage), tap * p.conv_cpad + cb * kBlockK,
                           (int)(nb * BN), 0, 0, 0);
             }

@@ -102,7 +102,17 @@ def _make_embedding(name: str, ref: nn.Module) -> nn.Module:
                            d_template=ref.proj.in_features - d_pair - 1 if use_template else 64)
 
 
-def accelerate(model: nn.Module, device=None, hop: bool = False, embeddings: bool = True) -> nn.Module:
+def _make_head(ref: nn.Module) -> nn.Module:
+    """PredictionHead (:1130-1172) with the reference's widths: in_channels from the LayerNorm, the number of residual
+    blocks from the ResNet's Sequential (3 input layers + blocks + 1 output projection, resnet.py:59-81)."""
+    from . import heads as H
+
+    resnet = ref.dist_head[0]
+    return H.PredictionHead(in_channels=ref.proj[0].normalized_shape[0], n_res_blocks=len(resnet.layer) - 4,
+                            p_dropout=ref.proj[2].p)
+
+
+def accelerate(model: nn.Module, device=None, hop: bool = False, embeddings: bool = True, heads: bool = True) -> nn.Module:
     """Replace the trunk of every block of a reference RoseTTAFold (rosettafold_pytorch.py:1220-1267) and, with
     `embeddings` (default), the two embeddings that feed it (`msa_emb`, `pair_emb`, :1205-1219): the reference's
     own embeddings cannot run on a GPU at all (CPU-resident tables gathered by Python loops).
@@ -113,7 +123,10 @@ def accelerate(model: nn.Module, device=None, hop: bool = False, embeddings: boo
     device of the module that consumes them. Tensors then cross PCIe only where the trunk meets the reference's own
     code: embeddings -> first block, trunk -> SE(3) structure track (msa, pair), structure track -> coordinate-
     conditioned MSA update (xyz, state), last block -> prediction head. No structure (attribute names,
-    `state_dict` keys) changes."""
+    `state_dict` keys) changes.
+
+    `heads` (default): `prediction_head` (:1269-1271, :1287) is replaced as well (PredictionHead / ResNet on librfk,
+    heads.py); the einops Rearrange layers of the reference hold no state, so the state_dict keys are unchanged."""
     blocks = list(getattr(model, "two_track_blocks", [])) + list(getattr(model, "three_track_blocks", []))
     if hasattr(model, "final_block"):
         blocks.append(model.final_block)
@@ -129,6 +142,12 @@ def accelerate(model: nn.Module, device=None, hop: bool = False, embeddings: boo
                 new = _make_embedding(name, old)
                 new.load_state_dict(old.state_dict(), strict=True)
                 setattr(model, name, new.eval().to(device) if device is not None else new.eval())
+    if heads and whole_model:
+        old = getattr(model, "prediction_head", None)
+        if old is not None and not type(old).__module__.startswith("rosettafold_pytorch_b200"):
+            new = _make_head(old)
+            new.load_state_dict(old.state_dict(), strict=True)
+            setattr(model, "prediction_head", new.eval().to(device) if device is not None else new.eval())
     if hop and whole_model:
         # the model's own direct children (embeddings, initial coordinates, prediction head); the block containers
         # are skipped, their blocks were handled above

@@ -188,15 +188,20 @@ class _CudaBackend:
         d.out_ts = out.stride(2)
         _lib.check(self.lib.rfk_favor_attention(C.byref(d), self._stream(q)), "rfk_favor_attention")
 
-    def conv3x3(self, x, w_packed, out):
+    def conv3x3(self, x, w_packed, out, dilation=1):
         B, H, L, Cin = x.shape
-        _lib.check(self.lib.rfk_conv3x3_nhwc_hw(_ptr(x), _ptr(w_packed), _ptr(out), _dt(out), B, H, L, Cin,
-                                                out.shape[3], self._stream(x)), "rfk_conv3x3_nhwc_hw")
+        _lib.check(self.lib.rfk_conv3x3_nhwc_dil(_ptr(x), _dt(x), _ptr(w_packed), _ptr(out), _dt(out), B, H, L, Cin,
+                                                 out.shape[3], int(dilation), self._stream(x)), "rfk_conv3x3_nhwc_dil")
 
-    def conv3x3_f32(self, x, w_packed, out):
+    def conv3x3_f32(self, x, w_packed, out, dilation=1):
         B, H, L, Cin = x.shape
-        _lib.check(self.lib.rfk_conv3x3_nhwc_f32(_ptr(x), _ptr(w_packed), _ptr(out), B, H, L, Cin, out.shape[3],
-                                                 self._stream(x)), "rfk_conv3x3_nhwc_f32")
+        _lib.check(self.lib.rfk_conv3x3_nhwc_f32_dil(_ptr(x), _ptr(w_packed), _ptr(out), B, H, L, Cin, out.shape[3],
+                                                     int(dilation), self._stream(x)), "rfk_conv3x3_nhwc_f32_dil")
+
+    def pair_symmetrize(self, x, out):
+        B, L, _, Cn = x.shape
+        _lib.check(self.lib.rfk_pair_symmetrize(_ptr(x), _ptr(out), _dt(x), B, L, Cn, self._stream(x)),
+                   "rfk_pair_symmetrize")
 
     def msa_embed(self, tokens, aa_idx, emb, pos_enc, query_enc, out):
         B, N, L = tokens.shape
@@ -521,28 +526,28 @@ def favor_attention(q, k, v, out, proj, *, kind, heads):
     return out
 
 
-def pack_conv3x3_weight(w: torch.Tensor) -> torch.Tensor:
-    """nn.Conv2d weight [Cout, Cin, 3, 3] -> bf16 [Cout, 9, Cpad] (tap-major, channels padded to a
-    multiple of 64 with zeros): the K-major B operand of the implicit GEMM."""
+def pack_conv3x3_weight(w: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+    """nn.Conv2d weight [Cout, Cin, 3, 3] -> 16-bit [Cout, 9, Cpad] (tap-major, channels padded to a
+    multiple of 64 with zeros): the K-major B operand of the implicit GEMM, in the dtype of the image it meets."""
     Cout, Cin = w.shape[:2]
     cpad = (Cin + 63) // 64 * 64
-    out = torch.zeros((Cout, 9, cpad), dtype=torch.bfloat16, device=w.device)
-    out[:, :, :Cin] = w.detach().permute(0, 2, 3, 1).reshape(Cout, 9, Cin).to(torch.bfloat16)
+    out = torch.zeros((Cout, 9, cpad), dtype=dtype, device=w.device)
+    out[:, :, :Cin] = w.detach().permute(0, 2, 3, 1).reshape(Cout, 9, Cin).to(dtype)
     return out
 
 
-def conv3x3(x, w_packed, out):
-    """3x3 'same' convolution without bias on a channels-last map: x bf16 [B,H,W,Cin] contiguous,
-    w_packed from pack_conv3x3_weight, out bf16/f32 [B,H,W,Cout] contiguous."""
-    if x.dim() != 4 or not x.is_contiguous() or x.dtype != torch.bfloat16:
-        raise ValueError("conv3x3: x must be contiguous bf16 [B,H,W,C]")
+def conv3x3(x, w_packed, out, dilation=1):
+    """3x3 'same' convolution (optionally dilated) without bias on a channels-last map: x bf16 / f16 [B,H,W,Cin]
+    contiguous, w_packed from pack_conv3x3_weight in x's dtype, out 16-bit / f32 [B,H,W,Cout] contiguous."""
+    if x.dim() != 4 or not x.is_contiguous() or x.dtype not in (torch.bfloat16, torch.float16):
+        raise ValueError("conv3x3: x must be contiguous bf16 / f16 [B,H,W,C]")
     Cout, taps, cpad = w_packed.shape
-    if taps != 9 or cpad != (x.shape[3] + 63) // 64 * 64 or w_packed.dtype != torch.bfloat16 or not w_packed.is_contiguous():
+    if taps != 9 or cpad != (x.shape[3] + 63) // 64 * 64 or w_packed.dtype != x.dtype or not w_packed.is_contiguous():
         raise ValueError("conv3x3: w_packed must come from pack_conv3x3_weight for this channel count")
     if tuple(out.shape) != (x.shape[0], x.shape[1], x.shape[2], Cout) or not out.is_contiguous():
         raise ValueError("conv3x3: bad output shape")
     with _Timed("conv3x3", 2.0 * x.shape[0] * x.shape[1] * x.shape[2] * 9 * x.shape[3] * Cout):
-        _call("conv3x3", x, w_packed, out)
+        _call("conv3x3", x, w_packed, out, int(dilation))
     return out
 
 
@@ -552,8 +557,8 @@ def pack_conv3x3_weight_f32(w: torch.Tensor) -> torch.Tensor:
     return w.detach().float().permute(2, 3, 1, 0).reshape(9, Cin, Cout).contiguous()
 
 
-def conv3x3_f32(x, w_packed, out):
-    """fp32 validation-mode 3x3 'same' convolution: x f32 [B,H,W,Cin], w_packed from pack_conv3x3_weight_f32,
+def conv3x3_f32(x, w_packed, out, dilation=1):
+    """fp32 validation-mode 3x3 'same' convolution (dilation 1..8): x f32 [B,H,W,Cin], w_packed from pack_conv3x3_weight_f32,
     out f32 [B,H,W,Cout], all contiguous."""
     if x.dim() != 4 or not x.is_contiguous() or x.dtype != torch.float32:
         raise ValueError("conv3x3_f32: x must be contiguous f32 [B,H,W,C]")
@@ -562,7 +567,20 @@ def conv3x3_f32(x, w_packed, out):
         raise ValueError("conv3x3_f32: w_packed must come from pack_conv3x3_weight_f32 for this channel count")
     if tuple(out.shape) != (*x.shape[:3], w_packed.shape[2]) or not out.is_contiguous() or out.dtype != torch.float32:
         raise ValueError("conv3x3_f32: bad output")
-    _call("conv3x3_f32", x, w_packed, out)
+    _call("conv3x3_f32", x, w_packed, out, int(dilation))
+    return out
+
+
+def pair_symmetrize(x, out):
+    """out[b,i,j,:] = 0.5 (x[b,i,j,:] + x[b,j,i,:]) on a contiguous channels-last [B,L,L,C] map (PredictionHead :1166);
+    f32 (C % 4 == 0) or 16-bit (C % 8 == 0), out of x's dtype and shape, not aliasing x."""
+    if x.dim() != 4 or x.shape[1] != x.shape[2] or not x.is_contiguous():
+        raise ValueError("pair_symmetrize: x must be contiguous [B,L,L,C]")
+    if out.shape != x.shape or out.dtype != x.dtype or not out.is_contiguous() or out.data_ptr() == x.data_ptr():
+        raise ValueError("pair_symmetrize: out must be a distinct contiguous tensor of x's shape and dtype")
+    if x.shape[3] % (4 if x.dtype == torch.float32 else 8):
+        raise ValueError("pair_symmetrize: channel count must fill 16-byte chunks")
+    _call("pair_symmetrize", x, out)
     return out
 
 

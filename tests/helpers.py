@@ -119,3 +119,14 @@ def build_embeddings(c, device="cpu"):
     m.load_state_dict(sd_m, strict=True)
     p.load_state_dict(sd_p, strict=True)
     return m.to(device), p.to(device), sd_m, sd_p, synth_embed_inputs(c)
+
+
+def build_heads(c, device="cpu"):
+    """The b200 PredictionHead with a fixture's synthetic weights (oracle/make_golden.py HEAD_CONFIGS) and its input."""
+    import rosettafold_pytorch_b200 as rf
+    from oracle.make_golden import synth_head_input
+
+    h = rf.PredictionHead(c["in_channels"], c["n_res_blocks"], 0.1).eval()
+    sd = synth_state_dict(h.state_dict(), seed=c["seed"])
+    h.load_state_dict(sd, strict=True)
+    return h.to(device), sd, synth_head_input(c)

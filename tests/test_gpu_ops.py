@@ -463,3 +463,42 @@ def test_convert_rows(cuda_device, cols, ys, h16):
     ops.convert_rows(got, back)
     torch.cuda.synchronize()
     assert torch.equal(back, got.float())
+
+
+@pytest.mark.parametrize("dilation", [2, 4, 8])
+@pytest.mark.parametrize("cfg", [(1, 28, 288, 288), (2, 130, 72, 96)])
+def test_conv3x3_dilated(cuda_device, cfg, dilation):
+    """Dilated 3x3 'same' convolution (ResBlock2D of the prediction heads, resnet.py:19-37): the tcgen05 implicit GEMM
+    shifts its nine TMA boxes by the dilation (zero fill outside the image), the fp32 SIMT kernel widens its window;
+    both against F.conv2d. L = 130 crosses the 128-column tile, dilation 8 reaches past it."""
+    dev = cuda_device
+    B, L, Cin, Cout = cfg
+    x = _rand((B, L, L, Cin), torch.bfloat16, dev, 190)
+    w = _rand((Cout, Cin, 3, 3), torch.float32, dev, 191, (9 * Cin) ** -0.5)
+    out = torch.empty((B, L, L, Cout), dtype=torch.float32, device=dev)
+    ops.conv3x3(x, ops.pack_conv3x3_weight(w), out, dilation)
+    ref = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w.to(torch.bfloat16).double(), padding=dilation,
+                                     dilation=dilation).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) < 1e-5
+    x32 = x.float()
+    out32 = torch.empty_like(out)
+    ops.conv3x3_f32(x32, ops.pack_conv3x3_weight_f32(w), out32, dilation)
+    ref32 = torch.nn.functional.conv2d(x32.double().permute(0, 3, 1, 2), w.double(), padding=dilation,
+                                       dilation=dilation).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    assert rel_l2(out32, ref32) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_pair_symmetrize(cuda_device, dtype):
+    """0.5 (x + x^T) over the two residue axes of a channels-last map (PredictionHead :1166)."""
+    dev = cuda_device
+    x = _rand((2, 37, 37, 72), dtype, dev, 195)
+    out = ops.pair_symmetrize(x, torch.empty_like(x))
+    torch.cuda.synchronize()
+    ref = 0.5 * (x.double() + x.double().transpose(1, 2))
+    assert rel_l2(out, ref) < tol(dtype)
+    assert torch.equal(out, out.transpose(1, 2))
+    with pytest.raises(ValueError):
+        ops.pair_symmetrize(x, x)

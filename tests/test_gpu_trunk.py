@@ -200,3 +200,44 @@ def test_embeddings_large_shape_vs_oracle(cuda_device):
     torch.cuda.synchronize()
     assert torch.equal(msa.cpu(), embed_ref.msa_embedding(tokens, aa_idx, sd_m, max_len))
     assert rel_l2(pair, embed_ref.pair_embedding(seq, aa_idx, sd_p, max_len)) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["small", "default"])
+def test_prediction_head_vs_golden(cuda_device, name):
+    """PredictionHead (:1130-1172; four ResNets, dilations 1 / 2 / 4 / 8) on librfk against the unmodified reference's
+    outputs: fp32 validation mode <= 1e-4, tensor-core mode <= 1e-2."""
+    from tests.helpers import build_heads
+
+    gold = load_golden("prediction_head")[name]
+    head, _, pair = build_heads(gold["config"], cuda_device)
+    pair = pair.to(cuda_device)
+    for mode, tol_ in (("fp32", 1e-4), ("bf16", 1e-2)):
+        rf.set_mode(mode)
+        out = head(pair)
+        torch.cuda.synchronize()
+        for k in ("theta", "phi", "dist", "omega"):
+            e = rel_l2(out[k], gold[k])
+            assert e < tol_, f"{mode} {k}: rel-l2 {e}"
+    rf.set_mode("bf16")
+
+
+def test_prediction_head_tile_crossing_vs_oracle(cuda_device):
+    """Default width at L = 136 (every convolution tile boundary crossed, dilation 8 reaching across it) against the CPU
+    restatement (pinned to the reference by tests/test_oracle.py), tensor-core mode."""
+    from oracle import heads_ref
+    from oracle.weights import synth_state_dict
+
+    C, n_blocks, L = 288, 4, 136
+    head = rf.PredictionHead(C, n_blocks, 0.1).eval()
+    sd = synth_state_dict(head.state_dict(), seed=95)
+    head.load_state_dict(sd)
+    head = head.to(cuda_device)
+    pair = torch.randn((1, L, L, C), generator=torch.Generator().manual_seed(96))
+    rf.set_mode("bf16")
+    out = head(pair.to(cuda_device))
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = heads_ref.prediction_head(pair, sd, n_blocks)
+    for k in ("theta", "phi", "dist", "omega"):
+        e = rel_l2(out[k], ref[k])
+        assert e < 1e-2, f"{k}: rel-l2 {e}"

@@ -346,3 +346,25 @@ def test_embeddings_match_golden(emulated_ops, name):
     if template is None:
         with pytest.raises(ValueError):
             p(seq, aa_idx, torch.zeros(1))
+
+
+@pytest.mark.parametrize("name", ["small", "default"])
+def test_prediction_head_matches_golden(emulated_ops, name):
+    """Host logic of PredictionHead / ResNet / ResBlock2D (channels-last bookkeeping, weight packing of the 1 x 1 and
+    dilated 3 x 3 convolutions, residual / InstanceNorm wiring, symmetrised input of the dist / omega heads) against
+    the unmodified reference's outputs; the kernels themselves are checked by `-m gpu`."""
+    from tests.helpers import build_heads
+
+    gold = load_golden("prediction_head")[name]
+    head, _, pair = build_heads(gold["config"])
+    rf.set_mode("fp32")
+    out = head(pair)
+    for k in ("theta", "phi", "dist", "omega"):
+        assert rel_l2(out[k], gold[k]) < 1e-4, k
+    # the NCHW entry points of the building blocks (API parity with resnet.py)
+    rn = head.theta_head[0]
+    x = torch.randn(1, gold["config"]["in_channels"], 9, 9)
+    assert rn(x).shape == (1, 37, 9, 9)
+    assert rn.layer[3](x).shape == x.shape
+    with pytest.raises(ValueError):
+        head(pair[:, :1, :1])

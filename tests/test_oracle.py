@@ -139,3 +139,20 @@ def test_embedding_restatement_matches_golden(name):
     pair = embed_ref.pair_embedding(seq, aa_idx, sd_p, c["max_len"], template=template)
     assert torch.equal(msa, gold["msa"])          # integer gathers and two fp32 adds in the reference's order: exact
     assert rel_l2(pair, gold["pair"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["small", "default"])
+def test_prediction_head_restatement_matches_golden(name):
+    """oracle/heads_ref.py against the outputs of the unmodified reference's PredictionHead (four ResNets with
+    dilations 1, 2, 4, 8; resnet.py, rosettafold_pytorch.py:1130-1172)."""
+    from oracle import heads_ref
+    from tests.helpers import build_heads
+
+    gold = load_golden("prediction_head")[name]
+    c = gold["config"]
+    _, sd, pair = build_heads(c)
+    with torch.no_grad():
+        out = heads_ref.prediction_head(pair, sd, c["n_res_blocks"])
+    for k in ("theta", "phi", "dist", "omega"):
+        assert out[k].shape == gold[k].shape
+        assert rel_l2(out[k], gold[k]) < 2e-5, k
