@@ -112,6 +112,9 @@ def test_performer_restatement_matches_the_package_when_importable(generalized):
     pp = pytest.importorskip("performer_pytorch")
     from oracle import performer_ref as P
 
+    if "oracle" in (getattr(pp, "__file__", None) or "oracle") or pp.SelfAttention is P.SelfAttention:
+        pytest.skip("`performer_pytorch` resolves to the oracle's own stand-in (oracle/shims), not to the real package")
+
     torch.manual_seed(5)
     dim, heads = 96, 3
     mine = P.SelfAttention(dim, heads=heads, generalized_attention=generalized).eval()
