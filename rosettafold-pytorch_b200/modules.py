@@ -121,6 +121,9 @@ class Residual(nn.Module):
         self.dropout = nn.Dropout(p_dropout) if p_dropout is not None else None
 
     def forward(self, x):
+        # generic container form only: every Residual the trunk builds is executed by its owner's fused path (the add
+        # lives in a GEMM / LayerNorm / InstanceNorm epilogue); this plain add serves a user-supplied `fn` and is
+        # eval-mode like the rest of the package (the dropout of :27 is the identity)
         return self.fn(x) + x
 
 
@@ -760,8 +763,11 @@ class Symmetrization(nn.Module):
 
     @torch.no_grad()
     def forward(self, x):
-        # API-parity helper; the fused path symmetrises inside rfk_pair2att_logits
-        return 0.5 * (x + x.transpose(1, 2))
+        """Standalone form (:550-556) on rfk_pair_symmetrize; the fused path symmetrises inside rfk_pair2att_logits."""
+        x = _as_f32(x).contiguous()
+        if x.dim() != 4 or x.shape[1] != x.shape[2] or x.shape[3] % 4:
+            raise ValueError("Symmetrization: expected [B, L, L, C] with C % 4 == 0")
+        return ops.pair_symmetrize(x, torch.empty_like(x))
 
 
 class MsaUpdateWithPairLayer(nn.Module):

@@ -4,6 +4,9 @@ against the golden vectors of the unmodified reference and against the oracle re
 Tolerances are the north star's: relative L2 <= 1e-4 in the fp32 validation mode and <= 1e-2 in
 the bf16 tensor-core mode, per trunk stage with each stage fed the reference's inputs AND for the free-running
 chain of the whole block. The BASELINE.json shapes are in tests/test_gpu_baseline_configs.py."""
+import json
+import os
+
 import pytest
 import torch
 
@@ -241,3 +244,47 @@ def test_prediction_head_tile_crossing_vs_oracle(cuda_device):
     for k in ("theta", "phi", "dist", "omega"):
         e = rel_l2(out[k], ref[k])
         assert e < 1e-2, f"{k}: rel-l2 {e}"
+
+
+def test_tokens_to_logits_pipeline_vs_oracle(cuda_device):
+    """Everything this package replaces, composed on the device: MsaEmbedding / PairEmbedding -> two-track trunk blocks ->
+    PredictionHead, from integer tokens to distance / orientation logits, against the same composition of the CPU
+    restatements (each pinned to the unmodified reference separately). This is the part of RoseTTAFold.forward
+    (:1273-1289) that does not need the SE(3) structure track; it measures how the trunk's 16-bit rounding arrives in
+    the heads' logits (row g of the verdict's table, on hardware)."""
+    from oracle import embed_ref, heads_ref, trunk_ref
+    from oracle.weights import synth_state_dict
+
+    B, N, L, max_len, n_blocks, n_layers, n_res = 1, 20, 72, 400, 2, 1, 4
+    emb_m, emb_p = rf.MsaEmbedding(21, 384, max_len).eval(), rf.PairEmbedding(21, 288, max_len).eval()
+    trunk = rf.TrunkBlocks(384, 288, n_blocks=n_blocks, n_encoder_layers=n_layers).eval()
+    head = rf.PredictionHead(288, n_res, 0.1).eval()
+    sds = []
+    for i, m in enumerate((emb_m, emb_p, trunk, head)):
+        sd = synth_state_dict(m.state_dict(), seed=300 + i)
+        m.load_state_dict(sd)
+        m.to(cuda_device)
+        sds.append(sd)
+    g = torch.Generator().manual_seed(310)
+    tokens, seq = torch.randint(0, 21, (B, N, L), generator=g), torch.randint(0, 21, (B, L), generator=g)
+    aa_idx = torch.arange(L).repeat(B, 1)
+    aa_idx[:, L // 2:] += 30
+    with torch.no_grad():
+        msa_r = embed_ref.msa_embedding(tokens, aa_idx, sds[0], max_len)
+        pair_r = embed_ref.pair_embedding(seq, aa_idx, sds[1], max_len)
+        for b in range(n_blocks):
+            msa_r, pair_r = trunk_ref.two_track_block(msa_r, pair_r, sds[2], n_layers, prefix=f"blocks.{b}.")
+        ref = heads_ref.prediction_head(pair_r, sds[3], n_res)
+    errs = {}
+    for mode, tol_ in (("fp32", 1e-4), ("bf16", 1e-2)):
+        rf.set_mode(mode)
+        msa, pair = trunk(emb_m(tokens, aa_idx), emb_p(seq, aa_idx))
+        out = head(pair)
+        torch.cuda.synchronize()
+        errs[mode] = dict(msa=rel_l2(msa, msa_r), pair=rel_l2(pair, pair_r), **{k: rel_l2(out[k], ref[k]) for k in ref})
+        assert max(errs[mode].values()) < tol_, (mode, errs[mode])
+    rf.set_mode("bf16")
+    print("tokens -> logits:", errs)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_r02.jsonl", "a") as f:
+        f.write(json.dumps(dict(test="tokens_to_logits_pipeline", shape=[B, N, L], blocks=n_blocks, errs=errs)) + "\n")
