@@ -117,6 +117,43 @@ def make_heads(ref, rf):
     print(os.path.getsize(path))
 
 
+GRAPH_CONFIGS = {
+    # GraphTransformerBlock (:613-677) at the widths the model builds it with (:1232-1240), ragged L; with and without mask
+    "default": dict(d_node=64, d_out=64, d_edge=64, n_heads=4, B=2, L=21, seed=110),
+    "narrow": dict(d_node=32, d_out=16, d_edge=24, n_heads=3, B=1, L=37, seed=111),
+}
+
+
+def synth_graph_inputs(c):
+    g = torch.Generator().manual_seed(c["seed"] + 100)
+    B, L = c["B"], c["L"]
+    node = torch.randn((B, L, c["d_node"]), generator=g)
+    edge = torch.randn((B, L, L, c["d_edge"]), generator=g)
+    mask = (torch.rand((B, L, L), generator=g) > 0.3).float()
+    mask[:, torch.arange(L), torch.arange(L)] = 1.0  # every node keeps at least its self edge
+    return node, edge, mask
+
+
+def make_graph(ref, rf):
+    out = {}
+    for name, c in GRAPH_CONFIGS.items():
+        mine = rf.GraphTransformerBlock(c["d_node"], c["d_out"], c["d_edge"], c["n_heads"])
+        sd = synth_state_dict(mine.state_dict(), seed=c["seed"])
+        rb = ref.GraphTransformerBlock(c["d_node"], c["d_out"], c["d_edge"], c["n_heads"])
+        rb.load_state_dict(sd, strict=True)
+        rb.eval()
+        node, edge, mask = synth_graph_inputs(c)
+        with torch.no_grad():
+            out[name] = dict(config=c, weight_checksum=checksum(sd), block=rb(node, edge, None),
+                             block_masked=rb(node, edge, mask), attn=rb.attn(node, edge, None),
+                             attn_masked=rb.attn(node, edge, mask))
+        print("graph", name, tuple(out[name]["block"].shape), tuple(out[name]["attn"].shape))
+    path = os.path.join(ROOT, "tests", "golden", "graph_transformer.pt")
+    out["generator"] = "oracle/make_golden.py --graph-only on the unmodified reference (CPU fp32, eval)"
+    torch.save(out, path)
+    print(os.path.getsize(path))
+
+
 COORD_CONFIGS = {
     # MsaUpdateWithPairAndCoord (:865-920) as built by the three-track blocks (:1028-1035), ragged N / L
     "msa_pair_coord": dict(d_msa=96, d_state=32, d_inner=32, d_ff=192, B=2, N=5, L=20, seed=6),
@@ -223,9 +260,12 @@ def main():
         return make_embeddings(ref, rf)
     if "--heads-only" in sys.argv:
         return make_heads(ref, rf)
+    if "--graph-only" in sys.argv:
+        return make_graph(ref, rf)
     if "--subset-only" not in sys.argv:
         make_embeddings(ref, rf)
         make_heads(ref, rf)
+        make_graph(ref, rf)
         make_coord(ref, rf)
     if "--coord-only" in sys.argv:
         return

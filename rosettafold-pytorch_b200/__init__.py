@@ -15,6 +15,8 @@ from .modules import (ColWise, EncoderLayer, FeedForward, MsaUpdateUsingSelfAtte
                       TwoTrackBlock, get_mode, load_reference_weights, set_bounded_operand_dtype, set_mode)
 from .embeddings import (MsaEmbedding, PairEmbedding, SinusoidalPositionalEncoding,  # noqa: E402,F401
                          SinusoidalPositionalEncoding2D)
+from . import graph  # noqa: E402,F401
+from .graph import GraphTransformer, GraphTransformerBlock  # noqa: E402,F401
 from . import heads  # noqa: E402,F401
 from .heads import PredictionHead, ResBlock2D, ResNet  # noqa: E402,F401
 from . import replicas  # noqa: E402,F401

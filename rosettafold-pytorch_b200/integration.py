@@ -112,6 +112,15 @@ def _make_head(ref: nn.Module) -> nn.Module:
                             p_dropout=ref.proj[2].p)
 
 
+def _make_graph_block(ref: nn.Module) -> nn.Module:
+    """GraphTransformerBlock (:667-677) with the reference block's widths."""
+    from . import graph as G
+
+    a = ref.attn
+    return G.GraphTransformerBlock(d_node_in=a.node_to_q.in_features, d_node_out=a.node_to_q.out_features // a.n_heads,
+                                   d_edge=a.edge_emb.in_features, n_heads=a.n_heads, p_dropout=a.att_dropout.p)
+
+
 def accelerate(model: nn.Module, device=None, hop: bool = False, embeddings: bool = True, heads: bool = True) -> nn.Module:
     """Replace the trunk of every block of a reference RoseTTAFold (rosettafold_pytorch.py:1220-1267) and, with
     `embeddings` (default), the two embeddings that feed it (`msa_emb`, `pair_emb`, :1205-1219): the reference's
@@ -126,7 +135,8 @@ def accelerate(model: nn.Module, device=None, hop: bool = False, embeddings: boo
     `state_dict` keys) changes.
 
     `heads` (default): `prediction_head` (:1269-1271, :1287) is replaced as well (PredictionHead / ResNet on librfk,
-    heads.py); the einops Rearrange layers of the reference hold no state, so the state_dict keys are unchanged."""
+    heads.py; the einops Rearrange layers of the reference hold no state, so the state_dict keys are unchanged), and so
+    are the dense GraphTransformerBlocks inside `initial_coord_generation_with_msa_and_pair` (graph.py)."""
     blocks = list(getattr(model, "two_track_blocks", [])) + list(getattr(model, "three_track_blocks", []))
     if hasattr(model, "final_block"):
         blocks.append(model.final_block)
@@ -148,6 +158,18 @@ def accelerate(model: nn.Module, device=None, hop: bool = False, embeddings: boo
             new = _make_head(old)
             new.load_state_dict(old.state_dict(), strict=True)
             setattr(model, "prediction_head", new.eval().to(device) if device is not None else new.eval())
+    if heads and whole_model:
+        # the dense graph-transformer blocks of the initial-coordinate generator (:699-702, :723-724): the reference
+        # keeps them in a plain Python list, so they are replaced in that list
+        gen = getattr(model, "initial_coord_generation_with_msa_and_pair", None)
+        held = gen.__dict__.get("blocks") if gen is not None else None
+        if isinstance(held, list):
+            for i, old in enumerate(held):
+                if type(old).__module__.startswith("rosettafold_pytorch_b200"):
+                    continue
+                new = _make_graph_block(old)
+                new.load_state_dict(old.state_dict(), strict=True)
+                held[i] = new.eval().to(device) if device is not None else new.eval()
     if hop and whole_model:
         # the model's own direct children (embeddings, initial coordinates, prediction head); the block containers
         # are skipped, their blocks were handled above

@@ -130,3 +130,14 @@ def build_heads(c, device="cpu"):
     sd = synth_state_dict(h.state_dict(), seed=c["seed"])
     h.load_state_dict(sd, strict=True)
     return h.to(device), sd, synth_head_input(c)
+
+
+def build_graph_block(c, device="cpu"):
+    """The b200 GraphTransformerBlock with a fixture's synthetic weights (oracle/make_golden.py GRAPH_CONFIGS) and inputs."""
+    import rosettafold_pytorch_b200 as rf
+    from oracle.make_golden import synth_graph_inputs
+
+    blk = rf.GraphTransformerBlock(c["d_node"], c["d_out"], c["d_edge"], c["n_heads"]).eval()
+    sd = synth_state_dict(blk.state_dict(), seed=c["seed"])
+    blk.load_state_dict(sd, strict=True)
+    return blk.to(device), sd, synth_graph_inputs(c)

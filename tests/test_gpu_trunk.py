@@ -288,3 +288,44 @@ def test_tokens_to_logits_pipeline_vs_oracle(cuda_device):
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/parity_r02.jsonl", "a") as f:
         f.write(json.dumps(dict(test="tokens_to_logits_pipeline", shape=[B, N, L], blocks=n_blocks, errs=errs)) + "\n")
+
+
+@pytest.mark.parametrize("name", ["default", "narrow"])
+def test_graph_transformer_vs_golden(cuda_device, name):
+    """GraphTransformer / GraphTransformerBlock (:613-677) on librfk against the unmodified reference, with and without an
+    edge mask: fp32 validation mode <= 1e-4, tensor-core mode <= 1e-2."""
+    from tests.helpers import build_graph_block
+
+    gold = load_golden("graph_transformer")[name]
+    blk, _, (node, edge, mask) = build_graph_block(gold["config"], cuda_device)
+    node, edge, mask = node.to(cuda_device), edge.to(cuda_device), mask.to(cuda_device)
+    for mode, tol_ in (("fp32", 1e-4), ("bf16", 1e-2)):
+        rf.set_mode(mode)
+        outs = dict(attn=blk.attn(node, edge), attn_masked=blk.attn(node, edge, mask), block=blk(node, edge, None),
+                    block_masked=blk(node, edge, mask))
+        torch.cuda.synchronize()
+        for k, v in outs.items():
+            e = rel_l2(v, gold[k])
+            assert e < tol_, f"{mode} {k}: rel-l2 {e}"
+    rf.set_mode("bf16")
+
+
+def test_graph_transformer_large_vs_oracle(cuda_device):
+    """L = 200 (tile-crossing, not a multiple of 8), model widths, against the CPU restatement, tensor-core mode."""
+    from oracle import graph_ref
+    from oracle.weights import synth_state_dict
+
+    B, L, Dn, d, De, H = 1, 200, 64, 64, 64, 4
+    blk = rf.GraphTransformerBlock(Dn, d, De, H).eval()
+    sd = synth_state_dict(blk.state_dict(), seed=120)
+    blk.load_state_dict(sd)
+    blk = blk.to(cuda_device)
+    g = torch.Generator().manual_seed(121)
+    node, edge = torch.randn((B, L, Dn), generator=g), torch.randn((B, L, L, De), generator=g)
+    rf.set_mode("bf16")
+    out = blk(node.to(cuda_device), edge.to(cuda_device), None)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = graph_ref.graph_transformer_block(node, edge, None, sd, H)
+    e = rel_l2(out, ref)
+    assert e < 1e-2, e

@@ -368,3 +368,20 @@ def test_prediction_head_matches_golden(emulated_ops, name):
     assert rn.layer[3](x).shape == x.shape
     with pytest.raises(ValueError):
         head(pair[:, :1, :1])
+
+
+@pytest.mark.parametrize("name", ["default", "narrow"])
+def test_graph_transformer_matches_golden(emulated_ops, name):
+    """Host logic of GraphTransformer(Block): the strided batched GEMM views that replace the reference's einsums over the
+    materialised edge embedding, the folded scale, the additive mask, ELU + residual epilogue."""
+    from tests.helpers import build_graph_block
+
+    gold = load_golden("graph_transformer")[name]
+    blk, _, (node, edge, mask) = build_graph_block(gold["config"])
+    rf.set_mode("fp32")
+    assert rel_l2(blk.attn(node, edge), gold["attn"]) < 1e-5
+    assert rel_l2(blk.attn(node, edge, mask), gold["attn_masked"]) < 1e-5
+    assert rel_l2(blk(node, edge, None), gold["block"]) < 1e-5
+    assert rel_l2(blk(node, edge, mask), gold["block_masked"]) < 1e-5
+    with pytest.raises(ValueError):
+        blk.attn(node, edge[:, :, :-1])

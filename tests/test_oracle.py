@@ -159,3 +159,20 @@ def test_prediction_head_restatement_matches_golden(name):
     for k in ("theta", "phi", "dist", "omega"):
         assert out[k].shape == gold[k].shape
         assert rel_l2(out[k], gold[k]) < 2e-5, k
+
+
+@pytest.mark.parametrize("name", ["default", "narrow"])
+def test_graph_transformer_restatement_matches_golden(name):
+    """oracle/graph_ref.py against the unmodified reference's GraphTransformer / GraphTransformerBlock (:613-677)."""
+    from oracle import graph_ref
+    from tests.helpers import build_graph_block
+
+    gold = load_golden("graph_transformer")[name]
+    c = gold["config"]
+    _, sd, (node, edge, mask) = build_graph_block(c)
+    attn_sd = {k[len("attn."):]: v for k, v in sd.items() if k.startswith("attn.")}
+    with torch.no_grad():
+        assert rel_l2(graph_ref.graph_transformer(node, edge, None, attn_sd, c["n_heads"]), gold["attn"]) < 2e-5
+        assert rel_l2(graph_ref.graph_transformer(node, edge, mask, attn_sd, c["n_heads"]), gold["attn_masked"]) < 2e-5
+        assert rel_l2(graph_ref.graph_transformer_block(node, edge, None, sd, c["n_heads"]), gold["block"]) < 2e-5
+        assert rel_l2(graph_ref.graph_transformer_block(node, edge, mask, sd, c["n_heads"]), gold["block_masked"]) < 2e-5
