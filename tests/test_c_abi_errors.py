@@ -103,3 +103,26 @@ def test_well_formed_calls_fail_loudly_without_a_gpu(lib):
         assert lib.rfk_strerror(c)
     assert torch.count_nonzero(buf) == 0
     assert lib.rfk_launch_count() >= before
+
+
+def test_heads_entry_points_reject_bad_arguments(lib):
+    """The entry points added for the prediction heads: dilated convolutions and the pair symmetrisation."""
+    buf = torch.zeros(64 * 64, dtype=torch.float32)
+    p = C.c_void_p(buf.data_ptr())
+    q = C.c_void_p(buf.data_ptr() + 4096)
+    F16 = 2
+    assert lib.rfk_conv3x3_nhwc_dil(None, BF16, p, p, F32, 1, 8, 8, 64, 64, 2, None) == NULL_PTR
+    assert lib.rfk_conv3x3_nhwc_dil(p, BF16, p, p, F32, 1, 8, 8, 64, 64, 0, None) == BAD_DIMS        # dilation < 1
+    assert lib.rfk_conv3x3_nhwc_dil(p, BF16, p, p, F32, 1, 8, 8, 64, 64, 65, None) == BAD_DIMS       # dilation > 64
+    assert lib.rfk_conv3x3_nhwc_dil(p, F32, p, p, F32, 1, 8, 8, 64, 64, 1, None) == BAD_DTYPE        # image must be 16-bit
+    assert lib.rfk_conv3x3_nhwc_dil(p, F16, p, p, 9, 1, 8, 8, 64, 64, 1, None) == BAD_DTYPE
+    assert lib.rfk_conv3x3_nhwc_dil(p, BF16, p, p, F32, 1, 8, 8, 60, 64, 1, None) == BAD_DIMS        # C % 8
+    assert lib.rfk_conv3x3_nhwc_f32_dil(p, None, p, 1, 8, 8, 64, 64, 1, None) == NULL_PTR
+    assert lib.rfk_conv3x3_nhwc_f32_dil(p, p, p, 1, 8, 8, 64, 64, 9, None) == BAD_DIMS              # SIMT form: dilation <= 8
+    assert lib.rfk_conv3x3_nhwc_f32_dil(p, p, p, 1, 0, 8, 64, 64, 1, None) == BAD_DIMS
+    assert lib.rfk_pair_symmetrize(None, q, F32, 1, 4, 8, None) == NULL_PTR
+    assert lib.rfk_pair_symmetrize(p, p, F32, 1, 4, 8, None) == 8                                  # in place: unsupported
+    assert lib.rfk_pair_symmetrize(p, q, F32, 1, 4, 6, None) == BAD_DIMS                           # C % 4
+    assert lib.rfk_pair_symmetrize(p, q, BF16, 1, 4, 12, None) == BAD_DIMS                         # 16-bit: C % 8
+    assert lib.rfk_pair_symmetrize(p, q, 7, 1, 4, 8, None) == BAD_DTYPE
+    assert lib.rfk_pair_symmetrize(p, q, F32, 0, 4, 8, None) == BAD_DIMS
