@@ -315,13 +315,23 @@ class SoftTiedAttentionOverResidues(nn.Module):
                            q_scale=self.scale, qt=qt, heads=H, d_head=dh, stats=stats)
         logits = _empty((B, H, L, L), torch.float32, xn4)
         ops.gemm(qt, kt, logits.view(1, B, H, 1, L, 1, L))
+        A = _empty((B, H, L, Lp), adt, xn4)
+        R = B * H * L  # rows of the attention map
         if shard is not None:
             # this shard's weights were normalised over its own sequences: rescale row (h, i) of the partial
             # logits to the global normalisation, then sum the partial logits over the shards
             logits.mul_(shard.softmax_correction(stats).permute(0, 2, 1).unsqueeze(-1))
-            shard.allreduce(logits)
-        A = _empty((B, H, L, Lp), adt, xn4)
-        ops.softmax_rows(logits.view(B * H * L, L), A.view(B * H * L, Lp)[:, :L])
+        if shard is not None and R % shard.world == 0:
+            # reduce-scatter by rows -> softmax of this rank's rows -> all-gather of the 16-bit probabilities: three
+            # quarters of the bytes of an all-reduce of the fp32 map, and 1 / P of the softmax
+            mine = shard.reduce_scatter_rows(logits.view(R, L))
+            A_mine = torch.zeros((mine.shape[0], Lp), dtype=adt, device=xn4.device)
+            ops.softmax_rows(mine, A_mine[:, :L])
+            shard.all_gather_rows(A_mine, A.view(R, Lp))
+        else:
+            if shard is not None:
+                shard.allreduce(logits)
+            ops.softmax_rows(logits.view(R, L), A.view(R, Lp)[:, :L])
         att = None
         if want_att:
             att = _empty((B, L, L, H), torch.float32, xn4)

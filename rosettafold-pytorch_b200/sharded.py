@@ -211,6 +211,18 @@ class SequenceShard:
     def allreduce(self, t: torch.Tensor) -> None:
         _collective(lambda: dist.all_reduce(t, group=self.group))
 
+    def reduce_scatter_rows(self, t: torch.Tensor) -> torch.Tensor:
+        """[R, C] contiguous partial sums on every rank -> [R / P, C]: rows [rank R / P, (rank + 1) R / P) of the sum."""
+        out = torch.empty((t.shape[0] // self.world, t.shape[1]), dtype=t.dtype, device=t.device)
+        src = t.reshape(-1)
+        _collective(lambda: dist.reduce_scatter_tensor(out.view(-1), src, group=self.group))
+        return out
+
+    def all_gather_rows(self, mine: torch.Tensor, full: torch.Tensor) -> None:
+        """[R / P, C] (this rank's rows) -> full [R, C] contiguous, rows in rank order."""
+        dst, src = full.view(-1), mine.reshape(-1)
+        _collective(lambda: dist.all_gather_into_tensor(dst, src, group=self.group))
+
 
 def all_to_all_seqs_to_residues(x_seqs: torch.Tensor, group=None) -> torch.Tensor:
     """[1, N/P, L, D] (my sequences, all residues) -> [1, N, L/P, D] (all sequences, my residues)."""
