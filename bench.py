@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=1, help="samples per GPU per step")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-shapes", default=None, help="write the eager pass's per-(op, algorithmic work) device times here")
     ap.add_argument("--no-long-protein", action="store_true", help="skip the config-4 record of multi-GPU runs")
     ap.add_argument("--long-L", type=int, default=1024)
     ap.add_argument("--long-N", type=int, default=256)
@@ -280,6 +281,16 @@ def run_b200(args):
     eager_ms = timed(step_eager, args.steps)
     fam = ops.stop_timing()
     launches = (rf._lib.launch_count() - n0) // max(1, args.steps) * args.steps
+    if args.dump_shapes and rank == 0:
+        rows = []
+        for k, v in fam.items():
+            for w, e in v["shapes"].items():
+                if e["calls"]:
+                    rows.append(dict(op=k, work=w, calls_per_step=e["calls"] / args.steps, avg_us=1e3 * e["ms"] / e["calls"],
+                                     ms_per_step=e["ms"] / args.steps, rate=w / (e["ms"] / e["calls"] * 1e-3) / 1e12))
+        rows.sort(key=lambda r: -r["ms_per_step"])
+        with open(args.dump_shapes, "w") as f:
+            json.dump(rows, f, indent=1)
     total_ms = timed(step_resident, args.steps)
     step_e2e()  # warm the pinned-copy path
     drain_e2e()
